@@ -1,0 +1,213 @@
+"""
+Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/slam_system) on seeded inputs.
+Run in the authoring container only:  python tests/golden/make_golden.py
+The .npz files are committed; the GPU box never needs /root/reference.
+
+Goldens (reference function -> file):
+  PTZCamera.project_ray / project_rays, TransFunction.from_ray_to_image           -> projection.npz
+  PTZCamera.back_project_to_ray(s), TransFunction.from_image_to_ray               -> backprojection.npz
+  PtzSlam.compute_h_jacobian                                                      -> h_jacobian.npz
+  PtzSlam.ekf_update + predict lines ptz_slam.py:418-426 (6 frames)               -> ekf.npz
+  bundle_adjustment._compute_residual                                             -> ba_residual.npz
+  scipy least_squares call of bundle_adjustment.py:200-202 (as-is and tight)      -> ba_solve.npz
+"""
+import copy
+import io
+import os
+import sys
+import contextlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+import ptz_slam_b200  # noqa: E402,F401
+from ptz_slam_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+ref = ref_import.load()
+U, V, W, H = synth.PP_U, synth.PP_V, synth.IMAGE_W, synth.IMAGE_H
+CC = np.array([13.0099, -14.8109, 6.1790])
+BASE_ROT = np.array([1.5804, -0.1186, 0.1249])
+DISP = np.array([0.012, -0.008, 0.05, 1.5e-6, -2.0e-6, 4.0e-6])   # a non-trivial displacement case
+
+
+def make_camera(ptz, disp=None):
+    cam = ref.PTZCamera((U, V), CC, BASE_ROT, None if disp is None else np.array(disp))
+    cam.set_ptz(ptz)
+    return cam
+
+
+def gen_projection():
+    rng = np.random.default_rng(11)
+    ptzs = np.array([[12.3, -7.5, 2500.0], [58.0, -9.0, 3500.0], [-33.0, -4.2, 1900.0], [71.5, -12.0, 4200.0]])
+    rays = np.stack([rng.uniform(-60, 100, 96), rng.uniform(-25, 8, 96)], axis=1)
+    out = {"ptzs": ptzs, "rays": rays, "disp": DISP, "uv": np.array([U, V])}
+    for tag, disp in (("nodisp", None), ("disp", DISP)):
+        xy = np.zeros((len(ptzs), len(rays), 2))
+        for c, ptz in enumerate(ptzs):
+            cam = make_camera(ptz, disp)
+            for r, ray in enumerate(rays):
+                xy[c, r] = cam.project_ray(ray)
+        out["project_ray_" + tag] = xy
+    t = np.zeros((len(ptzs), len(rays), 2))
+    for c, ptz in enumerate(ptzs):
+        for r, ray in enumerate(rays):
+            t[c, r] = ref.TransFunction.from_ray_to_image(U, V, ptz[2], ptz[0], ptz[1], ray[0], ray[1])
+    out["from_ray_to_image"] = t
+    # project_rays with the strict in-image filter, and without
+    for c, ptz in enumerate(ptzs):
+        cam = make_camera(ptz)
+        near = np.stack([ptz[0] + rng.uniform(-25, 25, 200), ptz[1] + rng.uniform(-14, 14, 200)], axis=1)
+        pts, idx = cam.project_rays(near, H, W)
+        out["prs_rays_%d" % c] = near
+        out["prs_points_%d" % c] = pts.astype(np.float64)
+        out["prs_index_%d" % c] = idx
+        pts2, idx2 = cam.project_rays(near[:17])
+        out["prs_all_points_%d" % c] = pts2.astype(np.float64)
+        assert len(idx2) == 0
+    np.savez(os.path.join(OUT, "projection.npz"), **out)
+
+
+def gen_backprojection():
+    rng = np.random.default_rng(12)
+    ptzs = np.array([[12.3, -7.5, 2500.0], [58.0, -9.0, 3500.0], [-33.0, -4.2, 1900.0]])
+    pts = np.stack([rng.uniform(-100, W + 100, 80), rng.uniform(-100, H + 100, 80)], axis=1)
+    out = {"ptzs": ptzs, "points": pts, "disp": DISP, "uv": np.array([U, V])}
+    for tag, disp in (("nodisp", None), ("disp", DISP)):
+        r = np.zeros((len(ptzs), len(pts), 2))
+        for c, ptz in enumerate(ptzs):
+            cam = make_camera(ptz, disp)
+            r[c] = cam.back_project_to_rays(pts)
+        out["back_project_" + tag] = r
+    t = np.zeros((len(ptzs), len(pts), 2))
+    for c, ptz in enumerate(ptzs):
+        for k, p in enumerate(pts):
+            t[c, k] = ref.TransFunction.from_image_to_ray(U, V, ptz[2], ptz[0], ptz[1], p[0], p[1])
+    out["from_image_to_ray"] = t
+    np.savez(os.path.join(OUT, "backprojection.npz"), **out)
+
+
+def gen_h_jacobian():
+    rng = np.random.default_rng(13)
+    out = {"uv": np.array([U, V]), "disp": DISP}
+    for tag, disp in (("nodisp", None), ("disp", DISP)):
+        slam = ref.PtzSlam()
+        ptz = np.array([10.0, -8.0, 2500.0])
+        slam.cameras = [make_camera(ptz, disp)]
+        rays = np.stack([ptz[0] + rng.uniform(-12, 12, 9), ptz[1] + rng.uniform(-6, 6, 9)], axis=1)
+        Hm = slam.compute_h_jacobian(ptz[0], ptz[1], ptz[2], rays)
+        out["ptz_" + tag] = ptz
+        out["rays_" + tag] = rays
+        out["H_" + tag] = Hm
+    np.savez(os.path.join(OUT, "h_jacobian.npz"), **out)
+
+
+def gen_ekf():
+    seq = synth.make_ekf_sequence(n_rays=60, n_frames=7, seed=1001, obs_noise=("gauss", 0.5))
+    slam = ref.PtzSlam()
+    cam0 = make_camera(seq.ptz_gt[0])
+    slam.cameras = [cam0]
+    slam.rays = seq.rays0.copy()
+    slam.state_cov = slam.angle_var * np.eye(3 + 2 * len(slam.rays))   # ptz_slam.py:199-200
+    slam.state_cov[2][2] = slam.f_var
+    out = {"rays0": seq.rays0, "ptz0": seq.ptz_gt[0], "uv": np.array([U, V]), "n_frames": np.array(6)}
+    for k in range(1, 7):
+        # predict, ptz_slam.py:418-426
+        slam.current_camera = copy.deepcopy(slam.cameras[-1])
+        slam.current_camera.set_ptz(slam.current_camera.get_ptz() + slam.velocity)
+        slam.cameras.append(slam.current_camera)
+        q_k = 5 * np.diag([slam.angle_var, slam.angle_var, slam.f_var])
+        slam.state_cov[0:3, 0:3] = slam.state_cov[0:3, 0:3] + q_k
+        slam.ekf_update(seq.obs_xy[k], seq.obs_idx[k], H, W)
+        out["obs_xy_%d" % k] = seq.obs_xy[k]
+        out["obs_idx_%d" % k] = seq.obs_idx[k]
+        out["rays_%d" % k] = slam.rays.copy()
+        out["cov_%d" % k] = slam.state_cov.copy()
+        out["ptz_%d" % k] = slam.current_camera.get_ptz()
+        out["vel_%d" % k] = np.array(slam.velocity)
+    np.savez_compressed(os.path.join(OUT, "ekf.npz"), **out)
+
+
+def _graph_to_npz(g, out):
+    n = len(g.points)
+    out["n_kf"] = np.array(n)
+    out["n_landmark"] = np.array(g.n_landmark)
+    out["ptz_init"] = g.ptz_init
+    out["ptz_gt"] = g.ptz_gt
+    out["rays_gt"] = g.rays_gt
+    for i in range(n):
+        out["points_%d" % i] = g.points[i]
+    pairs = []
+    for i in range(n):
+        for j in range(n):
+            if len(g.src_pt_index[i][j]):
+                pairs.append((i, j))
+                out["src_%d_%d" % (i, j)] = np.array(g.src_pt_index[i][j], dtype=np.int64)
+                out["dst_%d_%d" % (i, j)] = np.array(g.dst_pt_index[i][j], dtype=np.int64)
+                out["lmk_%d_%d" % (i, j)] = np.array(g.landmark_index[i][j], dtype=np.int64)
+    out["pairs"] = np.array(pairs, dtype=np.int64)
+
+
+def _x0_reference(g):
+    """bundle_adjustment.py:168-197 executed verbatim on the graph (the reference's own lines cannot be called
+    without images, so the landmark initialisation loop is driven here through TransFunction.from_image_to_ray)."""
+    N = len(g.points)
+    n_residual = sum(len(g.src_pt_index[i][j]) * 4 for i in range(N) for j in range(N))
+    x0 = np.zeros(N * 3 + g.n_landmark * 2)
+    for i in range(N):
+        x0[3 * i:3 * i + 3] = g.ptz_init[i]
+    ls = N * 3
+    for i in range(N):
+        ptz1 = x0[3 * i:3 * i + 3]
+        for j in range(N):
+            for idx1, idx2, idx3 in zip(g.src_pt_index[i][j], g.dst_pt_index[i][j], g.landmark_index[i][j]):
+                x1, y1 = g.points[i][idx1][0], g.points[i][idx1][1]
+                x0[ls + 2 * idx3:ls + 2 * idx3 + 2] = ref.TransFunction.from_image_to_ray(U, V, ptz1[2], ptz1[0], ptz1[1], x1, y1)
+    return x0[3:], n_residual
+
+
+def gen_ba():
+    g = synth.make_match_graph(n_kf=5, n_landmark=48, seed=1001, max_matches=30)
+    N = len(g.points)
+    x0, n_residual = _x0_reference(g)
+    args = (N, g.n_landmark, n_residual, g.points, g.src_pt_index, g.dst_pt_index, g.landmark_index, U, V, g.ptz_init[0])
+    out = {"uv": np.array([U, V])}
+    _graph_to_npz(g, out)
+    out["x0"] = x0
+    out["n_residual"] = np.array(n_residual)
+    out["residual_x0"] = ref.bundle_adjustment._compute_residual(x0, *args)
+    rng = np.random.default_rng(5)
+    x1 = x0 + rng.normal(0, 0.01, x0.shape)
+    out["x1"] = x1
+    out["residual_x1"] = ref.bundle_adjustment._compute_residual(x1, *args)
+    np.savez_compressed(os.path.join(OUT, "ba_residual.npz"), **out)
+
+    # the exact call of bundle_adjustment.py:200-202 (verbose silenced), and a tight-tolerance run that defines "converged"
+    with contextlib.redirect_stdout(io.StringIO()):
+        asis = ref.least_squares(ref.bundle_adjustment._compute_residual, x0, verbose=2, x_scale='jac', ftol=1e-4,
+                                 method='trf', args=args)
+        tight = ref.least_squares(ref.bundle_adjustment._compute_residual, x0, verbose=0, x_scale='jac',
+                                  ftol=1e-15, xtol=1e-15, gtol=1e-15, method='trf', args=args, max_nfev=60)
+    print("BA as-is: nfev %d status %d cost %.9g ; tight: nfev %d status %d cost %.12g" %
+          (asis.nfev, asis.status, asis.cost, tight.nfev, tight.status, tight.cost))
+    print("max |asis - tight| poses:", np.abs(asis.x[:3 * (N - 1)] - tight.x[:3 * (N - 1)]).reshape(-1, 3).max(0),
+          " rays:", np.abs(asis.x[3 * (N - 1):] - tight.x[3 * (N - 1):]).max())
+    out2 = {"uv": np.array([U, V])}
+    _graph_to_npz(g, out2)
+    out2.update(x0=x0, x_asis=asis.x, cost_asis=np.array(asis.cost), nfev_asis=np.array(asis.nfev),
+                status_asis=np.array(asis.status), x_tight=tight.x, cost_tight=np.array(tight.cost))
+    np.savez_compressed(os.path.join(OUT, "ba_solve.npz"), **out2)
+
+
+if __name__ == "__main__":
+    gen_projection()
+    gen_backprojection()
+    gen_h_jacobian()
+    gen_ekf()
+    gen_ba()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
