@@ -1,0 +1,53 @@
+// ba.h - the GPU-resident bundle-adjustment problem (keyframes x ray landmarks x observations) and the
+// device-level entry points shared between ba_kernels.cu (per-observation passes), dense.cu (reduced camera
+// system factorisation) and ba_solver.cu (trust-region driver).
+#pragma once
+#include "common.h"
+#include "ptz_math.cuh"
+
+// accumulator arena layout (one cudaMemsetAsync clears it): [cost | U N*6 | gc N*3 | V M*3 | gl M*2]
+struct BaAccum {
+    double* base = nullptr;
+    double* cost = nullptr;   // [0] 0.5*sum r^2 is formed on the host from sum r^2 stored here
+    double* U = nullptr;      // [N*6] packed (pp,pt,pf,tt,tf,ff), per degree / pixel units
+    double* gc = nullptr;     // [N*3]
+    double* V = nullptr;      // [M*3] packed (theta-theta, theta-phi, phi-phi)
+    double* gl = nullptr;     // [M*2]
+    size_t count = 0;
+};
+
+struct ptzba_ba {
+    ptzba_ctx* ctx = nullptr;
+    int n_pose = 0, n_lm = 0;
+    int64_t n_obs = 0;
+    double u = 0, v = 0;
+    bool identity_perm = true;      // caller order already landmark-major
+    int max_degree = 0;             // largest number of observations of one landmark
+    // observations, landmark-major (SoA, 24 B per observation)
+    DevBuf<int32_t> s_cam, s_lm, orig;
+    DevBuf<double> s_ox, s_oy;
+    DevBuf<int32_t> lm_ptr;         // [M+1] CSR offsets into the sorted arrays
+    // current parameters
+    DevBuf<double> poses;           // [N*3] incl. reference pose at 0
+    DevBuf<double> rays;            // [M*2]
+    DevBuf<CamTrig> cam_trig;       // [N]
+    DevBuf<LmTrig> lm_trig;         // [M]
+    DevBuf<double> accum_store;
+    BaAccum acc;
+    DevBuf<double> resid;           // [2*n_obs] caller order (only when the caller asks for device residuals)
+    // ---- solver workspace (allocated on first solve) ----
+    DevBuf<double> x_cur, x_trial;          // [3(N-1)+2M] packed parameter vectors
+    DevBuf<double> scale_inv;               // [3N + 2M] (camera part incl. slot for pose 0, then landmarks)
+    DevBuf<double> Sred;                    // [n x n] reduced camera system, column-major lower, n = 3(N-1)
+    DevBuf<double> rhs_c, rhs_l;            // [3N], [2M] right-hand sides / solutions (camera slot 0 unused)
+    DevBuf<double> sol_c, sol_l, sol2_c, sol2_l;
+    DevBuf<double> Vinv;                    // [M*3] (V + alpha D_l^2)^-1 packed
+    DevBuf<double> scal;                    // small device scalar block for reductions
+    int fused_grid = 0, fused_smem = 0;
+    bool fused_cam_smem = true;
+};
+
+// ---- device-level passes (all pointers device, enqueued on ba->ctx->stream) ----
+int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3);      // unpack + trig tables
+int ba_fused_pass(ptzba_ba* ba, double* d_resid_or_null);                            // -> ba->acc
+int ba_residual_pass(ptzba_ba* ba, double* d_resid_or_null, double* d_sumsq);        // r (caller order) and sum r^2

@@ -1,0 +1,480 @@
+// ba_kernels.cu - per-observation passes of keyframe bundle adjustment.
+//
+// Reference behaviour (slam_system/bundle_adjustment.py):
+//   _compute_residual :25-106  r = [proj(cam_i, l) - kp_i] per observation, camera 0 = fixed reference pose (:57-59)
+//   the Jacobian scipy forms by forward differences (:200-202) is replaced by the analytic 2x3 / 2x2 blocks of
+//   SURVEY.md Appendix A, and J^T J / J^T r are assembled directly into per-keyframe 3x3 (U, g_c) and per-landmark
+//   2x2 (V, g_l) blocks without ever materialising J.
+//
+// Data layout in HBM (per observation, landmark-major sorted, SoA): cam_idx int32 | lm_idx int32 | obs_x f64 | obs_y f64
+// = 24 B read; residual 16 B written (caller order).  Per-keyframe trig (sp,cp,st,ct,f) and per-landmark trig
+// (sin th, cos th, T, S) tables are rebuilt once per parameter update so that no transcendental is evaluated per
+// observation.  Algorithmic traffic of the fused pass: 40 B/obs + 56 B/landmark + 96 B/keyframe.
+#include <cub/cub.cuh>
+
+#include "ba.h"
+
+namespace {
+
+constexpr int kFusedThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------------
+// problem set-up kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_check_ranges(int64_t n_obs, const int32_t* __restrict__ cam, const int32_t* __restrict__ lm,
+                               int n_pose, int n_lm, int* __restrict__ bad) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_obs; k += (int64_t)gridDim.x * blockDim.x) {
+        if (cam[k] < 0 || cam[k] >= n_pose || lm[k] < 0 || lm[k] >= n_lm) atomicOr(bad, 1);
+        if (k > 0 && lm[k] < lm[k - 1]) atomicOr(bad, 2);   // not landmark-major
+    }
+}
+
+__global__ void k_iota(int64_t n, int32_t* __restrict__ a) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) a[k] = (int32_t)k;
+}
+
+__global__ void k_gather_obs(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ cam,
+                             const double* __restrict__ obs_xy, int32_t* __restrict__ s_cam,
+                             double* __restrict__ s_ox, double* __restrict__ s_oy) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t o = perm ? perm[k] : (int32_t)k;
+        s_cam[k] = cam[o];
+        const double2 p = __ldg(reinterpret_cast<const double2*>(obs_xy) + o);
+        s_ox[k] = p.x;
+        s_oy[k] = p.y;
+    }
+}
+
+// CSR offsets: lm_ptr[l] = first sorted position with lm >= l (binary search per landmark), lm_ptr[M] = n_obs
+__global__ void k_lm_ptr(int n_lm, int64_t n_obs, const int32_t* __restrict__ s_lm, int32_t* __restrict__ lm_ptr,
+                         int* __restrict__ max_degree) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > n_lm) return;
+    int64_t lo = 0, hi = n_obs;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (s_lm[mid] < l) lo = mid + 1; else hi = mid;
+    }
+    lm_ptr[l] = (int32_t)lo;
+    if (l < n_lm) {
+        int64_t lo2 = lo, hi2 = n_obs;
+        while (lo2 < hi2) {
+            const int64_t mid = (lo2 + hi2) >> 1;
+            if (s_lm[mid] <= l) lo2 = mid + 1; else hi2 = mid;
+        }
+        atomicMax(max_degree, (int)(lo2 - lo));
+    }
+}
+
+// x = [pose_1..pose_{N-1}, landmarks]; pose_0 = reference pose (bundle_adjustment.py:57-59)
+__global__ void k_set_params(int n_pose, int n_lm, const double* __restrict__ x, const double* __restrict__ ref3,
+                             double* __restrict__ poses, double* __restrict__ rays, CamTrig* __restrict__ cam_trig,
+                             LmTrig* __restrict__ lm_trig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pose) {
+        const double* src = (i == 0) ? ref3 : (x + 3 * (size_t)(i - 1));
+        const double p = src[0], t = src[1], f = src[2];
+        poses[3 * i] = p; poses[3 * i + 1] = t; poses[3 * i + 2] = f;
+        cam_trig[i] = make_cam_trig(p, t, f);
+    }
+    if (i < n_lm) {
+        const double2 r = __ldg(reinterpret_cast<const double2*>(x + 3 * (size_t)(n_pose - 1)) + i);
+        reinterpret_cast<double2*>(rays)[i] = r;
+        lm_trig[i] = make_lm_trig(r.x, r.y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused residual + Jacobian + normal-equation assembly
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+
+// sum of v over the run of equal keys that starts at this lane (keys are non-decreasing inside the warp)
+__device__ __forceinline__ void seg_reduce5(int key, int lane, double& a, double& b, double& c, double& d, double& e) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int ok = __shfl_down_sync(0xffffffffu, key, off);
+        const double ta = shfl_down_d(a, off), tb = shfl_down_d(b, off), tc = shfl_down_d(c, off),
+                     td = shfl_down_d(d, off), te = shfl_down_d(e, off);
+        if (lane + off < 32 && ok == key) { a += ta; b += tb; c += tc; d += td; e += te; }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// CAM_SMEM: per-CTA shared-memory copies of the keyframe trig table and of the 9 keyframe accumulators.
+template <bool CAM_SMEM>
+__global__ void __launch_bounds__(kFusedThreads)
+k_ba_fused(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+           const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+           const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
+           double* __restrict__ resid, double* __restrict__ gU, double* __restrict__ gGc, double* __restrict__ gV,
+           double* __restrict__ gGl, double* __restrict__ gCost) {
+    extern __shared__ __align__(16) double smem[];
+    double* sTrig = smem;                               // [n_pose*5]
+    double* sAcc = smem + (size_t)n_pose * 5;           // [n_pose*9]
+    __shared__ double sWarp[kFusedThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (CAM_SMEM) {
+        for (int i = tid; i < n_pose * 5; i += kFusedThreads) sTrig[i] = reinterpret_cast<const double*>(cam_trig)[i];
+        for (int i = tid; i < n_pose * 9; i += kFusedThreads) sAcc[i] = 0.0;
+        __syncthreads();
+    }
+    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > n_obs) end = n_obs;
+    double cost = 0.0;
+    for (int64_t base = begin; base < end; base += kFusedThreads) {
+        const int64_t k = base + tid;
+        const bool act = k < end;
+        int lm = -1, cam = 0;
+        double rx = 0, ry = 0;
+        ObsGeom g = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (act) {
+            lm = s_lm[k];
+            cam = s_cam[k];
+            const double ox = s_ox[k], oy = s_oy[k];
+            CamTrig c;
+            if (CAM_SMEM) {
+                const double* t = sTrig + 5 * cam;
+                c.sp = t[0]; c.cp = t[1]; c.st = t[2]; c.ct = t[3]; c.f = t[4];
+            } else {
+                c = cam_trig[cam];
+            }
+            const LmTrig l = lm_trig[lm];
+            double x, y;
+            project_fast_jac(c, l, u, v, x, y, g);
+            rx = x - ox;
+            ry = y - oy;
+            if (resid) {
+                const int64_t o = orig ? (int64_t)orig[k] : k;
+                reinterpret_cast<double2*>(resid)[o] = make_double2(rx, ry);
+            }
+            cost = fma(rx, rx, fma(ry, ry, cost));
+        }
+        // landmark blocks (radian units; scaled to degrees when flushed)
+        double vtt = fma(g.xa, g.xa, g.ya * g.ya);
+        double vtp = fma(g.xa, g.xp, g.ya * g.yp);
+        double vpp = fma(g.xp, g.xp, g.yp * g.yp);
+        double glt = fma(g.xa, rx, g.ya * ry);
+        double glp = fma(g.xp, rx, g.yp * ry);
+        // keyframe blocks: pan column = -alpha column; keyframe 0 is fixed (no block)
+        if (act && cam != 0) {
+            const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
+            const double upf = -fma(g.xa, g.px, g.ya * g.py);
+            const double utt = fma(g.xt, g.xt, g.yt * g.yt);
+            const double utf = fma(g.xt, g.px, g.yt * g.py);
+            const double uff = fma(g.px, g.px, g.py * g.py);
+            const double gct = fma(g.xt, rx, g.yt * ry);
+            const double gcf = fma(g.px, rx, g.py * ry);
+            double* a = (CAM_SMEM ? sAcc : gU) + (size_t)cam * (CAM_SMEM ? 9 : 6);
+            atomicAdd(a + 0, vtt);
+            atomicAdd(a + 1, upt);
+            atomicAdd(a + 2, upf);
+            atomicAdd(a + 3, utt);
+            atomicAdd(a + 4, utf);
+            atomicAdd(a + 5, uff);
+            double* b = CAM_SMEM ? (a + 6) : (gGc + (size_t)cam * 3);
+            atomicAdd(b + 0, -glt);
+            atomicAdd(b + 1, gct);
+            atomicAdd(b + 2, gcf);
+        }
+        seg_reduce5(lm, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, lm, 1);
+        if (act && (lane == 0 || prev != lm)) {
+            const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+            atomicAdd(gV + 3 * (size_t)lm + 0, vtt * k2);
+            atomicAdd(gV + 3 * (size_t)lm + 1, vtp * k2);
+            atomicAdd(gV + 3 * (size_t)lm + 2, vpp * k2);
+            atomicAdd(gGl + 2 * (size_t)lm + 0, glt * k1);
+            atomicAdd(gGl + 2 * (size_t)lm + 1, glp * k1);
+        }
+    }
+    // cost: warp -> CTA -> one atomic
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+    if (CAM_SMEM) {
+        // flush keyframe accumulators (converted to per-degree units): entries (pp,pt,pf,tt,tf,ff | gp,gt,gf)
+        const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+        for (int i = tid; i < n_pose * 9; i += kFusedThreads) {
+            const double val = sAcc[i];
+            if (val == 0.0) continue;
+            const int c = i / 9, e = i - 9 * c;
+            const double sc = (e == 0 || e == 1 || e == 3) ? k2 : (e == 2 || e == 4 || e == 6 || e == 7) ? k1 : 1.0;
+            if (e < 6) atomicAdd(gU + 6 * (size_t)c + e, val * sc);
+            else atomicAdd(gGc + 3 * (size_t)c + (e - 6), val * sc);
+        }
+    }
+}
+
+// global-accumulator variant leaves radian units in U/gc; this converts them in place
+__global__ void k_scale_cam_blocks(int n_pose, double* __restrict__ U, double* __restrict__ gc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pose * 9) return;
+    const int c = i / 9, e = i - 9 * c;
+    const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+    const double sc = (e == 0 || e == 1 || e == 3) ? k2 : (e == 2 || e == 4 || e == 6 || e == 7) ? k1 : 1.0;
+    if (e < 6) U[6 * (size_t)c + e] *= sc; else gc[3 * (size_t)c + (e - 6)] *= sc;
+}
+
+// residual-only pass (trial points of the trust-region loop, and _compute_residual itself)
+__global__ void __launch_bounds__(kFusedThreads)
+k_ba_residual(int64_t n_obs, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+              const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+              const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, double u, double v,
+              double* __restrict__ resid, double* __restrict__ gSumSq) {
+    __shared__ double sWarp[kFusedThreads / 32];
+    double cost = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * kFusedThreads + threadIdx.x; k < n_obs; k += (int64_t)gridDim.x * kFusedThreads) {
+        const CamTrig c = cam_trig[s_cam[k]];
+        const LmTrig l = lm_trig[s_lm[k]];
+        double x, y;
+        project_fast(c, l, u, v, x, y);
+        const double rx = x - s_ox[k], ry = y - s_oy[k];
+        if (resid) {
+            const int64_t o = orig ? (int64_t)orig[k] : k;
+            reinterpret_cast<double2*>(resid)[o] = make_double2(rx, ry);
+        }
+        cost = fma(rx, rx, fma(ry, ry, cost));
+    }
+    cost = warp_sum(cost);
+    if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = cost;
+    __syncthreads();
+    if (threadIdx.x == 0 && gSumSq) {
+        double s = 0;
+        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gSumSq, s);
+    }
+}
+
+int stream_grid(ptzba_ctx* ctx, int64_t n, int threads, int per_sm) {
+    int64_t g = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    if (g > cap) g = cap;
+    return g < 1 ? 1 : (int)g;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-level passes
+// ---------------------------------------------------------------------------------------------------------------
+int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3) {
+    ptzba_ctx* ctx = ba->ctx;
+    const int n = ba->n_pose > ba->n_lm ? ba->n_pose : ba->n_lm;
+    k_set_params<<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->n_pose, ba->n_lm, d_x, d_ref_pose3, ba->poses.p,
+                                                          ba->rays.p, ba->cam_trig.p, ba->lm_trig.p);
+    KERNEL_POST(ctx);
+    return PTZBA_OK;
+}
+
+int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
+    ptzba_ctx* ctx = ba->ctx;
+    cudaStream_t s = ctx->stream;
+    CU_CHECK(ctx, cudaMemsetAsync(ba->acc.base, 0, ba->acc.count * sizeof(double), s));
+    if (ba->n_obs == 0) return PTZBA_OK;
+    const int32_t* orig = ba->identity_perm ? nullptr : ba->orig.p;
+    // contiguous chunk per CTA, multiple of the CTA width so that warps stay aligned to 32 observations
+    int64_t chunk = (ba->n_obs + ba->fused_grid - 1) / ba->fused_grid;
+    chunk = (chunk + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+    const int grid = (int)((ba->n_obs + chunk - 1) / chunk);
+    if (ba->fused_cam_smem) {
+        k_ba_fused<true><<<grid, kFusedThreads, ba->fused_smem, s>>>(
+            ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+            ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        KERNEL_POST(ctx);
+    } else {
+        k_ba_fused<false><<<grid, kFusedThreads, 0, s>>>(
+            ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+            ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        KERNEL_POST(ctx);
+        k_scale_cam_blocks<<<div_up(ba->n_pose * 9, 256), 256, 0, s>>>(ba->n_pose, ba->acc.U, ba->acc.gc);
+        KERNEL_POST(ctx);
+    }
+    return PTZBA_OK;
+}
+
+int ba_residual_pass(ptzba_ba* ba, double* d_resid, double* d_sumsq) {
+    ptzba_ctx* ctx = ba->ctx;
+    cudaStream_t s = ctx->stream;
+    if (d_sumsq) CU_CHECK(ctx, cudaMemsetAsync(d_sumsq, 0, sizeof(double), s));
+    if (ba->n_obs == 0) return PTZBA_OK;
+    const int32_t* orig = ba->identity_perm ? nullptr : ba->orig.p;
+    k_ba_residual<<<stream_grid(ctx, ba->n_obs, kFusedThreads, 8), kFusedThreads, 0, s>>>(
+        ba->n_obs, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v,
+        d_resid, d_sumsq);
+    KERNEL_POST(ctx);
+    return PTZBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landmark, int64_t n_obs,
+                               const int32_t* cam_idx, const int32_t* lm_idx, const double* obs_xy, double u, double v,
+                               ptzba_ba** out) {
+    if (!ctx) return PTZBA_ERR_ARG;
+    ARG_CHECK(ctx, out && n_pose >= 1 && n_landmark >= 0 && n_obs >= 0 && n_obs < (int64_t)2147483000);
+    ARG_CHECK(ctx, n_obs == 0 || (cam_idx && lm_idx && obs_xy));
+    *out = nullptr;
+    cudaStream_t s = ctx->stream;
+    ptzba_ba* ba = new ptzba_ba();
+    ba->ctx = ctx; ba->n_pose = n_pose; ba->n_lm = n_landmark; ba->n_obs = n_obs; ba->u = u; ba->v = v;
+    auto fail = [&](int code) { delete ba; return code; };
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ptzba_fail(ctx, PTZBA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,   \
+                                   cudaGetErrorString(e__)));                                          \
+    } while (0)
+    InArray<int32_t> in_cam, in_lm;
+    InArray<double> in_xy;
+    CU_TRY(in_cam.stage(mem, cam_idx, (size_t)n_obs, s));
+    CU_TRY(in_lm.stage(mem, lm_idx, (size_t)n_obs, s));
+    CU_TRY(in_xy.stage(mem, obs_xy, (size_t)n_obs * 2, s));
+    CU_TRY(ba->s_cam.alloc(n_obs)); CU_TRY(ba->s_lm.alloc(n_obs));
+    CU_TRY(ba->s_ox.alloc(n_obs)); CU_TRY(ba->s_oy.alloc(n_obs));
+    CU_TRY(ba->lm_ptr.alloc((size_t)n_landmark + 1));
+    CU_TRY(ba->poses.alloc((size_t)n_pose * 3)); CU_TRY(ba->rays.alloc((size_t)n_landmark * 2));
+    CU_TRY(ba->cam_trig.alloc(n_pose)); CU_TRY(ba->lm_trig.alloc(n_landmark));
+    ba->acc.count = 1 + (size_t)n_pose * 9 + (size_t)n_landmark * 5;
+    CU_TRY(ba->accum_store.alloc(ba->acc.count));
+    ba->acc.base = ba->accum_store.p;
+    ba->acc.cost = ba->acc.base;
+    ba->acc.U = ba->acc.base + 1;
+    ba->acc.gc = ba->acc.U + (size_t)n_pose * 6;
+    ba->acc.V = ba->acc.gc + (size_t)n_pose * 3;
+    ba->acc.gl = ba->acc.V + (size_t)n_landmark * 3;
+    CU_TRY(ba->scal.alloc(64));
+
+    DevBuf<int> flags;
+    CU_TRY(flags.alloc(2));
+    CU_TRY(cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), s));
+    int h_flags[2] = {0, 0};
+    if (n_obs > 0) {
+        k_check_ranges<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, in_cam.d, in_lm.d, n_pose, n_landmark, flags.p);
+        ctx->launches++;
+        CU_TRY(cudaMemcpyAsync(h_flags, flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        if (h_flags[0] & 1) return fail(ptzba_fail(ctx, PTZBA_ERR_ARG, "observation index out of range"));
+        ba->identity_perm = !(h_flags[0] & 2);
+        if (ba->identity_perm) {
+            CU_TRY(cudaMemcpyAsync(ba->s_lm.p, in_lm.d, (size_t)n_obs * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+            k_gather_obs<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, nullptr, in_cam.d, in_xy.d, ba->s_cam.p,
+                                                                         ba->s_ox.p, ba->s_oy.p);
+            ctx->launches++;
+        } else {
+            // stable LSD radix sort by landmark id keeps the caller's order inside a landmark
+            DevBuf<int32_t> iota;
+            DevBuf<unsigned char> tmp;
+            CU_TRY(ba->orig.alloc(n_obs));
+            CU_TRY(iota.alloc(n_obs));
+            k_iota<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, iota.p);
+            ctx->launches++;
+            size_t bytes = 0;
+            int end_bit = 1;
+            while ((1ll << end_bit) < (long long)n_landmark && end_bit < 31) ++end_bit;
+            CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, in_lm.d, ba->s_lm.p, iota.p, ba->orig.p, (int)n_obs, 0,
+                                                   end_bit, s));
+            CU_TRY(tmp.alloc(bytes));
+            CU_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, in_lm.d, ba->s_lm.p, iota.p, ba->orig.p, (int)n_obs, 0,
+                                                   end_bit, s));
+            k_gather_obs<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, ba->orig.p, in_cam.d, in_xy.d, ba->s_cam.p,
+                                                                         ba->s_ox.p, ba->s_oy.p);
+            ctx->launches++;
+            CU_TRY(cudaStreamSynchronize(s));
+        }
+    }
+    CU_TRY(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), s));
+    k_lm_ptr<<<div_up(n_landmark + 1, 256), 256, 0, s>>>(n_landmark, n_obs, ba->s_lm.p, ba->lm_ptr.p, flags.p + 1);
+    ctx->launches++;
+    CU_TRY(cudaMemcpyAsync(h_flags + 1, flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(cudaGetLastError());
+    ba->max_degree = h_flags[1];
+
+    // launch geometry of the fused pass: one wave of resident CTAs; keyframe tables in shared memory when they fit
+    const size_t smem = (size_t)n_pose * 14 * sizeof(double);
+    int per_sm = 0;
+    ba->fused_cam_smem = smem <= 200 * 1024;
+    if (ba->fused_cam_smem) {
+        CU_TRY(cudaFuncSetAttribute(k_ba_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<true>, kFusedThreads, smem));
+        ba->fused_smem = (int)smem;
+    } else {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<false>, kFusedThreads, 0));
+        ba->fused_smem = 0;
+    }
+    if (per_sm < 1) per_sm = 1;
+    ba->fused_grid = ctx->sm_count * per_sm;
+#undef CU_TRY
+    *out = ba;
+    return PTZBA_OK;
+}
+
+extern "C" void ptzba_ba_destroy(ptzba_ba* ba) {
+    if (!ba) return;
+    cudaStreamSynchronize(ba->ctx->stream);
+    delete ba;
+}
+
+extern "C" int ptzba_ba_residual(ptzba_ba* ba, int mem, const double* x, const double* reference_pose3,
+                                 double* residual) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    ARG_CHECK(ctx, x && reference_pose3 && residual);
+    cudaStream_t s = ctx->stream;
+    const size_t nx = 3 * (size_t)(ba->n_pose - 1) + 2 * (size_t)ba->n_lm;
+    InArray<double> d_x, d_ref;
+    OutArray<double> d_r;
+    CU_CHECK(ctx, d_x.stage(mem, x, nx, s));
+    CU_CHECK(ctx, d_ref.stage(PTZBA_HOST, reference_pose3, 3, s));
+    CU_CHECK(ctx, d_r.stage(mem, residual, 2 * (size_t)ba->n_obs));
+    PROPAGATE(ba_set_params(ba, d_x.d, d_ref.d));
+    PROPAGATE(ba_residual_pass(ba, d_r.d, nullptr));
+    CU_CHECK(ctx, d_r.finish(s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_ba_normal_equations(ptzba_ba* ba, int mem, const double* x, const double* reference_pose3,
+                                         double* residual, double* U, double* gc, double* V, double* gl, double* cost) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    ARG_CHECK(ctx, x && reference_pose3);
+    cudaStream_t s = ctx->stream;
+    const size_t nx = 3 * (size_t)(ba->n_pose - 1) + 2 * (size_t)ba->n_lm;
+    InArray<double> d_x, d_ref;
+    OutArray<double> d_r;
+    CU_CHECK(ctx, d_x.stage(mem, x, nx, s));
+    CU_CHECK(ctx, d_ref.stage(PTZBA_HOST, reference_pose3, 3, s));
+    CU_CHECK(ctx, d_r.stage(mem, residual, 2 * (size_t)ba->n_obs));
+    PROPAGATE(ba_set_params(ba, d_x.d, d_ref.d));
+    PROPAGATE(ba_fused_pass(ba, d_r.d));
+    const cudaMemcpyKind kind = mem == PTZBA_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (U) CU_CHECK(ctx, cudaMemcpyAsync(U, ba->acc.U, (size_t)ba->n_pose * 6 * sizeof(double), kind, s));
+    if (gc) CU_CHECK(ctx, cudaMemcpyAsync(gc, ba->acc.gc, (size_t)ba->n_pose * 3 * sizeof(double), kind, s));
+    if (V) CU_CHECK(ctx, cudaMemcpyAsync(V, ba->acc.V, (size_t)ba->n_lm * 3 * sizeof(double), kind, s));
+    if (gl) CU_CHECK(ctx, cudaMemcpyAsync(gl, ba->acc.gl, (size_t)ba->n_lm * 2 * sizeof(double), kind, s));
+    CU_CHECK(ctx, d_r.finish(s));
+    if (cost) {
+        double sumsq = 0;
+        CU_CHECK(ctx, cudaMemcpyAsync(&sumsq, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        *cost = 0.5 * sumsq;
+    } else if (mem == PTZBA_HOST) {
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+    }
+    return PTZBA_OK;
+}

@@ -262,40 +262,28 @@ def make_flat_ba(n_kf, n_landmark, n_obs, seed, pan_sweep=120.0, obs_noise=0.5,
     th, ph = back_project_closed_form(pans[host], tilts[host], fs[host], px, py)
     rays_gt = np.stack([th, ph], axis=1)
 
-    per = int(math.ceil(n_obs / n_landmark))
-    cams_l, lms_l, xs_l, ys_l = [host.astype(np.int64)], [np.arange(n_landmark, dtype=np.int64)], [px], [py]
-    have = n_landmark
-    seen = set()
-    key_host = host.astype(np.int64) * n_landmark + np.arange(n_landmark, dtype=np.int64)
-    keys = [key_host]
-    tries = 0
-    while have < n_obs and tries < 40:
-        tries += 1
-        want = int((n_obs - have) * 2.5) + 1024
-        lm = rng.integers(0, n_landmark, want)
-        # candidate keyframe: nearest in pan to theta + jitter inside a +-20 deg band
-        target = rays_gt[lm, 0] + rng.uniform(-20.0, 20.0, want)
-        cam = np.clip(np.searchsorted(pans, target), 0, n_kf - 1)
-        x, y, z = project_closed_form(pans[cam], tilts[cam], fs[cam], rays_gt[lm, 0], rays_gt[lm, 1])
-        ok = (z > 0) & (x > 1) & (x < IMAGE_W - 1) & (y > 1) & (y < IMAGE_H - 1)
-        lm, cam, x, y = lm[ok], cam[ok], x[ok], y[ok]
-        key = cam.astype(np.int64) * n_landmark + lm
-        allk = np.concatenate(keys)
-        fresh = ~np.isin(key, allk)
-        _, first = np.unique(key, return_index=True)
-        m = np.zeros(len(key), bool)
-        m[first] = True
-        m &= fresh
-        lm, cam, x, y, key = lm[m], cam[m], x[m], y[m], key[m]
-        take = min(len(lm), n_obs - have)
-        cams_l.append(cam[:take]); lms_l.append(lm[:take]); xs_l.append(x[:take]); ys_l.append(y[:take])
-        keys.append(key[:take])
-        have += take
-    del seen, per
-    cam = np.concatenate(cams_l); lm = np.concatenate(lms_l)
-    x = np.concatenate(xs_l); y = np.concatenate(ys_l)
+    # pool of candidate (keyframe, landmark) pairs: the host observation of every landmark first, then seeded
+    # draws from the pan band that can see the landmark; verified in-image, de-duplicated once per round
+    cam = host.astype(np.int64)
+    lm = np.arange(n_landmark, dtype=np.int64)
+    x, y = px, py
+    for _ in range(60):
+        if len(cam) >= n_obs:
+            break
+        want = int((n_obs - len(cam)) * 3.0) + 65536
+        lm_c = rng.integers(0, n_landmark, want)
+        target = rays_gt[lm_c, 0] + rng.uniform(-20.0, 20.0, want)
+        cam_c = np.clip(np.searchsorted(pans, target), 0, n_kf - 1)
+        xc, yc, zc = project_closed_form(pans[cam_c], tilts[cam_c], fs[cam_c], rays_gt[lm_c, 0], rays_gt[lm_c, 1])
+        ok = (zc > 0) & (xc > 1) & (xc < IMAGE_W - 1) & (yc > 1) & (yc < IMAGE_H - 1)
+        cam = np.concatenate([cam, cam_c[ok]]); lm = np.concatenate([lm, lm_c[ok]])
+        x = np.concatenate([x, xc[ok]]); y = np.concatenate([y, yc[ok]])
+        _, first = np.unique(cam * n_landmark + lm, return_index=True)
+        first.sort()                                  # keep pool order (host observations stay first)
+        cam, lm, x, y = cam[first], lm[first], x[first], y[first]
     if len(cam) < n_obs:
         raise RuntimeError("could not place %d observations (got %d)" % (n_obs, len(cam)))
+    cam, lm, x, y = cam[:n_obs], lm[:n_obs], x[:n_obs], y[:n_obs]
     order = np.lexsort((cam, lm))  # landmark-major, camera ascending inside a landmark
     cam, lm, x, y = cam[order], lm[order], x[order], y[order]
     obs = np.stack([x, y], axis=1) + rng.normal(0, obs_noise, (len(x), 2))

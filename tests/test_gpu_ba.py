@@ -1,0 +1,103 @@
+"""GPU parity: BA residual and the fused residual + Jacobian + normal-equation pass vs reference goldens + oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, graph_from_npz
+from oracle import ptz_oracle as O
+import ptz_slam_b200  # noqa: F401
+from ptz_slam_b200 import synth
+from ptz_slam_b200 import bundle_adjustment as BA
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-9, 1e-9   # BASELINE.json: relative 1e-9 on residuals and Jacobians
+
+
+def test_compute_residual_golden():
+    d = load_golden("ba_residual.npz")
+    points, src, dst, lmk, M = graph_from_npz(d)
+    N = len(points)
+    for xk, rk in (("x0", "residual_x0"), ("x1", "residual_x1")):
+        r = BA._compute_residual(d[xk], N, M, int(d["n_residual"]), points, src, dst, lmk, d["uv"][0], d["uv"][1],
+                                 d["ptz_init"][0])
+        np.testing.assert_allclose(r, d[rk], rtol=RTOL, atol=ATOL)
+
+
+def test_initial_landmarks_match_reference_x0():
+    d = load_golden("ba_residual.npz")
+    points, src, dst, lmk, M = graph_from_npz(d)
+    N = len(points)
+    rays0 = BA.initial_landmarks(points, src, dst, lmk, M, d["ptz_init"], d["uv"][0], d["uv"][1])
+    np.testing.assert_allclose(rays0.ravel(), d["x0"][3 * (N - 1):], rtol=RTOL, atol=1e-10)
+
+
+def _check_normal_equations(fb, x, ref_pose, u, v):
+    prob = BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v)
+    out = prob.normal_equations(x, ref_pose)
+    poses, rays = O.ba_unpack(x, fb.n_pose, ref_pose)
+    r, U, gc, V, gl, cost = O.ba_normal_equations(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v)
+    np.testing.assert_allclose(out["residual"], r.ravel(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(prob.residual(x, ref_pose), r.ravel(), rtol=RTOL, atol=ATOL)
+    assert abs(out["cost"] - cost) <= 1e-11 * cost
+    su, sg = np.abs(U[1:]).max(), np.abs(gc[1:]).max()
+    np.testing.assert_allclose(out["U"][1:], U[1:], rtol=RTOL, atol=1e-12 * su)
+    np.testing.assert_allclose(out["gc"][1:], gc[1:], rtol=1e-8, atol=1e-11 * sg)
+    assert np.all(out["U"][0] == 0) and np.all(out["gc"][0] == 0)      # fixed reference pose
+    np.testing.assert_allclose(out["V"], V, rtol=RTOL, atol=1e-12 * np.abs(V).max())
+    np.testing.assert_allclose(out["gl"], gl, rtol=1e-8, atol=1e-11 * np.abs(gl).max())
+    prob.close()
+
+
+def test_normal_equations_small_unsorted():
+    """Reference pair-major order (not landmark-major, duplicates kept)."""
+    d = load_golden("ba_residual.npz")
+    points, src, dst, lmk, M = graph_from_npz(d)
+    cam, lm, xy = synth.flatten_match_graph(points, src, dst, lmk)
+    fb = synth.FlatBA(cam, lm, xy, d["ptz_gt"], d["rays_gt"], d["ptz_init"], d["rays_gt"])
+    _check_normal_equations(fb, d["x1"], d["ptz_init"][0], d["uv"][0], d["uv"][1])
+
+
+@pytest.mark.parametrize("n_kf,n_lm,n_obs", [(16, 500, 6000), (64, 20000, 300000), (300, 3000, 90000)])
+def test_normal_equations_flat(n_kf, n_lm, n_obs):
+    fb = synth.make_flat_ba(n_kf, n_lm, n_obs, seed=7)
+    _check_normal_equations(fb, fb.x0(), fb.ptz_init[0], synth.PP_U, synth.PP_V)
+
+
+def test_ragged_and_empty():
+    """Landmarks without observations keep zero blocks; an empty problem is valid."""
+    fb = synth.make_flat_ba(8, 200, 1500, seed=9)
+    keep = fb.lm_idx % 3 != 0
+    fb2 = synth.FlatBA(fb.cam_idx[keep], fb.lm_idx[keep], fb.obs_xy[keep], fb.ptz_gt, fb.rays_gt, fb.ptz_init, fb.rays_init)
+    prob = BA.BAProblem(fb2.n_pose, fb2.n_landmark, fb2.cam_idx, fb2.lm_idx, fb2.obs_xy, synth.PP_U, synth.PP_V)
+    out = prob.normal_equations(fb2.x0(), fb2.ptz_init[0])
+    assert np.all(out["V"][0::3] == 0) and np.all(out["gl"][0::3] == 0)
+    _check_normal_equations(fb2, fb2.x0(), fb2.ptz_init[0], synth.PP_U, synth.PP_V)
+    empty = BA.BAProblem(3, 5, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2)), 640.0, 360.0)
+    out = empty.normal_equations(np.zeros(3 * 2 + 10), np.array([1.0, 2.0, 2000.0]))
+    assert out["cost"] == 0 and out["residual"].shape == (0,)
+    with pytest.raises(Exception):
+        BA.BAProblem(3, 5, np.array([7], np.int32), np.array([0], np.int32), np.zeros((1, 2)), 640.0, 360.0)
+
+
+def test_full_size_cfg3_properties():
+    """Config 3 (256 kf x 100k rays x 2M obs): size-independent checks.
+    (1) residual pass == residual of the fused pass; (2) cost == 0.5*sum r^2; (3) trace identities
+    sum_c U_pp(c) + U(fixed cam) == sum_l V_tt(l) (pan column = -theta column); (4) subset parity vs oracle."""
+    fb = synth.make_flat_ba(256, 100000, 2000000, seed=1003)
+    prob = BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+    x = fb.x0()
+    out = prob.normal_equations(x, fb.ptz_init[0])
+    r2 = prob.residual(x, fb.ptz_init[0])
+    np.testing.assert_array_equal(out["residual"], r2)
+    assert abs(out["cost"] - 0.5 * np.dot(r2, r2)) <= 1e-11 * out["cost"]
+    sel = np.nonzero(fb.cam_idx != 0)[0]
+    poses, rays = O.ba_unpack(x, fb.n_pose, fb.ptz_init[0])
+    Jc, Jr = O.jacobian_blocks_analytic(poses[fb.cam_idx, 0], poses[fb.cam_idx, 1], poses[fb.cam_idx, 2],
+                                        rays[fb.lm_idx, 0], rays[fb.lm_idx, 1])
+    # theta-theta trace over observations of free cameras equals the pan-pan trace of U
+    tt_free = np.sum(Jr[sel, :, 0] ** 2)
+    assert abs(out["U"][:, 0, 0].sum() - tt_free) <= 1e-10 * tt_free
+    assert abs(out["V"][:, 0, 0].sum() - np.sum(Jr[:, :, 0] ** 2)) <= 1e-10 * tt_free
+    sub = slice(0, 200000)
+    ro = O.ba_residual_flat(poses, rays, fb.cam_idx[sub], fb.lm_idx[sub], fb.obs_xy[sub], synth.PP_U, synth.PP_V)
+    np.testing.assert_allclose(out["residual"][:400000], ro.ravel(), rtol=RTOL, atol=ATOL)
+    prob.close()
