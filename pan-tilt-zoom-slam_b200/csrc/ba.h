@@ -5,7 +5,7 @@
 #include "common.h"
 #include "ptz_math.cuh"
 
-// accumulator arena layout (one cudaMemsetAsync clears it): [cost | U N*6 | gc N*3 | V M*3 | gl M*2]
+// accumulator arena layout (one cudaMemsetAsync clears it): [cost | U N*6 | V M*3 | gc N*3 | gl M*2]
 struct BaAccum {
     double* base = nullptr;
     double* cost = nullptr;   // [0] 0.5*sum r^2 is formed on the host from sum r^2 stored here

@@ -78,9 +78,11 @@ __global__ void k_set_params(int n_pose, int n_lm, const double* __restrict__ x,
         cam_trig[i] = make_cam_trig(p, t, f);
     }
     if (i < n_lm) {
-        const double2 r = __ldg(reinterpret_cast<const double2*>(x + 3 * (size_t)(n_pose - 1)) + i);
-        reinterpret_cast<double2*>(rays)[i] = r;
-        lm_trig[i] = make_lm_trig(r.x, r.y);
+        // x + 3(N-1) is only 8-byte aligned when N is even: scalar loads
+        const double* lp = x + 3 * (size_t)(n_pose - 1) + 2 * (size_t)i;
+        const double th = lp[0], ph = lp[1];
+        reinterpret_cast<double2*>(rays)[i] = make_double2(th, ph);
+        lm_trig[i] = make_lm_trig(th, ph);
     }
 }
 
@@ -352,10 +354,11 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     CU_TRY(ba->accum_store.alloc(ba->acc.count));
     ba->acc.base = ba->accum_store.p;
     ba->acc.cost = ba->acc.base;
+    // [cost | U | V | gc | gl]: gc and gl are adjacent so that (gc, gl) is the gradient in the solver's full layout
     ba->acc.U = ba->acc.base + 1;
-    ba->acc.gc = ba->acc.U + (size_t)n_pose * 6;
-    ba->acc.V = ba->acc.gc + (size_t)n_pose * 3;
-    ba->acc.gl = ba->acc.V + (size_t)n_landmark * 3;
+    ba->acc.V = ba->acc.U + (size_t)n_pose * 6;
+    ba->acc.gc = ba->acc.V + (size_t)n_landmark * 3;
+    ba->acc.gl = ba->acc.gc + (size_t)n_pose * 3;
     CU_TRY(ba->scal.alloc(64));
 
     DevBuf<int> flags;

@@ -8,8 +8,6 @@ extern "C" void ptzba_ekf_batch_destroy(ptzba_ekf_batch*) {}
 extern "C" int ptzba_ekf_batch_step(ptzba_ekf_batch*, int, const double*, const int32_t*, const int32_t*, int32_t*) { return PTZBA_ERR_STATE; }
 extern "C" int ptzba_ekf_batch_get(ptzba_ekf_batch*, double*, double*, double*) { return PTZBA_ERR_STATE; }
 extern "C" int ptzba_ekf_batch_get_cov(ptzba_ekf_batch*, int, double*) { return PTZBA_ERR_STATE; }
-extern "C" int ptzba_ba_solve(ptzba_ba* ba, int, double*, const double*, const ptzba_ba_options*, ptzba_ba_report*) { return PTZBA_ERR_STATE; }
-extern "C" int ptzba_ba_lm_iteration(ptzba_ba*, int, const double*, const double*, double, double*, double*) { return PTZBA_ERR_STATE; }
 extern "C" int ptzba_comm_unique_id(ptzba_ctx* ctx, void*) { return NOT_YET(ctx); }
 extern "C" int ptzba_comm_init(ptzba_ctx* ctx, const void*, int, int) { return NOT_YET(ctx); }
 extern "C" int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double*, int64_t) { return NOT_YET(ctx); }

@@ -242,7 +242,7 @@ class FlatBA:
         return np.concatenate([self.ptz_init[1:].ravel(), self.rays_init.ravel()])
 
 
-def make_flat_ba(n_kf, n_landmark, n_obs, seed, pan_sweep=120.0, obs_noise=0.5,
+def make_flat_ba(n_kf, n_landmark, n_obs, seed, pan_sweep=None, obs_noise=0.5,
                  init_noise=(0.5, 0.5, 30.0, 0.05)):
     """Seeded flat BA problem with exactly n_obs observations, every one inside its image.
 
@@ -250,6 +250,8 @@ def make_flat_ba(n_kf, n_landmark, n_obs, seed, pan_sweep=120.0, obs_noise=0.5,
     and then verified), so cfg5 (20M observations) generates in seconds, not minutes.
     """
     rng = np.random.default_rng(seed)
+    if pan_sweep is None:      # cfg3 density: 256 keyframes over 120 degrees
+        pan_sweep = min(120.0, n_kf * 120.0 / 256.0)
     pans = np.sort(rng.uniform(0.0, pan_sweep, n_kf)) - pan_sweep / 2.0
     tilts = rng.uniform(-12.0, -4.0, n_kf)
     fs = rng.uniform(1800.0, 4500.0, n_kf)
