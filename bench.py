@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""
+bench.py - headline benchmark of the Pan-tilt-zoom-SLAM hot path on B200.
+
+Metric (BASELINE.json): residual + Jacobian + normal-equation assembly, OBSERVATIONS PER SECOND, on config 3
+(keyframe BA, 256 keyframes x 100k ray landmarks x 2M observations); BA LM iterations/s is reported beside it
+(`lm_iters_per_s`).  A step = one fused pass (ptzba_ba_normal_equations) over the whole observation list.
+
+  value     device-resident: x and all observation arrays already in HBM, K passes timed with CUDA events on the
+            launching stream; the passes rotate over R replicas of the problem so that every pass streams its
+            observations from HBM, not from the 126 MB L2 (config: l2 = "rotating replicas").
+  e2e       the same pass through the C-ABI with HOST (pinned) buffers: H2D of x, the kernels, D2H of the residual
+            vector, the U/g_c/V/g_l blocks and the cost, all inside the timed region.
+  roofline  algorithmic bytes of the fused kernel (40 B/obs + 56 B/landmark + 96 B/keyframe) divided
+            by that kernel's own average duration (CUDA events bracketing each launch) over the measured HBM peak.
+  cpu_baseline  oracle/ptz_oracle_c.c (plain-C port of the reference algorithm, all host threads) on the same workload.
+
+`--impl reference` times only that CPU port (the reference itself is pure Python and cannot travel to the GPU box).
+Multi-GPU (torchrun, one rank per GPU): observations are sharded by keyframe, every rank runs the fused pass on its
+shard and the landmark blocks are summed with an NCCL all-reduce inside the timed region (weak scaling: each rank
+holds a config-3 sized shard).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg3": dict(n_kf=256, n_lm=100000, n_obs=2000000, seed=1003, pan_sweep=None),
+    "cfg5": dict(n_kf=1024, n_lm=1000000, n_obs=20000000, seed=1005, pan_sweep=40.0),
+    "small": dict(n_kf=32, n_lm=5000, n_obs=60000, seed=1001, pan_sweep=None),
+}
+BYTES_PER_OBS, BYTES_PER_LM, BYTES_PER_KF = 40, 56, 96
+
+
+def algorithmic_bytes(n_obs, n_lm, n_kf):
+    return n_obs * BYTES_PER_OBS + n_lm * BYTES_PER_LM + n_kf * BYTES_PER_KF
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, rank=0):
+    import ptz_slam_b200  # noqa: F401
+    from ptz_slam_b200 import synth
+    w = WORKLOADS[name]
+    return synth.make_flat_ba(w["n_kf"], w["n_lm"], w["n_obs"], seed=w["seed"] + 17 * rank, pan_sweep=w["pan_sweep"])
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# -------------------------------------------------------------------------------------------------------------------
+def time_cpu_port(fb, steps, warmup, budget_s=20.0):
+    """Plain-C port (oracle/ptz_oracle_c.c), all host threads, full fused pass per step on the same workload.
+    Steps are bounded so the run stays within `budget_s` seconds of CPU work."""
+    from oracle import c_port, ptz_oracle as O
+    from ptz_slam_b200 import synth
+    poses, rays = O.ba_unpack(fb.x0(), fb.n_pose, fb.ptz_init[0])
+    threads = c_port.max_threads()
+    t0 = time.perf_counter()
+    c_port.ba_fused(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V, n_threads=threads)
+    one = time.perf_counter() - t0
+    k = max(1, min(steps, int(budget_s / max(one, 1e-6))))
+    for _ in range(min(warmup, 2)):
+        c_port.ba_fused(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(k):
+        c_port.ba_fused(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return dict(value=fb.n_obs * k / dt, steps=k, ms_per_step=1e3 * dt / k, cores=threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fb = make_workload(args.workload)
+    r = time_cpu_port(fb, args.steps, args.warmup, budget_s=60.0)
+    sample = "%d full fused passes over all %d observations of %s" % (r["steps"], fb.n_obs, args.workload)
+    line = {
+        "impl": "reference", "metric": "ba_residual_jacobian_normal_eq_obs_per_s", "value": r["value"], "unit": "obs/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + " keyframe BA: %d keyframes x %d ray landmarks x %d observations" %
+                   (fb.n_pose, fb.n_landmark, fb.n_obs)},
+        "cpu_baseline": {"value": r["value"], "unit": "obs/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ptz_slam_b200  # noqa: F401
+    from ptz_slam_b200 import _lib, synth
+    from ptz_slam_b200 import bundle_adjustment as BA
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.get_context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    fb = make_workload(args.workload, rank)
+    u, v = synth.PP_U, synth.PP_V
+    ref_pose = fb.ptz_init[0]
+    x0 = fb.x0()
+    R = args.replicas
+    probs = [BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v, ctx=ctx) for _ in range(R)]
+    x_dev = [torch.from_numpy(x0).cuda() for _ in range(R)]
+    r_dev = [torch.empty(2 * fb.n_obs, dtype=torch.float64, device="cuda") for _ in range(R)]
+    comm = None
+    if world > 1:
+        from ptz_slam_b200 import dist as pdist
+        comm = pdist.Communicator(ctx, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        p = probs[i % R]
+        p.normal_equations_device(x_dev[i % R].data_ptr(), ref_pose, r_dev[i % R].data_ptr())
+        if comm is not None:
+            comm.allreduce_landmark_blocks(p)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # clock ramp (untimed, in addition to the W warm-up steps): ~0.3 s of passes
+    t_end = time.perf_counter() + args.ramp
+    i = 0
+    while time.perf_counter() < t_end:
+        device_step(i); i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        device_step(i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_obs = fb.n_obs * world
+    value = total_obs * args.steps / (ms * 1e-3)
+
+    # ---- kernel-only duration of the fused kernel (events bracketing each launch) -> roofline ----------------------
+    import ctypes
+    ctx.check(ctx.lib.ptzba_profile_begin(ctx.handle))
+    for i in range(args.steps):
+        probs[i % R].normal_equations_device(x_dev[i % R].data_ptr(), ref_pose, r_dev[i % R].data_ptr())
+    n_l, tot = ctypes.c_int32(0), ctypes.c_double(0.0)
+    ctx.check(ctx.lib.ptzba_profile_end(ctx.handle, ctypes.byref(n_l), ctypes.byref(tot)))
+    kernel_ms = tot.value / max(n_l.value, 1)
+    peaks, peak_kind = measured_peaks()
+    abytes = algorithmic_bytes(fb.n_obs, fb.n_landmark, fb.n_pose)
+    achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
+                "kernel": "k_ba_fused", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
+
+    # ---- e2e: HOST (pinned) buffers through the C-ABI, copies inside the timed region ------------------------------
+    N, M = fb.n_pose, fb.n_landmark
+    pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    hx = pin(len(x0)); hx[:] = x0
+    hr, hU, hgc, hV, hgl = pin(2 * fb.n_obs), pin(N * 6), pin(N * 3), pin(M * 3), pin(M * 2)
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(min(args.warmup, 3)):
+        probs[i % R].normal_equations_into(hx, ref_pose, hr, hU, hgc, hV, hgl)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        cost = probs[i % R].normal_equations_into(hx, ref_pose, hr, hU, hgc, hV, hgl)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": total_obs * e2e_steps / e2e_s, "unit": "obs/s", "h2d_bytes_per_step": int(8 * (len(x0) + 3)),
+           "d2h_bytes_per_step": int(8 * (2 * fb.n_obs + N * 9 + M * 5 + 1)), "steps": e2e_steps,
+           "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "call": "ptzba_ba_normal_equations(mem=HOST): x in; residual, U, g_c, V, g_l, cost out (pinned buffers)"}
+
+    # ---- BA LM iterations/s (fused pass + Schur + Cholesky + back-substitution + trial residual pass) --------------
+    lm = None
+    if world == 1 and not args.no_lm:
+        for _ in range(2):
+            probs[0].lm_iteration(x0, ref_pose, alpha=1e-3)
+        torch.cuda.synchronize()
+        n_lm_it = 10
+        t0 = time.perf_counter()
+        for _ in range(n_lm_it):
+            probs[0].lm_iteration(x0, ref_pose, alpha=1e-3)
+        torch.cuda.synchronize()
+        lm_s = (time.perf_counter() - t0) / n_lm_it
+        t0 = time.perf_counter()
+        xs, rep = probs[0].solve(x0, ref_pose, ftol=1e-4)
+        solve_s = time.perf_counter() - t0
+        lm = {"lm_iters_per_s": 1.0 / lm_s, "ms_per_lm_iter": 1e3 * lm_s,
+              "solve": {"ftol": 1e-4, "ms": 1e3 * solve_s, "nfev": rep["nfev"], "njev": rep["njev"], "status": rep["status"],
+                        "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]}}
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c = time_cpu_port(fb, 20, 1, budget_s=15.0)
+        cpu = {"value": c["value"], "unit": "obs/s", "cores": c["cores"], "kind": "port",
+               "sample": "%d full fused passes over all %d observations of %s (oracle/ptz_oracle_c.c, %d threads)" %
+                         (c["steps"], fb.n_obs, args.workload, c["cores"])}
+
+    if rank == 0:
+        line = {
+            "metric": "ba_residual_jacobian_normal_eq_obs_per_s", "value": value, "unit": "obs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s keyframe BA: %d keyframes x %d ray landmarks x %d observations per GPU" %
+                       (args.workload, fb.n_pose, fb.n_landmark, fb.n_obs),
+                       "l2": "rotating over %d replicas of the observation arrays (%.0f MB per pass > 126 MB L2 in total)" %
+                             (R, abytes / 1e6),
+                       "parallelism": "keyframe-sharded observations, 1 rank per GPU" if world > 1 else "1 GPU",
+                       "step": "one fused residual+Jacobian+normal-equation pass (set_params + k_ba_fused)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if lm:
+            line.update(lm)
+        print(json.dumps(line), flush=True)
+    for p in probs:
+        p.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lm", action="store_true")
+    ap.add_argument("--ramp", type=float, default=0.3, help="seconds of untimed passes before warm-up (clock ramp)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,10 @@ int ptzba_set_stream(ptzba_ctx* ctx, void* cuda_stream);    /* cudaStream_t; NUL
 int ptzba_synchronize(ptzba_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t ptzba_launch_count(ptzba_ctx* ctx);
+/* per-launch CUDA-event timing of the dominant kernel (the fused BA pass): between begin and end every launch of
+ * that kernel is bracketed by two events on the launching stream; end synchronises and returns count and total. */
+int ptzba_profile_begin(ptzba_ctx* ctx);
+int ptzba_profile_end(ptzba_ctx* ctx, int32_t* n_launches, double* total_ms);
 
 /* ---- A1/A2: projection  (PTZCamera.project_ray ptz_camera.py:191-210, project_rays :212-234,
  *                           TransFunction.from_ray_to_image transformation.py:99-135) ------------------------- */

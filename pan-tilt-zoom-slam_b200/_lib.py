@@ -52,6 +52,8 @@ SIGNATURES = {
     "ptzba_set_stream": (_I, [_P, _P]),
     "ptzba_synchronize": (_I, [_P]),
     "ptzba_launch_count": (_L, [_P]),
+    "ptzba_profile_begin": (_I, [_P]),
+    "ptzba_profile_end": (_I, [_P, _P, _P]),
     "ptzba_project": (_I, [_P, _I, _I, _P, _D, _D, _P, _I, _P, _P]),
     "ptzba_project_rays_filtered": (_I, [_P, _I, _P, _D, _D, _P, _I, _P, _D, _D, _P, _P, _P]),
     "ptzba_project_pairs": (_I, [_P, _I, _I, _P, _D, _D, _I, _P, _L, _P, _P, _P]),

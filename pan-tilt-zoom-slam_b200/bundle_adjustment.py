@@ -84,6 +84,32 @@ class BAProblem:
         V[:, 0, 0], V[:, 0, 1], V[:, 1, 0], V[:, 1, 1] = Vp[:, 0], Vp[:, 1], Vp[:, 1], Vp[:, 2]
         return dict(residual=r, U=U, gc=gc, V=V, gl=gl, cost=cost.value)
 
+    def normal_equations_device(self, x_dev_ptr, reference_pose, resid_dev_ptr=None):
+        """Fused pass with device-resident x (and optional device residual buffer); asynchronous on the context
+        stream, results stay in the problem's accumulators on the GPU (no host copy, no synchronisation)."""
+        ref = _lib.f64(reference_pose)
+        self.ctx.check(self.ctx.lib.ptzba_ba_normal_equations(self.handle, _lib.DEVICE, _lib.ptr(int(x_dev_ptr)),
+                                                              _lib.ptr(ref), _lib.ptr(resid_dev_ptr and int(resid_dev_ptr)),
+                                                              None, None, None, None, None))
+
+    def normal_equations_into(self, x, reference_pose, r, Up, gc, Vp, gl):
+        """Fused pass through HOST buffers the caller owns (e.g. pinned): x in; r, packed U/gc/V/gl out; returns cost."""
+        ref = _lib.f64(reference_pose)
+        cost = ctypes.c_double(0.0)
+        self.ctx.check(self.ctx.lib.ptzba_ba_normal_equations(self.handle, _lib.HOST, _lib.ptr(x), _lib.ptr(ref),
+                                                              _lib.ptr(r), _lib.ptr(Up), _lib.ptr(gc), _lib.ptr(Vp),
+                                                              _lib.ptr(gl), ctypes.byref(cost)))
+        return cost.value
+
+    def lm_iteration(self, x, reference_pose, alpha=0.0):
+        """One LM iteration's device work at fixed damping (benchmark unit); returns (predicted_reduction, trial_cost)."""
+        x = _lib.f64(x)
+        ref = _lib.f64(reference_pose)
+        pred, trial = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        self.ctx.check(self.ctx.lib.ptzba_ba_lm_iteration(self.handle, _lib.HOST, _lib.ptr(x), _lib.ptr(ref), float(alpha),
+                                                          ctypes.byref(pred), ctypes.byref(trial)))
+        return pred.value, trial.value
+
     def solve(self, x0, reference_pose, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=0, verbose=0):
         """Trust-region solve with scipy-TRF semantics (least_squares(method='trf', x_scale='jac'))."""
         x = _lib.f64(x0).copy()

@@ -66,3 +66,28 @@ extern "C" int ptzba_synchronize(ptzba_ctx* ctx) {
 }
 
 extern "C" int64_t ptzba_launch_count(ptzba_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int ptzba_profile_begin(ptzba_ctx* ctx) {
+    if (!ctx) return PTZBA_ERR_ARG;
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    ctx->profiling = true;
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_profile_end(ptzba_ctx* ctx, int32_t* n_launches, double* total_ms) {
+    if (!ctx) return PTZBA_ERR_ARG;
+    ctx->profiling = false;
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0;
+    for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
+        float ms = 0;
+        CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        tot += ms;
+    }
+    if (n_launches) *n_launches = (int32_t)(ctx->prof_events.size() / 2);
+    if (total_ms) *total_ms = tot;
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    return PTZBA_OK;
+}

@@ -34,7 +34,8 @@ struct ptzba_ba {
     DevBuf<LmTrig> lm_trig;         // [M]
     DevBuf<double> accum_store;
     BaAccum acc;
-    DevBuf<double> resid;           // [2*n_obs] caller order (only when the caller asks for device residuals)
+    DevBuf<double> resid;           // [2*n_obs] caller order, staging for host-side residual requests
+    DevBuf<double> x_stage, ref_stage;   // persistent H2D staging of x and the reference pose
     // ---- solver workspace (allocated on first solve) ----
     DevBuf<double> x_cur, x_trial;          // [3(N-1)+2M] packed parameter vectors
     DevBuf<double> scale_inv;               // [3N + 2M] (camera part incl. slot for pose 0, then landmarks)

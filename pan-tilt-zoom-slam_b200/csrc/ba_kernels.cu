@@ -290,16 +290,26 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     int64_t chunk = (ba->n_obs + ba->fused_grid - 1) / ba->fused_grid;
     chunk = (chunk + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
     const int grid = (int)((ba->n_obs + chunk - 1) / chunk);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profiling) {
+        CU_CHECK(ctx, cudaEventCreate(&ev0));
+        CU_CHECK(ctx, cudaEventCreate(&ev1));
+        ctx->prof_events.push_back(ev0);
+        ctx->prof_events.push_back(ev1);
+        CU_CHECK(ctx, cudaEventRecord(ev0, s));
+    }
     if (ba->fused_cam_smem) {
         k_ba_fused<true><<<grid, kFusedThreads, ba->fused_smem, s>>>(
             ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
             ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
+        if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     } else {
         k_ba_fused<false><<<grid, kFusedThreads, 0, s>>>(
             ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
             ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
+        if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
         k_scale_cam_blocks<<<div_up(ba->n_pose * 9, 256), 256, 0, s>>>(ba->n_pose, ba->acc.U, ba->acc.gc);
         KERNEL_POST(ctx);
     }
@@ -432,22 +442,43 @@ extern "C" void ptzba_ba_destroy(ptzba_ba* ba) {
     delete ba;
 }
 
+// Persistent staging (no allocation on the hot path): x and the reference pose are copied into ba->x_stage /
+// ba->ref_stage; host residuals are produced into ba->resid and copied out.
+static int ba_stage_inputs(ptzba_ba* ba, int mem, const double* x, const double* reference_pose3, const double** d_x) {
+    ptzba_ctx* ctx = ba->ctx;
+    cudaStream_t s = ctx->stream;
+    const size_t nx = 3 * (size_t)(ba->n_pose - 1) + 2 * (size_t)ba->n_lm;
+    CU_CHECK(ctx, ba->ref_stage.alloc(4));
+    CU_CHECK(ctx, cudaMemcpyAsync(ba->ref_stage.p, reference_pose3, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (mem == PTZBA_DEVICE) {
+        *d_x = x;
+    } else {
+        CU_CHECK(ctx, ba->x_stage.alloc(nx + 2));
+        if (nx) CU_CHECK(ctx, cudaMemcpyAsync(ba->x_stage.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, s));
+        *d_x = ba->x_stage.p;
+    }
+    return PTZBA_OK;
+}
+
 extern "C" int ptzba_ba_residual(ptzba_ba* ba, int mem, const double* x, const double* reference_pose3,
                                  double* residual) {
     if (!ba) return PTZBA_ERR_ARG;
     ptzba_ctx* ctx = ba->ctx;
     ARG_CHECK(ctx, x && reference_pose3 && residual);
     cudaStream_t s = ctx->stream;
-    const size_t nx = 3 * (size_t)(ba->n_pose - 1) + 2 * (size_t)ba->n_lm;
-    InArray<double> d_x, d_ref;
-    OutArray<double> d_r;
-    CU_CHECK(ctx, d_x.stage(mem, x, nx, s));
-    CU_CHECK(ctx, d_ref.stage(PTZBA_HOST, reference_pose3, 3, s));
-    CU_CHECK(ctx, d_r.stage(mem, residual, 2 * (size_t)ba->n_obs));
-    PROPAGATE(ba_set_params(ba, d_x.d, d_ref.d));
-    PROPAGATE(ba_residual_pass(ba, d_r.d, nullptr));
-    CU_CHECK(ctx, d_r.finish(s));
-    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    const double* d_x = nullptr;
+    PROPAGATE(ba_stage_inputs(ba, mem, x, reference_pose3, &d_x));
+    double* d_r = residual;
+    if (mem == PTZBA_HOST) {
+        CU_CHECK(ctx, ba->resid.alloc(2 * (size_t)ba->n_obs));
+        d_r = ba->resid.p;
+    }
+    PROPAGATE(ba_set_params(ba, d_x, ba->ref_stage.p));
+    PROPAGATE(ba_residual_pass(ba, d_r, nullptr));
+    if (mem == PTZBA_HOST) {
+        if (ba->n_obs) CU_CHECK(ctx, cudaMemcpyAsync(residual, d_r, 2 * (size_t)ba->n_obs * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+    }
     return PTZBA_OK;
 }
 
@@ -457,25 +488,26 @@ extern "C" int ptzba_ba_normal_equations(ptzba_ba* ba, int mem, const double* x,
     ptzba_ctx* ctx = ba->ctx;
     ARG_CHECK(ctx, x && reference_pose3);
     cudaStream_t s = ctx->stream;
-    const size_t nx = 3 * (size_t)(ba->n_pose - 1) + 2 * (size_t)ba->n_lm;
-    InArray<double> d_x, d_ref;
-    OutArray<double> d_r;
-    CU_CHECK(ctx, d_x.stage(mem, x, nx, s));
-    CU_CHECK(ctx, d_ref.stage(PTZBA_HOST, reference_pose3, 3, s));
-    CU_CHECK(ctx, d_r.stage(mem, residual, 2 * (size_t)ba->n_obs));
-    PROPAGATE(ba_set_params(ba, d_x.d, d_ref.d));
-    PROPAGATE(ba_fused_pass(ba, d_r.d));
+    const double* d_x = nullptr;
+    PROPAGATE(ba_stage_inputs(ba, mem, x, reference_pose3, &d_x));
+    double* d_r = residual;
+    if (mem == PTZBA_HOST && residual) {
+        CU_CHECK(ctx, ba->resid.alloc(2 * (size_t)ba->n_obs));
+        d_r = ba->resid.p;
+    }
+    PROPAGATE(ba_set_params(ba, d_x, ba->ref_stage.p));
+    PROPAGATE(ba_fused_pass(ba, d_r));
     const cudaMemcpyKind kind = mem == PTZBA_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (U) CU_CHECK(ctx, cudaMemcpyAsync(U, ba->acc.U, (size_t)ba->n_pose * 6 * sizeof(double), kind, s));
     if (gc) CU_CHECK(ctx, cudaMemcpyAsync(gc, ba->acc.gc, (size_t)ba->n_pose * 3 * sizeof(double), kind, s));
-    if (V) CU_CHECK(ctx, cudaMemcpyAsync(V, ba->acc.V, (size_t)ba->n_lm * 3 * sizeof(double), kind, s));
-    if (gl) CU_CHECK(ctx, cudaMemcpyAsync(gl, ba->acc.gl, (size_t)ba->n_lm * 2 * sizeof(double), kind, s));
-    CU_CHECK(ctx, d_r.finish(s));
+    if (V && ba->n_lm) CU_CHECK(ctx, cudaMemcpyAsync(V, ba->acc.V, (size_t)ba->n_lm * 3 * sizeof(double), kind, s));
+    if (gl && ba->n_lm) CU_CHECK(ctx, cudaMemcpyAsync(gl, ba->acc.gl, (size_t)ba->n_lm * 2 * sizeof(double), kind, s));
+    if (mem == PTZBA_HOST && residual && ba->n_obs)
+        CU_CHECK(ctx, cudaMemcpyAsync(residual, d_r, 2 * (size_t)ba->n_obs * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (cost) {
-        double sumsq = 0;
-        CU_CHECK(ctx, cudaMemcpyAsync(&sumsq, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalars, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, s));
         CU_CHECK(ctx, cudaStreamSynchronize(s));
-        *cost = 0.5 * sumsq;
+        *cost = 0.5 * ctx->h_scalars[0];
     } else if (mem == PTZBA_HOST) {
         CU_CHECK(ctx, cudaStreamSynchronize(s));
     }

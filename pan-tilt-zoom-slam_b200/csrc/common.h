@@ -23,6 +23,9 @@ struct ptzba_ctx {
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // optional per-launch event timing of the dominant kernel
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // start/stop pairs
 };
 
 int ptzba_fail(ptzba_ctx* ctx, int code, const char* fmt, ...);
