@@ -175,7 +175,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _lib.get_context(local)
-    stream = torch.cuda.current_stream()
+    # an explicit side stream: the legacy default stream has handle 0, which the C-ABI reads as "use the context's own
+    # stream"; events below are recorded on the very stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     fb = make_workload(args.workload, rank)
@@ -318,6 +322,7 @@ def run_ours(args):
                        "parallelism": "keyframe-sharded observations, 1 rank per GPU" if world > 1 else "1 GPU",
                        "step": "one fused residual+Jacobian+normal-equation pass (set_params + k_ba_fused)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "fused_variant": os.environ.get("PTZBA_FUSED_VARIANT", "default"),
         }
         if lm:
             line.update(lm)

@@ -116,6 +116,13 @@ void ptzba_ekf_batch_destroy(ptzba_ekf_batch* b);
  * live in `mem`.  out_matched[n_seq] (host, may be NULL). */
 int ptzba_ekf_batch_step(ptzba_ekf_batch* b, int mem, const double* obs_xy, const int32_t* obs_index,
                          const int32_t* obs_count, int32_t* out_matched);
+/* update only (no predict): the contract of PtzSlam.ekf_update, where the caller has already predicted the pose */
+int ptzba_ekf_batch_update_only(ptzba_ekf_batch* b, int mem, const double* obs_xy, const int32_t* obs_index,
+                                const int32_t* obs_count, int32_t* out_matched);
+/* overwrite the state of one sequence from host buffers (any may be NULL): ptz3, velocity3, rays[n_ray*2],
+ * state_cov[(3+2 n_ray)^2] row-major */
+int ptzba_ekf_batch_set(ptzba_ekf_batch* b, int seq, const double* ptz3, const double* velocity3, const double* rays,
+                        const double* state_cov);
 /* copy state back to host: ptz[n_seq*3], velocity[n_seq*3], rays[n_seq*n_ray*2] (any may be NULL) */
 int ptzba_ekf_batch_get(ptzba_ekf_batch* b, double* ptz, double* velocity, double* rays);
 /* dense covariance of one sequence, (3+2 n_ray)^2 row-major, host */

@@ -64,6 +64,8 @@ SIGNATURES = {
     "ptzba_ekf_batch_create": (_I, [_P, ctypes.POINTER(EkfParams), _I, _I, _I, _P, _P, ctypes.POINTER(_P)]),
     "ptzba_ekf_batch_destroy": (None, [_P]),
     "ptzba_ekf_batch_step": (_I, [_P, _I, _P, _P, _P, _P]),
+    "ptzba_ekf_batch_update_only": (_I, [_P, _I, _P, _P, _P, _P]),
+    "ptzba_ekf_batch_set": (_I, [_P, _I, _P, _P, _P, _P]),
     "ptzba_ekf_batch_get": (_I, [_P, _P, _P, _P]),
     "ptzba_ekf_batch_get_cov": (_I, [_P, _I, _P]),
     "ptzba_ba_create": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _D, _D, ctypes.POINTER(_P)]),

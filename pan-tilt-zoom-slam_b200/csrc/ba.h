@@ -27,6 +27,11 @@ struct ptzba_ba {
     DevBuf<int32_t> s_cam, s_lm, orig;
     DevBuf<double> s_ox, s_oy;
     DevBuf<int32_t> lm_ptr;         // [M+1] CSR offsets into the sorted arrays
+    // second copy in keyframe-major order (landmark ascending inside a keyframe) for the fused pass:
+    // keyframe blocks accumulate in registers, landmark blocks go to L2 with RED atomics
+    DevBuf<int32_t> c_cam, c_lm, c_orig;
+    DevBuf<double> c_ox, c_oy;
+    int fused_variant = 1;          // 0: landmark-major + smem atomics, 1: keyframe-major + REDs, 2: + packed REDs
     // current parameters
     DevBuf<double> poses;           // [N*3] incl. reference pose at 0
     DevBuf<double> rays;            // [M*2]

@@ -11,6 +11,7 @@
 // (sin th, cos th, T, S) tables are rebuilt once per parameter update so that no transcendental is evaluated per
 // observation.  Algorithmic traffic of the fused pass: 40 B/obs + 56 B/landmark + 96 B/keyframe.
 #include <cub/cub.cuh>
+#include <stdlib.h>
 
 #include "ba.h"
 
@@ -42,6 +43,20 @@ __global__ void k_gather_obs(int64_t n, const int32_t* __restrict__ perm, const 
         const double2 p = __ldg(reinterpret_cast<const double2*>(obs_xy) + o);
         s_ox[k] = p.x;
         s_oy[k] = p.y;
+    }
+}
+
+// keyframe-major gather: position k takes landmark-major position perm[k]; c_orig = caller position of the residual
+__global__ void k_gather_cm(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ s_lm,
+                            const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+                            int32_t* __restrict__ c_lm, double* __restrict__ c_ox, double* __restrict__ c_oy,
+                            int32_t* __restrict__ c_orig) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t p = perm[k];
+        c_lm[k] = s_lm[p];
+        c_ox[k] = s_ox[p];
+        c_oy[k] = s_oy[p];
+        c_orig[k] = orig ? orig[p] : p;
     }
 }
 
@@ -219,6 +234,143 @@ k_ba_fused(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// keyframe-major fused pass.  Observations are sorted by keyframe (landmark ascending inside a keyframe), so a warp's
+// 32 observations almost always belong to ONE keyframe: its 9 accumulators live in registers across the whole chunk
+// and are committed with one warp reduction when the keyframe changes (no shared-memory atomics).  The per-landmark
+// blocks are committed with FP64 RED atomics that resolve in L2 (the 4 MB of landmark blocks stay L2 resident).
+// PACK = 1 regroups lanes with shuffles so that the 3 (V) / 2 (g_l) values of one landmark travel in one 32-byte sector.
+// ---------------------------------------------------------------------------------------------------------------
+template <int PACK, int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB)
+k_ba_fused_cm(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+              const double* __restrict__ c_ox, const double* __restrict__ c_oy, const int32_t* __restrict__ c_orig,
+              const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, double u, double v,
+              double* __restrict__ resid, double* __restrict__ gU, double* __restrict__ gGc, double* __restrict__ gV,
+              double* __restrict__ gGl, double* __restrict__ gCost) {
+    __shared__ double sWarp[kFusedThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double k1 = PTZ_DEG2RAD;
+    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > n_obs) end = n_obs;
+    double cost = 0.0;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // pp,pt,pf,tt,tf,ff | gp,gt,gf
+    int wcam = -1;                                                                    // warp-uniform current keyframe
+    // commit the register accumulators of keyframe wcam: warp reduction, lane 0 issues 9 REDs (per-degree units)
+    auto flush = [&]() {
+        if (wcam > 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
+            if (lane == 0) {
+                double* U = gU + 6 * (size_t)wcam;
+                double* G = gGc + 3 * (size_t)wcam;
+                atomicAdd(U + 0, a0); atomicAdd(U + 1, a1 * k1); atomicAdd(U + 2, a2);
+                atomicAdd(U + 3, a3 * k1 * k1); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
+                atomicAdd(G + 0, a6); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+            }
+        }
+        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
+    };
+    for (int64_t base = begin; base < end; base += kFusedThreads) {
+        const int64_t k = base + tid;
+        const bool act = k < end;
+        int lm = -1, cam = -1;
+        double rx = 0, ry = 0, kxa = 0, kya = 0, kxp = 0, kyp = 0, xt = 0, yt = 0, px = 0, py = 0;
+        if (act) {
+            cam = c_cam[k];
+            lm = c_lm[k];
+            const double ox = c_ox[k], oy = c_oy[k];
+            const CamTrig c = cam_trig[cam];
+            const LmTrig l = lm_trig[lm];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, l, u, v, x, y, g);
+            rx = x - ox;
+            ry = y - oy;
+            if (resid) reinterpret_cast<double2*>(resid)[c_orig[k]] = make_double2(rx, ry);
+            cost = fma(rx, rx, fma(ry, ry, cost));
+            kxa = k1 * g.xa; kya = k1 * g.ya; kxp = k1 * g.xp; kyp = k1 * g.yp;
+            xt = g.xt; yt = g.yt; px = g.px; py = g.py;
+        }
+        // landmark blocks, final (per-degree) units
+        const double vtt = fma(kxa, kxa, kya * kya);
+        const double vtp = fma(kxa, kxp, kya * kyp);
+        const double vpp = fma(kxp, kxp, kyp * kyp);
+        const double glt = fma(kxa, rx, kya * ry);
+        const double glp = fma(kxp, rx, kyp * ry);
+        if (PACK == 0) {
+            if (act) {
+                atomicAdd(gV + 3 * (size_t)lm + 0, vtt);
+                atomicAdd(gV + 3 * (size_t)lm + 1, vtp);
+                atomicAdd(gV + 3 * (size_t)lm + 2, vpp);
+                atomicAdd(gGl + 2 * (size_t)lm + 0, glt);
+                atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {            // V: 4-lane groups, 8 observations per instruction
+                const int src = 8 * j + (lane >> 2), e = lane & 3;
+                const int lmj = __shfl_sync(0xffffffffu, lm, src);
+                const double t0 = __shfl_sync(0xffffffffu, vtt, src), t1 = __shfl_sync(0xffffffffu, vtp, src),
+                             t2 = __shfl_sync(0xffffffffu, vpp, src);
+                if (e < 3 && lmj >= 0) atomicAdd(gV + 3 * (size_t)lmj + e, e == 0 ? t0 : e == 1 ? t1 : t2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {            // g_l: 2-lane groups, 16 observations per instruction
+                const int src = 16 * j + (lane >> 1), e = lane & 1;
+                const int lmj = __shfl_sync(0xffffffffu, lm, src);
+                const double t0 = __shfl_sync(0xffffffffu, glt, src), t1 = __shfl_sync(0xffffffffu, glp, src);
+                if (lmj >= 0) atomicAdd(gGl + 2 * (size_t)lmj + e, e ? t1 : t0);
+            }
+        }
+        // keyframe blocks
+        const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
+        const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
+        if (same == 0xffffffffu) {
+            if (cam_lo != wcam) { flush(); wcam = cam_lo; }
+            if (act && cam > 0) {
+                a0 += vtt;
+                a1 -= fma(kxa, xt, kya * yt);
+                a2 -= fma(kxa, px, kya * py);
+                a3 = fma(xt, xt, fma(yt, yt, a3));
+                a4 = fma(xt, px, fma(yt, py, a4));
+                a5 = fma(px, px, fma(py, py, a5));
+                a6 -= glt;
+                a7 = fma(xt, rx, fma(yt, ry, a7));
+                a8 = fma(px, rx, fma(py, ry, a8));
+            }
+        } else {
+            // the warp straddles a keyframe boundary (rare): commit what is in registers, then this iteration per lane
+            flush();
+            wcam = -1;
+            if (act && cam > 0) {
+                double* U = gU + 6 * (size_t)cam;
+                double* G = gGc + 3 * (size_t)cam;
+                atomicAdd(U + 0, vtt);
+                atomicAdd(U + 1, -k1 * fma(kxa, xt, kya * yt));
+                atomicAdd(U + 2, -fma(kxa, px, kya * py));
+                atomicAdd(U + 3, k1 * k1 * fma(xt, xt, yt * yt));
+                atomicAdd(U + 4, k1 * fma(xt, px, yt * py));
+                atomicAdd(U + 5, fma(px, px, py * py));
+                atomicAdd(G + 0, -glt);
+                atomicAdd(G + 1, k1 * fma(xt, rx, yt * ry));
+                atomicAdd(G + 2, fma(px, rx, py * ry));
+            }
+        }
+    }
+    flush();
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+}
+
 // global-accumulator variant leaves radian units in U/gc; this converts them in place
 __global__ void k_scale_cam_blocks(int n_pose, double* __restrict__ U, double* __restrict__ gc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,7 +450,21 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         ctx->prof_events.push_back(ev1);
         CU_CHECK(ctx, cudaEventRecord(ev0, s));
     }
-    if (ba->fused_cam_smem) {
+    if (ba->fused_variant >= 1) {
+#define LAUNCH_CM(P, B)                                                                                                    \
+    k_ba_fused_cm<P, B><<<grid, kFusedThreads, 0, s>>>(ba->n_obs, chunk, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,     \
+                                                       ba->c_orig.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, d_resid,  \
+                                                       ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost)
+        switch (ba->fused_variant) {
+            case 1: LAUNCH_CM(0, 2); break;
+            case 2: LAUNCH_CM(1, 2); break;
+            case 3: LAUNCH_CM(0, 3); break;
+            default: LAUNCH_CM(1, 3); break;
+        }
+#undef LAUNCH_CM
+        KERNEL_POST(ctx);
+        if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
+    } else if (ba->fused_cam_smem) {
         k_ba_fused<true><<<grid, kFusedThreads, ba->fused_smem, s>>>(
             ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
             ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
@@ -417,6 +583,32 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     CU_TRY(cudaGetLastError());
     ba->max_degree = h_flags[1];
 
+    // keyframe-major copy: stable sort of the landmark-major list by keyframe id
+    {
+        const char* env = getenv("PTZBA_FUSED_VARIANT");
+        if (env) ba->fused_variant = atoi(env);
+    }
+    if (n_obs > 0) {
+        DevBuf<int32_t> iota, perm2;
+        DevBuf<unsigned char> tmp;
+        CU_TRY(ba->c_cam.alloc(n_obs)); CU_TRY(ba->c_lm.alloc(n_obs)); CU_TRY(ba->c_orig.alloc(n_obs));
+        CU_TRY(ba->c_ox.alloc(n_obs)); CU_TRY(ba->c_oy.alloc(n_obs));
+        CU_TRY(iota.alloc(n_obs)); CU_TRY(perm2.alloc(n_obs));
+        k_iota<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, iota.p);
+        ctx->launches++;
+        size_t bytes = 0;
+        int end_bit = 1;
+        while ((1ll << end_bit) < (long long)n_pose && end_bit < 31) ++end_bit;
+        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ba->s_cam.p, ba->c_cam.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
+        CU_TRY(tmp.alloc(bytes));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ba->s_cam.p, ba->c_cam.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
+        k_gather_cm<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, perm2.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p,
+                                                                    ba->identity_perm ? nullptr : ba->orig.p, ba->c_lm.p,
+                                                                    ba->c_ox.p, ba->c_oy.p, ba->c_orig.p);
+        ctx->launches++;
+        CU_TRY(cudaStreamSynchronize(s));
+    }
+
     // launch geometry of the fused pass: one wave of resident CTAs; keyframe tables in shared memory when they fit
     const size_t smem = (size_t)n_pose * 14 * sizeof(double);
     int per_sm = 0;
@@ -428,6 +620,14 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     } else {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<false>, kFusedThreads, 0));
         ba->fused_smem = 0;
+    }
+    if (ba->fused_variant >= 1) {
+        switch (ba->fused_variant) {
+            case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<0, 2>, kFusedThreads, 0)); break;
+            case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 2>, kFusedThreads, 0)); break;
+            case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<0, 3>, kFusedThreads, 0)); break;
+            default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 3>, kFusedThreads, 0)); break;
+        }
     }
     if (per_sm < 1) per_sm = 1;
     ba->fused_grid = ctx->sm_count * per_sm;

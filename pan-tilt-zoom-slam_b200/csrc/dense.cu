@@ -15,8 +15,13 @@ constexpr int NB = 32;        // panel width
 constexpr int TS = 64;        // syrk tile
 
 // ---- potf2: Cholesky of one NB x NB diagonal block by a single warp; lane = row -----------------------------------
-__global__ void __launch_bounds__(32) k_potf2(double* __restrict__ A, int lda, int k, int nb, int* __restrict__ info) {
+__global__ void __launch_bounds__(32) k_potf2(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
+                                              int n_fixed, int k, int* __restrict__ info) {
     const int lane = threadIdx.x;
+    const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
+    if (k >= n) return;
+    const int nb = (n - k) < NB ? (n - k) : NB;
+    double* A = A0 + stride * blockIdx.y;
     double row[NB];
     double* blk = A + (size_t)k + (size_t)k * lda;
 #pragma unroll
@@ -47,7 +52,12 @@ __global__ void __launch_bounds__(32) k_potf2(double* __restrict__ A, int lda, i
 }
 
 // ---- trsm: rows below the diagonal block, X * L_kk^T = A_panel; one row per thread ------------------------------------
-__global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ A, int lda, int n, int k, int nb) {
+__global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ A0, int lda, size_t stride,
+                                                    const int* __restrict__ n_arr, int n_fixed, int k) {
+    const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
+    if (k + NB >= n) return;
+    const int nb = NB;
+    double* A = A0 + stride * blockIdx.y;
     __shared__ double L[NB][NB + 1];
     for (int e = threadIdx.x; e < NB * NB; e += 128) {
         const int i = e % NB, j = e / NB;
@@ -72,7 +82,12 @@ __global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ A, int 
 }
 
 // ---- syrk: C -= P P^T on the lower tiles of the trailing matrix; 256 threads, 4x4 outputs each -----------------------
-__global__ void __launch_bounds__(256) k_syrk_lower(double* __restrict__ A, int lda, int n, int k, int nb) {
+__global__ void __launch_bounds__(256) k_syrk_lower(double* __restrict__ A0, int lda, size_t stride,
+                                                    const int* __restrict__ n_arr, int n_fixed, int k) {
+    const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
+    if (k + NB >= n) return;
+    const int nb = NB;
+    double* A = A0 + stride * blockIdx.y;
     // tile pair (ti >= tj) from the linear block index
     const int t0 = k + nb;
     const int m = n - t0;
@@ -197,22 +212,26 @@ __global__ void __launch_bounds__(1024) k_trsv_lower(const double* __restrict__ 
 
 }  // namespace
 
-int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info) {
+int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
+                              int* d_info) {
     cudaStream_t s = ctx->stream;
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
-    for (int k = 0; k < n; k += NB) {
-        const int nb = (n - k) < NB ? (n - k) : NB;
-        k_potf2<<<1, 32, 0, s>>>(A, lda, k, nb, d_info);
+    for (int k = 0; k < n_max; k += NB) {
+        k_potf2<<<dim3(1, batch), 32, 0, s>>>(A, lda, stride, d_n_arr, n_max, k, d_info);
         KERNEL_POST(ctx);
-        const int m = n - k - nb;
+        const int m = n_max - k - NB;
         if (m <= 0) break;
-        k_trsm_panel<<<div_up(m, 128), 128, 0, s>>>(A, lda, n, k, nb);
+        k_trsm_panel<<<dim3(div_up(m, 128), batch), 128, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
         KERNEL_POST(ctx);
         const int nt = div_up(m, TS);
-        k_syrk_lower<<<nt * (nt + 1) / 2, 256, 0, s>>>(A, lda, n, k, nb);
+        k_syrk_lower<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;
+}
+
+int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info) {
+    return dense_potrf_lower_batched(ctx, A, lda, 0, nullptr, n, 1, d_info);
 }
 
 int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B, int ldb, int nrhs) {
@@ -230,6 +249,107 @@ int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B
         KERNEL_POST(ctx);
     } else {
         return ptzba_fail(ctx, PTZBA_ERR_ARG, "dense_potrs_lower: nrhs must be 1 or 2");
+    }
+    return PTZBA_OK;
+}
+
+namespace {
+
+// block row k of  L Z = G  (L column-major lower, G row-major [n x ncols], ld = ldg): solve the NB x NB triangle for every
+// column; one thread per column (coalesced along columns).
+__global__ void __launch_bounds__(128) k_fwd_diag_rows(const double* __restrict__ L0, int lda, size_t strideL,
+                                                       double* __restrict__ G0, int ldg, size_t strideG,
+                                                       const int* __restrict__ n_arr, int extra_cols, int k) {
+    const int n = n_arr[blockIdx.y];
+    if (k >= n) return;
+    const int nb = (n - k) < NB ? (n - k) : NB;
+    const int ncols = n + extra_cols;
+    const double* L = L0 + strideL * blockIdx.y;
+    double* G = G0 + strideG * blockIdx.y;
+    __shared__ double D[NB][NB + 1];
+    for (int e = threadIdx.x; e < NB * NB; e += 128) {
+        const int i = e % NB, j = e / NB;
+        D[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= ncols) return;
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) x[i] = i < nb ? G[(size_t)(k + i) * ldg + c] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        double s = x[i];
+#pragma unroll
+        for (int t = 0; t < i; ++t) s = fma(-D[i][t], x[t], s);
+        x[i] = s / D[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+        if (i < nb) G[(size_t)(k + i) * ldg + c] = x[i];
+}
+
+// trailing rows: G[r, c] -= sum_t L[r, k+t] * G[k+t, c]   for r >= k+NB ; 64 x 64 tiles, 4x4 per thread
+__global__ void __launch_bounds__(256) k_fwd_update_rows(const double* __restrict__ L0, int lda, size_t strideL,
+                                                         double* __restrict__ G0, int ldg, size_t strideG,
+                                                         const int* __restrict__ n_arr, int extra_cols, int k) {
+    const int n = n_arr[blockIdx.z];
+    const int r0 = k + NB + blockIdx.y * TS;
+    if (r0 >= n) return;
+    const int ncols = n + extra_cols;
+    const int c0 = blockIdx.x * TS;
+    if (c0 >= ncols) return;
+    const double* L = L0 + strideL * blockIdx.z;
+    double* G = G0 + strideG * blockIdx.z;
+    __shared__ double Lp[NB][TS + 1];   // Lp[t][r]
+    __shared__ double Zk[NB][TS + 1];   // Zk[t][c]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * TS; e += 256) {
+        const int rr = e % TS, t = e / TS;
+        Lp[t][rr] = (r0 + rr < n) ? L[(size_t)(r0 + rr) + (size_t)(k + t) * lda] : 0.0;
+        Zk[t][rr] = (c0 + rr < ncols) ? G[(size_t)(k + t) * ldg + c0 + rr] : 0.0;
+    }
+    __syncthreads();
+    const int tx = tid % 16, ty = tid / 16;   // cols tx + 16*b (coalesced), rows ty + 16*a
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < NB; ++t) {
+        double lr[4], zc[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { lr[a] = Lp[t][ty + 16 * a]; zc[a] = Zk[t][tx + 16 * a]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(lr[a], zc[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int r = r0 + ty + 16 * a, c = c0 + tx + 16 * b;
+            if (r < n && c < ncols) G[(size_t)r * ldg + c] -= acc[a][b];
+        }
+}
+
+}  // namespace
+
+// Z = L^-1 G in place for a batch; G row-major with n_b rows and n_b + extra_cols columns
+int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_t strideL, double* G, int ldg, size_t strideG,
+                                 const int* d_n_arr, int n_max, int extra_cols, int batch) {
+    cudaStream_t s = ctx->stream;
+    const int ncols_max = n_max + extra_cols;
+    for (int k = 0; k < n_max; k += NB) {
+        k_fwd_diag_rows<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
+        KERNEL_POST(ctx);
+        const int m = n_max - k - NB;
+        if (m <= 0) break;
+        k_fwd_update_rows<<<dim3(div_up(ncols_max, TS), div_up(m, TS), batch), 256, 0, s>>>(L, lda, strideL, G, ldg, strideG,
+                                                                                            d_n_arr, extra_cols, k);
+        KERNEL_POST(ctx);
     }
     return PTZBA_OK;
 }

@@ -7,3 +7,10 @@
 int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info);
 // solves L L^T X = B in place for nrhs (1 or 2) right-hand sides stored as columns of B (ldb)
 int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B, int ldb, int nrhs);
+
+// batched variants: matrix b lives at A + b*stride and has order d_n_arr[b] (device array; nullptr = n_max for all)
+int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
+                              int* d_info);
+// Z = L^-1 G in place; G is ROW-major with d_n_arr[b] rows and d_n_arr[b] + extra_cols columns (leading dimension ldg)
+int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_t strideL, double* G, int ldg, size_t strideG,
+                                 const int* d_n_arr, int n_max, int extra_cols, int batch);

@@ -1,0 +1,513 @@
+// ekf.cu - batched EKF predict / update for ray-landmark PTZ tracking.
+//
+// Reference behaviour (slam_system/ptz_slam.py):
+//   predict   :418-426   ptz += velocity ; P[0:3,0:3] += 5*diag(angle_var, angle_var, f_var)
+//   update    :210-289   project all rays with the predicted pose, keep strict in-image ones, intersect with the observed
+//                        ids (util.get_overlap_index :75-96); y = z - h ; gather P_s ; H from compute_h_jacobian (:73-138) ;
+//                        S = H P_s H^T + observe_var I ; K = P_s H^T S^-1 ; pose/velocity/rays += K y ;
+//                        P+ = (I - K H) P_s written back ONLY on the pose block and the theta-theta / phi-phi entries (:281-289).
+//
+// Device algorithm per sequence (n matched rays, s = 3 + 2n, n2 = 2n), P treated as symmetric:
+//   G = H P_s (n2 x s, columns de-interleaved [pose | theta_1..n | phi_1..n], plus y as an extra column)
+//   S = G H^T + R          -> Cholesky S = L L^T                  (dense.cu, batched)
+//   Z = L^-1 [G | y]       -> delta = Z^T w (w = last column), P+ = P_s - Z^T Z on the blocks the reference writes back
+// Many independent sequences are processed as one batch (grid z / y = sequence), in waves that share the G / S workspace.
+// FP64-pipe bound: ~ (n2^3/3 + n2^2 s + n^2 n2) flops per sequence-frame.
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+#include "dense.h"
+#include "ptz_jac.cuh"
+#include "ptz_math.cuh"
+
+struct ptzba_ekf_batch {
+    ptzba_ctx* ctx = nullptr;
+    ptzba_ekf_params prm;
+    int n_seq = 0, n_ray = 0, max_obs = 0, s_tot = 0;
+    bool has_disp = false;
+    DevBuf<double> rays, P, ptz, vel, disp;
+    // observations of the current step
+    DevBuf<double> obs_xy;
+    DevBuf<int32_t> obs_idx, obs_cnt;
+    // per-step results
+    DevBuf<int32_t> n_mat, n2, m_ray, flags;
+    DevBuf<double> Jc, Jr, y;
+    // wave workspace
+    int wave = 0, ldg = 0, lds = 0;
+    DevBuf<double> G, S;
+};
+
+namespace {
+
+constexpr int kT = 256;
+
+__global__ void k_ekf_predict(int n_seq, double* __restrict__ ptz, const double* __restrict__ vel, double* __restrict__ P,
+                              size_t strideP, int s_tot, double angle_var, double f_var) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_seq) return;
+    for (int e = 0; e < 3; ++e) ptz[3 * b + e] += vel[3 * b + e];            // ptz_slam.py:418-419
+    double* p = P + strideP * b;
+    p[0] += 5.0 * angle_var;                                                  // ptz_slam.py:425-426
+    p[(size_t)s_tot + 1] += 5.0 * angle_var;
+    p[2 * (size_t)s_tot + 2] += 5.0 * f_var;
+}
+
+// one CTA per sequence: in-image test of the observed rays, ordered compaction, innovation and Jacobian blocks
+__global__ void __launch_bounds__(kT) k_ekf_match(int n_ray, int max_obs, const double* __restrict__ ptz_all,
+                                                  const double* __restrict__ rays_all, const double* __restrict__ disp,
+                                                  ptzba_ekf_params prm, const double* __restrict__ obs_xy_all,
+                                                  const int32_t* __restrict__ obs_idx_all, const int32_t* __restrict__ obs_cnt,
+                                                  int32_t* __restrict__ n_mat, int32_t* __restrict__ n2,
+                                                  int32_t* __restrict__ m_ray_all, double* __restrict__ y_all,
+                                                  double* __restrict__ Jc_all, double* __restrict__ Jr_all,
+                                                  int* __restrict__ flags) {
+    const int b = blockIdx.x;
+    __shared__ CamFull cams[7];
+    __shared__ int warp_cnt[kT / 32];
+    __shared__ int carry;
+    const double* ptz = ptz_all + 3 * (size_t)b;
+    if (threadIdx.x < 7) cams[threadIdx.x] = h_cam_variant(threadIdx.x, ptz[0], ptz[1], ptz[2], prm.u, prm.v, disp);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const double* rays = rays_all + 2 * (size_t)n_ray * b;
+    const double* oxy = obs_xy_all + 2 * (size_t)max_obs * b;
+    const int32_t* oidx = obs_idx_all + (size_t)max_obs * b;
+    int32_t* m_ray = m_ray_all + (size_t)max_obs * b;
+    double* y = y_all + 2 * (size_t)max_obs * b;
+    double* Jc = Jc_all + 6 * (size_t)max_obs * b;
+    double* Jr = Jr_all + 4 * (size_t)max_obs * b;
+    int cnt = obs_cnt[b];
+    if (cnt > max_obs) { cnt = max_obs; if (threadIdx.x == 0) atomicOr(flags, 1); }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < cnt; base += kT) {
+        const int k = base + threadIdx.x;
+        bool keep = false;
+        int r = -1;
+        double px = 0, py = 0, th = 0, ph = 0;
+        if (k < cnt) {
+            r = oidx[k];
+            if (r < 0 || r >= n_ray) {
+                atomicOr(flags, 2);
+            } else {
+                th = rays[2 * (size_t)r];
+                ph = rays[2 * (size_t)r + 1];
+                double q;
+                project_full(cams[0], th, ph, px, py, q);
+                keep = (0.0 < px) && (px < prm.width) && (0.0 < py) && (py < prm.height);   // ptz_camera.py:226
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[w] = __popc(m);
+        __syncthreads();
+        int off = carry;
+        for (int q = 0; q < w; ++q) off += warp_cnt[q];
+        if (keep) {
+            const int j = off + __popc(m & ((1u << lane) - 1u));
+            m_ray[j] = r;
+            y[2 * j] = oxy[2 * (size_t)k] - px;                                             // ptz_slam.py:229
+            y[2 * j + 1] = oxy[2 * (size_t)k + 1] - py;
+            double jc[6], jr[4];
+            h_blocks_eval(cams, disp, th, ph, prm.jac_mode, jc, jr);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) Jc[6 * (size_t)j + e] = jc[e];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) Jr[4 * (size_t)j + e] = jr[e];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int q = 0; q < kT / 32; ++q) s += warp_cnt[q];
+            carry += s;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { n_mat[b] = carry; n2[b] = 2 * carry; }
+}
+
+// column c of the de-interleaved sub-state -> row/column index in the full interleaved covariance
+__device__ __forceinline__ int full_index(int c, int n, const int32_t* __restrict__ m_ray) {
+    if (c < 3) return c;
+    if (c < 3 + n) return 3 + 2 * m_ray[c - 3];
+    return 4 + 2 * m_ray[c - 3 - n];
+}
+
+// G[2j+a][c] = sum_b Jc[j][a][b] P[b][pc] + Jr[j][a][0] P[3+2r_j][pc] + Jr[j][a][1] P[4+2r_j][pc] ; column s holds y
+__global__ void __launch_bounds__(128) k_ekf_G(int b0, int max_obs, int s_tot, const double* __restrict__ P_all, size_t strideP,
+                                               const int32_t* __restrict__ n_mat, const int32_t* __restrict__ m_ray_all,
+                                               const double* __restrict__ Jc_all, const double* __restrict__ Jr_all,
+                                               const double* __restrict__ y_all, double* __restrict__ G_all, int ldg,
+                                               size_t strideG) {
+    const int wb = blockIdx.z, b = b0 + wb;
+    const int n = n_mat[b];
+    const int j = blockIdx.y;
+    if (j >= n) return;
+    const int s = 3 + 2 * n;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c > s) return;
+    const int32_t* m_ray = m_ray_all + (size_t)max_obs * b;
+    double* G = G_all + strideG * wb;
+    if (c == s) {
+        G[(size_t)(2 * j) * ldg + c] = y_all[2 * (size_t)max_obs * b + 2 * j];
+        G[(size_t)(2 * j + 1) * ldg + c] = y_all[2 * (size_t)max_obs * b + 2 * j + 1];
+        return;
+    }
+    const double* P = P_all + strideP * b;
+    const int pc = full_index(c, n, m_ray);
+    const int rj = 3 + 2 * m_ray[j];
+    const double p0 = P[pc], p1 = P[(size_t)s_tot + pc], p2 = P[2 * (size_t)s_tot + pc];
+    const double pt = P[(size_t)rj * s_tot + pc], pp = P[(size_t)(rj + 1) * s_tot + pc];
+    const double* jc = Jc_all + 6 * ((size_t)max_obs * b + j);
+    const double* jr = Jr_all + 4 * ((size_t)max_obs * b + j);
+    G[(size_t)(2 * j) * ldg + c] = jc[0] * p0 + jc[1] * p1 + jc[2] * p2 + jr[0] * pt + jr[1] * pp;
+    G[(size_t)(2 * j + 1) * ldg + c] = jc[3] * p0 + jc[4] * p1 + jc[5] * p2 + jr[2] * pt + jr[3] * pp;
+}
+
+// S = G H^T + observe_var I.  Thread (i, k) computes S[i][2k], S[i][2k+1] and stores them at (row 2k+a, column i) of the
+// column-major array the Cholesky reads (S is symmetric), i.e. contiguous along k.
+__global__ void __launch_bounds__(128) k_ekf_S(int b0, int max_obs, const int32_t* __restrict__ n_mat,
+                                               const double* __restrict__ Jc_all, const double* __restrict__ Jr_all,
+                                               const double* __restrict__ G_all, int ldg, size_t strideG,
+                                               double* __restrict__ S_all, int lds, size_t strideS, double observe_var) {
+    const int wb = blockIdx.z, b = b0 + wb;
+    const int n = n_mat[b];
+    const int i = blockIdx.y;
+    if (i >= 2 * n) return;
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= n) return;
+    const double* G = G_all + strideG * wb + (size_t)i * ldg;
+    const double* jc = Jc_all + 6 * ((size_t)max_obs * b + k);
+    const double* jr = Jr_all + 4 * ((size_t)max_obs * b + k);
+    const double g0 = G[0], g1 = G[1], g2 = G[2], gt = G[3 + k], gp = G[3 + n + k];
+    double s0 = g0 * jc[0] + g1 * jc[1] + g2 * jc[2] + gt * jr[0] + gp * jr[1];
+    double s1 = g0 * jc[3] + g1 * jc[4] + g2 * jc[5] + gt * jr[2] + gp * jr[3];
+    if (i == 2 * k) s0 += observe_var;                                                      // ptz_slam.py:256-257
+    if (i == 2 * k + 1) s1 += observe_var;
+    double* S = S_all + strideS * wb + (size_t)i * lds;
+    S[2 * k] = s0;
+    S[2 * k + 1] = s1;
+}
+
+// delta = Z^T w ; apply to pose / velocity / rays (ptz_slam.py:262-277)
+__global__ void __launch_bounds__(kT) k_ekf_delta(int b0, int max_obs, int n_ray, const int32_t* __restrict__ n_mat,
+                                                  const int32_t* __restrict__ m_ray_all, const double* __restrict__ Z_all,
+                                                  int ldg, size_t strideG, double* __restrict__ ptz, double* __restrict__ vel,
+                                                  double* __restrict__ rays_all) {
+    const int wb = blockIdx.y, b = b0 + wb;
+    const int n = n_mat[b];
+    const int s = 3 + 2 * n;
+    const int c = blockIdx.x * kT + threadIdx.x;
+    if (c >= s || n == 0) return;
+    const double* Z = Z_all + strideG * wb;
+    double acc = 0.0;
+    for (int i = 0; i < 2 * n; ++i) acc = fma(Z[(size_t)i * ldg + c], Z[(size_t)i * ldg + s], acc);
+    if (c < 3) {
+        ptz[3 * (size_t)b + c] += acc;
+        vel[3 * (size_t)b + c] = acc;
+    } else {
+        const int32_t* m_ray = m_ray_all + (size_t)max_obs * b;
+        double* rays = rays_all + 2 * (size_t)n_ray * b;
+        if (c < 3 + n) rays[2 * (size_t)m_ray[c - 3]] += acc;
+        else rays[2 * (size_t)m_ray[c - 3 - n] + 1] += acc;
+    }
+}
+
+// pose block: P[a][b] -= sum_i Z[i][a] Z[i][b]   (one warp per sequence)
+__global__ void __launch_bounds__(32) k_ekf_pp_pose(int b0, const int32_t* __restrict__ n_mat, const double* __restrict__ Z_all,
+                                                    int ldg, size_t strideG, double* __restrict__ P_all, size_t strideP,
+                                                    int s_tot) {
+    const int wb = blockIdx.x, b = b0 + wb;
+    const int n2 = 2 * n_mat[b];
+    const double* Z = Z_all + strideG * wb;
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n2; i += 32) {
+        const double z0 = Z[(size_t)i * ldg], z1 = Z[(size_t)i * ldg + 1], z2 = Z[(size_t)i * ldg + 2];
+        a[0] = fma(z0, z0, a[0]); a[1] = fma(z0, z1, a[1]); a[2] = fma(z0, z2, a[2]);
+        a[4] = fma(z1, z1, a[4]); a[5] = fma(z1, z2, a[5]); a[8] = fma(z2, z2, a[8]);
+    }
+    a[3] = a[1]; a[6] = a[2]; a[7] = a[5];
+#pragma unroll
+    for (int e = 0; e < 9; ++e)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a[e] += __shfl_xor_sync(0xffffffffu, a[e], off);
+    if (threadIdx.x < 9 && n2 > 0) {
+        double* P = P_all + strideP * b;
+        P[(size_t)(threadIdx.x / 3) * s_tot + threadIdx.x % 3] -= a[threadIdx.x];
+    }
+}
+
+// theta-theta (blockIdx.y = 0) and phi-phi (1) blocks: P[q_j][q_k] -= sum_i Z[i][off+j] Z[i][off+k], 64 x 64 tiles,
+// lower tile pairs only (mirrored on write), K loop over the n2 rows of Z in slabs of 32.
+__global__ void __launch_bounds__(256) k_ekf_pp_blocks(int b0, int max_obs, const int32_t* __restrict__ n_mat,
+                                                       const int32_t* __restrict__ m_ray_all, const double* __restrict__ Z_all,
+                                                       int ldg, size_t strideG, double* __restrict__ P_all, size_t strideP,
+                                                       int s_tot) {
+    const int wb = blockIdx.z, b = b0 + wb;
+    const int n = n_mat[b];
+    const int nt = (n + 63) / 64;
+    int blk = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= blk) ++ti;
+    while (ti * (ti + 1) / 2 > blk) --ti;
+    const int tj = blk - ti * (ti + 1) / 2;
+    if (ti >= nt) return;
+    const int e = blockIdx.y;                       // 0 theta, 1 phi
+    const int off = 3 + e * n;
+    const double* Z = Z_all + strideG * wb;
+    __shared__ double Ai[32][65];
+    __shared__ double Aj[32][65];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int j0 = ti * 64, k0 = tj * 64;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    const int n2 = 2 * n;
+    for (int i0 = 0; i0 < n2; i0 += 32) {
+        for (int q = tid; q < 32 * 64; q += 256) {
+            const int cc = q % 64, t = q / 64;
+            const int i = i0 + t;
+            Ai[t][cc] = (i < n2 && j0 + cc < n) ? Z[(size_t)i * ldg + off + j0 + cc] : 0.0;
+            Aj[t][cc] = (i < n2 && k0 + cc < n) ? Z[(size_t)i * ldg + off + k0 + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < 32; ++t) {
+            double vi[4], vj[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { vi[a] = Ai[t][ty + 16 * a]; vj[a] = Aj[t][tx + 16 * a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fma(vi[a], vj[c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+    const int32_t* m_ray = m_ray_all + (size_t)max_obs * b;
+    double* P = P_all + strideP * b;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + ty + 16 * a, k = k0 + tx + 16 * c;
+            if (j < n && k < n) {
+                const size_t qj = 3 + e + 2 * (size_t)m_ray[j], qk = 3 + e + 2 * (size_t)m_ray[k];
+                if (ti != tj) {
+                    P[qj * s_tot + qk] -= acc[a][c];
+                    P[qk * s_tot + qj] -= acc[a][c];
+                } else if (j >= k) {
+                    P[qj * s_tot + qk] -= acc[a][c];
+                    if (j != k) P[qk * s_tot + qj] -= acc[a][c];
+                }
+            }
+        }
+}
+
+__global__ void k_ekf_init_cov(int n_seq, int s_tot, double* __restrict__ P, size_t strideP, double angle_var, double f_var) {
+    // state_cov = angle_var * I ; [2][2] = f_var   (ptz_slam.py:199-200); P is pre-zeroed
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_seq || i >= s_tot) return;
+    P[strideP * b + (size_t)i * s_tot + i] = (i == 2) ? f_var : angle_var;
+}
+
+int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched) {
+    ptzba_ctx* ctx = B->ctx;
+    cudaStream_t s = ctx->stream;
+    const int n_seq = B->n_seq, max_obs = B->max_obs, s_tot = B->s_tot;
+    const size_t strideP = (size_t)s_tot * s_tot;
+    if (do_predict) {
+        k_ekf_predict<<<div_up(n_seq, 128), 128, 0, s>>>(n_seq, B->ptz.p, B->vel.p, B->P.p, strideP, s_tot, B->prm.angle_var,
+                                                        B->prm.f_var);
+        KERNEL_POST(ctx);
+    }
+    CU_CHECK(ctx, cudaMemsetAsync(B->flags.p, 0, 4 * sizeof(int), s));
+    k_ekf_match<<<n_seq, kT, 0, s>>>(B->n_ray, max_obs, B->ptz.p, B->rays.p, B->has_disp ? B->disp.p : nullptr, B->prm,
+                                     B->obs_xy.p, B->obs_idx.p, B->obs_cnt.p, B->n_mat.p, B->n2.p, B->m_ray.p, B->y.p, B->Jc.p,
+                                     B->Jr.p, B->flags.p);
+    KERNEL_POST(ctx);
+    std::vector<int32_t> h_n(n_seq);
+    int h_flags = 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(h_n.data(), B->n_mat.p, (size_t)n_seq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(&h_flags, B->flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    if (h_flags & 2) return ptzba_fail(ctx, PTZBA_ERR_ARG, "observed ray index out of range");
+    if (h_flags & 1) return ptzba_fail(ctx, PTZBA_ERR_ARG, "observation count exceeds max_obs");
+    if (out_matched) memcpy(out_matched, h_n.data(), (size_t)n_seq * sizeof(int32_t));
+    const size_t strideG = (size_t)B->ldg * (2 * (size_t)max_obs), strideS = (size_t)B->lds * B->lds;
+    for (int b0 = 0; b0 < n_seq; b0 += B->wave) {
+        const int wb = std::min(B->wave, n_seq - b0);
+        int n_max = 0;
+        for (int q = 0; q < wb; ++q) n_max = std::max(n_max, (int)h_n[b0 + q]);
+        if (n_max == 0) continue;
+        const int s_max = 3 + 2 * n_max;
+        k_ekf_G<<<dim3(div_up(s_max + 1, 128), n_max, wb), 128, 0, s>>>(b0, max_obs, s_tot, B->P.p, strideP, B->n_mat.p, B->m_ray.p,
+                                                                       B->Jc.p, B->Jr.p, B->y.p, B->G.p, B->ldg, strideG);
+        KERNEL_POST(ctx);
+        k_ekf_S<<<dim3(div_up(n_max, 128), 2 * n_max, wb), 128, 0, s>>>(b0, max_obs, B->n_mat.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
+                                                                       strideG, B->S.p, B->lds, strideS, B->prm.observe_var);
+        KERNEL_POST(ctx);
+        PROPAGATE(dense_potrf_lower_batched(ctx, B->S.p, B->lds, strideS, B->n2.p + b0, 2 * n_max, wb, B->flags.p + 2));
+        PROPAGATE(dense_fwd_solve_rows_batched(ctx, B->S.p, B->lds, strideS, B->G.p, B->ldg, strideG, B->n2.p + b0, 2 * n_max, 4, wb));
+        k_ekf_delta<<<dim3(div_up(s_max, kT), wb), kT, 0, s>>>(b0, max_obs, B->n_ray, B->n_mat.p, B->m_ray.p, B->G.p, B->ldg, strideG,
+                                                              B->ptz.p, B->vel.p, B->rays.p);
+        KERNEL_POST(ctx);
+        k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->n_mat.p, B->G.p, B->ldg, strideG, B->P.p, strideP, s_tot);
+        KERNEL_POST(ctx);
+        const int nt = div_up(n_max, 64);
+        k_ekf_pp_blocks<<<dim3(nt * (nt + 1) / 2, 2, wb), 256, 0, s>>>(b0, max_obs, B->n_mat.p, B->m_ray.p, B->G.p, B->ldg, strideG,
+                                                                      B->P.p, strideP, s_tot);
+        KERNEL_POST(ctx);
+    }
+    int info = 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(&info, B->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    if (info != 0) return ptzba_fail(ctx, PTZBA_ERR_NUMERIC, "innovation covariance is not positive definite (panel %d)", info);
+    return PTZBA_OK;
+}
+
+}  // namespace
+
+extern "C" int ptzba_ekf_batch_create(ptzba_ctx* ctx, const ptzba_ekf_params* prm, int n_seq, int n_ray, int max_obs,
+                                      const double* rays0, const double* ptz0, ptzba_ekf_batch** out) {
+    if (!ctx) return PTZBA_ERR_ARG;
+    ARG_CHECK(ctx, prm && out && n_seq > 0 && n_ray >= 0 && max_obs >= 0 && ptz0 && (n_ray == 0 || rays0));
+    ARG_CHECK(ctx, prm->jac_mode == PTZBA_JAC_ANALYTIC || prm->jac_mode == PTZBA_JAC_CENTRAL_FD);
+    *out = nullptr;
+    cudaStream_t s = ctx->stream;
+    ptzba_ekf_batch* B = new ptzba_ekf_batch();
+    B->ctx = ctx; B->prm = *prm; B->n_seq = n_seq; B->n_ray = n_ray;
+    if (max_obs > n_ray) max_obs = n_ray;
+    B->max_obs = max_obs; B->s_tot = 3 + 2 * n_ray;
+    for (int e = 0; e < 6; ++e) B->has_disp = B->has_disp || prm->disp[e] != 0.0;
+    const size_t strideP = (size_t)B->s_tot * B->s_tot;
+    B->ldg = (3 + 2 * max_obs + 1 + 3) / 4 * 4;
+    B->lds = 2 * max_obs > 0 ? 2 * max_obs : 1;
+    // wave size: share at most ~24 GB of G/S workspace
+    const size_t per_seq = ((size_t)B->ldg * 2 * (size_t)max_obs + (size_t)B->lds * B->lds) * sizeof(double);
+    size_t wave = per_seq ? (size_t)24e9 / per_seq : (size_t)n_seq;
+    if (wave < 1) wave = 1;
+    B->wave = (int)std::min<size_t>(wave, (size_t)n_seq);
+    auto fail = [&](int code) { delete B; return code; };
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ptzba_fail(ctx, PTZBA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,   \
+                                   cudaGetErrorString(e__)));                                          \
+    } while (0)
+    CU_TRY(B->rays.alloc((size_t)n_seq * n_ray * 2)); CU_TRY(B->P.alloc((size_t)n_seq * strideP));
+    CU_TRY(B->ptz.alloc((size_t)n_seq * 3)); CU_TRY(B->vel.alloc((size_t)n_seq * 3)); CU_TRY(B->disp.alloc(6));
+    CU_TRY(B->obs_xy.alloc((size_t)n_seq * max_obs * 2)); CU_TRY(B->obs_idx.alloc((size_t)n_seq * max_obs));
+    CU_TRY(B->obs_cnt.alloc(n_seq)); CU_TRY(B->n_mat.alloc(n_seq)); CU_TRY(B->n2.alloc(n_seq));
+    CU_TRY(B->m_ray.alloc((size_t)n_seq * max_obs)); CU_TRY(B->flags.alloc(4));
+    CU_TRY(B->Jc.alloc((size_t)n_seq * max_obs * 6)); CU_TRY(B->Jr.alloc((size_t)n_seq * max_obs * 4));
+    CU_TRY(B->y.alloc((size_t)n_seq * max_obs * 2));
+    CU_TRY(B->G.alloc((size_t)B->wave * B->ldg * 2 * (size_t)max_obs)); CU_TRY(B->S.alloc((size_t)B->wave * B->lds * B->lds));
+    if (n_ray) CU_TRY(cudaMemcpyAsync(B->rays.p, rays0, (size_t)n_seq * n_ray * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(B->ptz.p, ptz0, (size_t)n_seq * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(B->disp.p, prm->disp, 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemsetAsync(B->vel.p, 0, (size_t)n_seq * 3 * sizeof(double), s));
+    CU_TRY(cudaMemsetAsync(B->P.p, 0, (size_t)n_seq * strideP * sizeof(double), s));
+    k_ekf_init_cov<<<dim3(div_up(B->s_tot, 256), n_seq), 256, 0, s>>>(n_seq, B->s_tot, B->P.p, strideP, prm->angle_var, prm->f_var);
+    ctx->launches++;
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(cudaGetLastError());
+#undef CU_TRY
+    *out = B;
+    return PTZBA_OK;
+}
+
+extern "C" void ptzba_ekf_batch_destroy(ptzba_ekf_batch* B) {
+    if (!B) return;
+    cudaStreamSynchronize(B->ctx->stream);
+    delete B;
+}
+
+static int ekf_load_obs(ptzba_ekf_batch* B, int mem, const double* obs_xy, const int32_t* obs_index, const int32_t* obs_count) {
+    ptzba_ctx* ctx = B->ctx;
+    cudaStream_t s = ctx->stream;
+    const cudaMemcpyKind kind = mem == PTZBA_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t n = (size_t)B->n_seq * B->max_obs;
+    if (n) {
+        CU_CHECK(ctx, cudaMemcpyAsync(B->obs_xy.p, obs_xy, n * 2 * sizeof(double), kind, s));
+        CU_CHECK(ctx, cudaMemcpyAsync(B->obs_idx.p, obs_index, n * sizeof(int32_t), kind, s));
+    }
+    CU_CHECK(ctx, cudaMemcpyAsync(B->obs_cnt.p, obs_count, (size_t)B->n_seq * sizeof(int32_t), kind, s));
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_ekf_batch_step(ptzba_ekf_batch* B, int mem, const double* obs_xy, const int32_t* obs_index,
+                                    const int32_t* obs_count, int32_t* out_matched) {
+    if (!B) return PTZBA_ERR_ARG;
+    ARG_CHECK(B->ctx, obs_count && (B->max_obs == 0 || (obs_xy && obs_index)));
+    PROPAGATE(ekf_load_obs(B, mem, obs_xy, obs_index, obs_count));
+    return ekf_step(B, true, out_matched);
+}
+
+extern "C" int ptzba_ekf_batch_update_only(ptzba_ekf_batch* B, int mem, const double* obs_xy, const int32_t* obs_index,
+                                           const int32_t* obs_count, int32_t* out_matched) {
+    if (!B) return PTZBA_ERR_ARG;
+    ARG_CHECK(B->ctx, obs_count && (B->max_obs == 0 || (obs_xy && obs_index)));
+    PROPAGATE(ekf_load_obs(B, mem, obs_xy, obs_index, obs_count));
+    return ekf_step(B, false, out_matched);
+}
+
+extern "C" int ptzba_ekf_batch_get(ptzba_ekf_batch* B, double* ptz, double* velocity, double* rays) {
+    if (!B) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = B->ctx;
+    cudaStream_t s = ctx->stream;
+    if (ptz) CU_CHECK(ctx, cudaMemcpyAsync(ptz, B->ptz.p, (size_t)B->n_seq * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (velocity) CU_CHECK(ctx, cudaMemcpyAsync(velocity, B->vel.p, (size_t)B->n_seq * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rays && B->n_ray)
+        CU_CHECK(ctx, cudaMemcpyAsync(rays, B->rays.p, (size_t)B->n_seq * B->n_ray * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_ekf_batch_set(ptzba_ekf_batch* B, int seq, const double* ptz3, const double* velocity3, const double* rays,
+                                   const double* state_cov) {
+    if (!B) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = B->ctx;
+    ARG_CHECK(ctx, seq >= 0 && seq < B->n_seq);
+    cudaStream_t s = ctx->stream;
+    const size_t strideP = (size_t)B->s_tot * B->s_tot;
+    if (ptz3) CU_CHECK(ctx, cudaMemcpyAsync(B->ptz.p + 3 * (size_t)seq, ptz3, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (velocity3) CU_CHECK(ctx, cudaMemcpyAsync(B->vel.p + 3 * (size_t)seq, velocity3, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (rays && B->n_ray)
+        CU_CHECK(ctx, cudaMemcpyAsync(B->rays.p + 2 * (size_t)B->n_ray * seq, rays, (size_t)B->n_ray * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (state_cov) CU_CHECK(ctx, cudaMemcpyAsync(B->P.p + strideP * seq, state_cov, strideP * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_ekf_batch_get_cov(ptzba_ekf_batch* B, int seq, double* state_cov) {
+    if (!B) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = B->ctx;
+    ARG_CHECK(ctx, seq >= 0 && seq < B->n_seq && state_cov);
+    const size_t strideP = (size_t)B->s_tot * B->s_tot;
+    CU_CHECK(ctx, cudaMemcpyAsync(state_cov, B->P.p + strideP * seq, strideP * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PTZBA_OK;
+}
+
+// single sequence, HOST buffers, in place (the reference's PtzSlam.ekf_update contract)
+extern "C" int ptzba_ekf_update(ptzba_ctx* ctx, const ptzba_ekf_params* prm, int n_total, double* rays, double* state_cov,
+                                double* ptz3, double* velocity3, int m, const double* observed_xy, const int32_t* observed_index,
+                                int32_t* out_n_matched) {
+    if (!ctx) return PTZBA_ERR_ARG;
+    ARG_CHECK(ctx, prm && n_total >= 0 && state_cov && ptz3 && velocity3 && m >= 0 && (n_total == 0 || rays));
+    ARG_CHECK(ctx, m == 0 || (observed_xy && observed_index));
+    ARG_CHECK(ctx, m <= n_total);
+    ptzba_ekf_batch* B = nullptr;
+    PROPAGATE(ptzba_ekf_batch_create(ctx, prm, 1, n_total, m, rays, ptz3, &B));
+    int st = ptzba_ekf_batch_set(B, 0, nullptr, nullptr, nullptr, state_cov);
+    int32_t cnt = m, matched = 0;
+    if (st == PTZBA_OK) st = ptzba_ekf_batch_update_only(B, PTZBA_HOST, observed_xy, observed_index, &cnt, &matched);
+    if (st == PTZBA_OK) st = ptzba_ekf_batch_get(B, ptz3, velocity3, rays);
+    if (st == PTZBA_OK) st = ptzba_ekf_batch_get_cov(B, 0, state_cov);
+    if (out_n_matched) *out_n_matched = matched;
+    ptzba_ekf_batch_destroy(B);
+    return st;
+}

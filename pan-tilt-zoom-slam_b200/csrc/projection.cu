@@ -10,6 +10,7 @@
 // These kernels are HBM-bound: 16 B in + 16 B out per (camera, ray) pair.
 #include "common.h"
 #include "ptz_math.cuh"
+#include "ptz_jac.cuh"
 
 namespace {
 
@@ -164,89 +165,18 @@ __global__ void __launch_bounds__(kThreads) k_backproject(int64_t n, const doubl
     }
 }
 
-// ---- measurement Jacobian blocks ----------------------------------------------------------------------------------
-// analytic, general displacement: q = R_tilt R_pan d + disp(f); x = f q0/q2 + u, y = f q1/q2 + v.
-__device__ __forceinline__ void jac_analytic_full(const CamFull& c, const double* __restrict__ lam, double th_deg,
-                                                  double ph_deg, double* jc, double* jr) {
-    const double k = PTZ_DEG2RAD;
-    const double tx = tan(th_deg * k), tp = tan(ph_deg * k);
-    const double sec2t = 1.0 + tx * tx, sec2p = 1.0 + tp * tp;
-    const double sq = sqrt(sec2t);
-    const double r0 = tx, r1 = -tp * sq;
-    const double a0 = c.cp * r0 - c.sp, a2 = c.sp * r0 + c.cp;
-    const double q0 = a0 + c.d0;
-    const double q1 = c.ct * r1 + c.st * a2 + c.d1;
-    const double q2 = -c.st * r1 + c.ct * a2 + c.d2;
-    const double iz = 1.0 / q2;
-    const double px = q0 * iz, py = q1 * iz;
-    // d q / d pan (rad): d a0 = -sp r0 - cp = -a2 ; d a2 = cp r0 - sp = a0
-    const double q0p = -a2, q1p = c.st * a0, q2p = c.ct * a0;
-    // d q / d tilt (rad): q1 = ct r1 + st a2 -> -st r1 + ct a2 = q2 - d2 ; q2 -> -ct r1 - st a2 = -(q1 - d1)
-    const double q1t = q2 - c.d2, q2t = -(q1 - c.d1);
-    // d q / d f : disp derivative (l3, l4, l5)
-    const double l3 = lam ? lam[3] : 0.0, l4 = lam ? lam[4] : 0.0, l5 = lam ? lam[5] : 0.0;
-    // d q / d theta (rad): d r0 = sec2t ; d r1 = -tp * tx * sec2t / sq = -tp tx sq
-    const double r0h = sec2t, r1h = -tp * tx * sq;
-    const double q0h = c.cp * r0h, a2h = c.sp * r0h;
-    const double q1h = c.ct * r1h + c.st * a2h, q2h = -c.st * r1h + c.ct * a2h;
-    // d q / d phi (rad): d r1 = -sec2p sq
-    const double r1f = -sec2p * sq;
-    const double q1f = c.ct * r1f, q2f = -c.st * r1f;
-    const double fi = c.f * iz;
-#define DX(dq0, dq2) (fi * ((dq0) - px * (dq2)))
-#define DY(dq1, dq2) (fi * ((dq1) - py * (dq2)))
-    jc[0] = k * DX(q0p, q2p);  jc[3] = k * DY(q1p, q2p);
-    jc[1] = k * DX(0.0, q2t);  jc[4] = k * DY(q1t, q2t);
-    jc[2] = px + DX(l3, l5);   jc[5] = py + DY(l4, l5);
-    jr[0] = k * DX(q0h, q2h);  jr[2] = k * DY(q1h, q2h);
-    jr[1] = k * DX(0.0, q2f);  jr[3] = k * DY(q1f, q2f);
-#undef DX
-#undef DY
-}
-
+// ---- measurement Jacobian blocks (device functions in ptz_jac.cuh) -----------------------------------------------
 // mode 1 reproduces ptz_slam.py:95-136 operation by operation: 10 projections per ray, central differences.
 __global__ void __launch_bounds__(kThreads) k_h_blocks(int n_ray, const double* __restrict__ ptz3, double u, double v,
                                                        const double* __restrict__ disp, const double* __restrict__ rays,
                                                        int mode, double* __restrict__ jc_out, double* __restrict__ jr_out) {
     __shared__ CamFull cams[7];   // base, pan-/+, tilt-/+, f-/+
-    const double da = 0.001, df = 0.1;   // ptz_slam.py:87-88
-    if (threadIdx.x < 7) {
-        double p = ptz3[0], t = ptz3[1], f = ptz3[2];
-        switch (threadIdx.x) {
-            case 1: p = p - da; break;
-            case 2: p = p + da; break;
-            case 3: t = t - da; break;
-            case 4: t = t + da; break;
-            case 5: f = f - df; break;
-            case 6: f = f + df; break;
-            default: break;
-        }
-        cams[threadIdx.x] = make_cam(p, t, f, u, v, disp);
-    }
+    if (threadIdx.x < 7) cams[threadIdx.x] = h_cam_variant(threadIdx.x, ptz3[0], ptz3[1], ptz3[2], u, v, disp);
     __syncthreads();
     for (int r = blockIdx.x * kThreads + threadIdx.x; r < n_ray; r += gridDim.x * kThreads) {
         const double2 ray = ld2(rays, r);
         double jc[6], jr[4];
-        if (mode == PTZBA_JAC_ANALYTIC) {
-            jac_analytic_full(cams[0], disp, ray.x, ray.y, jc, jr);
-        } else {
-            double x1, y1, x2, y2, q;
-            project_full(cams[1], ray.x, ray.y, x1, y1, q);
-            project_full(cams[2], ray.x, ray.y, x2, y2, q);
-            jc[0] = (x2 - x1) / (2 * da); jc[3] = (y2 - y1) / (2 * da);
-            project_full(cams[3], ray.x, ray.y, x1, y1, q);
-            project_full(cams[4], ray.x, ray.y, x2, y2, q);
-            jc[1] = (x2 - x1) / (2 * da); jc[4] = (y2 - y1) / (2 * da);
-            project_full(cams[5], ray.x, ray.y, x1, y1, q);
-            project_full(cams[6], ray.x, ray.y, x2, y2, q);
-            jc[2] = (x2 - x1) / (2 * df); jc[5] = (y2 - y1) / (2 * df);
-            project_full(cams[0], ray.x - da, ray.y, x1, y1, q);
-            project_full(cams[0], ray.x + da, ray.y, x2, y2, q);
-            jr[0] = (x2 - x1) / (2 * da); jr[2] = (y2 - y1) / (2 * da);
-            project_full(cams[0], ray.x, ray.y - da, x1, y1, q);
-            project_full(cams[0], ray.x, ray.y + da, x2, y2, q);
-            jr[1] = (x2 - x1) / (2 * da); jr[3] = (y2 - y1) / (2 * da);
-        }
+        h_blocks_eval(cams, disp, ray.x, ray.y, mode, jc, jr);
 #pragma unroll
         for (int i = 0; i < 6; ++i) jc_out[(int64_t)r * 6 + i] = jc[i];
 #pragma unroll

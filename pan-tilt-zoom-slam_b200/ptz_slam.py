@@ -1,0 +1,178 @@
+"""
+PtzSlam drop-in for the EKF hot path (reference: slam_system/ptz_slam.py).
+
+    PtzSlam.compute_h_jacobian(pan, tilt, focal_length, rays)                    ptz_slam.py:73-138
+    PtzSlam.ekf_update(observed_keypoints, observed_keypoint_index, height, width)   ptz_slam.py:210-289
+    PtzSlam.predict()  - the predict lines of tracking()                          ptz_slam.py:418-426
+
+State attributes keep the reference's names and meaning (`rays`, `state_cov`, `cameras`, `current_camera`,
+`velocity`, `observe_var`, `angle_var`, `f_var`).  `ekf_update` mutates them in place like the reference; the
+computation (projection, in-image filter, innovation, central-difference Jacobian, S, Cholesky, gain, covariance
+write-back) runs in csrc/ekf.cu through the C-ABI.  The image front-end of the reference class (SIFT detection,
+optical-flow matching, relocalisation, keyframe maps) is out of scope.
+
+`BatchedEkfTracker` is the additive batched form for many independent sequences resident on the GPU (config 4).
+"""
+import copy
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _params(u, v, disp, observe_var, angle_var, f_var, height, width, jac_mode):
+    p = _lib.EkfParams()
+    p.u, p.v = float(u), float(v)
+    d = np.zeros(6) if disp is None else np.asarray(disp, dtype=np.float64)
+    for i in range(6):
+        p.disp[i] = float(d[i])
+    p.observe_var, p.angle_var, p.f_var = float(observe_var), float(angle_var), float(f_var)
+    p.height, p.width = float(height), float(width)
+    p.jac_mode = int(jac_mode)
+    return p
+
+
+class PtzSlam:
+    def __init__(self):
+        # global rays and covariance matrix (ptz_slam.py:29-31)
+        self.rays = np.ndarray([0, 2])
+        self.state_cov = np.zeros([3, 3])
+        self.current_camera = None
+        self.cameras = []
+        self.velocity = np.zeros(3)
+        # hyper parameters (ptz_slam.py:65-71)
+        self.keypoint_num = 500
+        self.observe_var = 0.1
+        self.angle_var = 0.001
+        self.f_var = 1
+        # PTZBA_JAC_CENTRAL_FD reproduces the reference's central differences; JAC_ANALYTIC is the closed form
+        self.jacobian_mode = _lib.JAC_CENTRAL_FD
+
+    # -- state initialisation without images (ptz_slam.py:186-208 minus keypoint detection) ----------------------
+    def init_rays(self, rays, camera):
+        """Set the ray landmarks and the initial covariance exactly as init_system does (:190-200, :208)."""
+        self.rays = np.array(rays, dtype=np.float64).reshape(-1, 2)
+        self.state_cov = self.angle_var * np.eye(3 + 2 * len(self.rays))
+        self.state_cov[2][2] = self.f_var
+        self.cameras = [camera]
+        self.current_camera = camera
+
+    def compute_h_jacobian(self, pan, tilt, focal_length, rays):
+        """ptz_slam.py:73-138: dense H [2n, 3+2n]; principal point / displacement come from self.cameras[0] (:92)."""
+        ctx = _lib.get_context()
+        cam = self.cameras[0]
+        rays = _lib.f64(rays).reshape(-1, 2)
+        n = rays.shape[0]
+        ptz = _lib.f64([pan, tilt, focal_length])
+        disp = _lib.f64(cam.displacement)
+        disp = disp if np.any(disp != 0.0) else None
+        H = np.empty((2 * n, 3 + 2 * n), np.float64)
+        ctx.check(ctx.lib.ptzba_h_jacobian_dense(ctx.handle, _lib.HOST, _lib.ptr(ptz), float(cam.principal_point[0]),
+                                                 float(cam.principal_point[1]), _lib.ptr(disp), n, _lib.ptr(rays),
+                                                 self.jacobian_mode, _lib.ptr(H)))
+        return H
+
+    def predict(self):
+        """ptz_slam.py:418-426: constant-velocity pose prediction, pose-block process noise."""
+        self.current_camera = copy.deepcopy(self.cameras[-1])
+        self.current_camera.set_ptz(self.current_camera.get_ptz() + self.velocity)
+        self.cameras.append(self.current_camera)
+        q_k = 5 * np.diag([self.angle_var, self.angle_var, self.f_var])
+        self.state_cov[0:3, 0:3] = self.state_cov[0:3, 0:3] + q_k
+
+    def ekf_update(self, observed_keypoints, observed_keypoint_index, height, width):
+        """ptz_slam.py:210-289.  Mutates rays, state_cov, current_camera (pan/tilt/focal_length) and velocity."""
+        ctx = _lib.get_context()
+        cam = self.current_camera
+        ref = self.cameras[0]
+        n_total = len(self.rays)
+        obs = _lib.f64(observed_keypoints).reshape(-1, 2)
+        idx = _lib.i32(np.asarray(observed_keypoint_index).astype(np.int64))
+        m = obs.shape[0]
+        assert idx.shape[0] == m
+        prm = _params(ref.principal_point[0], ref.principal_point[1], ref.displacement, self.observe_var, self.angle_var,
+                      self.f_var, height, width, self.jacobian_mode)
+        if not (self.rays.flags.c_contiguous and self.rays.dtype == np.float64):
+            self.rays = _lib.f64(self.rays)
+        if not (self.state_cov.flags.c_contiguous and self.state_cov.dtype == np.float64):
+            self.state_cov = _lib.f64(self.state_cov)
+        assert self.state_cov.shape == (3 + 2 * n_total, 3 + 2 * n_total)
+        ptz = _lib.f64([cam.pan, cam.tilt, cam.focal_length])
+        vel = np.zeros(3)
+        matched = ctypes.c_int32(0)
+        ctx.check(ctx.lib.ptzba_ekf_update(ctx.handle, ctypes.byref(prm), n_total, _lib.ptr(self.rays),
+                                           _lib.ptr(self.state_cov), _lib.ptr(ptz), _lib.ptr(vel), m, _lib.ptr(obs),
+                                           _lib.ptr(idx), ctypes.byref(matched)))
+        cam.pan, cam.tilt, cam.focal_length = float(ptz[0]), float(ptz[1]), float(ptz[2])
+        self.current_camera = cam
+        self.velocity = vel
+        return int(matched.value)
+
+
+class BatchedEkfTracker:
+    """Many independent EKF sequences resident on the GPU (one ptzba_ekf_batch); every sequence has n_ray rays."""
+
+    def __init__(self, rays0, ptz0, u, v, max_obs, height, width, displacement=None, observe_var=0.1, angle_var=0.001,
+                 f_var=1.0, jacobian_mode=_lib.JAC_ANALYTIC, ctx=None):
+        self.ctx = ctx or _lib.get_context()
+        rays0 = _lib.f64(rays0)
+        ptz0 = _lib.f64(ptz0).reshape(-1, 3)
+        self.n_seq = ptz0.shape[0]
+        rays0 = rays0.reshape(self.n_seq, -1, 2)
+        self.n_ray = rays0.shape[1]
+        self.max_obs = int(min(max_obs, self.n_ray))
+        prm = _params(u, v, displacement, observe_var, angle_var, f_var, height, width, jacobian_mode)
+        h = ctypes.c_void_p()
+        self.ctx.check(self.ctx.lib.ptzba_ekf_batch_create(self.ctx.handle, ctypes.byref(prm), self.n_seq, self.n_ray,
+                                                           self.max_obs, _lib.ptr(rays0), _lib.ptr(ptz0), ctypes.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.ptzba_ekf_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pack_observations(self, obs_xy_list, obs_idx_list):
+        """Ragged per-sequence observations -> padded [n_seq, max_obs, 2] / [n_seq, max_obs] / [n_seq] arrays."""
+        xy = np.zeros((self.n_seq, self.max_obs, 2))
+        ix = np.zeros((self.n_seq, self.max_obs), np.int32)
+        cnt = np.zeros(self.n_seq, np.int32)
+        for b, (o, i) in enumerate(zip(obs_xy_list, obs_idx_list)):
+            m = len(i)
+            assert m <= self.max_obs
+            xy[b, :m] = o
+            ix[b, :m] = i
+            cnt[b] = m
+        return xy, ix, cnt
+
+    def step(self, obs_xy, obs_idx, obs_cnt, predict=True, mem=_lib.HOST):
+        """One predict+update (or update only) for every sequence; returns matched counts [n_seq]."""
+        matched = np.zeros(self.n_seq, np.int32)
+        fn = self.ctx.lib.ptzba_ekf_batch_step if predict else self.ctx.lib.ptzba_ekf_batch_update_only
+        if mem == _lib.HOST:
+            obs_xy, obs_idx, obs_cnt = _lib.f64(obs_xy), _lib.i32(obs_idx), _lib.i32(obs_cnt)
+        self.ctx.check(fn(self.handle, mem, _lib.ptr(obs_xy), _lib.ptr(obs_idx), _lib.ptr(obs_cnt), _lib.ptr(matched)))
+        return matched
+
+    def get_state(self, want_rays=True):
+        ptz = np.empty((self.n_seq, 3)); vel = np.empty((self.n_seq, 3))
+        rays = np.empty((self.n_seq, self.n_ray, 2)) if want_rays else None
+        self.ctx.check(self.ctx.lib.ptzba_ekf_batch_get(self.handle, _lib.ptr(ptz), _lib.ptr(vel), _lib.ptr(rays)))
+        return ptz, vel, rays
+
+    def get_cov(self, seq):
+        s = 3 + 2 * self.n_ray
+        P = np.empty((s, s))
+        self.ctx.check(self.ctx.lib.ptzba_ekf_batch_get_cov(self.handle, int(seq), _lib.ptr(P)))
+        return P
+
+    def set_state(self, seq, ptz=None, velocity=None, rays=None, state_cov=None):
+        a = [None if x is None else _lib.f64(x) for x in (ptz, velocity, rays, state_cov)]
+        self.ctx.check(self.ctx.lib.ptzba_ekf_batch_set(self.handle, int(seq), *[_lib.ptr(x) for x in a]))

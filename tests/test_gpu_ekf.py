@@ -1,0 +1,106 @@
+"""GPU parity: EKF update (single sequence drop-in and batched) vs the reference golden run and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import ptz_oracle as O
+import ptz_slam_b200  # noqa: F401
+from ptz_slam_b200 import synth, _lib
+from ptz_slam_b200.ptz_camera import PTZCamera
+from ptz_slam_b200.ptz_slam import PtzSlam, BatchedEkfTracker
+
+pytestmark = pytest.mark.gpu
+H, W = synth.IMAGE_H, synth.IMAGE_W
+CC = np.array([13.0099, -14.8109, 6.1790])
+
+
+def _cam(ptz, uv, disp=None):
+    c = PTZCamera((uv[0], uv[1]), CC, np.eye(3), disp)
+    c.set_ptz(ptz)
+    return c
+
+
+def test_compute_h_jacobian_dropin():
+    d = load_golden("h_jacobian.npz")
+    for tag, disp in (("nodisp", None), ("disp", d["disp"])):
+        slam = PtzSlam()
+        slam.cameras = [_cam(d["ptz_" + tag], d["uv"], disp)]
+        Hm = slam.compute_h_jacobian(*d["ptz_" + tag], d["rays_" + tag])
+        np.testing.assert_allclose(Hm, d["H_" + tag], rtol=1e-9, atol=2e-9)
+
+
+def test_ekf_update_six_frames_golden():
+    """The reference's PtzSlam.ekf_update + predict lines over 6 frames (tests/golden/make_golden.py:gen_ekf)."""
+    d = load_golden("ekf.npz")
+    slam = PtzSlam()
+    slam.init_rays(d["rays0"], _cam(d["ptz0"], d["uv"]))
+    for k in range(1, int(d["n_frames"]) + 1):
+        slam.predict()
+        slam.ekf_update(d["obs_xy_%d" % k], d["obs_idx_%d" % k], H, W)
+        np.testing.assert_allclose(slam.current_camera.get_ptz(), d["ptz_%d" % k], rtol=1e-10, atol=1e-9)
+        np.testing.assert_allclose(slam.velocity, d["vel_%d" % k], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(slam.rays, d["rays_%d" % k], rtol=1e-10, atol=1e-9)
+        np.testing.assert_allclose(slam.state_cov, d["cov_%d" % k], rtol=1e-7, atol=1e-12)
+    # write-back quirk (ptz_slam.py:281-289): pose<->ray and theta<->phi covariances are never written
+    assert np.all(slam.state_cov[0:3, 3:] == 0) and np.all(slam.state_cov[3::2, 4::2] == 0)
+
+
+def test_ekf_analytic_mode_matches_fd_mode():
+    d = load_golden("ekf.npz")
+    res = []
+    for mode in (_lib.JAC_CENTRAL_FD, _lib.JAC_ANALYTIC):
+        slam = PtzSlam()
+        slam.jacobian_mode = mode
+        slam.init_rays(d["rays0"], _cam(d["ptz0"], d["uv"]))
+        for k in range(1, 4):
+            slam.predict()
+            slam.ekf_update(d["obs_xy_%d" % k], d["obs_idx_%d" % k], H, W)
+        res.append((slam.current_camera.get_ptz(), slam.rays.copy()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-9, atol=1e-8)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-9, atol=1e-8)
+
+
+def test_ekf_edge_cases():
+    """No observation in view -> nothing changes; observations outside the image are ignored like the reference."""
+    seq = synth.make_ekf_sequence(30, 2, seed=5)
+    slam = PtzSlam()
+    slam.init_rays(seq.rays0, _cam(seq.ptz_gt[0], (synth.PP_U, synth.PP_V)))
+    slam.predict()
+    P0, r0 = slam.state_cov.copy(), slam.rays.copy()
+    n = slam.ekf_update(np.zeros((0, 2)), np.zeros(0, np.int64), H, W)
+    assert n == 0 and np.array_equal(slam.state_cov, P0) and np.array_equal(slam.rays, r0)
+    assert np.all(slam.velocity == 0)
+    with pytest.raises(_lib.PtzbaError):
+        slam.ekf_update(np.zeros((1, 2)), np.array([9999]), H, W)
+
+
+def _run_oracle(seq, n_frames):
+    s = O.EkfState(seq.rays0, seq.ptz_gt[0], synth.PP_U, synth.PP_V)
+    for k in range(1, n_frames):
+        O.ekf_predict(s)
+        O.ekf_update(s, seq.obs_xy[k], seq.obs_idx[k], H, W)
+    return s
+
+
+@pytest.mark.parametrize("n_rays,n_frames", [(200, 5), (600, 3)])
+def test_batched_tracker_vs_oracle(n_rays, n_frames):
+    """Independent sequences with different seeds in one batch: each must equal its own oracle run."""
+    seqs = [synth.make_ekf_sequence(n_rays, n_frames, seed=2000 + i) for i in range(4)]
+    max_obs = max(len(i) for s in seqs for i in s.obs_idx)
+    trk = BatchedEkfTracker(np.stack([s.rays0 for s in seqs]), np.stack([s.ptz_gt[0] for s in seqs]), synth.PP_U, synth.PP_V,
+                            max_obs, H, W, jacobian_mode=_lib.JAC_CENTRAL_FD)
+    for k in range(1, n_frames):
+        xy, ix, cnt = trk.pack_observations([s.obs_xy[k] for s in seqs], [s.obs_idx[k] for s in seqs])
+        matched = trk.step(xy, ix, cnt)
+        assert np.all(matched > 0)
+    ptz, vel, rays = trk.get_state()
+    for b, s in enumerate(seqs):
+        o = _run_oracle(s, n_frames)
+        np.testing.assert_allclose(ptz[b], o.ptz, rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(vel[b], o.velocity, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(rays[b], o.rays, rtol=1e-9, atol=1e-8)
+        P = trk.get_cov(b)
+        np.testing.assert_allclose(P, o.state_cov, rtol=1e-6, atol=1e-11)
+        # tracking actually works: pose error against ground truth stays small
+        assert abs(ptz[b][0] - s.ptz_gt[n_frames - 1][0]) < 0.05
+    trk.close()
