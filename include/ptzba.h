@@ -177,6 +177,11 @@ int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, const double* 
 int ptzba_comm_unique_id(ptzba_ctx* ctx, void* unique_id128);
 int ptzba_comm_init(ptzba_ctx* ctx, const void* unique_id128, int rank, int world_size);
 int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int64_t count);
+/* sums the packed accumulators [cost | U | V | g_c | g_l] of the last fused pass over all ranks (in place, on the stream) */
+int ptzba_ba_allreduce(ptzba_ba* ba);
+/* copies the accumulators of the last fused pass to host buffers (any may be NULL): U[n_pose*6], gc[n_pose*3],
+ * V[n_landmark*3], gl[n_landmark*2], cost */
+int ptzba_ba_get_blocks(ptzba_ba* ba, double* U, double* gc, double* V, double* gl, double* cost);
 
 #ifdef __cplusplus
 }

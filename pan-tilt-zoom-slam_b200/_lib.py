@@ -77,6 +77,8 @@ SIGNATURES = {
     "ptzba_comm_unique_id": (_I, [_P, _P]),
     "ptzba_comm_init": (_I, [_P, _P, _I, _I]),
     "ptzba_comm_allreduce_f64": (_I, [_P, _P, _L]),
+    "ptzba_ba_allreduce": (_I, [_P]),
+    "ptzba_ba_get_blocks": (_I, [_P, _P, _P, _P, _P, _P]),
 }
 
 _lock = threading.Lock()

@@ -49,7 +49,7 @@ struct ptzba_ba {
     DevBuf<double> sol_c, sol_l, sol2_c, sol2_l;
     DevBuf<double> Vinv;                    // [M*3] (V + alpha D_l^2)^-1 packed
     DevBuf<double> scal;                    // small device scalar block for reductions
-    int fused_grid = 0, fused_smem = 0;
+    int fused_grid = 0, fused_grid_lm = 0, fused_smem = 0, grid_lm_pass = 0, grid_cam_pass = 0, grid_lm_pass4 = 0, grid_cam_pass4 = 0;
     bool fused_cam_smem = true;
 };
 

@@ -124,7 +124,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // CAM_SMEM: per-CTA shared-memory copies of the keyframe trig table and of the 9 keyframe accumulators.
-template <bool CAM_SMEM>
+template <bool CAM_SMEM, bool DO_CAM>
 __global__ void __launch_bounds__(kFusedThreads)
 k_ba_fused(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
            const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
@@ -138,7 +138,7 @@ k_ba_fused(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, cons
     const int tid = threadIdx.x, lane = tid & 31;
     if (CAM_SMEM) {
         for (int i = tid; i < n_pose * 5; i += kFusedThreads) sTrig[i] = reinterpret_cast<const double*>(cam_trig)[i];
-        for (int i = tid; i < n_pose * 9; i += kFusedThreads) sAcc[i] = 0.0;
+        if (DO_CAM) for (int i = tid; i < n_pose * 9; i += kFusedThreads) sAcc[i] = 0.0;
         __syncthreads();
     }
     const int64_t begin = (int64_t)blockIdx.x * chunk;
@@ -180,7 +180,7 @@ k_ba_fused(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, cons
         double glt = fma(g.xa, rx, g.ya * ry);
         double glp = fma(g.xp, rx, g.yp * ry);
         // keyframe blocks: pan column = -alpha column; keyframe 0 is fixed (no block)
-        if (act && cam != 0) {
+        if (DO_CAM && act && cam != 0) {
             const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
             const double upf = -fma(g.xa, g.px, g.ya * g.py);
             const double utt = fma(g.xt, g.xt, g.yt * g.yt);
@@ -220,7 +220,7 @@ k_ba_fused(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, cons
         for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
         atomicAdd(gCost, s);
     }
-    if (CAM_SMEM) {
+    if (CAM_SMEM && DO_CAM) {
         // flush keyframe accumulators (converted to per-degree units): entries (pp,pt,pf,tt,tf,ff | gp,gt,gf)
         const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
         for (int i = tid; i < n_pose * 9; i += kFusedThreads) {
@@ -289,8 +289,10 @@ k_ba_fused_cm(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, c
             project_fast_jac(c, l, u, v, x, y, g);
             rx = x - ox;
             ry = y - oy;
-            if (resid) reinterpret_cast<double2*>(resid)[c_orig[k]] = make_double2(rx, ry);
-            cost = fma(rx, rx, fma(ry, ry, cost));
+            if (PACK != 2) {
+                if (resid) reinterpret_cast<double2*>(resid)[c_orig[k]] = make_double2(rx, ry);
+                cost = fma(rx, rx, fma(ry, ry, cost));
+            }
             kxa = k1 * g.xa; kya = k1 * g.ya; kxp = k1 * g.xp; kyp = k1 * g.yp;
             xt = g.xt; yt = g.yt; px = g.px; py = g.py;
         }
@@ -308,7 +310,7 @@ k_ba_fused_cm(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, c
                 atomicAdd(gGl + 2 * (size_t)lm + 0, glt);
                 atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
             }
-        } else {
+        } else if (PACK == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {            // V: 4-lane groups, 8 observations per instruction
                 const int src = 8 * j + (lane >> 2), e = lane & 3;
@@ -361,6 +363,7 @@ k_ba_fused_cm(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, c
         }
     }
     flush();
+    if (PACK == 2) return;
     cost = warp_sum(cost);
     if (lane == 0) sWarp[tid >> 5] = cost;
     __syncthreads();
@@ -369,6 +372,390 @@ k_ba_fused_cm(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, c
         for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
         atomicAdd(gCost, s);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two coherent passes (fused_variant 6): every sum is formed where its operands are adjacent, nothing is scattered.
+//   k_ba_lm_pass   landmark-major: residual (written), cost, per-landmark V / g_l by warp-segmented reduction
+//   k_ba_cam_pass  keyframe-major: per-keyframe U / g_c in registers across the whole chunk
+// Both are latency-bound streaming kernels, so each thread keeps the NEXT observation's loads in flight (register
+// double buffering) while it computes the current one.
+// ---------------------------------------------------------------------------------------------------------------
+struct ObsLoad { int cam, lm; double ox, oy; };
+
+__global__ void __launch_bounds__(kFusedThreads, 4)
+k_ba_lm_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+             const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+             const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
+             double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+    extern __shared__ __align__(16) double smem[];      // keyframe trig, SoA: [5][n_pose]  (bank = keyframe id)
+    __shared__ double sWarp[kFusedThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
+        const int c = i / 5, e = i - 5 * c;
+        smem[(size_t)e * n_pose + c] = reinterpret_cast<const double*>(cam_trig)[i];
+    }
+    __syncthreads();
+    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > n_obs) end = n_obs;
+    double cost = 0.0;
+    const double k1 = PTZ_DEG2RAD;
+    // prologue: first observation of this thread
+    int64_t k = begin + tid;
+    ObsLoad cur = {0, -1, 0.0, 0.0};
+    LmTrig curT = {0, 1, 0, 1};
+    if (k < end) {
+        cur.cam = s_cam[k]; cur.lm = s_lm[k]; cur.ox = s_ox[k]; cur.oy = s_oy[k];
+        curT = lm_trig[cur.lm];
+    }
+    for (int64_t base = begin; base < end; base += kFusedThreads) {
+        const bool act = k < end;
+        // issue the next iteration's loads before touching the current data
+        const int64_t kn = k + kFusedThreads;
+        ObsLoad nxt = {0, -1, 0.0, 0.0};
+        LmTrig nxtT = {0, 1, 0, 1};
+        if (kn < end) {
+            nxt.cam = s_cam[kn]; nxt.lm = s_lm[kn]; nxt.ox = s_ox[kn]; nxt.oy = s_oy[kn];
+            nxtT = lm_trig[nxt.lm];
+        }
+        double rx = 0, ry = 0, kxa = 0, kya = 0, kxp = 0, kyp = 0;
+        const int lm = act ? cur.lm : -1;
+        if (act) {
+            CamTrig c;
+            c.sp = smem[cur.cam]; c.cp = smem[n_pose + cur.cam]; c.st = smem[2 * n_pose + cur.cam];
+            c.ct = smem[3 * n_pose + cur.cam]; c.f = smem[4 * n_pose + cur.cam];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, curT, u, v, x, y, g);
+            rx = x - cur.ox;
+            ry = y - cur.oy;
+            if (resid) {
+                const int64_t o = orig ? (int64_t)orig[k] : k;
+                reinterpret_cast<double2*>(resid)[o] = make_double2(rx, ry);
+            }
+            cost = fma(rx, rx, fma(ry, ry, cost));
+            kxa = k1 * g.xa; kya = k1 * g.ya; kxp = k1 * g.xp; kyp = k1 * g.yp;
+        }
+        double vtt = fma(kxa, kxa, kya * kya);
+        double vtp = fma(kxa, kxp, kya * kyp);
+        double vpp = fma(kxp, kxp, kyp * kyp);
+        double glt = fma(kxa, rx, kya * ry);
+        double glp = fma(kxp, rx, kyp * ry);
+        seg_reduce5(lm, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, lm, 1);
+        if (act && (lane == 0 || prev != lm)) {
+            atomicAdd(gV + 3 * (size_t)lm + 0, vtt);
+            atomicAdd(gV + 3 * (size_t)lm + 1, vtp);
+            atomicAdd(gV + 3 * (size_t)lm + 2, vpp);
+            atomicAdd(gGl + 2 * (size_t)lm + 0, glt);
+            atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
+        }
+        cur = nxt; curT = nxtT; k = kn;
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 3)
+k_ba_cam_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+              const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
+              const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double k1 = PTZ_DEG2RAD;
+    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > n_obs) end = n_obs;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
+    int wcam = -1;
+    CamTrig wc = {0, 1, 0, 1, 1};
+    auto flush = [&]() {
+        if (wcam > 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
+            if (lane == 0) {
+                double* U = gU + 6 * (size_t)wcam;
+                double* G = gGc + 3 * (size_t)wcam;
+                const double k2 = k1 * k1;
+                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
+                atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
+                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+            }
+        }
+        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
+    };
+    int64_t k = begin + tid;
+    int cam = -1, lm = 0;
+    double ox = 0, oy = 0;
+    LmTrig lt = {0, 1, 0, 1};
+    if (k < end) { cam = c_cam[k]; lm = c_lm[k]; ox = c_ox[k]; oy = c_oy[k]; lt = lm_trig[lm]; }
+    for (int64_t base = begin; base < end; base += kFusedThreads) {
+        const bool act = k < end;
+        const int64_t kn = k + kFusedThreads;
+        int ncam = -1, nlm = 0;
+        double nox = 0, noy = 0;
+        LmTrig nlt = {0, 1, 0, 1};
+        if (kn < end) { ncam = c_cam[kn]; nlm = c_lm[kn]; nox = c_ox[kn]; noy = c_oy[kn]; nlt = lm_trig[nlm]; }
+        const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
+        const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
+        const bool uniform = same == 0xffffffffu;
+        if (uniform) {
+            if (cam_lo != wcam) { flush(); wcam = cam_lo; if (wcam >= 0) wc = cam_trig[wcam]; }
+        } else {
+            flush();
+            wcam = -1;
+        }
+        if (act && cam > 0) {
+            const CamTrig c = uniform ? wc : cam_trig[cam];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            const double rx = x - ox, ry = y - oy;
+            const double upp = fma(g.xa, g.xa, g.ya * g.ya);
+            const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
+            const double upf = -fma(g.xa, g.px, g.ya * g.py);
+            const double utt = fma(g.xt, g.xt, g.yt * g.yt);
+            const double utf = fma(g.xt, g.px, g.yt * g.py);
+            const double uff = fma(g.px, g.px, g.py * g.py);
+            const double gp = -fma(g.xa, rx, g.ya * ry);
+            const double gt = fma(g.xt, rx, g.yt * ry);
+            const double gf = fma(g.px, rx, g.py * ry);
+            if (uniform) {
+                a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
+            } else {   // warp straddles a keyframe boundary (once per keyframe): commit per lane
+                double* U = gU + 6 * (size_t)cam;
+                double* G = gGc + 3 * (size_t)cam;
+                const double k2 = k1 * k1;
+                atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
+                atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
+                atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
+            }
+        }
+        cam = ncam; lm = nlm; ox = nox; oy = noy; lt = nlt; k = kn;
+    }
+    flush();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused_variant 7: the two coherent passes with FOUR consecutive observations per thread.
+//   * every thread issues 128-/256-bit vector loads (int4 indices, 4 x f64 pixels): 4x fewer load instructions, four
+//     independent gathers in flight per thread, and residuals leave as two 256-bit stores;
+//   * landmark-major pass: a run that ends inside a thread is committed directly, only the thread's LAST run enters the
+//     warp-segmented reduction, so the shuffle traffic per observation drops 4x;
+//   * keyframe-major pass: unchanged idea (register accumulators, one warp reduction per keyframe change).
+// Chunks are multiples of 1024 observations so that every thread's quad is 32-byte aligned.
+// ---------------------------------------------------------------------------------------------------------------
+struct __align__(32) D4 { double a, b, c, d; };
+constexpr int kQuad = 4;
+
+__device__ __forceinline__ void commit_lm(double* __restrict__ gV, double* __restrict__ gGl, int lm, double vtt, double vtp,
+                                          double vpp, double glt, double glp) {
+    atomicAdd(gV + 3 * (size_t)lm + 0, vtt);
+    atomicAdd(gV + 3 * (size_t)lm + 1, vtp);
+    atomicAdd(gV + 3 * (size_t)lm + 2, vpp);
+    atomicAdd(gGl + 2 * (size_t)lm + 0, glt);
+    atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 3)
+k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+              const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+              const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
+              double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+    extern __shared__ __align__(16) double smem[];      // keyframe trig, SoA [5][n_pose]
+    __shared__ double sWarp[kFusedThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
+        const int c = i / 5, e = i - 5 * c;
+        smem[(size_t)e * n_pose + c] = reinterpret_cast<const double*>(cam_trig)[i];
+    }
+    __syncthreads();
+    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > n_obs) end = n_obs;
+    const double k1 = PTZ_DEG2RAD;
+    double cost = 0.0;
+    for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
+        const int64_t k0 = base + (int64_t)tid * kQuad;
+        int cam[kQuad], lm[kQuad];
+        double ox[kQuad], oy[kQuad];
+        if (k0 + kQuad <= end) {
+            const int4 c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
+            const int4 l4 = __ldg(reinterpret_cast<const int4*>(s_lm + k0));
+            const D4 x4 = *reinterpret_cast<const D4*>(s_ox + k0);
+            const D4 y4 = *reinterpret_cast<const D4*>(s_oy + k0);
+            cam[0] = c4.x; cam[1] = c4.y; cam[2] = c4.z; cam[3] = c4.w;
+            lm[0] = l4.x; lm[1] = l4.y; lm[2] = l4.z; lm[3] = l4.w;
+            ox[0] = x4.a; ox[1] = x4.b; ox[2] = x4.c; ox[3] = x4.d;
+            oy[0] = y4.a; oy[1] = y4.b; oy[2] = y4.c; oy[3] = y4.d;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kQuad; ++i) {
+                const bool in = k0 + i < end;
+                cam[i] = in ? s_cam[k0 + i] : 0;
+                lm[i] = in ? s_lm[k0 + i] : -1;
+                ox[i] = in ? s_ox[k0 + i] : 0.0;
+                oy[i] = in ? s_oy[k0 + i] : 0.0;
+            }
+        }
+        double rx[kQuad], ry[kQuad];
+        int cur = -1;
+        LmTrig lt = {0, 1, 0, 1};
+        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            rx[i] = 0.0; ry[i] = 0.0;
+            if (lm[i] < 0) continue;
+            if (lm[i] != cur) {
+                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);   // run ended inside this thread
+                cur = lm[i];
+                lt = lm_trig[cur];
+                vtt = vtp = vpp = glt = glp = 0.0;
+            }
+            CamTrig c;
+            c.sp = smem[cam[i]]; c.cp = smem[n_pose + cam[i]]; c.st = smem[2 * n_pose + cam[i]];
+            c.ct = smem[3 * n_pose + cam[i]]; c.f = smem[4 * n_pose + cam[i]];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            rx[i] = x - ox[i];
+            ry[i] = y - oy[i];
+            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
+            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
+            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
+            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
+            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
+            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
+            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
+        }
+        if (resid) {
+            if (!orig && k0 + kQuad <= end) {
+                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
+                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
+                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
+            } else {
+#pragma unroll
+                for (int i = 0; i < kQuad; ++i)
+                    if (lm[i] >= 0) {
+                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
+                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
+                    }
+            }
+        }
+        // the thread's last run joins the warp-segmented reduction (keys non-decreasing across lanes, -1 = none)
+        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 3)
+k_ba_cam_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+               const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
+               const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > n_obs) end = n_obs;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
+    int wcam = -1;
+    CamTrig wc = {0, 1, 0, 1, 1};
+    auto flush = [&]() {
+        if (wcam > 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
+            if (lane == 0) {
+                double* U = gU + 6 * (size_t)wcam;
+                double* G = gGc + 3 * (size_t)wcam;
+                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
+                atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
+                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+            }
+        }
+        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
+    };
+    for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
+        const int64_t k0 = base + (int64_t)tid * kQuad;
+        int cam[kQuad], lm[kQuad];
+        double ox[kQuad], oy[kQuad];
+        if (k0 + kQuad <= end) {
+            const int4 c4 = __ldg(reinterpret_cast<const int4*>(c_cam + k0));
+            const int4 l4 = __ldg(reinterpret_cast<const int4*>(c_lm + k0));
+            const D4 x4 = *reinterpret_cast<const D4*>(c_ox + k0);
+            const D4 y4 = *reinterpret_cast<const D4*>(c_oy + k0);
+            cam[0] = c4.x; cam[1] = c4.y; cam[2] = c4.z; cam[3] = c4.w;
+            lm[0] = l4.x; lm[1] = l4.y; lm[2] = l4.z; lm[3] = l4.w;
+            ox[0] = x4.a; ox[1] = x4.b; ox[2] = x4.c; ox[3] = x4.d;
+            oy[0] = y4.a; oy[1] = y4.b; oy[2] = y4.c; oy[3] = y4.d;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kQuad; ++i) {
+                const bool in = k0 + i < end;
+                cam[i] = in ? c_cam[k0 + i] : -1;
+                lm[i] = in ? c_lm[k0 + i] : 0;
+                ox[i] = in ? c_ox[k0 + i] : 0.0;
+                oy[i] = in ? c_oy[k0 + i] : 0.0;
+            }
+        }
+        LmTrig lt[kQuad];
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) lt[i] = lm_trig[cam[i] >= 0 ? lm[i] : 0];     // four independent gathers in flight
+        // is the whole warp (128 observations) inside one keyframe?  (-1 = past the end, ignored)
+        const int first = __shfl_sync(0xffffffffu, cam[0], 0);
+        bool mine = true;
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) mine = mine && (cam[i] == first || cam[i] < 0);
+        const bool uniform = __all_sync(0xffffffffu, mine) && first >= 0;
+        if (uniform) {
+            if (first != wcam) { flush(); wcam = first; wc = cam_trig[wcam]; }
+        } else {
+            flush();
+            wcam = -1;
+        }
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            if (cam[i] <= 0) continue;                      // past the end, or the fixed reference keyframe
+            const CamTrig c = uniform ? wc : cam_trig[cam[i]];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt[i], u, v, x, y, g);
+            const double rx = x - ox[i], ry = y - oy[i];
+            const double upp = fma(g.xa, g.xa, g.ya * g.ya);
+            const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
+            const double upf = -fma(g.xa, g.px, g.ya * g.py);
+            const double utt = fma(g.xt, g.xt, g.yt * g.yt);
+            const double utf = fma(g.xt, g.px, g.yt * g.py);
+            const double uff = fma(g.px, g.px, g.py * g.py);
+            const double gp = -fma(g.xa, rx, g.ya * ry);
+            const double gt = fma(g.xt, rx, g.yt * ry);
+            const double gf = fma(g.px, rx, g.py * ry);
+            if (uniform) {
+                a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
+            } else {
+                double* U = gU + 6 * (size_t)cam[i];
+                double* G = gGc + 3 * (size_t)cam[i];
+                atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
+                atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
+                atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
+            }
+        }
+    }
+    flush();
 }
 
 // global-accumulator variant leaves radian units in U/gc; this converts them in place
@@ -459,19 +846,62 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
             case 1: LAUNCH_CM(0, 2); break;
             case 2: LAUNCH_CM(1, 2); break;
             case 3: LAUNCH_CM(0, 3); break;
-            default: LAUNCH_CM(1, 3); break;
+            case 4: LAUNCH_CM(1, 3); break;
+            case 7: {
+                const int64_t q = (int64_t)kFusedThreads * kQuad;
+                int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;
+                chunkA = (chunkA + q - 1) / q * q;
+                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
+                k_ba_lm_pass4<<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                ctx->launches++;
+                int64_t chunkB = (ba->n_obs + ba->grid_cam_pass4 - 1) / ba->grid_cam_pass4;
+                chunkB = (chunkB + q - 1) / q * q;
+                const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
+                k_ba_cam_pass4<<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                              ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+                break;
+            }
+            case 6: {
+                int64_t chunkA = (ba->n_obs + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
+                chunkA = (chunkA + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
+                k_ba_lm_pass<<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                ctx->launches++;
+                int64_t chunkB = (ba->n_obs + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
+                chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+                const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
+                k_ba_cam_pass<<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                             ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+                break;
+            }
+            default: {
+                // two coherent passes: landmark-major (r, V, g_l, cost) then keyframe-major (U, g_c); no scattered sums
+                int64_t chunkA = (ba->n_obs + ba->fused_grid_lm - 1) / ba->fused_grid_lm;
+                chunkA = (chunkA + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
+                k_ba_fused<true, false><<<gridA, kFusedThreads, ba->fused_smem, s>>>(
+                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                ctx->launches++;
+                LAUNCH_CM(2, 3);
+                break;
+            }
         }
 #undef LAUNCH_CM
         KERNEL_POST(ctx);
         if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     } else if (ba->fused_cam_smem) {
-        k_ba_fused<true><<<grid, kFusedThreads, ba->fused_smem, s>>>(
+        k_ba_fused<true, true><<<grid, kFusedThreads, ba->fused_smem, s>>>(
             ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
             ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
         if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     } else {
-        k_ba_fused<false><<<grid, kFusedThreads, 0, s>>>(
+        k_ba_fused<false, true><<<grid, kFusedThreads, 0, s>>>(
             ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
             ba->n_pose, ba->u, ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
@@ -521,8 +951,8 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     CU_TRY(in_cam.stage(mem, cam_idx, (size_t)n_obs, s));
     CU_TRY(in_lm.stage(mem, lm_idx, (size_t)n_obs, s));
     CU_TRY(in_xy.stage(mem, obs_xy, (size_t)n_obs * 2, s));
-    CU_TRY(ba->s_cam.alloc(n_obs)); CU_TRY(ba->s_lm.alloc(n_obs));
-    CU_TRY(ba->s_ox.alloc(n_obs)); CU_TRY(ba->s_oy.alloc(n_obs));
+    CU_TRY(ba->s_cam.alloc(n_obs + 4)); CU_TRY(ba->s_lm.alloc(n_obs + 4));
+    CU_TRY(ba->s_ox.alloc(n_obs + 4)); CU_TRY(ba->s_oy.alloc(n_obs + 4));
     CU_TRY(ba->lm_ptr.alloc((size_t)n_landmark + 1));
     CU_TRY(ba->poses.alloc((size_t)n_pose * 3)); CU_TRY(ba->rays.alloc((size_t)n_landmark * 2));
     CU_TRY(ba->cam_trig.alloc(n_pose)); CU_TRY(ba->lm_trig.alloc(n_landmark));
@@ -591,8 +1021,8 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     if (n_obs > 0) {
         DevBuf<int32_t> iota, perm2;
         DevBuf<unsigned char> tmp;
-        CU_TRY(ba->c_cam.alloc(n_obs)); CU_TRY(ba->c_lm.alloc(n_obs)); CU_TRY(ba->c_orig.alloc(n_obs));
-        CU_TRY(ba->c_ox.alloc(n_obs)); CU_TRY(ba->c_oy.alloc(n_obs));
+        CU_TRY(ba->c_cam.alloc(n_obs + 4)); CU_TRY(ba->c_lm.alloc(n_obs + 4)); CU_TRY(ba->c_orig.alloc(n_obs + 4));
+        CU_TRY(ba->c_ox.alloc(n_obs + 4)); CU_TRY(ba->c_oy.alloc(n_obs + 4));
         CU_TRY(iota.alloc(n_obs)); CU_TRY(perm2.alloc(n_obs));
         k_iota<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, iota.p);
         ctx->launches++;
@@ -614,19 +1044,39 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     int per_sm = 0;
     ba->fused_cam_smem = smem <= 200 * 1024;
     if (ba->fused_cam_smem) {
-        CU_TRY(cudaFuncSetAttribute(k_ba_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<true>, kFusedThreads, smem));
+        CU_TRY(cudaFuncSetAttribute(k_ba_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<true, true>, kFusedThreads, smem));
         ba->fused_smem = (int)smem;
     } else {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<false>, kFusedThreads, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused<false, true>, kFusedThreads, 0));
         ba->fused_smem = 0;
     }
     if (ba->fused_variant >= 1) {
+        {
+            int pa = 1, pb = 1;
+            const size_t sm5 = (size_t)n_pose * 5 * sizeof(double);
+            if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass, kFusedThreads, sm5));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass, kFusedThreads, 0));
+            int pa4 = 1, pb4 = 1;
+            if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa4, k_ba_lm_pass4, kFusedThreads, sm5));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb4, k_ba_cam_pass4, kFusedThreads, 0));
+            ba->grid_lm_pass4 = ctx->sm_count * (pa4 < 1 ? 1 : pa4);
+            ba->grid_cam_pass4 = ctx->sm_count * (pb4 < 1 ? 1 : pb4);
+            ba->grid_lm_pass = ctx->sm_count * (pa < 1 ? 1 : pa);
+            ba->grid_cam_pass = ctx->sm_count * (pb < 1 ? 1 : pb);
+        }
+        int per_sm_lm = 1;
+        CU_TRY(cudaFuncSetAttribute(k_ba_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lm, k_ba_fused<true, false>, kFusedThreads, smem));
+        ba->fused_grid_lm = ctx->sm_count * (per_sm_lm < 1 ? 1 : per_sm_lm);
         switch (ba->fused_variant) {
             case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<0, 2>, kFusedThreads, 0)); break;
             case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 2>, kFusedThreads, 0)); break;
             case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<0, 3>, kFusedThreads, 0)); break;
-            default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 3>, kFusedThreads, 0)); break;
+            case 4: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 3>, kFusedThreads, 0)); break;
+            default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<2, 3>, kFusedThreads, 0)); break;
         }
     }
     if (per_sm < 1) per_sm = 1;
@@ -711,5 +1161,20 @@ extern "C" int ptzba_ba_normal_equations(ptzba_ba* ba, int mem, const double* x,
     } else if (mem == PTZBA_HOST) {
         CU_CHECK(ctx, cudaStreamSynchronize(s));
     }
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_ba_get_blocks(ptzba_ba* ba, double* U, double* gc, double* V, double* gl, double* cost) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    cudaStream_t s = ctx->stream;
+    if (U) CU_CHECK(ctx, cudaMemcpyAsync(U, ba->acc.U, (size_t)ba->n_pose * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (gc) CU_CHECK(ctx, cudaMemcpyAsync(gc, ba->acc.gc, (size_t)ba->n_pose * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (V && ba->n_lm) CU_CHECK(ctx, cudaMemcpyAsync(V, ba->acc.V, (size_t)ba->n_lm * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (gl && ba->n_lm) CU_CHECK(ctx, cudaMemcpyAsync(gl, ba->acc.gl, (size_t)ba->n_lm * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    double sumsq = 0;
+    if (cost) CU_CHECK(ctx, cudaMemcpyAsync(&sumsq, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    if (cost) *cost = 0.5 * sumsq;
     return PTZBA_OK;
 }

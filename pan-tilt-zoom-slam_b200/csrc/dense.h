@@ -14,3 +14,12 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
 // Z = L^-1 G in place; G is ROW-major with d_n_arr[b] rows and d_n_arr[b] + extra_cols columns (leading dimension ldg)
 int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_t strideL, double* G, int ldg, size_t strideG,
                                  const int* d_n_arr, int n_max, int extra_cols, int batch);
+
+// ---- LU with partial pivoting (dense_lu.cu); same batching convention ---------------------------------------------
+// d_ipiv / d_perm: [batch x ld_ipiv] ints.  *d_info = 0, or 1 + the first column whose pivot was exactly zero.
+int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch, int* d_ipiv,
+                        int ld_ipiv, int* d_info);
+// X = A^-1 B; B, X row-major [n_b x (n_b + extra_cols)], leading dimension ldg; B is left untouched
+int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t stride, const int* d_ipiv, int* d_perm, int ld_ipiv,
+                             const double* B, double* X, int ldg, size_t strideG, const int* d_n_arr, int n_max, int extra_cols,
+                             int batch);

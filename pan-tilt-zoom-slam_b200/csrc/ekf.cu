@@ -9,8 +9,10 @@
 //
 // Device algorithm per sequence (n matched rays, s = 3 + 2n, n2 = 2n), P treated as symmetric:
 //   G = H P_s (n2 x s, columns de-interleaved [pose | theta_1..n | phi_1..n], plus y as an extra column)
-//   S = G H^T + R          -> Cholesky S = L L^T                  (dense.cu, batched)
-//   Z = L^-1 [G | y]       -> delta = Z^T w (w = last column), P+ = P_s - Z^T Z on the blocks the reference writes back
+//   S = G H^T + R          -> LU with partial pivoting (dense_lu.cu, batched).  S is symmetric but NOT positive definite in
+//                             general: the reference's write-back drops cross terms, P turns indefinite after a few frames and
+//                             numpy.linalg.inv (getrf) keeps going where a Cholesky would break down.
+//   X = S^-1 [G | y]       -> delta = G^T x_y (x_y = last column), P+ = P_s - G^T X on the blocks the reference writes back
 // Many independent sequences are processed as one batch (grid z / y = sequence), in waves that share the G / S workspace.
 // FP64-pipe bound: ~ (n2^3/3 + n2^2 s + n^2 n2) flops per sequence-frame.
 #include <algorithm>
@@ -35,7 +37,8 @@ struct ptzba_ekf_batch {
     DevBuf<double> Jc, Jr, y;
     // wave workspace
     int wave = 0, ldg = 0, lds = 0;
-    DevBuf<double> G, S;
+    DevBuf<double> G, X, S;
+    DevBuf<int32_t> ipiv, perm;
 };
 
 namespace {
@@ -188,19 +191,21 @@ __global__ void __launch_bounds__(128) k_ekf_S(int b0, int max_obs, const int32_
     S[2 * k + 1] = s1;
 }
 
-// delta = Z^T w ; apply to pose / velocity / rays (ptz_slam.py:262-277)
+// delta = G^T x_y (x_y = last column of X = S^-1 [G | y]); apply to pose / velocity / rays (ptz_slam.py:262-277)
 __global__ void __launch_bounds__(kT) k_ekf_delta(int b0, int max_obs, int n_ray, const int32_t* __restrict__ n_mat,
-                                                  const int32_t* __restrict__ m_ray_all, const double* __restrict__ Z_all,
-                                                  int ldg, size_t strideG, double* __restrict__ ptz, double* __restrict__ vel,
+                                                  const int32_t* __restrict__ m_ray_all, const double* __restrict__ G_all,
+                                                  const double* __restrict__ X_all, int ldg, size_t strideG,
+                                                  double* __restrict__ ptz, double* __restrict__ vel,
                                                   double* __restrict__ rays_all) {
     const int wb = blockIdx.y, b = b0 + wb;
     const int n = n_mat[b];
     const int s = 3 + 2 * n;
     const int c = blockIdx.x * kT + threadIdx.x;
     if (c >= s || n == 0) return;
-    const double* Z = Z_all + strideG * wb;
+    const double* G = G_all + strideG * wb;
+    const double* X = X_all + strideG * wb;
     double acc = 0.0;
-    for (int i = 0; i < 2 * n; ++i) acc = fma(Z[(size_t)i * ldg + c], Z[(size_t)i * ldg + s], acc);
+    for (int i = 0; i < 2 * n; ++i) acc = fma(G[(size_t)i * ldg + c], X[(size_t)i * ldg + s], acc);
     if (c < 3) {
         ptz[3 * (size_t)b + c] += acc;
         vel[3 * (size_t)b + c] = acc;
@@ -212,36 +217,41 @@ __global__ void __launch_bounds__(kT) k_ekf_delta(int b0, int max_obs, int n_ray
     }
 }
 
-// pose block: P[a][b] -= sum_i Z[i][a] Z[i][b]   (one warp per sequence)
-__global__ void __launch_bounds__(32) k_ekf_pp_pose(int b0, const int32_t* __restrict__ n_mat, const double* __restrict__ Z_all,
-                                                    int ldg, size_t strideG, double* __restrict__ P_all, size_t strideP,
-                                                    int s_tot) {
+// pose block: P[a][b] -= sum_i G[i][a] X[i][b]   (one warp per sequence)
+__global__ void __launch_bounds__(32) k_ekf_pp_pose(int b0, const int32_t* __restrict__ n_mat, const double* __restrict__ G_all,
+                                                    const double* __restrict__ X_all, int ldg, size_t strideG,
+                                                    double* __restrict__ P_all, size_t strideP, int s_tot) {
     const int wb = blockIdx.x, b = b0 + wb;
     const int n2 = 2 * n_mat[b];
-    const double* Z = Z_all + strideG * wb;
+    const double* G = G_all + strideG * wb;
+    const double* X = X_all + strideG * wb;
     double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = threadIdx.x; i < n2; i += 32) {
-        const double z0 = Z[(size_t)i * ldg], z1 = Z[(size_t)i * ldg + 1], z2 = Z[(size_t)i * ldg + 2];
-        a[0] = fma(z0, z0, a[0]); a[1] = fma(z0, z1, a[1]); a[2] = fma(z0, z2, a[2]);
-        a[4] = fma(z1, z1, a[4]); a[5] = fma(z1, z2, a[5]); a[8] = fma(z2, z2, a[8]);
+        const double g0 = G[(size_t)i * ldg], g1 = G[(size_t)i * ldg + 1], g2 = G[(size_t)i * ldg + 2];
+        const double x0 = X[(size_t)i * ldg], x1 = X[(size_t)i * ldg + 1], x2 = X[(size_t)i * ldg + 2];
+        a[0] = fma(g0, x0, a[0]); a[1] = fma(g0, x1, a[1]); a[2] = fma(g0, x2, a[2]);
+        a[3] = fma(g1, x0, a[3]); a[4] = fma(g1, x1, a[4]); a[5] = fma(g1, x2, a[5]);
+        a[6] = fma(g2, x0, a[6]); a[7] = fma(g2, x1, a[7]); a[8] = fma(g2, x2, a[8]);
     }
-    a[3] = a[1]; a[6] = a[2]; a[7] = a[5];
 #pragma unroll
     for (int e = 0; e < 9; ++e)
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) a[e] += __shfl_xor_sync(0xffffffffu, a[e], off);
     if (threadIdx.x < 9 && n2 > 0) {
         double* P = P_all + strideP * b;
-        P[(size_t)(threadIdx.x / 3) * s_tot + threadIdx.x % 3] -= a[threadIdx.x];
+        double val = a[0];
+#pragma unroll
+        for (int e = 1; e < 9; ++e) if (threadIdx.x == e) val = a[e];
+        P[(size_t)(threadIdx.x / 3) * s_tot + threadIdx.x % 3] -= val;
     }
 }
 
-// theta-theta (blockIdx.y = 0) and phi-phi (1) blocks: P[q_j][q_k] -= sum_i Z[i][off+j] Z[i][off+k], 64 x 64 tiles,
-// lower tile pairs only (mirrored on write), K loop over the n2 rows of Z in slabs of 32.
+// theta-theta (blockIdx.y = 0) and phi-phi (1) blocks: P[q_j][q_k] -= sum_i G[i][off+j] X[i][off+k], 64 x 64 tiles.
+// G^T S^-1 G is symmetric, so only the lower tile pairs are formed and mirrored on write; K loop over the n2 rows in slabs of 32.
 __global__ void __launch_bounds__(256) k_ekf_pp_blocks(int b0, int max_obs, const int32_t* __restrict__ n_mat,
-                                                       const int32_t* __restrict__ m_ray_all, const double* __restrict__ Z_all,
-                                                       int ldg, size_t strideG, double* __restrict__ P_all, size_t strideP,
-                                                       int s_tot) {
+                                                       const int32_t* __restrict__ m_ray_all, const double* __restrict__ G_all,
+                                                       const double* __restrict__ X_all, int ldg, size_t strideG,
+                                                       double* __restrict__ P_all, size_t strideP, int s_tot) {
     const int wb = blockIdx.z, b = b0 + wb;
     const int n = n_mat[b];
     const int nt = (n + 63) / 64;
@@ -253,7 +263,8 @@ __global__ void __launch_bounds__(256) k_ekf_pp_blocks(int b0, int max_obs, cons
     if (ti >= nt) return;
     const int e = blockIdx.y;                       // 0 theta, 1 phi
     const int off = 3 + e * n;
-    const double* Z = Z_all + strideG * wb;
+    const double* G = G_all + strideG * wb;
+    const double* X = X_all + strideG * wb;
     __shared__ double Ai[32][65];
     __shared__ double Aj[32][65];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -268,8 +279,8 @@ __global__ void __launch_bounds__(256) k_ekf_pp_blocks(int b0, int max_obs, cons
         for (int q = tid; q < 32 * 64; q += 256) {
             const int cc = q % 64, t = q / 64;
             const int i = i0 + t;
-            Ai[t][cc] = (i < n2 && j0 + cc < n) ? Z[(size_t)i * ldg + off + j0 + cc] : 0.0;
-            Aj[t][cc] = (i < n2 && k0 + cc < n) ? Z[(size_t)i * ldg + off + k0 + cc] : 0.0;
+            Ai[t][cc] = (i < n2 && j0 + cc < n) ? G[(size_t)i * ldg + off + j0 + cc] : 0.0;
+            Aj[t][cc] = (i < n2 && k0 + cc < n) ? X[(size_t)i * ldg + off + k0 + cc] : 0.0;
         }
         __syncthreads();
 #pragma unroll 8
@@ -348,22 +359,23 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched) {
         k_ekf_S<<<dim3(div_up(n_max, 128), 2 * n_max, wb), 128, 0, s>>>(b0, max_obs, B->n_mat.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
                                                                        strideG, B->S.p, B->lds, strideS, B->prm.observe_var);
         KERNEL_POST(ctx);
-        PROPAGATE(dense_potrf_lower_batched(ctx, B->S.p, B->lds, strideS, B->n2.p + b0, 2 * n_max, wb, B->flags.p + 2));
-        PROPAGATE(dense_fwd_solve_rows_batched(ctx, B->S.p, B->lds, strideS, B->G.p, B->ldg, strideG, B->n2.p + b0, 2 * n_max, 4, wb));
-        k_ekf_delta<<<dim3(div_up(s_max, kT), wb), kT, 0, s>>>(b0, max_obs, B->n_ray, B->n_mat.p, B->m_ray.p, B->G.p, B->ldg, strideG,
-                                                              B->ptz.p, B->vel.p, B->rays.p);
+        PROPAGATE(dense_getrf_batched(ctx, B->S.p, B->lds, strideS, B->n2.p + b0, 2 * n_max, wb, B->ipiv.p, B->lds, B->flags.p + 2));
+        PROPAGATE(dense_getrs_rows_batched(ctx, B->S.p, B->lds, strideS, B->ipiv.p, B->perm.p, B->lds, B->G.p, B->X.p, B->ldg, strideG,
+                                           B->n2.p + b0, 2 * n_max, 4, wb));
+        k_ekf_delta<<<dim3(div_up(s_max, kT), wb), kT, 0, s>>>(b0, max_obs, B->n_ray, B->n_mat.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
+                                                              strideG, B->ptz.p, B->vel.p, B->rays.p);
         KERNEL_POST(ctx);
-        k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->n_mat.p, B->G.p, B->ldg, strideG, B->P.p, strideP, s_tot);
+        k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->n_mat.p, B->G.p, B->X.p, B->ldg, strideG, B->P.p, strideP, s_tot);
         KERNEL_POST(ctx);
         const int nt = div_up(n_max, 64);
-        k_ekf_pp_blocks<<<dim3(nt * (nt + 1) / 2, 2, wb), 256, 0, s>>>(b0, max_obs, B->n_mat.p, B->m_ray.p, B->G.p, B->ldg, strideG,
-                                                                      B->P.p, strideP, s_tot);
+        k_ekf_pp_blocks<<<dim3(nt * (nt + 1) / 2, 2, wb), 256, 0, s>>>(b0, max_obs, B->n_mat.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
+                                                                      strideG, B->P.p, strideP, s_tot);
         KERNEL_POST(ctx);
     }
     int info = 0;
     CU_CHECK(ctx, cudaMemcpyAsync(&info, B->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_CHECK(ctx, cudaStreamSynchronize(s));
-    if (info != 0) return ptzba_fail(ctx, PTZBA_ERR_NUMERIC, "innovation covariance is not positive definite (panel %d)", info);
+    if (info != 0) return ptzba_fail(ctx, PTZBA_ERR_NUMERIC, "innovation covariance is singular (zero pivot in column %d)", info - 1);
     return PTZBA_OK;
 }
 
@@ -385,7 +397,7 @@ extern "C" int ptzba_ekf_batch_create(ptzba_ctx* ctx, const ptzba_ekf_params* pr
     B->ldg = (3 + 2 * max_obs + 1 + 3) / 4 * 4;
     B->lds = 2 * max_obs > 0 ? 2 * max_obs : 1;
     // wave size: share at most ~24 GB of G/S workspace
-    const size_t per_seq = ((size_t)B->ldg * 2 * (size_t)max_obs + (size_t)B->lds * B->lds) * sizeof(double);
+    const size_t per_seq = (2 * (size_t)B->ldg * 2 * (size_t)max_obs + (size_t)B->lds * B->lds) * sizeof(double);
     size_t wave = per_seq ? (size_t)24e9 / per_seq : (size_t)n_seq;
     if (wave < 1) wave = 1;
     B->wave = (int)std::min<size_t>(wave, (size_t)n_seq);
@@ -404,7 +416,9 @@ extern "C" int ptzba_ekf_batch_create(ptzba_ctx* ctx, const ptzba_ekf_params* pr
     CU_TRY(B->m_ray.alloc((size_t)n_seq * max_obs)); CU_TRY(B->flags.alloc(4));
     CU_TRY(B->Jc.alloc((size_t)n_seq * max_obs * 6)); CU_TRY(B->Jr.alloc((size_t)n_seq * max_obs * 4));
     CU_TRY(B->y.alloc((size_t)n_seq * max_obs * 2));
-    CU_TRY(B->G.alloc((size_t)B->wave * B->ldg * 2 * (size_t)max_obs)); CU_TRY(B->S.alloc((size_t)B->wave * B->lds * B->lds));
+    CU_TRY(B->G.alloc((size_t)B->wave * B->ldg * 2 * (size_t)max_obs)); CU_TRY(B->X.alloc((size_t)B->wave * B->ldg * 2 * (size_t)max_obs));
+    CU_TRY(B->S.alloc((size_t)B->wave * B->lds * B->lds));
+    CU_TRY(B->ipiv.alloc((size_t)B->wave * B->lds)); CU_TRY(B->perm.alloc((size_t)B->wave * B->lds));
     if (n_ray) CU_TRY(cudaMemcpyAsync(B->rays.p, rays0, (size_t)n_seq * n_ray * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(B->ptz.p, ptz0, (size_t)n_seq * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(B->disp.p, prm->disp, 6 * sizeof(double), cudaMemcpyHostToDevice, s));

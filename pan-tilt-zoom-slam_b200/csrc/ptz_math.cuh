@@ -75,7 +75,7 @@ __device__ __forceinline__ void backproject_full(const CamFull& c, double x, dou
 //   Nx = sa, Ny = -ct T + st ca, z = st T + ct ca, x = u + f Nx / z, y = v + f Ny / z
 // ---------------------------------------------------------------------------------------------------------------
 struct CamTrig { double sp, cp, st, ct, f; };
-struct LmTrig { double sth, cth, T, S; };
+struct __align__(32) LmTrig { double sth, cth, T, S; };   // one 256-bit load (LDG.E.ENL2.256) per gather
 
 __device__ __forceinline__ CamTrig make_cam_trig(double pan, double tilt, double f) {
     CamTrig c;

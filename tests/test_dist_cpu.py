@@ -1,0 +1,72 @@
+"""CPU, world_size 2 over gloo: the keyframe sharding of the multi-GPU BA path is a partition and the all-reduced
+shard blocks equal the single-process normal equations (host logic of ptz_slam_b200.dist; the GPU path replaces the
+oracle call by the CUDA fused pass and gloo by ncclAllReduce)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import ptz_slam_b200  # noqa: F401
+from ptz_slam_b200 import synth
+from ptz_slam_b200 import dist as pdist
+from oracle import ptz_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fb = synth.make_flat_ba(12, 300, 2400, seed=77)
+    cam, lm, xy, (lo, hi) = pdist.shard_by_keyframe(fb.cam_idx, fb.lm_idx, fb.obs_xy, fb.n_pose, rank, world)
+    poses, rays = O.ba_unpack(fb.x0(), fb.n_pose, fb.ptz_init[0])
+    r, U, gc, V, gl, cost = O.ba_normal_equations(poses, rays, cam, lm, xy, synth.PP_U, synth.PP_V)
+    U[0] = 0; gc[0] = 0          # fixed reference pose, as the CUDA pass
+    packed = torch.from_numpy(np.concatenate([[cost], U.ravel(), V.ravel(), gc.ravel(), gl.ravel()]))
+    dist.all_reduce(packed)      # the data-path collective: one sum over the packed blocks
+    n_obs = torch.tensor([len(cam)])
+    dist.all_reduce(n_obs)
+    seqs = pdist.shard_sequences(11, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, seqs.tolist())
+    if rank == 0:
+        np.save(os.path.join(out_dir, "packed.npy"), packed.numpy())
+        np.save(os.path.join(out_dir, "meta.npy"), np.array([int(n_obs.item()), lo, hi]))
+        np.save(os.path.join(out_dir, "seqs.npy"), np.array(sorted(sum(gathered, []))))
+    dist.destroy_process_group()
+
+
+def test_keyframe_ranges_partition():
+    rng = np.random.default_rng(0)
+    cam = rng.integers(0, 50, 10000)
+    for w in (1, 2, 4, 8):
+        ranges = pdist.keyframe_ranges(cam, 50, w)
+        assert ranges[0][0] == 0 and ranges[-1][1] == 50
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(w - 1))
+        counts = [np.sum((cam >= lo) & (cam < hi)) for lo, hi in ranges]
+        assert sum(counts) == len(cam) and max(counts) < 1.5 * len(cam) / w + 400
+
+
+def test_world2_sharded_blocks_sum_to_full(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    packed = np.load(tmp_path / "packed.npy")
+    meta = np.load(tmp_path / "meta.npy")
+    fb = synth.make_flat_ba(12, 300, 2400, seed=77)
+    assert meta[0] == fb.n_obs
+    poses, rays = O.ba_unpack(fb.x0(), fb.n_pose, fb.ptz_init[0])
+    r, U, gc, V, gl, cost = O.ba_normal_equations(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+    U[0] = 0; gc[0] = 0
+    full = np.concatenate([[cost], U.ravel(), V.ravel(), gc.ravel(), gl.ravel()])
+    np.testing.assert_allclose(packed, full, rtol=1e-11, atol=1e-9 * np.abs(full).max())
+    np.testing.assert_array_equal(np.load(tmp_path / "seqs.npy"), np.arange(11))
