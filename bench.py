@@ -257,7 +257,7 @@ def run_ours(args):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                "kernel": "k_ba_fused", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
+                "kernel": "fused pass (k_ba_lm_pass4 + k_ba_cam_pass)", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
 
     # ---- e2e: HOST (pinned) buffers through the C-ABI, copies inside the timed region ------------------------------
     N, M = fb.n_pose, fb.n_landmark

@@ -31,7 +31,7 @@ struct ptzba_ba {
     // keyframe blocks accumulate in registers, landmark blocks go to L2 with RED atomics
     DevBuf<int32_t> c_cam, c_lm, c_orig;
     DevBuf<double> c_ox, c_oy;
-    int fused_variant = 1;          // 0: landmark-major + smem atomics, 1: keyframe-major + REDs, 2: + packed REDs
+    int fused_variant = 8;          // see ba_fused_pass(): 0 one pass + smem atomics ... 8 two coherent passes (default)
     // current parameters
     DevBuf<double> poses;           // [N*3] incl. reference pose at 0
     DevBuf<double> rays;            // [M*2]

@@ -847,6 +847,23 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
             case 2: LAUNCH_CM(1, 2); break;
             case 3: LAUNCH_CM(0, 3); break;
             case 4: LAUNCH_CM(1, 3); break;
+            case 8: {
+                // best measured combination so far: quad landmark-major pass + prefetching keyframe-major pass
+                const int64_t q = (int64_t)kFusedThreads * kQuad;
+                int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;
+                chunkA = (chunkA + q - 1) / q * q;
+                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
+                k_ba_lm_pass4<<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                ctx->launches++;
+                int64_t chunkB = (ba->n_obs + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
+                chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+                const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
+                k_ba_cam_pass<<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                             ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+                break;
+            }
             case 7: {
                 const int64_t q = (int64_t)kFusedThreads * kQuad;
                 int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;

@@ -1,0 +1,60 @@
+"""
+Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs; not collected by pytest):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/multi_gpu_check.py
+Every rank takes the keyframe shard of ONE global BA problem, runs the CUDA fused pass on it and all-reduces the packed
+blocks with ncclAllReduce (ptzba_ba_allreduce); rank 0 compares the result with the oracle on the full problem.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ptz_slam_b200  # noqa: E402,F401
+from ptz_slam_b200 import _lib, synth  # noqa: E402
+from ptz_slam_b200 import bundle_adjustment as BA  # noqa: E402
+from ptz_slam_b200 import dist as pdist  # noqa: E402
+from oracle import ptz_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.get_context(local)
+    comm = pdist.Communicator(ctx, rank, world)
+    fb = synth.make_flat_ba(48, 6000, 90000, seed=31)
+    cam, lm, xy, (lo, hi) = pdist.shard_by_keyframe(fb.cam_idx, fb.lm_idx, fb.obs_xy, fb.n_pose, rank, world)
+    prob = BA.BAProblem(fb.n_pose, fb.n_landmark, cam, lm, xy, synth.PP_U, synth.PP_V, ctx=ctx)
+    x = torch.from_numpy(fb.x0()).cuda()
+    prob.normal_equations_device(x.data_ptr(), fb.ptz_init[0])
+    comm.allreduce_landmark_blocks(prob)
+    ctx.synchronize()
+    N, M = fb.n_pose, fb.n_landmark
+    U, gc, V, gl = np.empty((N, 6)), np.empty((N, 3)), np.empty((M, 3)), np.empty((M, 2))
+    import ctypes
+    cost = ctypes.c_double()
+    ctx.check(ctx.lib.ptzba_ba_get_blocks(prob.handle, _lib.ptr(U), _lib.ptr(gc), _lib.ptr(V), _lib.ptr(gl), ctypes.byref(cost)))
+    ok = True
+    if rank == 0:
+        poses, rays = O.ba_unpack(fb.x0(), N, fb.ptz_init[0])
+        r, Uo, gco, Vo, glo, costo = O.ba_normal_equations(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+        Up = np.stack([Uo[:, 0, 0], Uo[:, 0, 1], Uo[:, 0, 2], Uo[:, 1, 1], Uo[:, 1, 2], Uo[:, 2, 2]], 1)
+        Vp = np.stack([Vo[:, 0, 0], Vo[:, 0, 1], Vo[:, 1, 1]], 1)
+        np.testing.assert_allclose(U[1:], Up[1:], rtol=1e-9, atol=1e-12 * np.abs(Up).max())
+        np.testing.assert_allclose(V, Vp, rtol=1e-9, atol=1e-12 * np.abs(Vp).max())
+        np.testing.assert_allclose(gc[1:], gco[1:], rtol=1e-8, atol=1e-11 * np.abs(gco).max())
+        np.testing.assert_allclose(gl, glo, rtol=1e-8, atol=1e-11 * np.abs(glo).max())
+        assert abs(cost.value - costo) < 1e-11 * costo
+        print("multi_gpu_check OK: world=%d, rank-0 shard keyframes [%d,%d), all-reduced blocks match the oracle" % (world, lo, hi))
+    dist.barrier()
+    prob.close()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
