@@ -156,6 +156,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bench_ekf(ctx, n_seq, n_rays, n_frames):
+    """Batched independent EKF sequences (BASELINE config 4 recipe at a bounded batch): predict+update per frame."""
+    import torch
+    from ptz_slam_b200 import synth, _lib
+    from ptz_slam_b200.ptz_slam import BatchedEkfTracker
+    seqs = [synth.make_ekf_sequence(n_rays, n_frames + 1, seed=2000 + i) for i in range(n_seq)]
+    max_obs = max(len(i) for q in seqs for i in q.obs_idx)
+    trk = BatchedEkfTracker(np.stack([q.rays0 for q in seqs]), np.stack([q.ptz_gt[0] for q in seqs]), synth.PP_U, synth.PP_V,
+                            max_obs, synth.IMAGE_H, synth.IMAGE_W, jacobian_mode=_lib.JAC_CENTRAL_FD, ctx=ctx)
+    packed = [trk.pack_observations([q.obs_xy[k] for q in seqs], [q.obs_idx[k] for q in seqs]) for k in range(1, n_frames + 1)]
+    matched = trk.step(*packed[0])          # warm-up frame
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tot = 0
+    for k in range(1, n_frames):
+        m = trk.step(*packed[k])
+        tot += int(m.sum())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    trk.close()
+    frames = n_frames - 1
+    return {"workload": "%d independent sequences x %d rays, %d timed frames, host observations in / matched counts out" %
+                        (n_seq, n_rays, frames),
+            "sequence_frames_per_s": n_seq * frames / dt, "matched_obs_per_s": tot / dt,
+            "mean_matched_rays": tot / (n_seq * frames), "ms_per_frame_batch": 1e3 * dt / frames}
+
+
 # -------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------------
@@ -316,6 +343,11 @@ def run_ours(args):
               "solve": {"ftol": 1e-4, "ms": 1e3 * solve_s, "nfev": rep["nfev"], "njev": rep["njev"], "status": rep["status"],
                         "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]}}
 
+    # ---- batched EKF tracking (config 4 shape, bounded batch): sequence-frames/s and matched observations/s ----------
+    ekf = None
+    if world == 1 and not args.no_ekf:
+        ekf = bench_ekf(ctx, args.ekf_seqs, args.ekf_rays, args.ekf_frames)
+
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -342,6 +374,8 @@ def run_ours(args):
         }
         if lm:
             line.update(lm)
+        if ekf:
+            line["ekf"] = ekf
         print(json.dumps(line), flush=True)
     for p in probs:
         p.close()
@@ -359,6 +393,10 @@ def main():
     ap.add_argument("--replicas", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
+    ap.add_argument("--no-ekf", action="store_true")
+    ap.add_argument("--ekf-seqs", type=int, default=16)
+    ap.add_argument("--ekf-rays", type=int, default=2000)
+    ap.add_argument("--ekf-frames", type=int, default=4)
     ap.add_argument("--ramp", type=float, default=0.3, help="seconds of untimed passes before warm-up (clock ramp)")
     args = ap.parse_args()
     if args.warmup < 3:

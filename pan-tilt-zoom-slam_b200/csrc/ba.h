@@ -49,7 +49,10 @@ struct ptzba_ba {
     DevBuf<double> sol_c, sol_l, sol2_c, sol2_l;
     DevBuf<double> Vinv;                    // [M*3] (V + alpha D_l^2)^-1 packed
     DevBuf<double> scal;                    // small device scalar block for reductions
-    int fused_grid = 0, fused_grid_lm = 0, fused_smem = 0, grid_lm_pass = 0, grid_cam_pass = 0, grid_lm_pass4 = 0, grid_cam_pass4 = 0;
+    DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
+    DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
+    int fused_grid = 0, fused_grid_lm = 0, fused_smem = 0, grid_lm_pass = 0, grid_cam_pass = 0, grid_lm_pass4 = 0, grid_cam_pass4 = 0, grid_tma_lm = 0, grid_tma_cam = 0;
+    DevBuf<int2> tile_lm;           // per 1024-observation tile: (first landmark id, number of landmark ids)
     bool fused_cam_smem = true;
 };
 

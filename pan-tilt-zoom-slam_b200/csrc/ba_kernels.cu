@@ -463,7 +463,8 @@ k_ba_lm_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, co
     }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 3)
+template <int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_cam_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
               const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
               const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
@@ -563,7 +564,8 @@ __device__ __forceinline__ void commit_lm(double* __restrict__ gV, double* __res
     atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 3)
+template <int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
               const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
@@ -758,6 +760,315 @@ k_ba_cam_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, 
     flush();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fused_variant 9: the two coherent passes fed by a TMA (cp.async.bulk) ring buffer.
+// One elected thread per CTA streams 1024-observation tiles of the four SoA arrays (and, in the landmark-major pass, the
+// tile's contiguous slice of the landmark trig table) into shared memory, kStages tiles ahead, completing on an mbarrier;
+// all warps consume the current tile from shared memory (conflict-free 128-bit LDS).  HBM latency is therefore hidden by
+// the copy engine instead of by occupancy, and the streaming loads cost no LSU instruction slots.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTile = kFusedThreads * kQuad;     // 1024 observations
+constexpr int kStages = 3;
+constexpr int kTileTrig = 256;                   // landmark trig entries staged per tile (more -> direct global loads)
+
+struct __align__(128) TileBuf {
+    int cam[kTile];
+    int lm[kTile];
+    double ox[kTile];
+    double oy[kTile];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// producer side: issue the copies of global tile `t` into ring slot `slot`
+__device__ __forceinline__ void issue_tile(TileBuf* buf, uint64_t* bar, int64_t t, int64_t n_obs, const int32_t* cam,
+                                           const int32_t* lm, const double* ox, const double* oy, LmTrig* trig_dst,
+                                           const LmTrig* lm_trig, const int2* tile_lm, int* trig_info) {
+    const int64_t k0 = t * kTile;
+    int64_t cnt = n_obs - k0;
+    if (cnt > kTile) cnt = kTile;
+    const uint32_t c4 = (uint32_t)((cnt + 3) / 4 * 4);          // arrays are padded by 4 entries
+    uint32_t bytes = c4 * 4u * 2u + c4 * 8u * 2u;
+    int n_trig = 0, lo = 0;
+    if (trig_dst) {
+        const int2 r = tile_lm[t];                              // (first landmark id, number of landmark ids) of the tile
+        lo = r.x;
+        if (r.y <= kTileTrig) { n_trig = r.y; bytes += (uint32_t)n_trig * (uint32_t)sizeof(LmTrig); }
+        trig_info[0] = lo;
+        trig_info[1] = n_trig;
+    }
+    mbar_expect_tx(bar, bytes);
+    tma_load(buf->cam, cam + k0, c4 * 4u, bar);
+    tma_load(buf->lm, lm + k0, c4 * 4u, bar);
+    tma_load(buf->ox, ox + k0, c4 * 8u, bar);
+    tma_load(buf->oy, oy + k0, c4 * 8u, bar);
+    if (n_trig > 0) tma_load(trig_dst, lm_trig + lo, (uint32_t)n_trig * (uint32_t)sizeof(LmTrig), bar);
+}
+
+__global__ void k_tile_lm_ranges(int64_t n_obs, int64_t n_tiles, const int32_t* __restrict__ s_lm, int2* __restrict__ tile_lm) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int64_t k0 = t * kTile;
+    int64_t k1 = k0 + kTile;
+    if (k1 > n_obs) k1 = n_obs;
+    const int lo = s_lm[k0], hi = s_lm[k1 - 1];
+    tile_lm[t] = make_int2(lo, hi - lo + 1);
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 2)
+k_ba_lm_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_t* __restrict__ s_cam,
+                 const int32_t* __restrict__ s_lm, const double* __restrict__ s_ox, const double* __restrict__ s_oy,
+                 const int32_t* __restrict__ orig, const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig,
+                 const int2* __restrict__ tile_lm, int n_pose, double u, double v, double* __restrict__ resid,
+                 double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    TileBuf* tiles = reinterpret_cast<TileBuf*>(dyn);
+    LmTrig* trigs = reinterpret_cast<LmTrig*>(dyn + sizeof(TileBuf) * kStages);
+    double* sCam = reinterpret_cast<double*>(dyn + sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages);   // SoA [5][n_pose]
+    __shared__ uint64_t full[kStages];
+    __shared__ int trig_info[kStages][2];
+    __shared__ double sWarp[kFusedThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
+    int64_t t_end = t_begin + tiles_per_cta;
+    if (t_end > n_tiles) t_end = n_tiles;
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
+        const int c = i / 5, e = i - 5 * c;
+        sCam[(size_t)e * n_pose + c] = reinterpret_cast<const double*>(cam_trig)[i];
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < kStages - 1; ++i)
+            if (t_begin + i < t_end)
+                issue_tile(&tiles[i], &full[i], t_begin + i, n_obs, s_cam, s_lm, s_ox, s_oy, trigs + (size_t)i * kTileTrig,
+                           lm_trig, tile_lm, trig_info[i]);
+    const double k1 = PTZ_DEG2RAD;
+    double cost = 0.0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int it = (int)(t - t_begin);
+        const int slot = it % kStages;
+        if (tid == 0) {
+            const int64_t tn = t + kStages - 1;
+            if (tn < t_end) {
+                const int ns = (it + kStages - 1) % kStages;
+                issue_tile(&tiles[ns], &full[ns], tn, n_obs, s_cam, s_lm, s_ox, s_oy, trigs + (size_t)ns * kTileTrig, lm_trig,
+                           tile_lm, trig_info[ns]);
+            }
+        }
+        mbar_wait(&full[slot], (uint32_t)((it / kStages) & 1));
+        const TileBuf& tb = tiles[slot];
+        const LmTrig* sTrig = trigs + (size_t)slot * kTileTrig;
+        const int tlo = trig_info[slot][0], tn_trig = trig_info[slot][1];
+        const int64_t k0 = t * kTile + (int64_t)tid * kQuad;
+        const int q = tid * kQuad;
+        const int4 c4 = *reinterpret_cast<const int4*>(tb.cam + q);
+        const int4 l4 = *reinterpret_cast<const int4*>(tb.lm + q);
+        const double2 xa = *reinterpret_cast<const double2*>(tb.ox + q), xb = *reinterpret_cast<const double2*>(tb.ox + q + 2);
+        const double2 ya = *reinterpret_cast<const double2*>(tb.oy + q), yb = *reinterpret_cast<const double2*>(tb.oy + q + 2);
+        int cam[kQuad] = {c4.x, c4.y, c4.z, c4.w};
+        int lm[kQuad] = {l4.x, l4.y, l4.z, l4.w};
+        const double ox[kQuad] = {xa.x, xa.y, xb.x, xb.y};
+        const double oy[kQuad] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i)
+            if (k0 + i >= n_obs) lm[i] = -1;
+        double rx[kQuad], ry[kQuad];
+        int cur = -1;
+        LmTrig lt = {0, 1, 0, 1};
+        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            rx[i] = 0.0; ry[i] = 0.0;
+            if (lm[i] < 0) continue;
+            if (lm[i] != cur) {
+                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+                cur = lm[i];
+                lt = (tn_trig > 0) ? sTrig[cur - tlo] : lm_trig[cur];
+                vtt = vtp = vpp = glt = glp = 0.0;
+            }
+            CamTrig c;
+            c.sp = sCam[cam[i]]; c.cp = sCam[n_pose + cam[i]]; c.st = sCam[2 * n_pose + cam[i]];
+            c.ct = sCam[3 * n_pose + cam[i]]; c.f = sCam[4 * n_pose + cam[i]];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            rx[i] = x - ox[i];
+            ry[i] = y - oy[i];
+            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
+            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
+            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
+            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
+            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
+            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
+            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
+        }
+        if (resid) {
+            if (!orig && k0 + kQuad <= n_obs) {
+                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
+                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
+                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
+            } else {
+#pragma unroll
+                for (int i = 0; i < kQuad; ++i)
+                    if (lm[i] >= 0) {
+                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
+                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
+                    }
+            }
+        }
+        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+        __syncthreads();      // every warp is done with this slot before the producer refills it
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 2)
+k_ba_cam_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_t* __restrict__ c_cam,
+                  const int32_t* __restrict__ c_lm, const double* __restrict__ c_ox, const double* __restrict__ c_oy,
+                  const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, double u, double v,
+                  double* __restrict__ gU, double* __restrict__ gGc) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    TileBuf* tiles = reinterpret_cast<TileBuf*>(dyn);
+    __shared__ uint64_t full[kStages];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+    const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
+    int64_t t_end = t_begin + tiles_per_cta;
+    if (t_end > n_tiles) t_end = n_tiles;
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < kStages - 1; ++i)
+            if (t_begin + i < t_end)
+                issue_tile(&tiles[i], &full[i], t_begin + i, n_obs, c_cam, c_lm, c_ox, c_oy, nullptr, nullptr, nullptr, nullptr);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+    int wcam = -1;
+    CamTrig wc = {0, 1, 0, 1, 1};
+    auto flush = [&]() {
+        if (wcam > 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
+            if (lane == 0) {
+                double* U = gU + 6 * (size_t)wcam;
+                double* G = gGc + 3 * (size_t)wcam;
+                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
+                atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
+                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+            }
+        }
+        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
+    };
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int it = (int)(t - t_begin);
+        const int slot = it % kStages;
+        if (tid == 0) {
+            const int64_t tn = t + kStages - 1;
+            if (tn < t_end) {
+                const int ns = (it + kStages - 1) % kStages;
+                issue_tile(&tiles[ns], &full[ns], tn, n_obs, c_cam, c_lm, c_ox, c_oy, nullptr, nullptr, nullptr, nullptr);
+            }
+        }
+        mbar_wait(&full[slot], (uint32_t)((it / kStages) & 1));
+        const TileBuf& tb = tiles[slot];
+        const int64_t k0 = t * kTile + (int64_t)tid * kQuad;
+        const int q = tid * kQuad;
+        const int4 c4 = *reinterpret_cast<const int4*>(tb.cam + q);
+        const int4 l4 = *reinterpret_cast<const int4*>(tb.lm + q);
+        int cam[kQuad] = {c4.x, c4.y, c4.z, c4.w};
+        const int lm[kQuad] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i)
+            if (k0 + i >= n_obs) cam[i] = -1;
+        LmTrig lt[kQuad];
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) lt[i] = lm_trig[cam[i] >= 0 ? lm[i] : 0];     // four independent gathers in flight
+        const double2 xa = *reinterpret_cast<const double2*>(tb.ox + q), xb = *reinterpret_cast<const double2*>(tb.ox + q + 2);
+        const double2 ya = *reinterpret_cast<const double2*>(tb.oy + q), yb = *reinterpret_cast<const double2*>(tb.oy + q + 2);
+        const double ox[kQuad] = {xa.x, xa.y, xb.x, xb.y};
+        const double oy[kQuad] = {ya.x, ya.y, yb.x, yb.y};
+        const int first = __shfl_sync(0xffffffffu, cam[0], 0);
+        bool mine = true;
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) mine = mine && (cam[i] == first || cam[i] < 0);
+        const bool uniform = __all_sync(0xffffffffu, mine) && first >= 0;
+        if (uniform) {
+            if (first != wcam) { flush(); wcam = first; wc = cam_trig[wcam]; }
+        } else {
+            flush();
+            wcam = -1;
+        }
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            if (cam[i] <= 0) continue;
+            const CamTrig c = uniform ? wc : cam_trig[cam[i]];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt[i], u, v, x, y, g);
+            const double rx = x - ox[i], ry = y - oy[i];
+            const double upp = fma(g.xa, g.xa, g.ya * g.ya);
+            const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
+            const double upf = -fma(g.xa, g.px, g.ya * g.py);
+            const double utt = fma(g.xt, g.xt, g.yt * g.yt);
+            const double utf = fma(g.xt, g.px, g.yt * g.py);
+            const double uff = fma(g.px, g.px, g.py * g.py);
+            const double gp = -fma(g.xa, rx, g.ya * ry);
+            const double gt = fma(g.xt, rx, g.yt * ry);
+            const double gf = fma(g.px, rx, g.py * ry);
+            if (uniform) {
+                a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
+            } else {
+                double* U = gU + 6 * (size_t)cam[i];
+                double* G = gGc + 3 * (size_t)cam[i];
+                atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
+                atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
+                atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
+            }
+        }
+        __syncthreads();
+    }
+    flush();
+}
+
 // global-accumulator variant leaves radian units in U/gc; this converts them in place
 __global__ void k_scale_cam_blocks(int n_pose, double* __restrict__ U, double* __restrict__ gc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -847,20 +1158,53 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
             case 2: LAUNCH_CM(1, 2); break;
             case 3: LAUNCH_CM(0, 3); break;
             case 4: LAUNCH_CM(1, 3); break;
+            case 10: {
+                const int64_t q = (int64_t)kFusedThreads * kQuad;
+                const int gA = ctx->sm_count * 4, gB = ctx->sm_count * 4;
+                int64_t chunkA = (ba->n_obs + gA - 1) / gA;
+                chunkA = (chunkA + q - 1) / q * q;
+                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
+                k_ba_lm_pass4<4><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                ctx->launches++;
+                int64_t chunkB = (ba->n_obs + gB - 1) / gB;
+                chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+                const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
+                k_ba_cam_pass<4><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                                ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+                break;
+            }
+            case 9: {
+                const int64_t n_tiles = (ba->n_obs + kTile - 1) / kTile;
+                const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)ba->n_pose * 5 * sizeof(double);
+                const size_t smB = sizeof(TileBuf) * kStages;
+                int tpcA = (int)((n_tiles + ba->grid_tma_lm - 1) / ba->grid_tma_lm);
+                int tpcB = (int)((n_tiles + ba->grid_tma_cam - 1) / ba->grid_tma_cam);
+                const int gridA = (int)((n_tiles + tpcA - 1) / tpcA), gridB = (int)((n_tiles + tpcB - 1) / tpcB);
+                k_ba_lm_pass_tma<<<gridA, kFusedThreads, smA, s>>>(ba->n_obs, n_tiles, tpcA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+                                                                 ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->tile_lm.p,
+                                                                 ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                ctx->launches++;
+                k_ba_cam_pass_tma<<<gridB, kFusedThreads, smB, s>>>(ba->n_obs, n_tiles, tpcB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p,
+                                                                  ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U,
+                                                                  ba->acc.gc);
+                break;
+            }
             case 8: {
                 // best measured combination so far: quad landmark-major pass + prefetching keyframe-major pass
                 const int64_t q = (int64_t)kFusedThreads * kQuad;
                 int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;
                 chunkA = (chunkA + q - 1) / q * q;
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass4<<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
                     ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
                 ctx->launches++;
                 int64_t chunkB = (ba->n_obs + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
                 chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
                 const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
-                k_ba_cam_pass<<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
                                                              ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
                 break;
             }
@@ -869,7 +1213,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;
                 chunkA = (chunkA + q - 1) / q * q;
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass4<<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
                     ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
                 ctx->launches++;
@@ -891,7 +1235,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 int64_t chunkB = (ba->n_obs + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
                 chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
                 const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
-                k_ba_cam_pass<<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
                                                              ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
                 break;
             }
@@ -1074,13 +1418,34 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
             const size_t sm5 = (size_t)n_pose * 5 * sizeof(double);
             if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass, kFusedThreads, sm5));
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass, kFusedThreads, 0));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<3>, kFusedThreads, 0));
             int pa4 = 1, pb4 = 1;
-            if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa4, k_ba_lm_pass4, kFusedThreads, sm5));
+            if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa4, k_ba_lm_pass4<3>, kFusedThreads, sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb4, k_ba_cam_pass4, kFusedThreads, 0));
             ba->grid_lm_pass4 = ctx->sm_count * (pa4 < 1 ? 1 : pa4);
             ba->grid_cam_pass4 = ctx->sm_count * (pb4 < 1 ? 1 : pb4);
+            {
+                const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)n_pose * 5 * sizeof(double);
+                const size_t smB = sizeof(TileBuf) * kStages;
+                int qa = 1, qb = 1;
+                if (smA <= 220 * 1024) {
+                    CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+                    CU_TRY(cudaFuncSetAttribute(k_ba_cam_pass_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB));
+                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qa, k_ba_lm_pass_tma, kFusedThreads, smA));
+                    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qb, k_ba_cam_pass_tma, kFusedThreads, smB));
+                } else if (ba->fused_variant == 9) {
+                    ba->fused_variant = 8;
+                }
+                ba->grid_tma_lm = ctx->sm_count * (qa < 1 ? 1 : qa);
+                ba->grid_tma_cam = ctx->sm_count * (qb < 1 ? 1 : qb);
+                const int64_t n_tiles = (n_obs + kTile - 1) / kTile;
+                CU_TRY(ba->tile_lm.alloc((size_t)n_tiles + 1));
+                if (n_tiles > 0) {
+                    k_tile_lm_ranges<<<div_up(n_tiles, 256), 256, 0, s>>>(n_obs, n_tiles, ba->s_lm.p, ba->tile_lm.p);
+                    ctx->launches++;
+                }
+            }
             ba->grid_lm_pass = ctx->sm_count * (pa < 1 ? 1 : pa);
             ba->grid_cam_pass = ctx->sm_count * (pb < 1 ? 1 : pb);
         }

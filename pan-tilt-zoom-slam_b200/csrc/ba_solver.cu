@@ -320,8 +320,9 @@ struct Solver {
     int pair_warps_smem = 0, pair_grid = 0;
     int n_factor = 0;
     double *g, *D, *Dc, *Dl;
-    DevBuf<int> flags;       // [0] singular V blocks, [1] potrf info
-    DevBuf<double> tmp_l, w_full;
+    DevBuf<int>& flags;      // persistent scratch owned by the problem (no allocation per solve)
+    DevBuf<double>&tmp_l, &w_full, &dinv;
+    explicit Solver(ptzba_ba* b) : ba(b), ctx(b->ctx), s(b->ctx->stream), flags(b->sol_flags), tmp_l(b->sol_tmp_l), w_full(b->sol_w), dinv(b->sol_dinv) {}
 
     int init() {
         N = ba->n_pose; M = ba->n_lm; n = 3 * (N - 1); nF = 3 * N + 2 * M;
@@ -332,6 +333,7 @@ struct Solver {
         CU_CHECK(ctx, ba->rhs_l.alloc(nF));   // reduced rhs scratch (camera part only)
         CU_CHECK(ctx, ba->Vinv.alloc((size_t)M * 3));
         CU_CHECK(ctx, flags.alloc(4)); CU_CHECK(ctx, tmp_l.alloc((size_t)2 * M)); CU_CHECK(ctx, w_full.alloc(nF));
+        CU_CHECK(ctx, dinv.alloc((size_t)(n / 32 + 1) * 1024));
         g = ba->acc.gc;           // gc | gl contiguous = full layout
         D = ba->scale_inv.p; Dc = D; Dl = D + 3 * N;
         obs_grid = ctx->sm_count * 4;
@@ -374,6 +376,7 @@ struct Solver {
                 KERNEL_POST(ctx);
             }
             PROPAGATE(dense_potrf_lower(ctx, ba->Sred.p, n, n, flags.p + 1));
+            PROPAGATE(dense_diag_inverse(ctx, ba->Sred.p, n, n, dinv.p));
         }
         ++n_factor;
         int h[2];
@@ -395,7 +398,7 @@ struct Solver {
                 ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p, ba->Vinv.p, rhs_l, N, use_smem, red);
             KERNEL_POST(ctx);
         }
-        if (n > 0) PROPAGATE(dense_potrs_lower(ctx, ba->Sred.p, n, n, red + 3, n, 1));
+        if (n > 0) PROPAGATE(dense_potrs_dinv(ctx, ba->Sred.p, n, n, dinv.p, red + 3));
         CU_CHECK(ctx, cudaMemcpyAsync(y, red, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CU_CHECK(ctx, cudaMemsetAsync(y, 0, 3 * sizeof(double), s));
         CU_CHECK(ctx, cudaMemsetAsync(tmp_l.p, 0, (size_t)2 * M * sizeof(double), s));
@@ -452,8 +455,7 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
     ptzba_ctx* ctx = ba->ctx;
     ARG_CHECK(ctx, x && reference_pose3 && opt);
     const auto t_start = std::chrono::steady_clock::now();
-    Solver S;
-    S.ba = ba; S.ctx = ctx; S.s = ctx->stream;
+    Solver S(ba);
     PROPAGATE(S.init());
     cudaStream_t s = S.s;
     const int N = S.N, M = S.M, nF = S.nF;
@@ -461,8 +463,9 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
     const double ftol = opt->ftol, xtol = opt->xtol, gtol = opt->gtol;
     int max_nfev = opt->max_nfev > 0 ? opt->max_nfev : 100 * (nx > 0 ? nx : 1);
 
-    InArray<double> d_ref;
-    CU_CHECK(ctx, d_ref.stage(PTZBA_HOST, reference_pose3, 3, s));
+    CU_CHECK(ctx, ba->ref_stage.alloc(4));
+    CU_CHECK(ctx, cudaMemcpyAsync(ba->ref_stage.p, reference_pose3, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    struct { const double* d; } d_ref = {ba->ref_stage.p};
     double* xc = ba->x_cur.p + 3;      // packed view of the full layout
     double* xt = ba->x_trial.p + 3;
     CU_CHECK(ctx, cudaMemsetAsync(ba->x_cur.p, 0, 3 * sizeof(double), s));
@@ -645,14 +648,14 @@ extern "C" int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, con
     if (!ba) return PTZBA_ERR_ARG;
     ptzba_ctx* ctx = ba->ctx;
     ARG_CHECK(ctx, x && reference_pose3);
-    Solver S;
-    S.ba = ba; S.ctx = ctx; S.s = ctx->stream;
+    Solver S(ba);
     PROPAGATE(S.init());
     cudaStream_t s = S.s;
     const int N = S.N, M = S.M, nF = S.nF;
     const int nx = 3 * (N - 1) + 2 * M;
-    InArray<double> d_ref;
-    CU_CHECK(ctx, d_ref.stage(PTZBA_HOST, reference_pose3, 3, s));
+    CU_CHECK(ctx, ba->ref_stage.alloc(4));
+    CU_CHECK(ctx, cudaMemcpyAsync(ba->ref_stage.p, reference_pose3, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    struct { const double* d; } d_ref = {ba->ref_stage.p};
     double* xc = ba->x_cur.p + 3;
     double* xt = ba->x_trial.p + 3;
     CU_CHECK(ctx, cudaMemsetAsync(ba->x_cur.p, 0, 3 * sizeof(double), s));

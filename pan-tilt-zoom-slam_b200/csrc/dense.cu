@@ -353,3 +353,90 @@ int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_
     }
     return PTZBA_OK;
 }
+
+namespace {
+
+// ---- inverses of the 32 x 32 diagonal blocks of L (one warp per block; lane j solves L x = e_j) ----------------------------
+// Dinv block b is stored column-major: Dinv[b*1024 + i + 32*j] = (L_bb^-1)[i][j]
+__global__ void __launch_bounds__(32) k_diag_inverse(const double* __restrict__ L, int lda, int n, double* __restrict__ Dinv) {
+    __shared__ double T[NB][NB + 1];
+    const int b = blockIdx.x, k = b * NB, lane = threadIdx.x;
+    const int nb = (n - k) < NB ? (n - k) : NB;
+    for (int e = lane; e < NB * NB; e += 32) {
+        const int i = e % NB, j = e / NB;
+        T[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int t = 0; t < i; ++t) s = fma(-T[i][t], x[t], s);
+        x[i] = s / T[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) Dinv[(size_t)b * NB * NB + i + NB * lane] = x[i];
+}
+
+// ---- single right-hand side solves with the inverted diagonal blocks: every block step is a 32 x 32 mat-vec by one warp
+// followed by a panel update spread over the whole CTA (no sequential triangle solve on the critical path) -----------------
+__global__ void __launch_bounds__(1024) k_trsv_dinv(const double* __restrict__ L, int lda, int n, const double* __restrict__ Dinv,
+                                                    double* __restrict__ bvec, int backward) {
+    __shared__ double xs[NB];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nblk = (n + NB - 1) / NB;
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int blk = backward ? (nblk - 1 - bi) : bi;
+        const int k = blk * NB;
+        const int nb = (n - k) < NB ? (n - k) : NB;
+        if (w == 0) {
+            // forward: x = Dinv * b_k ; backward: x = Dinv^T * b_k
+            const double* D = Dinv + (size_t)blk * NB * NB;
+            double s = 0.0;
+            for (int t = 0; t < nb; ++t) {
+                const double bt = bvec[k + t];
+                const double d = backward ? D[t + NB * lane] : D[lane + NB * t];
+                s = fma(d, bt, s);
+            }
+            xs[lane] = lane < nb ? s : 0.0;
+        }
+        __syncthreads();
+        if (w == 0 && lane < nb) bvec[k + lane] = xs[lane];
+        if (!backward) {
+            for (int r = k + nb + tid; r < n; r += 1024) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int j = 0; j < NB; ++j) s = fma(j < nb ? L[(size_t)r + (size_t)(k + j) * lda] : 0.0, xs[j], s);
+                bvec[r] -= s;
+            }
+        } else {
+            for (int c = tid; c < k; c += 1024) {
+                const double* col = L + (size_t)k + (size_t)c * lda;
+                double s = 0.0;
+#pragma unroll 8
+                for (int i = 0; i < NB; ++i) s = fma(i < nb ? col[i] : 0.0, xs[i], s);
+                bvec[c] -= s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int dense_diag_inverse(ptzba_ctx* ctx, const double* L, int n, int lda, double* Dinv) {
+    if (n <= 0) return PTZBA_OK;
+    k_diag_inverse<<<div_up(n, NB), 32, 0, ctx->stream>>>(L, lda, n, Dinv);
+    KERNEL_POST(ctx);
+    return PTZBA_OK;
+}
+
+int dense_potrs_dinv(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv, double* b) {
+    if (n <= 0) return PTZBA_OK;
+    k_trsv_dinv<<<1, 1024, 0, ctx->stream>>>(L, lda, n, Dinv, b, 0);
+    KERNEL_POST(ctx);
+    k_trsv_dinv<<<1, 1024, 0, ctx->stream>>>(L, lda, n, Dinv, b, 1);
+    KERNEL_POST(ctx);
+    return PTZBA_OK;
+}

@@ -23,3 +23,8 @@ int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const
 int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t stride, const int* d_ipiv, int* d_perm, int ld_ipiv,
                              const double* B, double* X, int ldg, size_t strideG, const int* d_n_arr, int n_max, int extra_cols,
                              int batch);
+
+// inverses of the 32 x 32 diagonal blocks of a Cholesky factor (Dinv: ceil(n/32) * 1024 doubles) and the single-RHS solve
+// L L^T x = b that uses them (mat-vec per block step instead of a sequential triangle solve)
+int dense_diag_inverse(ptzba_ctx* ctx, const double* L, int n, int lda, double* Dinv);
+int dense_potrs_dinv(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv, double* b);
