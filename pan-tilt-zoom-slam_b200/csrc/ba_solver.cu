@@ -11,6 +11,9 @@
 // W blocks (3x2 per observation) are never stored: each pass recomputes them from the keyframe / landmark trig tables.
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
+#include <utility>
+#include <vector>
 
 #include "ba.h"
 #include "dense.h"
@@ -145,7 +148,10 @@ __global__ void k_schur_diag(int n_pose, const double* __restrict__ U, const dou
 }
 
 // ---- reduced system: - W Vinv W^T over all observation pairs of each landmark; one warp per landmark -------------------
-// smem per warp: dmax * (6 doubles + 1 int).  Only blocks with cam_i >= cam_j are written (lower triangle).
+// smem per warp: dmax * (12 doubles + 1 int): W_i and Y_i = W_i Vinv of every observation of the landmark.
+// The d(d+1)/2 unordered pairs x 9 block entries are spread over the lanes ENTRY by ENTRY with the row index fastest, so
+// the three lanes of one block column hit one 32-byte sector of the column-major S: the L2 atomic unit sees 3 sectors per
+// pair instead of 9 (the FP64 RED rate is per sector).  Only the lower triangle of S is written.
 __global__ void __launch_bounds__(kThreads)
 k_schur_pairs(int n_lm, const int32_t* __restrict__ lm_ptr, const int32_t* __restrict__ s_cam,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ Vinv,
@@ -153,8 +159,8 @@ k_schur_pairs(int n_lm, const int32_t* __restrict__ lm_ptr, const int32_t* __res
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warps = kThreads / 32;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* Wsm = reinterpret_cast<double*>(smem_raw) + (size_t)wid * dmax * 6;
-    int* Csm = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)warps * dmax * 6) + (size_t)wid * dmax;
+    double* Wsm = reinterpret_cast<double*>(smem_raw) + (size_t)wid * dmax * 12;
+    int* Csm = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)warps * dmax * 12) + (size_t)wid * dmax;
     const int total_warps = gridDim.x * warps;
     for (int l = blockIdx.x * warps + wid; l < n_lm; l += total_warps) {
         const int b = lm_ptr[l], d = lm_ptr[l + 1] - b;
@@ -167,27 +173,44 @@ k_schur_pairs(int n_lm, const int32_t* __restrict__ lm_ptr, const int32_t* __res
             if (cam > 0) {
                 double w[6];
                 obs_W(cam_trig[cam], lt, w);
-                // store Y = W Vinv in place of W?  both are needed: keep W, recompute Y per pair (12 FMA)
 #pragma unroll
-                for (int e = 0; e < 6; ++e) Wsm[i * 6 + e] = w[e];
+                for (int r = 0; r < 3; ++r) {
+                    Wsm[i * 12 + 2 * r] = w[2 * r];
+                    Wsm[i * 12 + 2 * r + 1] = w[2 * r + 1];
+                    Wsm[i * 12 + 6 + 2 * r] = fma(w[2 * r], v00, w[2 * r + 1] * v01);       // Y = W Vinv
+                    Wsm[i * 12 + 6 + 2 * r + 1] = fma(w[2 * r], v01, w[2 * r + 1] * v11);
+                }
             }
         }
         __syncwarp();
-        const int np = d * d;
-        for (int p = lane; p < np; p += 32) {
-            const int i = p / d, j = p - i * d;
+        const int nval = d * (d + 1) / 2 * 9;
+        for (int pv = lane; pv < nval; pv += 32) {
+            const int p = pv / 9, e = pv - 9 * p;
+            const int sc = e / 3, r = e - 3 * sc;                       // row index fastest
+            int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= p) ++i;
+            while (i * (i + 1) / 2 > p) --i;
+            const int j = p - i * (i + 1) / 2;                          // j <= i
             const int ci = Csm[i], cj = Csm[j];
-            if (ci <= 0 || cj <= 0 || ci < cj) continue;
-            const double* wi = Wsm + i * 6;
-            const double* wj = Wsm + j * 6;
-            double* dst = S + (size_t)(3 * (ci - 1)) + (size_t)(3 * (cj - 1)) * ld;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double y0 = fma(wi[2 * r], v00, wi[2 * r + 1] * v01);
-                const double y1 = fma(wi[2 * r], v01, wi[2 * r + 1] * v11);
-#pragma unroll
-                for (int s = 0; s < 3; ++s) atomicAdd(dst + r + (size_t)s * ld, -fma(y0, wj[2 * s], y1 * wj[2 * s + 1]));
+            if (ci <= 0 || cj <= 0) continue;
+            const double* wi = Wsm + i * 12;
+            const double* yi = wi + 6;
+            const double* wj = Wsm + j * 12;
+            // B = Y_i W_j^T ; B[r][s] = yi[2r] wj[2s] + yi[2r+1] wj[2s+1]
+            double val;
+            int cr, cc;
+            if (ci > cj) {
+                val = fma(yi[2 * r], wj[2 * sc], yi[2 * r + 1] * wj[2 * sc + 1]);
+                cr = ci; cc = cj;
+            } else if (ci < cj) {                                        // block (cj, ci) receives B^T
+                val = fma(yi[2 * sc], wj[2 * r], yi[2 * sc + 1] * wj[2 * r + 1]);
+                cr = cj; cc = ci;
+            } else {
+                val = fma(yi[2 * r], wj[2 * sc], yi[2 * r + 1] * wj[2 * sc + 1]);
+                if (i != j) val += fma(yi[2 * sc], wj[2 * r], yi[2 * sc + 1] * wj[2 * r + 1]);   // same keyframe twice: B + B^T
+                cr = cc = ci;
             }
+            atomicAdd(S + (size_t)(3 * (cr - 1) + r) + (size_t)(3 * (cc - 1) + sc) * ld, -val);
         }
         __syncwarp();
     }
@@ -310,7 +333,35 @@ k_jvp_sumsq(int64_t n_obs, const int32_t* __restrict__ s_cam, const int32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+struct PhaseTrace {      // PTZBA_TRACE=1: CUDA-event time of each solver phase, printed to stderr (debug aid)
+    bool on = false;
+    cudaStream_t s = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    void begin(cudaStream_t st) { on = getenv("PTZBA_TRACE") != nullptr; s = st; mark("start"); }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back({name, e});
+    }
+    void report(const char* title) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[ptzba trace] %s:", title);
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            fprintf(stderr, " %s=%.1fus", ev[i].first, ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+        for (auto& p : ev) cudaEventDestroy(p.second);
+        ev.clear();
+    }
+};
+
 struct Solver {
+    PhaseTrace tr;
     ptzba_ba* ba;
     ptzba_ctx* ctx;
     cudaStream_t s;
@@ -342,7 +393,7 @@ struct Solver {
         if (chunk < kThreads) chunk = kThreads;
         obs_grid = (int)((ba->n_obs + chunk - 1) / chunk);
         if (obs_grid < 1) obs_grid = 1;
-        const size_t per_warp = (size_t)(ba->max_degree > 0 ? ba->max_degree : 1) * (6 * sizeof(double) + sizeof(int));
+        const size_t per_warp = (size_t)(ba->max_degree > 0 ? ba->max_degree : 1) * (12 * sizeof(double) + sizeof(int));
         const size_t need = per_warp * (kThreads / 32) + 16;
         if (need > 200 * 1024)
             return ptzba_fail(ctx, PTZBA_ERR_ARG, "a landmark has %d observations: exceeds the shared-memory tile of the Schur kernel",
@@ -362,6 +413,7 @@ struct Solver {
 
     // forms and factors S(alpha); *ok = false when the factorisation broke down or an observed landmark block is singular
     int factor(double alpha, bool* ok) {
+        tr.begin(s);
         CU_CHECK(ctx, cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), s));
         k_vinv<<<div_up(M, 256), 256, 0, s>>>(M, ba->acc.V, Dl, alpha, ba->lm_ptr.p, ba->Vinv.p, flags.p);
         KERNEL_POST(ctx);
@@ -369,15 +421,20 @@ struct Solver {
             CU_CHECK(ctx, cudaMemsetAsync(ba->Sred.p, 0, (size_t)n * n * sizeof(double), s));
             k_schur_diag<<<div_up(N, 128), 128, 0, s>>>(N, ba->acc.U, Dc, alpha, ba->Sred.p, n);
             KERNEL_POST(ctx);
+            tr.mark("vinv+memset+diag");
             if (ba->n_obs > 0) {
                 k_schur_pairs<<<pair_grid, kThreads, pair_warps_smem, s>>>(M, ba->lm_ptr.p, ba->s_cam.p, ba->cam_trig.p,
                                                                           ba->lm_trig.p, ba->Vinv.p, ba->max_degree,
                                                                           ba->Sred.p, n);
                 KERNEL_POST(ctx);
             }
+            tr.mark("schur_pairs");
             PROPAGATE(dense_potrf_lower(ctx, ba->Sred.p, n, n, flags.p + 1));
+            tr.mark("potrf");
             PROPAGATE(dense_diag_inverse(ctx, ba->Sred.p, n, n, dinv.p));
+            tr.mark("diag_inverse");
         }
+        tr.report("factor");
         ++n_factor;
         int h[2];
         CU_CHECK(ctx, cudaMemcpyAsync(h, flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -388,6 +445,7 @@ struct Solver {
 
     // y = (A + alpha D^2)^-1 rhs using the current factorisation; rhs / y in the full layout
     int solve(const double* rhs, double* y) {
+        tr.begin(s);
         const double* rhs_c = rhs;
         const double* rhs_l = rhs + 3 * N;
         double* red = ba->rhs_l.p;     // reduced camera rhs (full camera layout, slot 0 unused)
@@ -398,7 +456,9 @@ struct Solver {
                 ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p, ba->Vinv.p, rhs_l, N, use_smem, red);
             KERNEL_POST(ctx);
         }
+        tr.mark("reduce_rhs");
         if (n > 0) PROPAGATE(dense_potrs_dinv(ctx, ba->Sred.p, n, n, dinv.p, red + 3));
+        tr.mark("potrs");
         CU_CHECK(ctx, cudaMemcpyAsync(y, red, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CU_CHECK(ctx, cudaMemsetAsync(y, 0, 3 * sizeof(double), s));
         CU_CHECK(ctx, cudaMemsetAsync(tmp_l.p, 0, (size_t)2 * M * sizeof(double), s));
@@ -409,6 +469,8 @@ struct Solver {
         }
         k_backsub_final<<<div_up(M, 256), 256, 0, s>>>(M, ba->Vinv.p, rhs_l, tmp_l.p, y + 3 * N);
         KERNEL_POST(ctx);
+        tr.mark("backsub");
+        tr.report("solve");
         return PTZBA_OK;
     }
 

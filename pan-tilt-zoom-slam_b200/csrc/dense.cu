@@ -81,6 +81,63 @@ __global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ A0, int
         if (j < nb) A[(size_t)r + (size_t)(k + j) * lda] = x[j];
 }
 
+
+// ---- fused panel step: every CTA factors the NB x NB diagonal block redundantly in shared memory (128 threads, rsqrt on the
+// critical path) and then solves its own 128 rows of the panel; CTA 0 also writes the factored diagonal block back.
+// Replaces k_potf2 + k_trsm_panel (one launch less per panel and no single-warp kernel on the critical path).
+__global__ void __launch_bounds__(128) k_potf2_trsm(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
+                                                    int n_fixed, int k, int* __restrict__ info) {
+    const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
+    if (k >= n) return;
+    const int nb = (n - k) < NB ? (n - k) : NB;
+    double* A = A0 + stride * blockIdx.y;
+    __shared__ double L[NB][NB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 128) {
+        const int i = e % NB, j = e / NB;
+        L[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    bool bad = false;
+    for (int j = 0; j < NB; ++j) {
+        double piv = L[j][j];
+        if (!(piv > 0.0)) { bad = true; piv = 1.0; }
+        const double inv = rsqrt(piv);
+        __syncthreads();
+        if (tid < NB) {
+            if (tid == j) L[j][j] = piv * inv;
+            else if (tid > j) L[tid][j] *= inv;
+        }
+        __syncthreads();
+        // trailing update of the lower triangle: (i, c) with i >= c > j
+        for (int e = tid; e < NB * NB; e += 128) {
+            const int i = e % NB, c = e / NB;
+            if (c > j && i >= c) L[i][c] = fma(-L[i][j], L[c][j], L[i][c]);
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0 && blockIdx.x == 0) atomicMax(info, k + 1);
+    if (blockIdx.x == 0)
+        for (int e = tid; e < NB * NB; e += 128) {
+            const int i = e % NB, j = e / NB;
+            if (i < nb && j < nb && j <= i) A[(size_t)(k + i) + (size_t)(k + j) * lda] = L[i][j];
+        }
+    const int r = k + nb + blockIdx.x * 128 + tid;
+    if (r >= n || nb < NB) return;
+    double x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) x[j] = A[(size_t)r + (size_t)(k + j) * lda];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        double sacc = x[j];
+#pragma unroll
+        for (int t = 0; t < j; ++t) sacc = fma(-x[t], L[j][t], sacc);
+        x[j] = sacc / L[j][j];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) A[(size_t)r + (size_t)(k + j) * lda] = x[j];
+}
+
 // ---- syrk: C -= P P^T on the lower tiles of the trailing matrix; 256 threads, 4x4 outputs each -----------------------
 __global__ void __launch_bounds__(256) k_syrk_lower(double* __restrict__ A0, int lda, size_t stride,
                                                     const int* __restrict__ n_arr, int n_fixed, int k) {
@@ -217,12 +274,10 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
     cudaStream_t s = ctx->stream;
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
     for (int k = 0; k < n_max; k += NB) {
-        k_potf2<<<dim3(1, batch), 32, 0, s>>>(A, lda, stride, d_n_arr, n_max, k, d_info);
-        KERNEL_POST(ctx);
         const int m = n_max - k - NB;
-        if (m <= 0) break;
-        k_trsm_panel<<<dim3(div_up(m, 128), batch), 128, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
+        k_potf2_trsm<<<dim3(m > 0 ? div_up(m, 128) : 1, batch), 128, 0, s>>>(A, lda, stride, d_n_arr, n_max, k, d_info);
         KERNEL_POST(ctx);
+        if (m <= 0) break;
         const int nt = div_up(m, TS);
         k_syrk_lower<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
         KERNEL_POST(ctx);
@@ -390,16 +445,16 @@ __global__ void __launch_bounds__(1024) k_trsv_dinv(const double* __restrict__ L
         const int blk = backward ? (nblk - 1 - bi) : bi;
         const int k = blk * NB;
         const int nb = (n - k) < NB ? (n - k) : NB;
-        if (w == 0) {
-            // forward: x = Dinv * b_k ; backward: x = Dinv^T * b_k
+        {
+            // x = Dinv * b_k (forward) or Dinv^T * b_k (backward): warp w forms entry w, one product per lane, all loads
+            // independent (1024 threads = 32 x 32 entries of the block)
             const double* D = Dinv + (size_t)blk * NB * NB;
-            double s = 0.0;
-            for (int t = 0; t < nb; ++t) {
-                const double bt = bvec[k + t];
-                const double d = backward ? D[t + NB * lane] : D[lane + NB * t];
-                s = fma(d, bt, s);
-            }
-            xs[lane] = lane < nb ? s : 0.0;
+            const double bt = lane < nb ? bvec[k + lane] : 0.0;
+            const double d = backward ? D[lane + NB * w] : D[w + NB * lane];
+            double sacc = d * bt;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+            if (lane == 0) xs[w] = w < nb ? sacc : 0.0;
         }
         __syncthreads();
         if (w == 0 && lane < nb) bvec[k + lane] = xs[lane];
