@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-ekf", action="store_true")
-    ap.add_argument("--ekf-seqs", type=int, default=16)
+    ap.add_argument("--ekf-seqs", type=int, default=64)
     ap.add_argument("--ekf-rays", type=int, default=2000)
     ap.add_argument("--ekf-frames", type=int, default=4)
     ap.add_argument("--ramp", type=float, default=0.3, help="seconds of untimed passes before warm-up (clock ramp)")

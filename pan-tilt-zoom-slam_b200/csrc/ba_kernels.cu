@@ -665,114 +665,6 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
     }
 }
 
-// fused_variant 11/12: landmark-major quad pass with branch-free geometry: the four observations of a thread are projected
-// back to back (four independent FP64 dependency chains for the scheduler), the run logic follows on the finished partials.
-template <int MINB>
-__global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_lm_pass5(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
-              const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
-              const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
-              double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
-    extern __shared__ __align__(16) double smem[];      // keyframe trig, SoA [5][n_pose]
-    __shared__ double sWarp[kFusedThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
-        const int c = i / 5, e = i - 5 * c;
-        smem[(size_t)e * n_pose + c] = reinterpret_cast<const double*>(cam_trig)[i];
-    }
-    __syncthreads();
-    const int64_t begin = (int64_t)blockIdx.x * chunk;
-    int64_t end = begin + chunk;
-    if (end > n_obs) end = n_obs;
-    const double k1 = PTZ_DEG2RAD;
-    double cost = 0.0;
-    for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
-        const int64_t k0 = base + (int64_t)tid * kQuad;
-        int cam[kQuad], lm[kQuad];
-        double ox[kQuad], oy[kQuad];
-        if (k0 + kQuad <= end) {
-            const int4 c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
-            const int4 l4 = __ldg(reinterpret_cast<const int4*>(s_lm + k0));
-            const D4 x4 = *reinterpret_cast<const D4*>(s_ox + k0);
-            const D4 y4 = *reinterpret_cast<const D4*>(s_oy + k0);
-            cam[0] = c4.x; cam[1] = c4.y; cam[2] = c4.z; cam[3] = c4.w;
-            lm[0] = l4.x; lm[1] = l4.y; lm[2] = l4.z; lm[3] = l4.w;
-            ox[0] = x4.a; ox[1] = x4.b; ox[2] = x4.c; ox[3] = x4.d;
-            oy[0] = y4.a; oy[1] = y4.b; oy[2] = y4.c; oy[3] = y4.d;
-        } else {
-#pragma unroll
-            for (int i = 0; i < kQuad; ++i) {
-                const bool in = k0 + i < end;
-                cam[i] = in ? s_cam[k0 + i] : 0;
-                lm[i] = in ? s_lm[k0 + i] : -1;
-                ox[i] = in ? s_ox[k0 + i] : 0.0;
-                oy[i] = in ? s_oy[k0 + i] : 0.0;
-            }
-        }
-        LmTrig lt[kQuad];
-#pragma unroll
-        for (int i = 0; i < kQuad; ++i) lt[i] = lm_trig[lm[i] >= 0 ? lm[i] : 0];
-        double rx[kQuad], ry[kQuad], ptt[kQuad], ptp[kQuad], ppp[kQuad], plt[kQuad], plp[kQuad];
-#pragma unroll
-        for (int i = 0; i < kQuad; ++i) {
-            CamTrig c;
-            c.sp = smem[cam[i]]; c.cp = smem[n_pose + cam[i]]; c.st = smem[2 * n_pose + cam[i]];
-            c.ct = smem[3 * n_pose + cam[i]]; c.f = smem[4 * n_pose + cam[i]];
-            double x, y;
-            ObsGeom g;
-            project_fast_jac(c, lt[i], u, v, x, y, g);
-            const double act = lm[i] >= 0 ? 1.0 : 0.0;
-            rx[i] = (x - ox[i]) * act;
-            ry[i] = (y - oy[i]) * act;
-            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
-            const double kxa = k1 * g.xa * act, kya = k1 * g.ya * act, kxp = k1 * g.xp * act, kyp = k1 * g.yp * act;
-            ptt[i] = fma(kxa, kxa, kya * kya);
-            ptp[i] = fma(kxa, kxp, kya * kyp);
-            ppp[i] = fma(kxp, kxp, kyp * kyp);
-            plt[i] = fma(kxa, rx[i], kya * ry[i]);
-            plp[i] = fma(kxp, rx[i], kyp * ry[i]);
-        }
-        if (resid) {
-            if (!orig && k0 + kQuad <= end) {
-                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
-                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
-                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
-            } else {
-#pragma unroll
-                for (int i = 0; i < kQuad; ++i)
-                    if (lm[i] >= 0) {
-                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
-                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
-                    }
-            }
-        }
-        // runs inside the thread: a run that ends here is committed directly, the last one joins the warp reduction
-        int cur = lm[0];
-        double vtt = ptt[0], vtp = ptp[0], vpp = ppp[0], glt = plt[0], glp = plp[0];
-#pragma unroll
-        for (int i = 1; i < kQuad; ++i) {
-            if (lm[i] == cur) {
-                vtt += ptt[i]; vtp += ptp[i]; vpp += ppp[i]; glt += plt[i]; glp += plp[i];
-            } else {
-                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
-                cur = lm[i];
-                vtt = ptt[i]; vtp = ptp[i]; vpp = ppp[i]; glt = plt[i]; glp = plp[i];
-            }
-        }
-        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
-        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
-        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
-    }
-    cost = warp_sum(cost);
-    if (lane == 0) sWarp[tid >> 5] = cost;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0;
-        for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
-        atomicAdd(gCost, s);
-    }
-}
-
 template <int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_cam_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
@@ -1267,32 +1159,6 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
             case 2: LAUNCH_CM(1, 2); break;
             case 3: LAUNCH_CM(0, 3); break;
             case 4: LAUNCH_CM(1, 3); break;
-            case 11:
-            case 12: {
-                const int64_t q = (int64_t)kFusedThreads * kQuad;
-                const int gA = ctx->sm_count * 2, gB = ctx->sm_count * (ba->fused_variant == 11 ? 2 : 3);
-                int64_t chunkA = (ba->n_obs + gA - 1) / gA;
-                chunkA = (chunkA + q - 1) / q * q;
-                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass5<2><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
-                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
-                ctx->launches++;
-                if (ba->fused_variant == 11) {
-                    int64_t chunkB = (ba->n_obs + gB - 1) / gB;
-                    chunkB = (chunkB + q - 1) / q * q;
-                    const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
-                    k_ba_cam_pass4<2><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                                     ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
-                } else {
-                    int64_t chunkB = (ba->n_obs + gB - 1) / gB;
-                    chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
-                    const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
-                    k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                                    ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
-                }
-                break;
-            }
             case 10: {
                 const int64_t q = (int64_t)kFusedThreads * kQuad;
                 const int gA = ctx->sm_count * 4, gB = ctx->sm_count * 4;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ A0, int
 // critical path) and then solves its own 128 rows of the panel; CTA 0 also writes the factored diagonal block back.
 // Replaces k_potf2 + k_trsm_panel (one launch less per panel and no single-warp kernel on the critical path).
 __global__ void __launch_bounds__(128) k_potf2_trsm(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
-                                                    int n_fixed, int k, int* __restrict__ info) {
+                                                    int n_fixed, int k, int* __restrict__ info, int* __restrict__ info_b) {
     const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
     if (k >= n) return;
     const int nb = (n - k) < NB ? (n - k) : NB;
@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(128) k_potf2_trsm(double* __restrict__ A0, int
         }
         __syncthreads();
     }
-    if (bad && tid == 0 && blockIdx.x == 0) atomicMax(info, k + 1);
+    if (bad && tid == 0 && blockIdx.x == 0) {
+        atomicMax(info, k + 1);
+        if (info_b) info_b[blockIdx.y] = k + 1;
+    }
     if (blockIdx.x == 0)
         for (int e = tid; e < NB * NB; e += 128) {
             const int i = e % NB, j = e / NB;
@@ -270,12 +273,12 @@ __global__ void __launch_bounds__(1024) k_trsv_lower(const double* __restrict__ 
 }  // namespace
 
 int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
-                              int* d_info) {
+                              int* d_info, int* d_info_per_batch) {
     cudaStream_t s = ctx->stream;
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
     for (int k = 0; k < n_max; k += NB) {
         const int m = n_max - k - NB;
-        k_potf2_trsm<<<dim3(m > 0 ? div_up(m, 128) : 1, batch), 128, 0, s>>>(A, lda, stride, d_n_arr, n_max, k, d_info);
+        k_potf2_trsm<<<dim3(m > 0 ? div_up(m, 128) : 1, batch), 128, 0, s>>>(A, lda, stride, d_n_arr, n_max, k, d_info, d_info_per_batch);
         KERNEL_POST(ctx);
         if (m <= 0) break;
         const int nt = div_up(m, TS);
@@ -286,7 +289,7 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
 }
 
 int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info) {
-    return dense_potrf_lower_batched(ctx, A, lda, 0, nullptr, n, 1, d_info);
+    return dense_potrf_lower_batched(ctx, A, lda, 0, nullptr, n, 1, d_info, nullptr);
 }
 
 int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B, int ldb, int nrhs) {

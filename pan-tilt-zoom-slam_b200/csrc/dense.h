@@ -9,8 +9,9 @@ int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info);
 int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B, int ldb, int nrhs);
 
 // batched variants: matrix b lives at A + b*stride and has order d_n_arr[b] (device array; nullptr = n_max for all)
+// d_info_per_batch (may be nullptr): entry b is set non-zero when matrix b is not positive definite (must be pre-zeroed)
 int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
-                              int* d_info);
+                              int* d_info, int* d_info_per_batch);
 // Z = L^-1 G in place; G is ROW-major with d_n_arr[b] rows and d_n_arr[b] + extra_cols columns (leading dimension ldg)
 int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_t strideL, double* G, int ldg, size_t strideG,
                                  const int* d_n_arr, int n_max, int extra_cols, int batch);

@@ -37,8 +37,10 @@ struct ptzba_ekf_batch {
     DevBuf<double> Jc, Jr, y;
     // wave workspace
     int wave = 0, ldg = 0, lds = 0;
+    long n_lu_total = 0;               // waves that needed the LU route (diagnostic)
     DevBuf<double> G, X, S;
     DevBuf<int32_t> ipiv, perm;
+    DevBuf<int32_t> chol_fail, nm_chol, n2_chol, nm_lu, n2_lu;   // per-sequence path selection (Cholesky first, LU on breakdown)
 };
 
 namespace {
@@ -315,6 +317,32 @@ __global__ void __launch_bounds__(256) k_ekf_pp_blocks(int b0, int max_obs, cons
         }
 }
 
+
+// path selection after the Cholesky attempt: sequences whose S was positive definite finish on the Cholesky path, the others
+// are redone with pivoted LU (their n is zero on the other path, which makes every batched kernel skip them)
+__global__ void k_ekf_split(int n_seq, const int32_t* __restrict__ fail, const int32_t* __restrict__ n_mat,
+                            int32_t* __restrict__ nm_chol, int32_t* __restrict__ n2_chol, int32_t* __restrict__ nm_lu,
+                            int32_t* __restrict__ n2_lu) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_seq) return;
+    const int n = n_mat[b];
+    const bool f = fail[b] != 0;
+    nm_chol[b] = f ? 0 : n; n2_chol[b] = f ? 0 : 2 * n;
+    nm_lu[b] = f ? n : 0;   n2_lu[b] = f ? 2 * n : 0;
+}
+
+// X = G for the rows / columns in use (row-major, n2 rows, n2 + extra columns)
+__global__ void __launch_bounds__(256) k_copy_rows(const double* __restrict__ G0, double* __restrict__ X0, int ldg, size_t strideG,
+                                                   const int32_t* __restrict__ n2_arr, int extra_cols) {
+    const int b = blockIdx.z;
+    const int n = n2_arr[b];
+    const int i = blockIdx.y;
+    if (i >= n) return;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n + extra_cols) return;
+    X0[strideG * b + (size_t)i * ldg + c] = G0[strideG * b + (size_t)i * ldg + c];
+}
+
 __global__ void k_ekf_init_cov(int n_seq, int s_tot, double* __restrict__ P, size_t strideP, double angle_var, double f_var) {
     // state_cov = angle_var * I ; [2][2] = f_var   (ptz_slam.py:199-200); P is pre-zeroed
     const int b = blockIdx.y;
@@ -333,7 +361,7 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched) {
                                                         B->prm.f_var);
         KERNEL_POST(ctx);
     }
-    CU_CHECK(ctx, cudaMemsetAsync(B->flags.p, 0, 4 * sizeof(int), s));
+    CU_CHECK(ctx, cudaMemsetAsync(B->flags.p, 0, 8 * sizeof(int), s));
     k_ekf_match<<<n_seq, kT, 0, s>>>(B->n_ray, max_obs, B->ptz.p, B->rays.p, B->has_disp ? B->disp.p : nullptr, B->prm,
                                      B->obs_xy.p, B->obs_idx.p, B->obs_cnt.p, B->n_mat.p, B->n2.p, B->m_ray.p, B->y.p, B->Jc.p,
                                      B->Jr.p, B->flags.p);
@@ -359,18 +387,60 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched) {
         k_ekf_S<<<dim3(div_up(n_max, 128), 2 * n_max, wb), 128, 0, s>>>(b0, max_obs, B->n_mat.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
                                                                        strideG, B->S.p, B->lds, strideS, B->prm.observe_var);
         KERNEL_POST(ctx);
-        PROPAGATE(dense_getrf_batched(ctx, B->S.p, B->lds, strideS, B->n2.p + b0, 2 * n_max, wb, B->ipiv.p, B->lds, B->flags.p + 2));
-        PROPAGATE(dense_getrs_rows_batched(ctx, B->S.p, B->lds, strideS, B->ipiv.p, B->perm.p, B->lds, B->G.p, B->X.p, B->ldg, strideG,
-                                           B->n2.p + b0, 2 * n_max, 4, wb));
-        k_ekf_delta<<<dim3(div_up(s_max, kT), wb), kT, 0, s>>>(b0, max_obs, B->n_ray, B->n_mat.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
-                                                              strideG, B->ptz.p, B->vel.p, B->rays.p);
-        KERNEL_POST(ctx);
-        k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->n_mat.p, B->G.p, B->X.p, B->ldg, strideG, B->P.p, strideP, s_tot);
-        KERNEL_POST(ctx);
+        // ---- Cholesky first: S is positive definite for most sequence-frames; pivoted LU only where it breaks down ----
         const int nt = div_up(n_max, 64);
-        k_ekf_pp_blocks<<<dim3(nt * (nt + 1) / 2, 2, wb), 256, 0, s>>>(b0, max_obs, B->n_mat.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
-                                                                      strideG, B->P.p, strideP, s_tot);
+        CU_CHECK(ctx, cudaMemsetAsync(B->chol_fail.p + b0, 0, (size_t)wb * sizeof(int32_t), s));
+        PROPAGATE(dense_potrf_lower_batched(ctx, B->S.p, B->lds, strideS, B->n2.p + b0, 2 * n_max, wb, B->flags.p + 3,
+                                            B->chol_fail.p + b0));
+        k_ekf_split<<<div_up(wb, 128), 128, 0, s>>>(wb, B->chol_fail.p + b0, B->n_mat.p + b0, B->nm_chol.p + b0, B->n2_chol.p + b0,
+                                                   B->nm_lu.p + b0, B->n2_lu.p + b0);
         KERNEL_POST(ctx);
+        std::vector<int32_t> h_fail(wb);
+        CU_CHECK(ctx, cudaMemcpyAsync(h_fail.data(), B->chol_fail.p + b0, (size_t)wb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        int n_max_chol = 0, n_max_lu = 0;
+        for (int q = 0; q < wb; ++q) {
+            if (h_fail[q]) n_max_lu = std::max(n_max_lu, (int)h_n[b0 + q]);
+            else n_max_chol = std::max(n_max_chol, (int)h_n[b0 + q]);
+        }
+        if (n_max_chol > 0) {
+            // Z = L^-1 [G | y] in X ; delta = Z^T z_y ; P+ = P - Z^T Z   (same kernels with G := X := Z)
+            const int sm = 3 + 2 * n_max_chol;
+            k_copy_rows<<<dim3(div_up(sm + 1, 256), 2 * n_max_chol, wb), 256, 0, s>>>(B->G.p, B->X.p, B->ldg, strideG, B->n2_chol.p + b0, 4);
+            KERNEL_POST(ctx);
+            PROPAGATE(dense_fwd_solve_rows_batched(ctx, B->S.p, B->lds, strideS, B->X.p, B->ldg, strideG, B->n2_chol.p + b0,
+                                                   2 * n_max_chol, 4, wb));
+            k_ekf_delta<<<dim3(div_up(sm, kT), wb), kT, 0, s>>>(b0, max_obs, B->n_ray, B->nm_chol.p, B->m_ray.p, B->X.p, B->X.p, B->ldg,
+                                                               strideG, B->ptz.p, B->vel.p, B->rays.p);
+            KERNEL_POST(ctx);
+            k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->nm_chol.p, B->X.p, B->X.p, B->ldg, strideG, B->P.p, strideP, s_tot);
+            KERNEL_POST(ctx);
+            const int ntc = div_up(n_max_chol, 64);
+            k_ekf_pp_blocks<<<dim3(ntc * (ntc + 1) / 2, 2, wb), 256, 0, s>>>(b0, max_obs, B->nm_chol.p, B->m_ray.p, B->X.p, B->X.p, B->ldg,
+                                                                            strideG, B->P.p, strideP, s_tot);
+            KERNEL_POST(ctx);
+        }
+        if (n_max_lu > 0) {
+            // indefinite S (the reference's write-back made P indefinite): rebuild S and take the getrf route
+            const int sm = 3 + 2 * n_max_lu;
+            k_ekf_S<<<dim3(div_up(n_max_lu, 128), 2 * n_max_lu, wb), 128, 0, s>>>(b0, max_obs, B->nm_lu.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
+                                                                                 strideG, B->S.p, B->lds, strideS, B->prm.observe_var);
+            KERNEL_POST(ctx);
+            PROPAGATE(dense_getrf_batched(ctx, B->S.p, B->lds, strideS, B->n2_lu.p + b0, 2 * n_max_lu, wb, B->ipiv.p, B->lds, B->flags.p + 2));
+            PROPAGATE(dense_getrs_rows_batched(ctx, B->S.p, B->lds, strideS, B->ipiv.p, B->perm.p, B->lds, B->G.p, B->X.p, B->ldg, strideG,
+                                               B->n2_lu.p + b0, 2 * n_max_lu, 4, wb));
+            k_ekf_delta<<<dim3(div_up(sm, kT), wb), kT, 0, s>>>(b0, max_obs, B->n_ray, B->nm_lu.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
+                                                               strideG, B->ptz.p, B->vel.p, B->rays.p);
+            KERNEL_POST(ctx);
+            k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->nm_lu.p, B->G.p, B->X.p, B->ldg, strideG, B->P.p, strideP, s_tot);
+            KERNEL_POST(ctx);
+            const int ntl = div_up(n_max_lu, 64);
+            k_ekf_pp_blocks<<<dim3(ntl * (ntl + 1) / 2, 2, wb), 256, 0, s>>>(b0, max_obs, B->nm_lu.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
+                                                                            strideG, B->P.p, strideP, s_tot);
+            KERNEL_POST(ctx);
+            B->n_lu_total += 1;
+        }
+        (void)nt;
     }
     int info = 0;
     CU_CHECK(ctx, cudaMemcpyAsync(&info, B->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -413,12 +483,14 @@ extern "C" int ptzba_ekf_batch_create(ptzba_ctx* ctx, const ptzba_ekf_params* pr
     CU_TRY(B->ptz.alloc((size_t)n_seq * 3)); CU_TRY(B->vel.alloc((size_t)n_seq * 3)); CU_TRY(B->disp.alloc(6));
     CU_TRY(B->obs_xy.alloc((size_t)n_seq * max_obs * 2)); CU_TRY(B->obs_idx.alloc((size_t)n_seq * max_obs));
     CU_TRY(B->obs_cnt.alloc(n_seq)); CU_TRY(B->n_mat.alloc(n_seq)); CU_TRY(B->n2.alloc(n_seq));
-    CU_TRY(B->m_ray.alloc((size_t)n_seq * max_obs)); CU_TRY(B->flags.alloc(4));
+    CU_TRY(B->m_ray.alloc((size_t)n_seq * max_obs)); CU_TRY(B->flags.alloc(8));
     CU_TRY(B->Jc.alloc((size_t)n_seq * max_obs * 6)); CU_TRY(B->Jr.alloc((size_t)n_seq * max_obs * 4));
     CU_TRY(B->y.alloc((size_t)n_seq * max_obs * 2));
     CU_TRY(B->G.alloc((size_t)B->wave * B->ldg * 2 * (size_t)max_obs)); CU_TRY(B->X.alloc((size_t)B->wave * B->ldg * 2 * (size_t)max_obs));
     CU_TRY(B->S.alloc((size_t)B->wave * B->lds * B->lds));
     CU_TRY(B->ipiv.alloc((size_t)B->wave * B->lds)); CU_TRY(B->perm.alloc((size_t)B->wave * B->lds));
+    CU_TRY(B->chol_fail.alloc(n_seq)); CU_TRY(B->nm_chol.alloc(n_seq)); CU_TRY(B->n2_chol.alloc(n_seq));
+    CU_TRY(B->nm_lu.alloc(n_seq)); CU_TRY(B->n2_lu.alloc(n_seq));
     if (n_ray) CU_TRY(cudaMemcpyAsync(B->rays.p, rays0, (size_t)n_seq * n_ray * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(B->ptz.p, ptz0, (size_t)n_seq * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(B->disp.p, prm->disp, 6 * sizeof(double), cudaMemcpyHostToDevice, s));
