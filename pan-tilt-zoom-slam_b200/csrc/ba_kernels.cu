@@ -106,14 +106,18 @@ __global__ void k_set_params(int n_pose, int n_lm, const double* __restrict__ x,
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
 
-// sum of v over the run of equal keys that starts at this lane (keys are non-decreasing inside the warp)
+// sum of v over the run of equal keys that starts at this lane (keys are non-decreasing inside the warp).
+// Keys are sorted, so once no lane has an equal key at distance `off` none has one further away: the remaining steps
+// (10 SHFL each) are skipped - runs are ~5 lanes long in the quad kernels, i.e. 3 of 5 steps are usually enough.
 __device__ __forceinline__ void seg_reduce5(int key, int lane, double& a, double& b, double& c, double& d, double& e) {
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const int ok = __shfl_down_sync(0xffffffffu, key, off);
+        const bool eq = (lane + off < 32) && (ok == key) && (key >= 0);
+        if (!__any_sync(0xffffffffu, eq)) break;
         const double ta = shfl_down_d(a, off), tb = shfl_down_d(b, off), tc = shfl_down_d(c, off),
                      td = shfl_down_d(d, off), te = shfl_down_d(e, off);
-        if (lane + off < 32 && ok == key) { a += ta; b += tb; c += tc; d += td; e += te; }
+        if (eq) { a += ta; b += tb; c += tc; d += td; e += te; }
     }
 }
 
@@ -570,12 +574,12 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
               const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
               double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
-    extern __shared__ __align__(16) double smem[];      // keyframe trig, SoA [5][n_pose]
+    extern __shared__ __align__(16) double smem[];      // keyframe trig, 48 B per keyframe: {sp,cp} {st,ct} {f,-}: two LDS.128 + one LDS.64
     __shared__ double sWarp[kFusedThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
         const int c = i / 5, e = i - 5 * c;
-        smem[(size_t)e * n_pose + c] = reinterpret_cast<const double*>(cam_trig)[i];
+        smem[(size_t)c * 6 + e] = reinterpret_cast<const double*>(cam_trig)[i];
     }
     __syncthreads();
     const int64_t begin = (int64_t)blockIdx.x * chunk;
@@ -621,8 +625,11 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
                 vtt = vtp = vpp = glt = glp = 0.0;
             }
             CamTrig c;
-            c.sp = smem[cam[i]]; c.cp = smem[n_pose + cam[i]]; c.st = smem[2 * n_pose + cam[i]];
-            c.ct = smem[3 * n_pose + cam[i]]; c.f = smem[4 * n_pose + cam[i]];
+            {
+                const double2* t = reinterpret_cast<const double2*>(smem + (size_t)cam[i] * 6);
+                const double2 pa = t[0], ti = t[1];
+                c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = smem[(size_t)cam[i] * 6 + 4];
+            }
             double x, y;
             ObsGeom g;
             project_fast_jac(c, lt, u, v, x, y, g);
@@ -863,7 +870,7 @@ k_ba_lm_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_
     }
     for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
         const int c = i / 5, e = i - 5 * c;
-        sCam[(size_t)e * n_pose + c] = reinterpret_cast<const double*>(cam_trig)[i];
+        sCam[(size_t)c * 6 + e] = reinterpret_cast<const double*>(cam_trig)[i];
     }
     __syncthreads();
     if (tid == 0)
@@ -916,8 +923,11 @@ k_ba_lm_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_
                 vtt = vtp = vpp = glt = glp = 0.0;
             }
             CamTrig c;
-            c.sp = sCam[cam[i]]; c.cp = sCam[n_pose + cam[i]]; c.st = sCam[2 * n_pose + cam[i]];
-            c.ct = sCam[3 * n_pose + cam[i]]; c.f = sCam[4 * n_pose + cam[i]];
+            {
+                const double2* tq = reinterpret_cast<const double2*>(sCam + (size_t)cam[i] * 6);
+                const double2 pa = tq[0], ti = tq[1];
+                c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = sCam[(size_t)cam[i] * 6 + 4];
+            }
             double x, y;
             ObsGeom g;
             project_fast_jac(c, lt, u, v, x, y, g);
@@ -1165,7 +1175,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 int64_t chunkA = (ba->n_obs + gA - 1) / gA;
                 chunkA = (chunkA + q - 1) / q * q;
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass4<4><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                k_ba_lm_pass4<4><<<gridA, kFusedThreads, (size_t)ba->n_pose * 6 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
                     ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
                 ctx->launches++;
@@ -1178,7 +1188,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
             }
             case 9: {
                 const int64_t n_tiles = (ba->n_obs + kTile - 1) / kTile;
-                const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)ba->n_pose * 5 * sizeof(double);
+                const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)ba->n_pose * 6 * sizeof(double);
                 const size_t smB = sizeof(TileBuf) * kStages;
                 int tpcA = (int)((n_tiles + ba->grid_tma_lm - 1) / ba->grid_tma_lm);
                 int tpcB = (int)((n_tiles + ba->grid_tma_cam - 1) / ba->grid_tma_cam);
@@ -1198,7 +1208,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;
                 chunkA = (chunkA + q - 1) / q * q;
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 6 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
                     ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
                 ctx->launches++;
@@ -1214,7 +1224,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 int64_t chunkA = (ba->n_obs + ba->grid_lm_pass4 - 1) / ba->grid_lm_pass4;
                 chunkA = (chunkA + q - 1) / q * q;
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 5 * sizeof(double), s>>>(
+                k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 6 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
                     ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
                 ctx->launches++;
@@ -1416,7 +1426,7 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     if (ba->fused_variant >= 1) {
         {
             int pa = 1, pb = 1;
-            const size_t sm5 = (size_t)n_pose * 5 * sizeof(double);
+            const size_t sm5 = (size_t)n_pose * 6 * sizeof(double);
             if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass, kFusedThreads, sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<3>, kFusedThreads, 0));
@@ -1427,7 +1437,7 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
             ba->grid_lm_pass4 = ctx->sm_count * (pa4 < 1 ? 1 : pa4);
             ba->grid_cam_pass4 = ctx->sm_count * (pb4 < 1 ? 1 : pb4);
             {
-                const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)n_pose * 5 * sizeof(double);
+                const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)n_pose * 6 * sizeof(double);
                 const size_t smB = sizeof(TileBuf) * kStages;
                 int qa = 1, qb = 1;
                 if (smA <= 220 * 1024) {
