@@ -1167,25 +1167,6 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         switch (ba->fused_variant) {
             case 1: LAUNCH_CM(0, 2); break;
             case 2: LAUNCH_CM(1, 2); break;
-            case 3: LAUNCH_CM(0, 3); break;
-            case 4: LAUNCH_CM(1, 3); break;
-            case 10: {
-                const int64_t q = (int64_t)kFusedThreads * kQuad;
-                const int gA = ctx->sm_count * 4, gB = ctx->sm_count * 4;
-                int64_t chunkA = (ba->n_obs + gA - 1) / gA;
-                chunkA = (chunkA + q - 1) / q * q;
-                const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-                k_ba_lm_pass4<4><<<gridA, kFusedThreads, (size_t)ba->n_pose * 6 * sizeof(double), s>>>(
-                    ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
-                ctx->launches++;
-                int64_t chunkB = (ba->n_obs + gB - 1) / gB;
-                chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
-                const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
-                k_ba_cam_pass<4><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                                ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
-                break;
-            }
             case 9: {
                 const int64_t n_tiles = (ba->n_obs + kTile - 1) / kTile;
                 const size_t smA = sizeof(TileBuf) * kStages + sizeof(LmTrig) * kTileTrig * kStages + (size_t)ba->n_pose * 6 * sizeof(double);
@@ -1467,8 +1448,6 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         switch (ba->fused_variant) {
             case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<0, 2>, kFusedThreads, 0)); break;
             case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 2>, kFusedThreads, 0)); break;
-            case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<0, 3>, kFusedThreads, 0)); break;
-            case 4: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<1, 3>, kFusedThreads, 0)); break;
             default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_fused_cm<2, 3>, kFusedThreads, 0)); break;
         }
     }
