@@ -210,8 +210,7 @@ def bundle_adjustment(images, image_indices, feature_method, initial_ptzs, cente
     """bundle_adjustment.py:109-251.  Step 1 (SIFT/ORB matching, image_process.build_matching_graph) is the vision
     front-end and is out of scope of this library: pass it as `build_matching_graph`
     (a callable with the reference's signature (images, image_match_mask, feature_method, verbose) -> the 7-tuple
-    of bundle_adjustment.py:147-150).  Steps 2-5 follow the reference; keyframes are returned as dicts carrying the
-    fields the reference stores on KeyFrame objects (:219-246)."""
+    of bundle_adjustment.py:147-150).  Steps 2-5 follow the reference and return KeyFrame objects (:214-248)."""
     N = len(images)
     initial_ptzs = np.asarray(initial_ptzs, dtype=np.float64)
     center, rotation = np.asarray(center), np.asarray(rotation)
@@ -233,6 +232,7 @@ def bundle_adjustment(images, image_indices, feature_method, initial_ptzs, cente
         build_matching_graph(images, mask, feature_method, verbose)
     all_poses, optimized_landmarks, _ = bundle_adjustment_core(points, src_pt_index, dst_pt_index, landmark_index,
                                                                n_landmark, initial_ptzs, u, v, verbose=verbose)
+    from .key_frame import KeyFrame
     keyframes = []
     for i in range(N):
         pairs = set()
@@ -241,11 +241,11 @@ def bundle_adjustment(images, image_indices, feature_method, initial_ptzs, cente
             pairs.update(zip(dst_pt_index[j][i], landmark_index[j][i]))
         local_index = [p[0] for p in pairs]
         global_index = [p[1] for p in pairs]
-        keyframes.append(dict(img=images[i], img_index=image_indices[i], center=center, base_rotation=rotation, u=u, v=v,
-                              pan=all_poses[i, 0], tilt=all_poses[i, 1], f=all_poses[i, 2],
-                              feature_pts=[keypoints[i][j] for j in local_index],
-                              feature_des=None if descriptors is None else np.asarray(descriptors[i]).take(local_index, axis=0),
-                              landmark_index=np.array(global_index, dtype=np.int32)))
+        key_frame = KeyFrame(images[i], image_indices[i], center, rotation, u, v, all_poses[i, 0], all_poses[i, 1], all_poses[i, 2])
+        key_frame.feature_pts = [keypoints[i][j] for j in local_index]                      # bundle_adjustment.py:243-245
+        key_frame.feature_des = None if descriptors is None else np.asarray(descriptors[i]).take(local_index, axis=0)
+        key_frame.landmark_index = np.array(global_index, dtype=np.int32)
+        keyframes.append(key_frame)
     return optimized_landmarks, keyframes
 
 

@@ -1408,11 +1408,11 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         {
             int pa = 1, pb = 1;
             const size_t sm5 = (size_t)n_pose * 6 * sizeof(double);
-            if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+            if (sm5 > 40 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass, kFusedThreads, sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<3>, kFusedThreads, 0));
             int pa4 = 1, pb4 = 1;
-            if (sm5 > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+            if (sm5 > 40 * 1024) CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa4, k_ba_lm_pass4<3>, kFusedThreads, sm5));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb4, k_ba_cam_pass4<3>, kFusedThreads, 0));
             ba->grid_lm_pass4 = ctx->sm_count * (pa4 < 1 ? 1 : pa4);

@@ -400,7 +400,7 @@ struct Solver {
                               ba->max_degree);
         pair_warps_smem = (int)need;
         CU_CHECK(ctx, cudaFuncSetAttribute(k_schur_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_warps_smem));
-        if ((size_t)N * 3 * sizeof(double) > 48 * 1024)
+        if ((size_t)N * 3 * sizeof(double) > 40 * 1024)
             CU_CHECK(ctx, cudaFuncSetAttribute(k_reduce_rhs, cudaFuncAttributeMaxDynamicSharedMemorySize, N * 3 * (int)sizeof(double)));
         int per_sm = 1;
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_schur_pairs, kThreads, pair_warps_smem));

@@ -1,0 +1,79 @@
+"""
+Keyframe map orchestration, image-free (reference: slam_system/scene_map.py:18-149).
+
+`Map` keeps the keyframe list and the global ray landmarks; `add_keyframe_with_ba` re-runs bundle adjustment over all
+keyframes on the GPU (bundle_adjustment.bundle_adjustment -> libptzba) and `good_new_keyframe` is the pan-overlap rule.
+The vision front-end that matches keyframe images is injected (`build_matching_graph`), as in bundle_adjustment().
+"""
+import time
+
+import numpy as np
+
+from .bundle_adjustment import bundle_adjustment, overlap_pan_angle
+from .key_frame import KeyFrame
+
+
+class Map:
+    def __init__(self, feature_method, build_matching_graph=None):
+        assert feature_method in ('sift', 'orb', 'latch')
+        self.global_ray = np.ndarray([0, 2])        # [N, 2] float64 ray landmarks
+        self.keyframe_list = []
+        self.feature_method = feature_method
+        self.build_matching_graph = build_matching_graph
+        self.last_ba_seconds = None
+
+    def add_first_keyframe(self, keyframe, verbose=False):
+        """scene_map.py:30-40: first keyframe, no bundle adjustment."""
+        assert isinstance(keyframe, KeyFrame)
+        self.keyframe_list = [keyframe]
+        if verbose:
+            print('first key frame is added, no bundle adjustment and landmark')
+
+    def add_keyframe_without_ba(self, keyframe, verbose=False):
+        """scene_map.py:42-51."""
+        assert isinstance(keyframe, KeyFrame)
+        self.keyframe_list.append(keyframe)
+
+    def add_keyframe_with_ba(self, keyframe, save_path, verbose=False):
+        """scene_map.py:53-117: add one keyframe and bundle-adjust all keyframes; the map is replaced by the result."""
+        assert isinstance(keyframe, KeyFrame)
+        assert len(self.keyframe_list) >= 1
+        ref_frame = self.keyframe_list[0]
+        camera_center, base_rotation = ref_frame.center, ref_frame.base_rotation
+        u, v = ref_frame.u, ref_frame.v
+        self.add_keyframe_without_ba(keyframe, False)
+        N = len(self.keyframe_list)
+        images, image_indices = [], []
+        initial_ptzs = np.zeros((N, 3))
+        for i, kf in enumerate(self.keyframe_list):
+            images.append(kf.img)
+            image_indices.append(kf.img_index)
+            initial_ptzs[i] = kf.pan, kf.tilt, kf.f
+        start = time.time()
+        landmarks, keyframes = bundle_adjustment(images, image_indices, self.feature_method, initial_ptzs, camera_center,
+                                                 base_rotation, u, v, save_path, verbose,
+                                                 build_matching_graph=self.build_matching_graph)
+        self.last_ba_seconds = time.time() - start
+        self.keyframe_list.pop()
+        self.global_ray = landmarks
+        self.keyframe_list = []
+        for i, kf in enumerate(keyframes):
+            if kf.get_feature_num() > 0:
+                self.keyframe_list.append(kf)
+            elif verbose:
+                print('warning: key frame, %d, image index %d is not included in the map' % (i, image_indices[i]))
+        if verbose:
+            print('updated map, number of key frame: %d, number of landmark %d' % (len(self.keyframe_list), len(landmarks)))
+        return landmarks, self.keyframe_list
+
+    def good_new_keyframe(self, ptz, threshold1=5, threshold2=20, im_width=1280, verbose=False):
+        """scene_map.py:119-149: True when the largest pan overlap with the existing keyframes lies in (threshold1, threshold2)."""
+        ptz = np.asarray(ptz)
+        assert ptz.shape[0] == 3
+        if len(self.keyframe_list) == 0:
+            return False
+        overlaps = [overlap_pan_angle(ptz[2], ptz[0], kf.f, kf.pan, im_width) for kf in self.keyframe_list]
+        if verbose:
+            print('candidate key frame overlap: ', overlaps)
+        max_overlap = max(overlaps)
+        return max_overlap > threshold1 and max_overlap < threshold2

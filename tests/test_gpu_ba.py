@@ -148,7 +148,7 @@ def test_bundle_adjustment_core_matches_reference():
     lms, kfs = BA.bundle_adjustment([None] * N, list(range(N)), 'sift', d["ptz_init"], np.zeros(3), np.eye(3),
                                     d["uv"][0], d["uv"][1], "/tmp", build_matching_graph=lambda *a: graph)
     np.testing.assert_allclose(lms, landmarks, rtol=0, atol=1e-12)
-    assert len(kfs) == N and kfs[1]["landmark_index"].dtype == np.int32
+    assert len(kfs) == N and kfs[1].landmark_index.dtype == np.int32 and kfs[1].get_feature_num() > 0
 
 
 @pytest.mark.parametrize("n_kf,n_lm,n_obs", [(10, 300, 1500), (40, 4000, 40000)])
