@@ -31,6 +31,7 @@ struct ptzba_ba {
     // keyframe blocks accumulate in registers, landmark blocks go to L2 with RED atomics
     DevBuf<int32_t> c_cam, c_lm, c_orig;
     DevBuf<double> c_ox, c_oy;
+    int l2_pf = 0;                  // iterations of look-ahead of the L2 bulk prefetch in the two-pass kernels (0 = off)
     int fused_variant = 8;          // see ba_fused_pass(): 0 one pass + smem atomics ... 8 two coherent passes (default)
     // current parameters
     DevBuf<double> poses;           // [N*3] incl. reference pose at 0
@@ -52,6 +53,11 @@ struct ptzba_ba {
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int fused_grid = 0, fused_grid_lm = 0, fused_smem = 0, grid_lm_pass = 0, grid_cam_pass = 0, grid_lm_pass4 = 0, grid_cam_pass4 = 0, grid_tma_lm = 0, grid_tma_cam = 0;
+    int dual_grid = 0, dual_lm_ctas = 0, dual_camrep = 1, dual_only = 0;   // fused_variant 13: CTAs, landmark-role CTAs, table copies
+    // fused_variant 14 (single pass): static per-tile keyframe sort
+    int one_grid = 0, one_tiles_per_cta = 0, one_debug = 0;
+    int64_t one_chunk = 0;
+    DevBuf<uint16_t> kslot, kptr;
     DevBuf<int2> tile_lm;           // per 1024-observation tile: (first landmark id, number of landmark ids)
     bool fused_cam_smem = true;
 };

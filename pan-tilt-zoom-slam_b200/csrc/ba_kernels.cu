@@ -104,6 +104,11 @@ __global__ void k_set_params(int n_pose, int n_lm, const double* __restrict__ x,
 // ---------------------------------------------------------------------------------------------------------------
 // fused residual + Jacobian + normal-equation assembly
 // ---------------------------------------------------------------------------------------------------------------
+// L2 prefetch of a contiguous byte range (no registers, no shared memory): the demand loads that follow hit L2
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
 
 // sum of v over the run of equal keys that starts at this lane (keys are non-decreasing inside the warp).
@@ -471,7 +476,8 @@ template <int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_cam_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
               const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
-              const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
+              const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc,
+              int pf) {
     const int tid = threadIdx.x, lane = tid & 31;
     const double k1 = PTZ_DEG2RAD;
     const int64_t begin = (int64_t)blockIdx.x * chunk;
@@ -501,6 +507,15 @@ k_ba_cam_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, c
     LmTrig lt = {0, 1, 0, 1};
     if (k < end) { cam = c_cam[k]; lm = c_lm[k]; ox = c_ox[k]; oy = c_oy[k]; lt = lm_trig[lm]; }
     for (int64_t base = begin; base < end; base += kFusedThreads) {
+        if (pf > 0 && tid < 4 && ((base - begin) & (4 * kFusedThreads - 1)) == 0) {
+            const int64_t pb = base + (int64_t)pf * 4 * kFusedThreads;
+            if (pb + 4 * kFusedThreads <= end) {
+                if (tid == 0) l2_prefetch(c_cam + pb, kFusedThreads * 4 * 4);
+                else if (tid == 1) l2_prefetch(c_lm + pb, kFusedThreads * 4 * 4);
+                else if (tid == 2) l2_prefetch(c_ox + pb, kFusedThreads * 4 * 8);
+                else l2_prefetch(c_oy + pb, kFusedThreads * 4 * 8);
+            }
+        }
         const bool act = k < end;
         const int64_t kn = k + kFusedThreads;
         int ncam = -1, nlm = 0;
@@ -573,7 +588,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
               const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
-              double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+              double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost,
+              int pf) {
     extern __shared__ __align__(16) double smem[];      // keyframe trig, 48 B per keyframe: {sp,cp} {st,ct} {f,-}: two LDS.128 + one LDS.64
     __shared__ double sWarp[kFusedThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -588,6 +604,16 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
     const double k1 = PTZ_DEG2RAD;
     double cost = 0.0;
     for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
+        if (pf > 0 && tid < 4) {
+            // one lane per stream asks L2 for the CTA's 1024 observations `pf` iterations ahead
+            const int64_t pb = base + (int64_t)pf * kFusedThreads * kQuad;
+            if (pb + kFusedThreads * kQuad <= end) {
+                if (tid == 0) l2_prefetch(s_cam + pb, kFusedThreads * kQuad * 4);
+                else if (tid == 1) l2_prefetch(s_lm + pb, kFusedThreads * kQuad * 4);
+                else if (tid == 2) l2_prefetch(s_ox + pb, kFusedThreads * kQuad * 8);
+                else l2_prefetch(s_oy + pb, kFusedThreads * kQuad * 8);
+            }
+        }
         const int64_t k0 = base + (int64_t)tid * kQuad;
         int cam[kQuad], lm[kQuad];
         double ox[kQuad], oy[kQuad];
@@ -769,6 +795,530 @@ k_ba_cam_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fused_variant 13: ONE launch, two CTA roles running side by side on every SM.
+//   landmark role  (k_ba_lm_pass4's work): residual, cost, V / g_l, quads of consecutive observations per thread
+//   keyframe role  (k_ba_cam_pass's work): U / g_c in registers, one observation per thread
+// The two roles touch disjoint accumulators, so they need no ordering; launched together they overlap each other's
+// memory latency and share the FP64 / LSU pipes, and the second launch (and its tail) disappears.
+// Both roles are software pipelined TWO iterations deep: index loads run two iterations ahead, so that the dependent
+// landmark-trig gather (address = a loaded index) can itself be issued a full iteration before its use.
+// CAMREP = 8 replicates the keyframe trig table 8x in shared memory, one copy per 16-byte bank group, so that the
+// per-observation keyframe lookups (random rows) are bank-conflict free: lane l reads copy (l & 7).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDualThreads = 256;
+
+template <int CAMREP>
+__device__ __forceinline__ void dual_fill_cam(double* __restrict__ sCam, const CamTrig* __restrict__ cam_trig, int n_pose) {
+    const int tid = threadIdx.x;
+    if (CAMREP == 1) {
+        for (int i = tid; i < n_pose * 5; i += kDualThreads) {
+            const int c = i / 5, e = i - 5 * c;
+            sCam[(size_t)c * 6 + e] = reinterpret_cast<const double*>(cam_trig)[i];
+        }
+    } else {
+        // part j in {0: (sp,cp), 1: (st,ct), 2: (f,0)}; entry (row c, copy g) at ((j * n_pose + c) * 8 + g) * 16 bytes
+        double2* s2 = reinterpret_cast<double2*>(sCam);
+        for (int i = tid; i < n_pose * 3 * 8; i += kDualThreads) {
+            const int cj = i >> 3, c = cj % n_pose, j = cj / n_pose;
+            const double* t = reinterpret_cast<const double*>(cam_trig) + 5 * (size_t)c;
+            s2[i] = (j == 0) ? make_double2(t[0], t[1]) : (j == 1) ? make_double2(t[2], t[3]) : make_double2(t[4], 0.0);
+        }
+    }
+}
+
+template <int CAMREP>
+__device__ __forceinline__ CamTrig dual_cam(const double* __restrict__ sCam, int cam, int n_pose, int lane) {
+    CamTrig c;
+    if (CAMREP == 1) {
+        const double2* t = reinterpret_cast<const double2*>(sCam + (size_t)cam * 6);
+        const double2 pa = t[0], ti = t[1];
+        c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = sCam[(size_t)cam * 6 + 4];
+    } else {
+        const double2* s2 = reinterpret_cast<const double2*>(sCam) + (lane & 7);
+        const double2 pa = s2[(size_t)cam * 8], ti = s2[((size_t)n_pose + cam) * 8], ff = s2[((size_t)2 * n_pose + cam) * 8];
+        c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = ff.x;
+    }
+    return c;
+}
+
+template <int CAMREP>
+__device__ __forceinline__ void dual_lm_role(const double* __restrict__ sCam, double* __restrict__ sWarp, int64_t begin,
+                                             int64_t end, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+                                             const double* __restrict__ s_ox, const double* __restrict__ s_oy,
+                                             const int32_t* __restrict__ orig, const LmTrig* __restrict__ lm_trig, int n_pose,
+                                             double u, double v, double* __restrict__ resid, double* __restrict__ gV,
+                                             double* __restrict__ gGl, double* __restrict__ gCost) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int64_t kStep = (int64_t)kDualThreads * kQuad;
+    const double k1 = PTZ_DEG2RAD;
+    // masked quad loads: arrays are padded by 4 entries, positions >= end read as "no observation" (lm = -1)
+    auto ld_lm4 = [&](int64_t k) {
+        int4 r = make_int4(-1, -1, -1, -1);
+        if (k < end) {
+            r = __ldg(reinterpret_cast<const int4*>(s_lm + k));
+            if (k + 1 >= end) r.y = -1;
+            if (k + 2 >= end) r.z = -1;
+            if (k + 3 >= end) r.w = -1;
+        }
+        return r;
+    };
+    int4 camC = make_int4(0, 0, 0, 0), camN = camC, lmC, lmN, lmN2;
+    D4 oxC = {0, 0, 0, 0}, oyC = oxC, oxN = oxC, oyN = oxC;
+    const LmTrig unitT = {0, 1, 0, 1};
+    LmTrig tAC = unitT, tBC = unitT, tAN = unitT, tBN = unitT;
+    int64_t k0 = begin + (int64_t)tid * kQuad;
+    // prologue: quad 0 complete, index quad 1, (index quad 2 and the rest of quad 1 are issued at the top of iteration 0)
+    lmC = ld_lm4(k0);
+    lmN = ld_lm4(k0 + kStep);
+    if (k0 < end) {
+        camC = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
+        oxC = *reinterpret_cast<const D4*>(s_ox + k0);
+        oyC = *reinterpret_cast<const D4*>(s_oy + k0);
+    }
+    if (lmC.x >= 0) tAC = lm_trig[lmC.x];
+    if (lmC.w >= 0 && lmC.w != lmC.x) tBC = lm_trig[lmC.w];
+    double cost = 0.0;
+    for (int64_t base = begin; base < end; base += kStep, k0 += kStep) {
+        // ---- issue everything the NEXT iterations need before touching the current quad ----
+        lmN2 = ld_lm4(k0 + 2 * kStep);
+        if (k0 + kStep < end) {
+            camN = __ldg(reinterpret_cast<const int4*>(s_cam + k0 + kStep));
+            oxN = *reinterpret_cast<const D4*>(s_ox + k0 + kStep);
+            oyN = *reinterpret_cast<const D4*>(s_oy + k0 + kStep);
+        }
+        if (lmN.x >= 0) tAN = lm_trig[lmN.x];
+        if (lmN.w >= 0 && lmN.w != lmN.x) tBN = lm_trig[lmN.w];
+        // ---- current quad ----
+        const int cam[kQuad] = {camC.x, camC.y, camC.z, camC.w};
+        const int lm[kQuad] = {lmC.x, lmC.y, lmC.z, lmC.w};
+        const double ox[kQuad] = {oxC.a, oxC.b, oxC.c, oxC.d};
+        const double oy[kQuad] = {oyC.a, oyC.b, oyC.c, oyC.d};
+        double rx[kQuad], ry[kQuad];
+        int cur = -1;
+        LmTrig lt = unitT;
+        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            rx[i] = 0.0; ry[i] = 0.0;
+            if (lm[i] < 0) continue;
+            if (lm[i] != cur) {
+                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);   // run ended inside this thread
+                cur = lm[i];
+                lt = (cur == lm[0]) ? tAC : (cur == lm[3]) ? tBC : lm_trig[cur];
+                vtt = vtp = vpp = glt = glp = 0.0;
+            }
+            const CamTrig c = dual_cam<CAMREP>(sCam, cam[i], n_pose, lane);
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            rx[i] = x - ox[i];
+            ry[i] = y - oy[i];
+            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
+            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
+            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
+            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
+            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
+            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
+            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
+        }
+        if (resid) {
+            if (!orig && k0 + kQuad <= end) {
+                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
+                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
+                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
+            } else {
+#pragma unroll
+                for (int i = 0; i < kQuad; ++i)
+                    if (lm[i] >= 0) {
+                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
+                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
+                    }
+            }
+        }
+        // the thread's last run joins the warp-segmented reduction (keys non-decreasing across lanes, -1 = none)
+        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+        // ---- rotate the pipeline registers ----
+        camC = camN; oxC = oxN; oyC = oyN; lmC = lmN; tAC = tAN; tBC = tBN; lmN = lmN2;
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kDualThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+}
+
+__device__ __forceinline__ void dual_cam_role(int64_t begin, int64_t end, const int32_t* __restrict__ c_cam,
+                                              const int32_t* __restrict__ c_lm, const double* __restrict__ c_ox,
+                                              const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
+                                              const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU,
+                                              double* __restrict__ gGc) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
+    int wcam = -1;
+    CamTrig wc = {0, 1, 0, 1, 1};
+    auto flush = [&]() {
+        if (wcam > 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
+            if (lane == 0) {
+                double* U = gU + 6 * (size_t)wcam;
+                double* G = gGc + 3 * (size_t)wcam;
+                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
+                atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
+                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+            }
+        }
+        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
+    };
+    const LmTrig unitT = {0, 1, 0, 1};
+    int64_t k = begin + tid;
+    int cam = -1, camN = -1, lmN = -1, lmN2 = -1;
+    double ox = 0, oy = 0, oxN = 0, oyN = 0;
+    LmTrig lt = unitT, ltN = unitT;
+    if (k < end) { cam = c_cam[k]; ox = c_ox[k]; oy = c_oy[k]; lt = lm_trig[c_lm[k]]; }
+    if (k + kDualThreads < end) lmN = c_lm[k + kDualThreads];
+    for (int64_t base = begin; base < end; base += kDualThreads, k += kDualThreads) {
+        // ---- issue the next iterations' loads ----
+        lmN2 = (k + 2 * kDualThreads < end) ? c_lm[k + 2 * kDualThreads] : -1;
+        camN = -1;
+        if (k + kDualThreads < end) { camN = c_cam[k + kDualThreads]; oxN = c_ox[k + kDualThreads]; oyN = c_oy[k + kDualThreads]; }
+        if (lmN >= 0) ltN = lm_trig[lmN];
+        // ---- current observation ----
+        const bool act = cam >= 0;
+        const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
+        const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
+        const bool uniform = same == 0xffffffffu;
+        if (uniform) {
+            if (cam_lo != wcam) { flush(); wcam = cam_lo; if (wcam >= 0) wc = cam_trig[wcam]; }
+        } else {
+            flush();
+            wcam = -1;
+        }
+        if (act && cam > 0) {
+            const CamTrig c = uniform ? wc : cam_trig[cam];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            const double rx = x - ox, ry = y - oy;
+            const double upp = fma(g.xa, g.xa, g.ya * g.ya);
+            const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
+            const double upf = -fma(g.xa, g.px, g.ya * g.py);
+            const double utt = fma(g.xt, g.xt, g.yt * g.yt);
+            const double utf = fma(g.xt, g.px, g.yt * g.py);
+            const double uff = fma(g.px, g.px, g.py * g.py);
+            const double gp = -fma(g.xa, rx, g.ya * ry);
+            const double gt = fma(g.xt, rx, g.yt * ry);
+            const double gf = fma(g.px, rx, g.py * ry);
+            if (uniform) {
+                a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
+            } else {   // warp straddles a keyframe boundary (once per keyframe): commit per lane
+                double* U = gU + 6 * (size_t)cam;
+                double* G = gGc + 3 * (size_t)cam;
+                atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
+                atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
+                atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
+            }
+        }
+        cam = camN; ox = oxN; oy = oyN; lt = ltN; lmN = lmN2;
+    }
+    flush();
+}
+
+// CTA b takes the landmark role when the Bresenham line b * n_lm_ctas / gridDim steps, so the two roles alternate in
+// dispatch order and every SM hosts both.
+template <int CAMREP>
+__global__ void __launch_bounds__(kDualThreads, 2)
+k_ba_dual(int64_t n_obs, int n_lm_ctas, int only, int64_t chunk_lm, int64_t chunk_cam, const int32_t* __restrict__ s_cam,
+          const int32_t* __restrict__ s_lm, const double* __restrict__ s_ox, const double* __restrict__ s_oy,
+          const int32_t* __restrict__ orig, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+          const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
+          const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v, double* __restrict__ resid,
+          double* __restrict__ gU, double* __restrict__ gGc, double* __restrict__ gV, double* __restrict__ gGl,
+          double* __restrict__ gCost) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double sWarp[kDualThreads / 32];
+    const int64_t b = blockIdx.x, G = gridDim.x;
+    const int lm_before = (int)(b * n_lm_ctas / G);
+    const bool is_lm = (int)((b + 1) * n_lm_ctas / G) > lm_before;
+    if ((is_lm && only == 2) || (!is_lm && only == 1)) return;     // role isolation for profiling (PTZBA_DUAL_ONLY)
+    if (is_lm) {
+        const int64_t begin = (int64_t)lm_before * chunk_lm;
+        int64_t end = begin + chunk_lm;
+        if (end > n_obs) end = n_obs;
+        if (begin >= end) return;
+        dual_fill_cam<CAMREP>(smem, cam_trig, n_pose);
+        __syncthreads();
+        dual_lm_role<CAMREP>(smem, sWarp, begin, end, s_cam, s_lm, s_ox, s_oy, orig, lm_trig, n_pose, u, v, resid, gV, gGl, gCost);
+    } else {
+        const int64_t begin = (b - lm_before) * chunk_cam;
+        int64_t end = begin + chunk_cam;
+        if (end > n_obs) end = n_obs;
+        if (begin >= end) return;
+        dual_cam_role(begin, end, c_cam, c_lm, c_ox, c_oy, cam_trig, lm_trig, u, v, gU, gGc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused_variant 14: ONE pass over the landmark-major list; the geometry of an observation is evaluated exactly once.
+//
+// The landmark side (V, g_l) is reduced where it is adjacent, as in k_ba_lm_pass4.  The keyframe side (U, g_c) is
+// transposed through shared memory with a STATIC schedule: the observation structure never changes between passes, so
+// ptzba_ba_create sorts every tile of kOneTile consecutive observations by keyframe once (k_build_tiles) and stores
+//   kslot[obs]           uint16  position of the observation in its tile's keyframe-sorted order
+//   kptr[tile][N + 1]    uint16  start of every keyframe's run in that order
+// Phase A (thread = 4 consecutive observations): projection, residual, analytic blocks, landmark sums; the six numbers the
+//   keyframe side needs (d/d alpha, N/z, residual) are written to the staging slot kslot[obs].
+// Phase B (thread = keyframe): walks its run of staging slots, forms the 9 unique entries of J_c^T J_c / J_c^T r in
+//   registers and adds them to the CTA's private keyframe table (row owned by this thread: no atomics anywhere).
+// The table is flushed with one RED per entry when the CTA has finished its chunk.
+// Traffic: 24 B + 2 B (kslot) read and 16 B written per observation, (N + 1) * 2 B per tile.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kOneThreads = 384;
+constexpr int kOneTile = kOneThreads * kQuad;      // 1536 observations
+constexpr int kOneWarpTrig = 16;                   // landmark ids are contiguous inside a warp's 128 observations
+
+// one CTA per tile: counting sort of the tile's observations by keyframe (deterministic: stable inside a keyframe)
+__global__ void __launch_bounds__(256)
+k_build_tiles(int64_t n_obs, int64_t chunk, int tiles_per_cta, int n_pose, const int32_t* __restrict__ s_cam,
+              uint16_t* __restrict__ kslot, uint16_t* __restrict__ kptr) {
+    extern __shared__ int sb[];
+    int* sKey = sb;                       // [kOneTile]
+    int* sCnt = sb + kOneTile;            // [n_pose + 1]
+    const int tile = blockIdx.x, cta = tile / tiles_per_cta, t = tile - cta * tiles_per_cta;
+    const int64_t cbeg = (int64_t)cta * chunk;
+    int64_t cend = cbeg + chunk;
+    if (cend > n_obs) cend = n_obs;
+    const int64_t tbeg = cbeg + (int64_t)t * kOneTile;
+    int64_t cnt64 = cend - tbeg;
+    if (cnt64 > kOneTile) cnt64 = kOneTile;
+    const int cnt = cnt64 < 0 ? 0 : (int)cnt64;
+    for (int i = threadIdx.x; i <= n_pose; i += blockDim.x) sCnt[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int c = s_cam[tbeg + i];
+        sKey[i] = c;
+        atomicAdd(&sCnt[c + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c <= n_pose; ++c) { run += sCnt[c]; sCnt[c] = run; }      // sCnt[c] = start of keyframe c
+    }
+    __syncthreads();
+    uint16_t* kp = kptr + (size_t)tile * (n_pose + 1);
+    for (int c = threadIdx.x; c <= n_pose; c += blockDim.x) kp[c] = (uint16_t)sCnt[c];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int c = sKey[i];
+        int rank = 0;
+        for (int j = 0; j < i; ++j) rank += (sKey[j] == c);
+        kslot[tbeg + i] = (uint16_t)(sCnt[c] + rank);
+    }
+}
+
+struct OneSmem {            // carve-up of the dynamic shared memory of k_ba_onepass
+    double2* p0;            // [kOneTile] (d x / d alpha, d y / d alpha)
+    double2* p1;            // [kOneTile] (Nx / z, Ny / z)
+    double2* p2;            // [kOneTile] (r_x, r_y)
+    double* cam;            // [n_pose * 6] keyframe trig rows {sp,cp,st,ct,f,-}
+    double* tab;            // [n_pose * 9] keyframe accumulators, radian units
+    uint16_t* kptr;         // [n_pose + 1]
+    LmTrig* wtrig;          // [warps][kOneWarpTrig] per-warp cache of the landmark trig rows of the warp's 128 observations
+};
+
+__device__ __forceinline__ OneSmem one_smem(unsigned char* base, int n_pose) {
+    OneSmem s;
+    s.p0 = reinterpret_cast<double2*>(base);
+    s.p1 = s.p0 + kOneTile;
+    s.p2 = s.p1 + kOneTile;
+    s.cam = reinterpret_cast<double*>(s.p2 + kOneTile);
+    s.tab = s.cam + (size_t)n_pose * 6;
+    s.wtrig = reinterpret_cast<LmTrig*>(s.cam + ((size_t)n_pose * 15 + 3) / 4 * 4);      // 32-byte aligned
+    s.kptr = reinterpret_cast<uint16_t*>(s.wtrig + (kOneThreads / 32) * kOneWarpTrig);
+    return s;
+}
+
+static size_t one_smem_bytes(int n_pose) {
+    return (size_t)kOneTile * 48 + ((size_t)n_pose * 15 + 3) / 4 * 4 * sizeof(double) + (kOneThreads / 32) * kOneWarpTrig * sizeof(LmTrig) +
+           ((size_t)n_pose + 1 + 7) / 8 * 8 * sizeof(uint16_t);
+}
+
+__global__ void __launch_bounds__(kOneThreads, 2)
+k_ba_onepass(int64_t n_obs, int64_t chunk, int tiles_per_cta, int debug, const int32_t* __restrict__ s_cam,
+             const int32_t* __restrict__ s_lm, const double* __restrict__ s_ox, const double* __restrict__ s_oy,
+             const int32_t* __restrict__ orig, const uint16_t* __restrict__ kslot, const uint16_t* __restrict__ kptr,
+             const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, int n_lm, double u,
+             double v, double* __restrict__ resid, double* __restrict__ gU, double* __restrict__ gGc,
+             double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+    extern __shared__ __align__(32) unsigned char dyn[];
+    __shared__ double sWarp[kOneThreads / 32];
+    const OneSmem sm = one_smem(dyn, n_pose);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t cbeg = (int64_t)blockIdx.x * chunk;
+    int64_t cend = cbeg + chunk;
+    if (cend > n_obs) cend = n_obs;
+    if (cbeg >= cend) return;
+    for (int i = tid; i < n_pose * 5; i += kOneThreads) {
+        const int c = i / 5, e = i - 5 * c;
+        sm.cam[(size_t)c * 6 + e] = reinterpret_cast<const double*>(cam_trig)[i];
+    }
+    for (int i = tid; i < n_pose * 9; i += kOneThreads) sm.tab[i] = 0.0;
+    const double k1 = PTZ_DEG2RAD, k2 = PTZ_DEG2RAD * PTZ_DEG2RAD;
+    double cost = 0.0;
+    int tile = blockIdx.x * tiles_per_cta;
+    // software pipeline across the tile loop: the quad of tile i+1 is requested right after phase A of tile i (its
+    // registers are dead during phase B), the two landmark trig rows it needs right after phase B
+    int4 cq = make_int4(0, 0, 0, 0), lq = make_int4(-1, -1, -1, -1);
+    D4 xq = {0, 0, 0, 0}, yq = {0, 0, 0, 0};
+    ushort4 sq = make_ushort4(0, 0, 0, 0);
+    const LmTrig unitT = {0, 1, 0, 1};
+    LmTrig* wTrig = sm.wtrig + (tid >> 5) * kOneWarpTrig;
+    LmTrig tpre = unitT;        // row (wfirst + lane) of the trig table, lanes < kOneWarpTrig
+    int wfirst = -1;            // first landmark id of the warp's quads in the coming tile
+    // arrays are padded by >= 4 entries: a quad that starts inside the chunk is always loadable, its tail is masked
+#define ONE_LOAD_QUAD(K0)                                                                  \
+    do {                                                                                   \
+        const int64_t kk = (K0);                                                           \
+        lq = make_int4(-1, -1, -1, -1);                                                    \
+        if (kk < cend) {                                                                   \
+            cq = __ldg(reinterpret_cast<const int4*>(s_cam + kk));                         \
+            lq = __ldg(reinterpret_cast<const int4*>(s_lm + kk));                          \
+            xq = *reinterpret_cast<const D4*>(s_ox + kk);                                  \
+            yq = *reinterpret_cast<const D4*>(s_oy + kk);                                  \
+            sq = __ldg(reinterpret_cast<const ushort4*>(kslot + kk));                      \
+            if (kk + 1 >= cend) lq.y = -1;                                                 \
+            if (kk + 2 >= cend) lq.z = -1;                                                 \
+            if (kk + 3 >= cend) lq.w = -1;                                                 \
+        }                                                                                  \
+    } while (0)
+#define ONE_LOAD_TRIGS()                                                                   \
+    do {                                                                                   \
+        wfirst = __shfl_sync(0xffffffffu, lq.x, 0);                                        \
+        if (lane < kOneWarpTrig && wfirst >= 0 && wfirst + lane < n_lm) tpre = lm_trig[wfirst + lane];   \
+    } while (0)
+    ONE_LOAD_QUAD(cbeg + (int64_t)tid * kQuad);
+    ONE_LOAD_TRIGS();
+    for (int64_t tbeg = cbeg; tbeg < cend; tbeg += kOneTile, ++tile) {
+        // ---- phase A: this thread's quad ----
+        const uint16_t* kp = kptr + (size_t)tile * (n_pose + 1);
+        for (int i = tid; i <= n_pose; i += kOneThreads) sm.kptr[i] = kp[i];
+        const int64_t k0 = tbeg + (int64_t)tid * kQuad;
+        const int cam[kQuad] = {cq.x, cq.y, cq.z, cq.w}, lm[kQuad] = {lq.x, lq.y, lq.z, lq.w};
+        const int slot[kQuad] = {sq.x, sq.y, sq.z, sq.w};
+        const double ox[kQuad] = {xq.a, xq.b, xq.c, xq.d}, oy[kQuad] = {yq.a, yq.b, yq.c, yq.d};
+        double rx[kQuad], ry[kQuad];
+        int cur = -1;
+        LmTrig lt = unitT;
+        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
+        if (lane < kOneWarpTrig) wTrig[lane] = tpre;
+        const int wf = wfirst;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            rx[i] = 0.0; ry[i] = 0.0;
+            if (lm[i] < 0) continue;
+            if (lm[i] != cur) {
+                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);   // run ended inside this thread
+                cur = lm[i];
+                lt = (cur - wf < kOneWarpTrig) ? wTrig[cur - wf] : lm_trig[cur];
+                vtt = vtp = vpp = glt = glp = 0.0;
+            }
+            CamTrig c;
+            {
+                const double2* t = reinterpret_cast<const double2*>(sm.cam + (size_t)cam[i] * 6);
+                const double2 pa = t[0], ti = t[1];
+                c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = sm.cam[(size_t)cam[i] * 6 + 4];
+            }
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            rx[i] = x - ox[i];
+            ry[i] = y - oy[i];
+            if (!(debug & 2)) {
+                sm.p0[slot[i]] = make_double2(g.xa, g.ya);
+                sm.p1[slot[i]] = make_double2(g.px, g.py);
+                sm.p2[slot[i]] = make_double2(rx[i], ry[i]);
+            }
+            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
+            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
+            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
+            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
+            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
+            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
+            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
+        }
+        if (resid) {
+            if (!orig && k0 + kQuad <= cend) {
+                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
+                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
+                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
+            } else {
+#pragma unroll
+                for (int i = 0; i < kQuad; ++i)
+                    if (lm[i] >= 0) {
+                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
+                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
+                    }
+            }
+        }
+        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+        ONE_LOAD_QUAD(k0 + kOneTile);      // next tile's quad: in flight during phase B
+        __syncthreads();
+        // ---- phase B: this thread's keyframes (keyframe 0 is the fixed reference pose: no block) ----
+        for (int key = tid; key < n_pose && !(debug & 1); key += kOneThreads) {
+            const int s0 = sm.kptr[key], s1 = sm.kptr[key + 1];
+            if (key == 0 || s0 == s1) continue;
+            const double f = sm.cam[(size_t)key * 6 + 4];
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+            for (int s = s0; s < s1; ++s) {
+                const double2 da = sm.p0[s], pz = sm.p1[s], r = sm.p2[s];
+                const double xt = f * pz.x * pz.y;                 // f Nx Ny / z^2
+                const double yt = fma(f * pz.y, pz.y, f);          // f (1 + Ny^2 / z^2)
+                a0 = fma(da.x, da.x, fma(da.y, da.y, a0));
+                a1 = fma(da.x, xt, fma(da.y, yt, a1));
+                a2 = fma(da.x, pz.x, fma(da.y, pz.y, a2));
+                a3 = fma(xt, xt, fma(yt, yt, a3));
+                a4 = fma(xt, pz.x, fma(yt, pz.y, a4));
+                a5 = fma(pz.x, pz.x, fma(pz.y, pz.y, a5));
+                a6 = fma(da.x, r.x, fma(da.y, r.y, a6));
+                a7 = fma(xt, r.x, fma(yt, r.y, a7));
+                a8 = fma(pz.x, r.x, fma(pz.y, r.y, a8));
+            }
+            double* t = sm.tab + (size_t)key * 9;
+            t[0] += a0; t[1] -= a1; t[2] -= a2; t[3] += a3; t[4] += a4; t[5] += a5; t[6] -= a6; t[7] += a7; t[8] += a8;
+        }
+        ONE_LOAD_TRIGS();
+        __syncthreads();
+    }
+#undef ONE_LOAD_QUAD
+#undef ONE_LOAD_TRIGS
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0;
+        for (int w = 0; w < kOneThreads / 32; ++w) s += sWarp[w];
+        atomicAdd(gCost, s);
+    }
+    // flush the keyframe table (converted to per-degree units): entries (pp,pt,pf,tt,tf,ff | gp,gt,gf)
+    for (int i = tid; i < n_pose * 9; i += kOneThreads) {
+        const double val = sm.tab[i];
+        if (val == 0.0) continue;
+        const int c = i / 9, e = i - 9 * c;
+        const double sc = (e == 0 || e == 1 || e == 3) ? k2 : (e == 2 || e == 4 || e == 6 || e == 7) ? k1 : 1.0;
+        if (e < 6) atomicAdd(gU + 6 * (size_t)c + e, val * sc);
+        else atomicAdd(gGc + 3 * (size_t)c + (e - 6), val * sc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // fused_variant 9: the two coherent passes fed by a TMA (cp.async.bulk) ring buffer.
 // One elected thread per CTA streams 1024-observation tiles of the four SoA arrays (and, in the landmark-major pass, the
 // tile's contiguous slice of the landmark trig table) into shared memory, kStages tiles ahead, completing on an mbarrier;
@@ -776,8 +1326,8 @@ k_ba_cam_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, 
 // the copy engine instead of by occupancy, and the streaming loads cost no LSU instruction slots.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTile = kFusedThreads * kQuad;     // 1024 observations
-constexpr int kStages = 3;
-constexpr int kTileTrig = 256;                   // landmark trig entries staged per tile (more -> direct global loads)
+constexpr int kStages = 2;
+constexpr int kTileTrig = 128;                   // landmark trig entries staged per tile (more -> direct global loads)
 
 struct __align__(128) TileBuf {
     int cam[kTile];
@@ -847,7 +1397,7 @@ __global__ void k_tile_lm_ranges(int64_t n_obs, int64_t n_tiles, const int32_t* 
     tile_lm[t] = make_int2(lo, hi - lo + 1);
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, 3)
 k_ba_lm_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_t* __restrict__ s_cam,
                  const int32_t* __restrict__ s_lm, const double* __restrict__ s_ox, const double* __restrict__ s_oy,
                  const int32_t* __restrict__ orig, const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig,
@@ -970,7 +1520,7 @@ k_ba_lm_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_
     }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, 3)
 k_ba_cam_pass_tma(int64_t n_obs, int64_t n_tiles, int tiles_per_cta, const int32_t* __restrict__ c_cam,
                   const int32_t* __restrict__ c_lm, const double* __restrict__ c_ox, const double* __restrict__ c_oy,
                   const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, double u, double v,
@@ -1183,6 +1733,31 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                                                                   ba->acc.gc);
                 break;
             }
+            case 14: {
+                k_ba_onepass<<<ba->one_grid, kOneThreads, one_smem_bytes(ba->n_pose), s>>>(
+                    ba->n_obs, ba->one_chunk, ba->one_tiles_per_cta, ba->one_debug, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig,
+                    ba->kslot.p, ba->kptr.p, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->n_lm, ba->u, ba->v, d_resid, ba->acc.U,
+                    ba->acc.gc, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                break;
+            }
+            case 13: {
+                const int n_lm_ctas = ba->dual_lm_ctas, n_cam_ctas = ba->dual_grid - ba->dual_lm_ctas;
+                const int64_t q = (int64_t)kDualThreads * kQuad;
+                int64_t chunkA = (ba->n_obs + n_lm_ctas - 1) / n_lm_ctas;
+                chunkA = (chunkA + q - 1) / q * q;
+                int64_t chunkB = (ba->n_obs + n_cam_ctas - 1) / n_cam_ctas;
+                chunkB = (chunkB + kDualThreads - 1) / kDualThreads * kDualThreads;
+                const size_t sm = (size_t)ba->n_pose * (ba->dual_camrep == 8 ? 384 : 48);
+#define LAUNCH_DUAL(REP)                                                                                                    \
+    k_ba_dual<REP><<<ba->dual_grid, kDualThreads, sm, s>>>(ba->n_obs, n_lm_ctas, ba->dual_only, chunkA, chunkB, ba->s_cam.p, ba->s_lm.p,      \
+                                                           ba->s_ox.p, ba->s_oy.p, orig, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, \
+                                                           ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u,     \
+                                                           ba->v, d_resid, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl,     \
+                                                           ba->acc.cost)
+                if (ba->dual_camrep == 8) LAUNCH_DUAL(8); else LAUNCH_DUAL(1);
+#undef LAUNCH_DUAL
+                break;
+            }
             case 8: {
                 // best measured combination so far: quad landmark-major pass + prefetching keyframe-major pass
                 const int64_t q = (int64_t)kFusedThreads * kQuad;
@@ -1191,13 +1766,14 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
                 k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 6 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost, ba->l2_pf);
                 ctx->launches++;
                 int64_t chunkB = (ba->n_obs + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
                 chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
                 const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
                 k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                             ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+                                                             ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc,
+                                                             ba->l2_pf);
                 break;
             }
             case 7: {
@@ -1207,7 +1783,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
                 k_ba_lm_pass4<3><<<gridA, kFusedThreads, (size_t)ba->n_pose * 6 * sizeof(double), s>>>(
                     ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+                    ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost, ba->l2_pf);
                 ctx->launches++;
                 int64_t chunkB = (ba->n_obs + ba->grid_cam_pass4 - 1) / ba->grid_cam_pass4;
                 chunkB = (chunkB + q - 1) / q * q;
@@ -1228,7 +1804,8 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                 chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
                 const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
                 k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                             ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+                                                             ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc,
+                                                             ba->l2_pf);
                 break;
             }
             default: {
@@ -1370,6 +1947,7 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     {
         const char* env = getenv("PTZBA_FUSED_VARIANT");
         if (env) ba->fused_variant = atoi(env);
+        if (const char* e = getenv("PTZBA_L2_PREFETCH")) ba->l2_pf = atoi(e);
     }
     if (n_obs > 0) {
         DevBuf<int32_t> iota, perm2;
@@ -1440,6 +2018,60 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
             }
             ba->grid_lm_pass = ctx->sm_count * (pa < 1 ? 1 : pa);
             ba->grid_cam_pass = ctx->sm_count * (pb < 1 ? 1 : pb);
+        }
+        {
+            // dual-role kernel: 8x replicated keyframe trig table while it fits beside a second resident CTA
+            ba->dual_camrep = ((size_t)n_pose * 384 <= 100 * 1024) ? 8 : 1;
+            if (const char* e = getenv("PTZBA_DUAL_REP")) ba->dual_camrep = atoi(e) == 8 ? 8 : 1;
+            const size_t smd = (size_t)n_pose * (ba->dual_camrep == 8 ? 384 : 48);
+            int pd = 1;
+            if (ba->dual_camrep == 8) {
+                CU_TRY(cudaFuncSetAttribute(k_ba_dual<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smd));
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd, k_ba_dual<8>, kDualThreads, smd));
+            } else if (smd <= 220 * 1024) {
+                CU_TRY(cudaFuncSetAttribute(k_ba_dual<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smd));
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd, k_ba_dual<1>, kDualThreads, smd));
+            } else if (ba->fused_variant == 13) {
+                ba->fused_variant = 8;
+            }
+            if (pd < 2) pd = 2;                      // at least one CTA of each role per SM (queued if not co-resident)
+            ba->dual_grid = ctx->sm_count * pd;
+            int pct = 55;                            // share of the CTAs that take the landmark role
+            if (const char* e = getenv("PTZBA_DUAL_SPLIT")) pct = atoi(e);
+            if (pct < 5) pct = 5;
+            if (pct > 95) pct = 95;
+            ba->dual_lm_ctas = ba->dual_grid * pct / 100;
+            if (const char* e = getenv("PTZBA_DUAL_ONLY")) ba->dual_only = atoi(e);
+        }
+        if (n_obs > 0) {
+            // single-pass kernel: static per-tile keyframe sort (falls back to the two-pass kernels when the keyframe
+            // tables do not fit in shared memory or a keyframe id does not fit the 16-bit run offsets)
+            const size_t smo = one_smem_bytes(n_pose);
+            if (smo <= 220 * 1024) {
+                int po = 1;
+                CU_TRY(cudaFuncSetAttribute(k_ba_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smo));
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&po, k_ba_onepass, kOneThreads, smo));
+                if (po < 1) po = 1;
+                int grid = ctx->sm_count * po;
+                int64_t chunk = (n_obs + grid - 1) / grid;
+                chunk = (chunk + kQuad - 1) / kQuad * kQuad;
+                grid = (int)((n_obs + chunk - 1) / chunk);
+                ba->one_grid = grid;
+                ba->one_chunk = chunk;
+                ba->one_tiles_per_cta = (int)((chunk + kOneTile - 1) / kOneTile);
+                if (const char* e = getenv("PTZBA_ONE_DEBUG")) ba->one_debug = atoi(e);
+                const size_t n_tiles = (size_t)grid * ba->one_tiles_per_cta;
+                CU_TRY(ba->kslot.alloc((size_t)n_obs + 8));
+                CU_TRY(ba->kptr.alloc(n_tiles * ((size_t)n_pose + 1)));
+                const size_t smb = ((size_t)kOneTile + n_pose + 1) * sizeof(int);
+                if (smb > 40 * 1024) CU_TRY(cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+                k_build_tiles<<<(unsigned)n_tiles, 256, smb, s>>>(n_obs, chunk, ba->one_tiles_per_cta, n_pose, ba->s_cam.p,
+                                                                  ba->kslot.p, ba->kptr.p);
+                ctx->launches++;
+                CU_TRY(cudaGetLastError());
+            } else if (ba->fused_variant == 14) {
+                ba->fused_variant = 8;
+            }
         }
         int per_sm_lm = 1;
         CU_TRY(cudaFuncSetAttribute(k_ba_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
