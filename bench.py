@@ -370,7 +370,6 @@ def run_ours(args):
                                        "(%d doubles) every pass" % (1 + 9 * fb.n_pose + 5 * fb.n_landmark)) if world > 1 else "1 GPU",
                        "step": "one fused residual+Jacobian+normal-equation pass (k_set_params + k_ba_lm_pass4 + k_ba_cam_pass)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "fused_variant": os.environ.get("PTZBA_FUSED_VARIANT", "default"),
         }
         if lm:
             line.update(lm)

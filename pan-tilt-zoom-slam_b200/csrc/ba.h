@@ -27,12 +27,10 @@ struct ptzba_ba {
     DevBuf<int32_t> s_cam, s_lm, orig;
     DevBuf<double> s_ox, s_oy;
     DevBuf<int32_t> lm_ptr;         // [M+1] CSR offsets into the sorted arrays
-    // second copy in keyframe-major order (landmark ascending inside a keyframe) for the fused pass:
-    // keyframe blocks accumulate in registers, landmark blocks go to L2 with RED atomics
+    // second copy in keyframe-major order (landmark ascending inside a keyframe) for the keyframe pass of the fused
+    // pass: keyframe blocks accumulate in registers there
     DevBuf<int32_t> c_cam, c_lm, c_orig;
     DevBuf<double> c_ox, c_oy;
-    int l2_pf = 0;                  // iterations of look-ahead of the L2 bulk prefetch in the two-pass kernels (0 = off)
-    int fused_variant = 8;          // see ba_fused_pass(): 0 one pass + smem atomics ... 8 two coherent passes (default)
     // current parameters
     DevBuf<double> poses;           // [N*3] incl. reference pose at 0
     DevBuf<double> rays;            // [M*2]
@@ -52,17 +50,12 @@ struct ptzba_ba {
     DevBuf<double> scal;                    // small device scalar block for reductions
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
-    int fused_grid = 0, fused_grid_lm = 0, fused_smem = 0, grid_lm_pass = 0, grid_cam_pass = 0, grid_lm_pass4 = 0, grid_cam_pass4 = 0, grid_tma_lm = 0, grid_tma_cam = 0;
-    int dual_grid = 0, dual_lm_ctas = 0, dual_camrep = 1, dual_only = 0;   // fused_variant 13: CTAs, landmark-role CTAs, table copies
-    // fused_variant 14 (single pass): static per-tile keyframe sort
-    int one_grid = 0, one_tiles_per_cta = 0, one_debug = 0;
-    int64_t one_chunk = 0;
-    DevBuf<uint16_t> kslot, kptr;
-    DevBuf<int2> tile_lm;           // per 1024-observation tile: (first landmark id, number of landmark ids)
-    bool fused_cam_smem = true;
+    int grid_lm_pass = 0, grid_cam_pass = 0;   // one wave of resident CTAs per pass
+    bool cam_smem = true;           // keyframe trig table fits in shared memory
+    bool acc_zeroed = false;        // the arena was cleared by ba_set_params(..., zero_acc = true)
 };
 
 // ---- device-level passes (all pointers device, enqueued on ba->ctx->stream) ----
-int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3);      // unpack + trig tables
+int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3, bool zero_acc = false);   // unpack + trig tables (+ clear ba->acc)
 int ba_fused_pass(ptzba_ba* ba, double* d_resid_or_null);                            // -> ba->acc
 int ba_residual_pass(ptzba_ba* ba, double* d_resid_or_null, double* d_sumsq);        // r (caller order) and sum r^2

@@ -536,7 +536,7 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
                                   mem == PTZBA_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
 
     auto eval_normal = [&](const double* xp, double* cost) -> int {
-        PROPAGATE(ba_set_params(ba, xp, d_ref.d));
+        PROPAGATE(ba_set_params(ba, xp, d_ref.d, true));
         PROPAGATE(ba_fused_pass(ba, nullptr));
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalars, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, s));
         CU_CHECK(ctx, cudaStreamSynchronize(s));
@@ -723,7 +723,7 @@ extern "C" int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, con
     CU_CHECK(ctx, cudaMemsetAsync(ba->x_cur.p, 0, 3 * sizeof(double), s));
     CU_CHECK(ctx, cudaMemcpyAsync(xc, x, (size_t)nx * sizeof(double),
                                   mem == PTZBA_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    PROPAGATE(ba_set_params(ba, xc, d_ref.d));
+    PROPAGATE(ba_set_params(ba, xc, d_ref.d, true));
     PROPAGATE(ba_fused_pass(ba, nullptr));
     k_scale_update<<<div_up(nF, 256), 256, 0, s>>>(N, M, ba->acc.U, ba->acc.V, S.D, 1);
     KERNEL_POST(ctx);
