@@ -384,7 +384,8 @@ struct Solver {
         CU_CHECK(ctx, ba->rhs_l.alloc(nF));   // reduced rhs scratch (camera part only)
         CU_CHECK(ctx, ba->Vinv.alloc((size_t)M * 3));
         CU_CHECK(ctx, flags.alloc(4)); CU_CHECK(ctx, tmp_l.alloc((size_t)2 * M)); CU_CHECK(ctx, w_full.alloc(nF));
-        CU_CHECK(ctx, dinv.alloc((size_t)(n / 32 + 1) * 1024));
+        CU_CHECK(ctx, dinv.alloc(dense_coop_dinv_doubles(n > 0 ? n : 1)));
+
         g = ba->acc.gc;           // gc | gl contiguous = full layout
         D = ba->scale_inv.p; Dc = D; Dl = D + 3 * N;
         obs_grid = ctx->sm_count * 4;
@@ -429,10 +430,8 @@ struct Solver {
                 KERNEL_POST(ctx);
             }
             tr.mark("schur_pairs");
-            PROPAGATE(dense_potrf_lower(ctx, ba->Sred.p, n, n, flags.p + 1));
-            tr.mark("potrf");
-            PROPAGATE(dense_diag_inverse(ctx, ba->Sred.p, n, n, dinv.p));
-            tr.mark("diag_inverse");
+            PROPAGATE(dense_potrf_coop(ctx, ba->Sred.p, n, n, flags.p + 1, dinv.p));
+            tr.mark("potrf+block_inverses");
         }
         tr.report("factor");
         ++n_factor;
@@ -457,7 +456,7 @@ struct Solver {
             KERNEL_POST(ctx);
         }
         tr.mark("reduce_rhs");
-        if (n > 0) PROPAGATE(dense_potrs_dinv(ctx, ba->Sred.p, n, n, dinv.p, red + 3));
+        if (n > 0) PROPAGATE(dense_potrs_coop(ctx, ba->Sred.p, n, n, dinv.p, red + 3));
         tr.mark("potrs");
         CU_CHECK(ctx, cudaMemcpyAsync(y, red, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CU_CHECK(ctx, cudaMemsetAsync(y, 0, 3 * sizeof(double), s));

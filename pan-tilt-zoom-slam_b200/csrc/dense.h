@@ -29,3 +29,9 @@ int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t s
 // L L^T x = b that uses them (mat-vec per block step instead of a sequential triangle solve)
 int dense_diag_inverse(ptzba_ctx* ctx, const double* L, int n, int lda, double* Dinv);
 int dense_potrs_dinv(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv, double* b);
+
+// ---- single-matrix, latency-optimised path (dense_coop.cu): one persistent cooperative kernel factors A = L L^T and
+// inverts the 128 x 128 diagonal blocks of L into Dinv_store (dense_coop_dinv_doubles(n) doubles).  *d_info as dense_potrf_lower.
+size_t dense_coop_dinv_doubles(int n);
+int dense_potrf_coop(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info, double* Dinv_store);
+int dense_potrs_coop(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv_store, double* b);

@@ -1,0 +1,517 @@
+// dense_coop.cu - latency-optimised FP64 Cholesky / solves for ONE matrix of moderate order (the Schur-reduced camera
+// system of keyframe bundle adjustment: order 3(N-1) = 765 at 256 keyframes, 3069 at 1024).
+//
+// The blocked factorisation of dense.cu launches two kernels per 32-wide panel; at n = 765 that is 48 dependent launches
+// whose critical path (single-CTA panel factorisation, launch gaps) costs ~0.94 ms for 1.5e8 flops.  Here the whole
+// factorisation is ONE persistent cooperative kernel (one CTA per SM, device-wide barriers between the phases of a panel):
+//     per panel k:   every CTA factors the 32 x 32 diagonal block redundantly (one warp, registers + shuffles) and inverts
+//                    it, so the panel solve X = A_panel L_kk^-T is a small mat-mul with independent dot products;
+//                    barrier; lower 64 x 64 tiles of the trailing matrix are updated, tiles round-robin over the CTAs;
+//                    barrier.
+//     afterwards:    inverses of the 128 x 128 diagonal blocks of L by two levels of block doubling
+//                        inv [[A 0] [C B]] = [[A^-1 0] [-B^-1 C A^-1  B^-1]]
+//                    so that a triangular solve is 6 block steps (n = 765) instead of 24.
+// Loads of matrix entries written by other CTAs inside the kernel bypass L1 (__ldcg): L1 is not coherent across SMs.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "common.h"
+#include "dense.h"
+
+namespace {
+
+constexpr int NB = 32;         // panel width
+constexpr int TS = 64;         // trailing-update tile
+constexpr int IB = 128;        // order of the inverted diagonal blocks used by the solves
+constexpr int kCoopWorkers = 256;                  // threads of the panel solve / trailing update
+constexpr int kCoopHelpers = 128;                  // look-ahead group: updates and factors the NEXT diagonal block during the trailing update
+constexpr int kCoopCta = kCoopWorkers + kCoopHelpers;
+
+// C(32x32 tile at rows r0, cols c0 of an m x m product) helpers are not needed: the doubling levels use this generic
+// small product  Out = -(Bi * (C * Ai))  on square blocks of order h (32 or 64), all operands in shared memory.
+__device__ __forceinline__ void block_inverse_offdiag(int h, const double* __restrict__ Ai, const double* __restrict__ Bi,
+                                                      const double* __restrict__ C, double* __restrict__ T,
+                                                      double* __restrict__ Out) {
+    // T = C * Ai (Ai lower triangular: sum over t >= j), Out = -Bi * T (Bi lower triangular: sum over t <= i); column-major h x h
+    for (int e = threadIdx.x; e < h * h; e += kCoopCta) {
+        const int i = e % h, j = e / h;
+        double s = 0.0;
+        for (int t = j; t < h; ++t) s = fma(C[i + h * t], Ai[t + h * j], s);
+        T[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < h * h; e += kCoopCta) {
+        const int i = e % h, j = e / h;
+        double s = 0.0;
+        for (int t = 0; t <= i; ++t) s = fma(Bi[i + h * t], T[t + h * j], s);
+        Out[e] = -s;
+    }
+    __syncthreads();
+}
+
+constexpr int kTri = NB * (NB + 1) / 2;            // entries of a 32 x 32 lower triangle
+
+// column-major list of the lower-triangle positions (i << 8 | c): the entries right of column j are the suffix that starts at
+// tri_offset(j + 1), so the trailing update of a Cholesky column is spread evenly over the lanes of one warp
+__device__ __forceinline__ int tri_offset(int c) { return NB * c - c * (c - 1) / 2; }
+__device__ __forceinline__ void warp_build_tri(unsigned short* tab, int lane) {
+    for (int c = 0; c < NB; ++c)
+        if (lane >= c) tab[tri_offset(c) + lane - c] = (unsigned short)((lane << 8) | c);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void helper_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// look-ahead group (128 threads): Cholesky of the 32 x 32 block held in Ls (lower, identity padded); 1 / L_jj into sInv.
+// Thread h owns the triangle entries e = h, h + 128, ... of the column-major list (<= 5 entries) in REGISTERS for the whole
+// factorisation; per column only the column itself travels through shared memory (col[]): owners publish it unscaled, every
+// thread reads the pivot and the two column entries each of its trailing entries needs (all loads issued before any use).
+constexpr int kOwn = (kTri + kCoopHelpers - 1) / kCoopHelpers;             // 5
+__device__ __forceinline__ bool group_potf2(double (*Ls)[NB + 1], double* sInv, double* col, const unsigned short* tab, int hid) {
+    int ii[kOwn], cc[kOwn];
+    double v[kOwn];
+#pragma unroll
+    for (int u = 0; u < kOwn; ++u) {
+        const int e = hid + kCoopHelpers * u;
+        const int code = e < kTri ? tab[e] : 0xff00;          // padding entry: column 255 > any j, never published
+        ii[u] = e < kTri ? (code >> 8) : 0;
+        cc[u] = e < kTri ? (code & 255) : 255;
+        v[u] = e < kTri ? Ls[ii[u]][cc[u]] : 0.0;
+    }
+    bool bad = false;
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int u = 0; u < kOwn; ++u)
+            if (cc[u] == j) col[ii[u]] = v[u];
+        helper_sync();
+        double piv = col[j];
+        if (!(piv > 0.0)) { bad = true; piv = 1.0; }
+        double ci[kOwn], cj[kOwn];
+#pragma unroll
+        for (int u = 0; u < kOwn; ++u) { ci[u] = col[ii[u]]; cj[u] = col[cc[u] & 31]; }
+        const double inv = rsqrt(piv);
+        const double rp = inv * inv;
+        if (hid == 0) sInv[j] = inv;
+#pragma unroll
+        for (int u = 0; u < kOwn; ++u) {
+            const bool own = cc[u] == j, trail = cc[u] > j && cc[u] < NB;
+            const double upd = fma(-(ci[u] * rp), cj[u], v[u]);
+            const double fin = (ii[u] == j) ? piv * inv : v[u] * inv;
+            v[u] = own ? fin : (trail ? upd : v[u]);
+            if (own) Ls[ii[u]][j] = v[u];
+        }
+        helper_sync();
+    }
+    return bad;
+}
+
+// one warp: X = L^-1 for the 32 x 32 lower-triangular block in Ls (diagonal inverses in sInv) by right-looking forward
+// substitution on X = I; lane = column of X, row t is final after step t; 4 rows per lane updated with hoisted loads
+__device__ __forceinline__ void warp_inverse32(double (*Ls)[NB + 1], double (*Li)[NB + 1], const double* sInv, int lane) {
+    for (int i = 0; i < NB; ++i) Li[i][lane] = (i == lane) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int t = 0; t < NB; ++t) {
+        if (lane <= t) {
+            const double xt = Li[t][lane] * sInv[t];
+            Li[t][lane] = xt;
+            for (int i0 = t + 1; i0 < NB; i0 += 4) {
+                double l[4], x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u < NB) { l[u] = Ls[i0 + u][t]; x[u] = Li[i0 + u][lane]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u < NB) Li[i0 + u][lane] = fma(-l[u], xt, x[u]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kCoopCta)
+k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, double* __restrict__ Dinv32,
+             double* __restrict__ Dinv, long long* __restrict__ dbg) {
+    // dbg (PTZBA_TRACE): SM clock cycles of CTA 0 per phase {first block, panel solve, barrier, trailing update | look-ahead, barrier, block inverses}
+    long long tprev = dbg ? clock64() : 0;
+#define COOP_TICK(slot)                                                         \
+    do {                                                                        \
+        if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {                       \
+            const long long tn = clock64();                                     \
+            dbg[slot] += tn - tprev;                                            \
+            tprev = tn;                                                         \
+        }                                                                       \
+    } while (0)
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    extern __shared__ __align__(16) double sm[];
+    // shared-memory map (doubles): Ls[32][33] | Li[32][33] | Pi[32][65] | Pj[32][65] | Ws[32][33]  (the doubling levels reuse all of it)
+    double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    double (*Li)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+    double (*Pi)[TS + 1] = reinterpret_cast<double (*)[TS + 1]>(sm + 2 * NB * (NB + 1));
+    double (*Pj)[TS + 1] = reinterpret_cast<double (*)[TS + 1]>(sm + 2 * NB * (NB + 1) + NB * (TS + 1));
+    double (*Ws)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + 2 * NB * (NB + 1) + 2 * NB * (TS + 1));
+    __shared__ double sInv[NB];
+    __shared__ unsigned short sTri[kTri];
+    __shared__ double sCol[NB];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool helper = tid >= kCoopWorkers;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int nblk = (n + NB - 1) / NB;
+    // ---- first diagonal block (every CTA, redundantly) ----
+    for (int e = tid; e < NB * NB; e += kCoopCta) {
+        const int i = e % NB, j = e / NB;
+        Ls[i][j] = (i < n && j < n && j <= i) ? A[(size_t)i + (size_t)j * lda] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (helper) {
+        if (tid < kCoopWorkers + 32) warp_build_tri(sTri, lane);
+        helper_sync();
+        if (group_potf2(Ls, sInv, sCol, sTri, tid - kCoopWorkers) && tid == kCoopWorkers && cta == 0) atomicMax(info, 1);
+    }
+    __syncthreads();
+    COOP_TICK(0);
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k = kb * NB;
+        const int nb = (n - k) < NB ? (n - k) : NB;
+        // Ls holds the factor of diagonal block kb, sInv the reciprocals of its diagonal
+        if (cta == 0) {
+            for (int e = tid; e < NB * NB; e += kCoopCta) {
+                const int i = e % NB, j = e / NB;
+                if (i < nb && j < nb && j <= i) A[(size_t)(k + i) + (size_t)(k + j) * lda] = Ls[i][j];
+            }
+        }
+        const int m0 = k + NB;                      // first row below the panel (only full panels have rows below)
+        if (m0 >= n) break;
+        // ---- panel rows below the block: X = A_panel * L_kk^-T; 64 rows per CTA staged in shared memory, 4 threads per row ----
+        if (tid < 64) {
+            // row r of the panel: x L_kk^T = a by right-looking substitution in registers (32 loads in flight, 528 FMAs)
+            for (int rb = cta * 64; m0 + rb < n; rb += G * 64) {
+                const int r = m0 + rb + tid;
+                if (r < n) {
+                    double a[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) a[j] = __ldcg(A + (size_t)r + (size_t)(k + j) * lda);
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        a[t] *= sInv[t];
+#pragma unroll
+                        for (int j = t + 1; j < NB; ++j) a[j] = fma(-a[t], Ls[j][t], a[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) A[(size_t)r + (size_t)(k + j) * lda] = a[j];
+                }
+            }
+        }
+        COOP_TICK(1);
+        grid.sync();
+        COOP_TICK(2);
+        if (helper) {
+            // ---- look-ahead: the next diagonal block, updated with this panel's rows, factored and inverted ----
+            const int k1 = m0, nb1 = (n - k1) < NB ? (n - k1) : NB;
+            long long th = dbg ? clock64() : 0;
+#define HELP_TICK(slot)                                                         \
+    do {                                                                        \
+        if (dbg && blockIdx.x == 0 && threadIdx.x == kCoopWorkers) {             \
+            const long long tn = clock64();                                     \
+            dbg[slot] += tn - th;                                               \
+            th = tn;                                                            \
+        }                                                                       \
+    } while (0)
+            const int hid = tid - kCoopWorkers;
+            {
+                // thread (row = hid & 31, 8 columns): 16 independent loads in flight
+                const int row = hid & 31, j0 = (hid >> 5) * 8;
+                double w[8], d[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = j0 + jj;
+                    w[jj] = row < nb1 ? __ldcg(A + (size_t)(k1 + row) + (size_t)(k + j) * lda) : 0.0;                    // L(k1 + row, k + j)
+                    d[jj] = (row < nb1 && j < nb1 && j <= row) ? __ldcg(A + (size_t)(k1 + row) + (size_t)(k1 + j) * lda) : (row == j ? 1.0 : 0.0);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { Ws[row][j0 + jj] = w[jj]; Ls[row][j0 + jj] = d[jj]; }
+            }
+            helper_sync();
+            HELP_TICK(6);
+            for (int e = hid; e < kTri; e += kCoopHelpers) {    // Ls(i, c) -= sum_t W(i, t) W(c, t), entries spread evenly
+                const int code = sTri[e], i = code >> 8, c = code & 255;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; t += 4) {
+                    s0 = fma(Ws[i][t], Ws[c][t], s0);
+                    s1 = fma(Ws[i][t + 1], Ws[c][t + 1], s1);
+                    s2 = fma(Ws[i][t + 2], Ws[c][t + 2], s2);
+                    s3 = fma(Ws[i][t + 3], Ws[c][t + 3], s3);
+                }
+                Ls[i][c] -= (s0 + s1) + (s2 + s3);
+            }
+            helper_sync();
+            HELP_TICK(7);
+            if (group_potf2(Ls, sInv, sCol, sTri, hid) && hid == 0 && cta == 0) atomicMax(info, k1 + 1);
+            if (dbg && blockIdx.x == 0 && threadIdx.x == kCoopWorkers) dbg[16 + kb] = clock64() - th;
+            HELP_TICK(8);
+#undef HELP_TICK
+        } else {
+            // ---- trailing update: lower 64 x 64 tiles, C -= P_i P_j^T (the tile's old values are requested first) ----
+            const int m = n - m0;
+            const int nt = (m + TS - 1) / TS;
+            const int ntiles = nt * (nt + 1) / 2;
+            for (int b = cta; b < ntiles; b += G) {
+                int ti = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+                while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
+                while (ti * (ti + 1) / 2 > b) --ti;
+                const int tj = b - ti * (ti + 1) / 2;
+                const int r0 = m0 + ti * TS, c0 = m0 + tj * TS;
+                const int tx = tid % 16, ty = tid / 16;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int gi = r0 + tx + 16 * a, gj = c0 + ty + 16 * c;
+                        acc[a][c] = (gi < n && gj < n && gi >= gj) ? __ldcg(A + (size_t)gi + (size_t)gj * lda) : 0.0;
+                    }
+                worker_sync();
+                for (int e = tid; e < NB * TS; e += kCoopWorkers) {
+                    const int rr = e % TS, t = e / TS;
+                    const int gi = r0 + rr, gj = c0 + rr;
+                    Pi[t][rr] = gi < n ? __ldcg(A + (size_t)gi + (size_t)(k + t) * lda) : 0.0;
+                    Pj[t][rr] = gj < n ? __ldcg(A + (size_t)gj + (size_t)(k + t) * lda) : 0.0;
+                }
+                worker_sync();
+#pragma unroll 8
+                for (int t = 0; t < NB; ++t) {
+                    double pi[4], pj[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { pi[a] = Pi[t][tx + 16 * a]; pj[a] = Pj[t][ty + 16 * a]; }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[a][c] = fma(-pi[a], pj[c], acc[a][c]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int gi = r0 + tx + 16 * a, gj = c0 + ty + 16 * c;
+                        // the next diagonal block is private to the look-ahead warps (every CTA updates its own copy)
+                        if (gi < n && gj < n && gi >= gj && !(gi < m0 + NB && gj < m0 + NB)) A[(size_t)gi + (size_t)gj * lda] = acc[a][c];
+                    }
+            }
+        }
+        COOP_TICK(3);
+        grid.sync();
+        COOP_TICK(4);
+    }
+    grid.sync();
+    // ---- inverses of the 32 x 32 diagonal blocks of L (one block per CTA, one warp each) ----
+    for (int b = cta; b < nblk; b += G) {
+        if (tid < 32) {
+            const int k = b * NB, nb = (n - k) < NB ? (n - k) : NB;
+            double d[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                d[j] = (lane < nb && j < nb && j <= lane) ? __ldcg(A + (size_t)(k + lane) + (size_t)(k + j) * lda) : (lane == j ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                Ls[lane][j] = d[j];
+                if (j == lane) sInv[lane] = 1.0 / d[j];
+            }
+            __syncwarp();
+            warp_inverse32(Ls, Li, sInv, lane);
+            for (int i = 0; i < NB; ++i) Dinv32[(size_t)b * NB * NB + i + NB * lane] = Li[i][lane];
+        }
+        __syncthreads();
+    }
+    grid.sync();
+    COOP_TICK(9);
+    // ---- inverses of the 128 x 128 diagonal blocks: level 1 (64-blocks from 32-blocks), level 2 (128 from 64) ----
+    // shared memory (doubles) at level h: Ai[h*h] | Bi[h*h] | C[h*h] | T[h*h] ; Dinv block layout: column-major IB x IB
+    const int nib = (n + IB - 1) / IB;
+    double* sA = sm;
+    for (int level = 0; level < 2; ++level) {
+        const int h = NB << level;                 // order of the inverted halves: 32, then 64
+        const int per = IB / (2 * h);              // merges per 128-block: 2, then 1
+        double* sAi = sA; double* sBi = sA + h * h; double* sC = sA + 2 * h * h; double* sT = sA + 3 * h * h;
+        for (int job = cta; job < nib * per; job += G) {
+            const int ib = job / per, q = job - ib * per;
+            const int o = ib * IB + q * 2 * h;     // first row/col of this merge inside the matrix
+            double* D = Dinv + (size_t)ib * IB * IB;
+            const int lo = q * 2 * h;              // offset inside the 128-block
+            __syncthreads();
+            for (int e = tid; e < h * h; e += kCoopCta) {
+                const int i = e % h, j = e / h;
+                if (level == 0) {
+                    const int ba = (o >> 5), bb = ba + 1;        // 32-block indices (may lie beyond the matrix: identity)
+                    sAi[e] = ba < nblk ? __ldcg(Dinv32 + (size_t)ba * NB * NB + e) : (i == j ? 1.0 : 0.0);
+                    sBi[e] = bb < nblk ? __ldcg(Dinv32 + (size_t)bb * NB * NB + e) : (i == j ? 1.0 : 0.0);
+                } else {
+                    sAi[e] = __ldcg(D + (size_t)(lo + i) + (size_t)(lo + j) * IB);
+                    sBi[e] = __ldcg(D + (size_t)(lo + h + i) + (size_t)(lo + h + j) * IB);
+                }
+                const int gi = o + h + i, gj = o + j;
+                sC[e] = (gi < n && gj < n) ? __ldcg(A + (size_t)gi + (size_t)gj * lda) : 0.0;
+            }
+            __syncthreads();
+            block_inverse_offdiag(h, sAi, sBi, sC, sT, sC);      // sC <- -Bi C Ai
+            for (int e = tid; e < h * h; e += kCoopCta) {
+                const int i = e % h, j = e / h;
+                D[(size_t)(lo + h + i) + (size_t)(lo + j) * IB] = sC[e];
+                D[(size_t)(lo + i) + (size_t)(lo + h + j) * IB] = 0.0;
+                if (level == 0) {
+                    D[(size_t)(lo + i) + (size_t)(lo + j) * IB] = sAi[e];
+                    D[(size_t)(lo + h + i) + (size_t)(lo + h + j) * IB] = sBi[e];
+                }
+            }
+        }
+        grid.sync();
+    }
+    COOP_TICK(5);
+#undef COOP_TICK
+}
+
+// ---- L L^T x = b with the inverted 128 x 128 diagonal blocks; single CTA, 1024 threads -----------------------------------
+// block step: x_k = Dinv_k b_k (forward) or Dinv_k^T b_k (backward), then the rest of b is updated with the block column
+// (forward) or block row (backward) of L.  All matrix reads are coalesced along the column-major storage.
+__global__ void __launch_bounds__(1024) k_potrs_dinv128(const double* __restrict__ L, int lda, int n,
+                                                        const double* __restrict__ Dinv, double* __restrict__ bvec) {
+    __shared__ double xs[IB];
+    __shared__ double bs[IB];
+    __shared__ double part[8][IB];
+    __shared__ double red4[4][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nib = (n + IB - 1) / IB;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool backward = pass == 1;
+        for (int bi = 0; bi < nib; ++bi) {
+            const int blk = backward ? (nib - 1 - bi) : bi;
+            const int k = blk * IB;
+            const int nb = (n - k) < IB ? (n - k) : IB;
+            const double* D = Dinv + (size_t)blk * IB * IB;
+            if (tid < IB) bs[tid] = tid < nb ? bvec[k + tid] : 0.0;
+            __syncthreads();
+            if (!backward) {
+                // x_r = sum_{c <= r} D[r][c] b_c: thread (r, q) takes the columns c = q mod 8, rows contiguous across threads
+                const int r = tid & (IB - 1), q = tid >> 7;
+                double dv[16];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) dv[m] = (q + 8 * m <= r) ? D[r + (size_t)(q + 8 * m) * IB] : 0.0;      // 16 loads in flight
+                double s = 0.0;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) s = fma(dv[m], bs[q + 8 * m], s);
+                part[q][r] = s;
+                __syncthreads();
+                if (tid < IB) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) t += part[qq][tid];
+                    xs[tid] = tid < nb ? t : 0.0;
+                }
+            } else {
+                // x_r = sum_{c >= r} D[c][r] b_c: warp per row, lanes along the contiguous column r of D
+#pragma unroll
+                for (int rr4 = 0; rr4 < 4; ++rr4) {
+                    const int r = warp + 32 * rr4;
+                    double dv[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) dv[m] = (lane + 32 * m >= r) ? D[lane + 32 * m + (size_t)r * IB] : 0.0;
+                    double s = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) s = fma(dv[m], bs[lane + 32 * m], s);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0) xs[r] = r < nb ? s : 0.0;
+                }
+            }
+            __syncthreads();
+            if (tid < nb) bvec[k + tid] = xs[tid];
+            if (!backward) {
+                // b[r] -= sum_j L[r][k + j] x_j for the rows below the block: 256 rows at a time, the 128 columns split
+                // over 4 threads per row with 32 independent loads each (one L2 round trip per chunk)
+                const int rr = tid & 255, q = tid >> 8;
+                for (int r0 = k + nb; r0 < n; r0 += 256) {
+                    const int r = r0 + rr;
+                    double s = 0.0;
+                    if (r < n) {
+                        const double* row = L + (size_t)r + (size_t)(k + 32 * q) * lda;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            double v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = (32 * q + 16 * h + j < nb) ? row[(size_t)(16 * h + j) * lda] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) s = fma(v[j], xs[32 * q + 16 * h + j], s);
+                        }
+                    }
+                    red4[q][rr] = s;
+                    __syncthreads();
+                    if (q == 0 && r < n) bvec[r] -= (red4[0][rr] + red4[1][rr]) + (red4[2][rr] + red4[3][rr]);
+                    __syncthreads();
+                }
+            } else {
+                // b[c] -= sum_i L[k + i][c] x_i for the columns left of the block: one warp per column, lanes along i
+                // (4 independent 256-byte loads per lane-column)
+                for (int c = warp; c < k; c += 32) {
+                    const double* col = L + (size_t)k + (size_t)c * lda;
+                    double v[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) v[m] = (lane + 32 * m < nb) ? col[lane + 32 * m] : 0.0;
+                    double s = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) s = fma(v[m], xs[lane + 32 * m], s);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0) bvec[c] -= s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+size_t dense_coop_dinv_doubles(int n) { return (size_t)((n + IB - 1) / IB) * IB * IB + (size_t)((n + NB - 1) / NB) * NB * NB + 16; }
+
+int dense_potrf_coop(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info, double* Dinv_store) {
+    if (n <= 0) return PTZBA_OK;
+    const size_t smem = (size_t)4 * TS * TS * sizeof(double);      // 128 KB: four 64 x 64 blocks of the doubling level
+    static bool configured = false;
+    if (!configured) {
+        CU_CHECK(ctx, cudaFuncSetAttribute(k_potrf_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int nib = (n + IB - 1) / IB;
+    double* Dinv = Dinv_store;
+    double* Dinv32 = Dinv_store + (size_t)nib * IB * IB;
+    int grid = ctx->sm_count;
+    long long* dbg = nullptr;
+    static const bool trace = getenv("PTZBA_TRACE") != nullptr;
+    if (trace) {
+        CU_CHECK(ctx, cudaMalloc((void**)&dbg, 64 * sizeof(long long)));
+        CU_CHECK(ctx, cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), ctx->stream));
+    }
+    void* args[] = {&A, &n, &lda, &d_info, &Dinv32, &Dinv, &dbg};
+    CU_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_potrf_coop, dim3(grid), dim3(kCoopCta), args, smem, ctx->stream));
+    ctx->launches++;
+    if (trace) {
+        long long h[64];
+        CU_CHECK(ctx, cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[ptzba trace] potrf_coop n=%d cycles: first_block=%lld panel=%lld bar=%lld update|lookahead=%lld bar=%lld inv32=%lld blockinv=%lld | helper: loads=%lld update=%lld potf2=%lld\n", n,
+                h[0], h[1], h[2], h[3], h[4], h[9], h[5], h[6], h[7], h[8]);
+        fprintf(stderr, "[ptzba trace] potf2 per panel:");
+        for (int i = 0; i < 24; ++i) fprintf(stderr, " %lld", h[16 + i]);
+        fprintf(stderr, "\n");
+        cudaFree(dbg);
+    }
+    return PTZBA_OK;
+}
+
+int dense_potrs_coop(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv_store, double* b) {
+    if (n <= 0) return PTZBA_OK;
+    k_potrs_dinv128<<<1, 1024, 0, ctx->stream>>>(L, lda, n, Dinv_store, b);
+    KERNEL_POST(ctx);
+    return PTZBA_OK;
+}
