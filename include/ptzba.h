@@ -179,6 +179,16 @@ int ptzba_comm_init(ptzba_ctx* ctx, const void* unique_id128, int rank, int worl
 int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int64_t count);
 /* sums the packed accumulators [cost | U | V | g_c | g_l] of the last fused pass over all ranks (in place, on the stream) */
 int ptzba_ba_allreduce(ptzba_ba* ba);
+/* Second multi-GPU mode - replicated data, partitioned work (the distributed SOLVE): every rank creates its ptzba_ba from
+ * the WHOLE observation list and then restricts the per-observation kernels to its slice: landmarks [lm_lo, lm_hi) of the
+ * landmark-major list (all observations of a landmark stay on one rank, so landmark blocks, Schur pair products and
+ * back-substituted landmark steps are complete locally) and positions [cm_lo, cm_hi) of the keyframe-major list
+ * (pan-tilt-zoom-slam_b200/dist.py:solve_partition computes balanced slices).  ptzba_ba_normal_equations, ptzba_ba_solve
+ * and ptzba_ba_lm_iteration then all-reduce the partial sums themselves (packed blocks, the reduced camera system, the
+ * reduced right-hand side, landmark steps, two scalars per trial point) with ncclAllReduce on the context stream, and every
+ * rank ends with the same solution.  The residual VECTOR is only written for the rank's own observations.
+ * ptzba_comm_init(rank, world_size) must have been called first.  Do not combine with ptzba_ba_allreduce. */
+int ptzba_ba_set_partition(ptzba_ba* ba, int rank, int world_size, int lm_lo, int lm_hi, int64_t cm_lo, int64_t cm_hi);
 /* copies the accumulators of the last fused pass to host buffers (any may be NULL): U[n_pose*6], gc[n_pose*3],
  * V[n_landmark*3], gl[n_landmark*2], cost */
 int ptzba_ba_get_blocks(ptzba_ba* ba, double* U, double* gc, double* V, double* gl, double* cost);

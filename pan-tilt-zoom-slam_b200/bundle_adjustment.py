@@ -43,6 +43,12 @@ class BAProblem:
     def n_params(self):
         return 3 * (self.n_pose - 1) + 2 * self.n_landmark
 
+    def set_partition(self, rank, world_size, lm_range, cm_range):
+        """Distributed solve (replicated data, partitioned work): this rank visits landmarks lm_range = (lo, hi) of the
+        landmark-major list and positions cm_range = (lo, hi) of the keyframe-major list; see dist.solve_partition."""
+        self.ctx.check(self.ctx.lib.ptzba_ba_set_partition(self.handle, int(rank), int(world_size), int(lm_range[0]),
+                                                           int(lm_range[1]), int(cm_range[0]), int(cm_range[1])))
+
     def close(self):
         if getattr(self, "handle", None):
             self.ctx.lib.ptzba_ba_destroy(self.handle)

@@ -51,6 +51,11 @@ struct ptzba_ba {
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int grid_lm_pass = 0, grid_cam_pass = 0;   // one wave of resident CTAs per pass
+    // work partition (ptzba_ba_set_partition); defaults = everything on this rank
+    int part_rank = 0, part_world = 1;
+    int lm_lo = 0, lm_hi = 0;                  // landmark slice
+    int64_t lmo_lo = 0, lmo_hi = 0;            // its observations in the landmark-major list
+    int64_t cmo_lo = 0, cmo_hi = 0;            // slice of the keyframe-major list
     bool cam_smem = true;           // keyframe trig table fits in shared memory
     bool acc_zeroed = false;        // the arena was cleared by ba_set_params(..., zero_acc = true)
 };
@@ -59,3 +64,4 @@ struct ptzba_ba {
 int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3, bool zero_acc = false);   // unpack + trig tables (+ clear ba->acc)
 int ba_fused_pass(ptzba_ba* ba, double* d_resid_or_null);                            // -> ba->acc
 int ba_residual_pass(ptzba_ba* ba, double* d_resid_or_null, double* d_sumsq);        // r (caller order) and sum r^2
+extern "C" int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int64_t count);

@@ -155,14 +155,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------------------------
 template <int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_cam_pass(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+k_ba_cam_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
               const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
               const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
     const int tid = threadIdx.x, lane = tid & 31;
     const double k1 = PTZ_DEG2RAD;
-    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
     int64_t end = begin + chunk;
-    if (end > n_obs) end = n_obs;
+    if (end > hi) end = hi;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
     int wcam = -1;
     CamTrig wc = {0, 1, 0, 1, 1};
@@ -248,7 +248,7 @@ __device__ __forceinline__ void commit_lm(double* __restrict__ gV, double* __res
 
 template <int MINB, bool CAM_SMEM>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
               const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
               double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
@@ -262,16 +262,17 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
         }
         __syncthreads();
     }
-    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    // this CTA's observations: [max(begin, lo), end); quads stay aligned to multiples of 4 of the array index
+    const int64_t begin = (lo & ~(int64_t)3) + (int64_t)blockIdx.x * chunk;
     int64_t end = begin + chunk;
-    if (end > n_obs) end = n_obs;
+    if (end > hi) end = hi;
     const double k1 = PTZ_DEG2RAD;
     double cost = 0.0;
     for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
         const int64_t k0 = base + (int64_t)tid * kQuad;
         int cam[kQuad], lm[kQuad];
         double ox[kQuad], oy[kQuad];
-        if (k0 + kQuad <= end) {
+        if (k0 >= lo && k0 + kQuad <= end) {
             const int4 c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
             const int4 l4 = __ldg(reinterpret_cast<const int4*>(s_lm + k0));
             const D4 x4 = *reinterpret_cast<const D4*>(s_ox + k0);
@@ -283,7 +284,7 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
         } else {
 #pragma unroll
             for (int i = 0; i < kQuad; ++i) {
-                const bool in = k0 + i < end;
+                const bool in = k0 + i >= lo && k0 + i < end;
                 cam[i] = in ? s_cam[k0 + i] : 0;
                 lm[i] = in ? s_lm[k0 + i] : -1;
                 ox[i] = in ? s_ox[k0 + i] : 0.0;
@@ -326,7 +327,7 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
             glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
         }
         if (resid) {
-            if (!orig && k0 + kQuad <= end) {
+            if (!orig && k0 >= lo && k0 + kQuad <= end) {
                 D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
                 dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
                 dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
@@ -356,13 +357,13 @@ k_ba_lm_pass4(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, c
 
 // residual-only pass (trial points of the trust-region loop, and _compute_residual itself)
 __global__ void __launch_bounds__(kFusedThreads)
-k_ba_residual(int64_t n_obs, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+k_ba_residual(int64_t lo, int64_t hi, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
               const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, double u, double v,
               double* __restrict__ resid, double* __restrict__ gSumSq) {
     __shared__ double sWarp[kFusedThreads / 32];
     double cost = 0.0;
-    for (int64_t k = (int64_t)blockIdx.x * kFusedThreads + threadIdx.x; k < n_obs; k += (int64_t)gridDim.x * kFusedThreads) {
+    for (int64_t k = lo + (int64_t)blockIdx.x * kFusedThreads + threadIdx.x; k < hi; k += (int64_t)gridDim.x * kFusedThreads) {
         const CamTrig c = cam_trig[s_cam[k]];
         const LmTrig l = lm_trig[s_lm[k]];
         double x, y;
@@ -429,27 +430,35 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         CU_CHECK(ctx, cudaEventRecord(ev0, s));
     }
     // contiguous chunk per CTA: a multiple of 128 observations (every warp iteration starts on a 32-byte boundary of
-    // all four streams), sized so that all resident CTAs of the single wave get the same amount of work
+    // all four streams), sized so that all resident CTAs of the single wave get the same amount of work.  With a
+    // partition (ptzba_ba_set_partition) only this rank's slices of the two sorted lists are visited.
     const size_t smA = ba->cam_smem ? (size_t)ba->n_pose * 6 * sizeof(double) : 0;
-    int64_t chunkA = (ba->n_obs + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
-    chunkA = (chunkA + 127) / 128 * 128;
-    const int gridA = (int)((ba->n_obs + chunkA - 1) / chunkA);
-    if (ba->cam_smem)
-        k_ba_lm_pass4<3, true><<<gridA, kFusedThreads, smA, s>>>(ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p,
-                                                                orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v, d_resid,
-                                                                ba->acc.V, ba->acc.gl, ba->acc.cost);
-    else
-        k_ba_lm_pass4<3, false><<<gridA, kFusedThreads, 0, s>>>(ba->n_obs, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p,
-                                                               orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v, d_resid,
-                                                               ba->acc.V, ba->acc.gl, ba->acc.cost);
-    KERNEL_POST(ctx);
-    int64_t chunkB = (ba->n_obs + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
-    chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
-    const int gridB = (int)((ba->n_obs + chunkB - 1) / chunkB);
-    k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->n_obs, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                     ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
-    KERNEL_POST(ctx);
+    const int64_t nA = ba->lmo_hi - (ba->lmo_lo & ~(int64_t)3);
+    if (nA > 0) {
+        int64_t chunkA = (nA + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
+        chunkA = (chunkA + 127) / 128 * 128;
+        const int gridA = (int)((nA + chunkA - 1) / chunkA);
+        if (ba->cam_smem)
+            k_ba_lm_pass4<3, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+                                                                    ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
+                                                                    d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        else
+            k_ba_lm_pass4<3, false><<<gridA, kFusedThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+                                                                   ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
+                                                                   d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        KERNEL_POST(ctx);
+    }
+    const int64_t nB = ba->cmo_hi - ba->cmo_lo;
+    if (nB > 0) {
+        int64_t chunkB = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
+        chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
+        const int gridB = (int)((nB + chunkB - 1) / chunkB);
+        k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                         ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+        KERNEL_POST(ctx);
+    }
     if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
+    if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count));
     return PTZBA_OK;
 }
 
@@ -459,10 +468,13 @@ int ba_residual_pass(ptzba_ba* ba, double* d_resid, double* d_sumsq) {
     if (d_sumsq) CU_CHECK(ctx, cudaMemsetAsync(d_sumsq, 0, sizeof(double), s));
     if (ba->n_obs == 0) return PTZBA_OK;
     const int32_t* orig = ba->identity_perm ? nullptr : ba->orig.p;
-    k_ba_residual<<<stream_grid(ctx, ba->n_obs, kFusedThreads, 8), kFusedThreads, 0, s>>>(
-        ba->n_obs, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v,
-        d_resid, d_sumsq);
-    KERNEL_POST(ctx);
+    if (ba->lmo_hi > ba->lmo_lo) {
+        k_ba_residual<<<stream_grid(ctx, ba->lmo_hi - ba->lmo_lo, kFusedThreads, 8), kFusedThreads, 0, s>>>(
+            ba->lmo_lo, ba->lmo_hi, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v,
+            d_resid, d_sumsq);
+        KERNEL_POST(ctx);
+    }
+    if (ba->part_world > 1 && d_sumsq) PROPAGATE(ptzba_comm_allreduce_f64(ctx, d_sumsq, 1));
     return PTZBA_OK;
 }
 
@@ -479,6 +491,7 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     cudaStream_t s = ctx->stream;
     ptzba_ba* ba = new ptzba_ba();
     ba->ctx = ctx; ba->n_pose = n_pose; ba->n_lm = n_landmark; ba->n_obs = n_obs; ba->u = u; ba->v = v;
+    ba->lm_hi = n_landmark; ba->lmo_hi = n_obs; ba->cmo_hi = n_obs;
     auto fail = [&](int code) { delete ba; return code; };
 #define CU_TRY(expr)                                                                                   \
     do {                                                                                               \
@@ -594,6 +607,29 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     }
 #undef CU_TRY
     *out = ba;
+    return PTZBA_OK;
+}
+
+// Replicated data, partitioned work: every rank holds the whole observation list and visits only its slice of it in
+// the per-observation kernels - landmarks [lm_lo, lm_hi) of the landmark-major list (all observations of a landmark stay
+// on one rank, so landmark blocks, Schur pair products and back-substituted landmark steps are complete locally) and
+// positions [cm_lo, cm_hi) of the keyframe-major list.  Partial sums are combined with ncclAllReduce on the context
+// stream inside the passes and the solver; ptzba_comm_init must have been called with the same rank / world size.
+extern "C" int ptzba_ba_set_partition(ptzba_ba* ba, int rank, int world_size, int lm_lo, int lm_hi, int64_t cm_lo, int64_t cm_hi) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    ARG_CHECK(ctx, world_size >= 1 && rank >= 0 && rank < world_size);
+    ARG_CHECK(ctx, lm_lo >= 0 && lm_lo <= lm_hi && lm_hi <= ba->n_lm && cm_lo >= 0 && cm_lo <= cm_hi && cm_hi <= ba->n_obs);
+    if (world_size > 1 && (!ctx->nccl_comm || ctx->world != world_size || ctx->rank != rank))
+        return ptzba_fail(ctx, PTZBA_ERR_STATE, "ptzba_comm_init(rank=%d, world=%d) must precede ptzba_ba_set_partition", rank, world_size);
+    int32_t ends[2] = {0, 0};
+    CU_CHECK(ctx, cudaMemcpyAsync(&ends[0], ba->lm_ptr.p + lm_lo, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(&ends[1], ba->lm_ptr.p + lm_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ba->part_rank = rank; ba->part_world = world_size;
+    ba->lm_lo = lm_lo; ba->lm_hi = lm_hi;
+    ba->lmo_lo = ends[0]; ba->lmo_hi = ends[1];
+    ba->cmo_lo = cm_lo; ba->cmo_hi = cm_hi;
     return PTZBA_OK;
 }
 

@@ -153,7 +153,7 @@ __global__ void k_schur_diag(int n_pose, const double* __restrict__ U, const dou
 // the three lanes of one block column hit one 32-byte sector of the column-major S: the L2 atomic unit sees 3 sectors per
 // pair instead of 9 (the FP64 RED rate is per sector).  Only the lower triangle of S is written.
 __global__ void __launch_bounds__(kThreads)
-k_schur_pairs(int n_lm, const int32_t* __restrict__ lm_ptr, const int32_t* __restrict__ s_cam,
+k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const int32_t* __restrict__ s_cam,
               const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ Vinv,
               int dmax, double* __restrict__ S, int ld) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -162,7 +162,7 @@ k_schur_pairs(int n_lm, const int32_t* __restrict__ lm_ptr, const int32_t* __res
     double* Wsm = reinterpret_cast<double*>(smem_raw) + (size_t)wid * dmax * 12;
     int* Csm = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)warps * dmax * 12) + (size_t)wid * dmax;
     const int total_warps = gridDim.x * warps;
-    for (int l = blockIdx.x * warps + wid; l < n_lm; l += total_warps) {
+    for (int l = lm_lo + blockIdx.x * warps + wid; l < lm_hi; l += total_warps) {
         const int b = lm_ptr[l], d = lm_ptr[l + 1] - b;
         if (d == 0) continue;
         const double v00 = Vinv[3 * (size_t)l], v01 = Vinv[3 * (size_t)l + 1], v11 = Vinv[3 * (size_t)l + 2];
@@ -218,7 +218,7 @@ k_schur_pairs(int n_lm, const int32_t* __restrict__ lm_ptr, const int32_t* __res
 
 // ---- reduced right-hand side: out_c[cam] -= W_i Vinv rhs_l  (keyframe accumulators privatised in shared memory) --------
 __global__ void __launch_bounds__(kThreads)
-k_reduce_rhs(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+k_reduce_rhs(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
              const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ Vinv,
              const double* __restrict__ rhs_l, int n_pose, int use_smem, double* __restrict__ out_c) {
     extern __shared__ __align__(16) double sacc[];     // [n_pose*3] when use_smem
@@ -226,9 +226,9 @@ k_reduce_rhs(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, co
         for (int i = threadIdx.x; i < n_pose * 3; i += kThreads) sacc[i] = 0.0;
         __syncthreads();
     }
-    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
     int64_t end = begin + chunk;
-    if (end > n_obs) end = n_obs;
+    if (end > hi) end = hi;
     for (int64_t k = begin + threadIdx.x; k < end; k += kThreads) {
         const int cam = s_cam[k];
         if (cam == 0) continue;
@@ -254,13 +254,13 @@ k_reduce_rhs(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, co
 
 // ---- back-substitution: tmp_l[l] += W_i^T y_c[cam_i]  (segmented warp reduction, heads commit atomically) --------------
 __global__ void __launch_bounds__(kThreads)
-k_backsub_accum(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+k_backsub_accum(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
                 const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ y_c,
                 double* __restrict__ tmp_l) {
     const int lane = threadIdx.x & 31;
-    const int64_t begin = (int64_t)blockIdx.x * chunk;
+    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
     int64_t end = begin + chunk;
-    if (end > n_obs) end = n_obs;
+    if (end > hi) end = hi;
     for (int64_t base = begin; base < end; base += kThreads) {
         const int64_t k = base + threadIdx.x;
         const bool act = k < end;
@@ -292,10 +292,12 @@ k_backsub_accum(int64_t n_obs, int64_t chunk, const int32_t* __restrict__ s_cam,
 }
 
 // y_l = Vinv (rhs_l - tmp_l)
-__global__ void k_backsub_final(int n_lm, const double* __restrict__ Vinv, const double* __restrict__ rhs_l,
+// landmarks outside [lm_lo, lm_hi) belong to other ranks: zero here, filled in by the all-reduce that follows
+__global__ void k_backsub_final(int n_lm, int lm_lo, int lm_hi, const double* __restrict__ Vinv, const double* __restrict__ rhs_l,
                                 const double* __restrict__ tmp_l, double* __restrict__ y_l) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_lm) return;
+    if (l < lm_lo || l >= lm_hi) { y_l[2 * (size_t)l] = 0.0; y_l[2 * (size_t)l + 1] = 0.0; return; }
     const double r0 = rhs_l[2 * (size_t)l] - tmp_l[2 * (size_t)l], r1 = rhs_l[2 * (size_t)l + 1] - tmp_l[2 * (size_t)l + 1];
     const double v00 = Vinv[3 * (size_t)l], v01 = Vinv[3 * (size_t)l + 1], v11 = Vinv[3 * (size_t)l + 2];
     y_l[2 * (size_t)l] = fma(v00, r0, v01 * r1);
@@ -304,12 +306,12 @@ __global__ void k_backsub_final(int n_lm, const double* __restrict__ Vinv, const
 
 // ---- ||J delta||^2 ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_jvp_sumsq(int64_t n_obs, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+k_jvp_sumsq(int64_t lo, int64_t hi, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
             const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ d_c,
             const double* __restrict__ d_l, double* __restrict__ out) {
     __shared__ double sw[kThreads / 32];
     double acc = 0.0;
-    for (int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x; k < n_obs; k += (int64_t)gridDim.x * kThreads) {
+    for (int64_t k = lo + (int64_t)blockIdx.x * kThreads + threadIdx.x; k < hi; k += (int64_t)gridDim.x * kThreads) {
         const int cam = s_cam[k], l = s_lm[k];
         double x, y;
         ObsGeom g;
@@ -389,10 +391,11 @@ struct Solver {
         g = ba->acc.gc;           // gc | gl contiguous = full layout
         D = ba->scale_inv.p; Dc = D; Dl = D + 3 * N;
         obs_grid = ctx->sm_count * 4;
-        chunk = (ba->n_obs + obs_grid - 1) / obs_grid;
+        const int64_t n_part = ba->lmo_hi - ba->lmo_lo;          // this rank's observations (landmark-major slice)
+        chunk = (n_part + obs_grid - 1) / obs_grid;
         chunk = (chunk + kThreads - 1) / kThreads * kThreads;
         if (chunk < kThreads) chunk = kThreads;
-        obs_grid = (int)((ba->n_obs + chunk - 1) / chunk);
+        obs_grid = (int)((n_part + chunk - 1) / chunk);
         if (obs_grid < 1) obs_grid = 1;
         const size_t per_warp = (size_t)(ba->max_degree > 0 ? ba->max_degree : 1) * (12 * sizeof(double) + sizeof(int));
         const size_t need = per_warp * (kThreads / 32) + 16;
@@ -407,7 +410,7 @@ struct Solver {
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_schur_pairs, kThreads, pair_warps_smem));
         if (per_sm < 1) per_sm = 1;
         pair_grid = ctx->sm_count * per_sm;
-        const int max_grid = div_up(M, kThreads / 32);
+        const int max_grid = div_up(ba->lm_hi - ba->lm_lo, kThreads / 32);
         if (pair_grid > max_grid) pair_grid = max_grid > 0 ? max_grid : 1;
         return PTZBA_OK;
     }
@@ -420,15 +423,18 @@ struct Solver {
         KERNEL_POST(ctx);
         if (n > 0) {
             CU_CHECK(ctx, cudaMemsetAsync(ba->Sred.p, 0, (size_t)n * n * sizeof(double), s));
-            k_schur_diag<<<div_up(N, 128), 128, 0, s>>>(N, ba->acc.U, Dc, alpha, ba->Sred.p, n);
-            KERNEL_POST(ctx);
+            if (ba->part_rank == 0) {                       // the diagonal blocks enter the all-reduced sum once
+                k_schur_diag<<<div_up(N, 128), 128, 0, s>>>(N, ba->acc.U, Dc, alpha, ba->Sred.p, n);
+                KERNEL_POST(ctx);
+            }
             tr.mark("vinv+memset+diag");
-            if (ba->n_obs > 0) {
-                k_schur_pairs<<<pair_grid, kThreads, pair_warps_smem, s>>>(M, ba->lm_ptr.p, ba->s_cam.p, ba->cam_trig.p,
+            if (ba->lm_hi > ba->lm_lo && ba->n_obs > 0) {
+                k_schur_pairs<<<pair_grid, kThreads, pair_warps_smem, s>>>(ba->lm_lo, ba->lm_hi, ba->lm_ptr.p, ba->s_cam.p, ba->cam_trig.p,
                                                                           ba->lm_trig.p, ba->Vinv.p, ba->max_degree,
                                                                           ba->Sred.p, n);
                 KERNEL_POST(ctx);
             }
+            if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->Sred.p, (int64_t)n * n));
             tr.mark("schur_pairs");
             PROPAGATE(dense_potrf_coop(ctx, ba->Sred.p, n, n, flags.p + 1, dinv.p));
             tr.mark("potrf+block_inverses");
@@ -448,26 +454,29 @@ struct Solver {
         const double* rhs_c = rhs;
         const double* rhs_l = rhs + 3 * N;
         double* red = ba->rhs_l.p;     // reduced camera rhs (full camera layout, slot 0 unused)
-        CU_CHECK(ctx, cudaMemcpyAsync(red, rhs_c, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
-        if (ba->n_obs > 0 && n > 0) {
+        if (ba->part_rank == 0) CU_CHECK(ctx, cudaMemcpyAsync(red, rhs_c, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        else CU_CHECK(ctx, cudaMemsetAsync(red, 0, (size_t)3 * N * sizeof(double), s));
+        if (ba->lmo_hi > ba->lmo_lo && n > 0) {
             const int use_smem = (size_t)N * 3 * sizeof(double) <= 200 * 1024;
             k_reduce_rhs<<<obs_grid, kThreads, use_smem ? N * 3 * sizeof(double) : 0, s>>>(
-                ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p, ba->Vinv.p, rhs_l, N, use_smem, red);
+                ba->lmo_lo, ba->lmo_hi, chunk, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p, ba->Vinv.p, rhs_l, N, use_smem, red);
             KERNEL_POST(ctx);
         }
+        if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, red, (int64_t)3 * N));
         tr.mark("reduce_rhs");
         if (n > 0) PROPAGATE(dense_potrs_coop(ctx, ba->Sred.p, n, n, dinv.p, red + 3));
         tr.mark("potrs");
         CU_CHECK(ctx, cudaMemcpyAsync(y, red, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CU_CHECK(ctx, cudaMemsetAsync(y, 0, 3 * sizeof(double), s));
         CU_CHECK(ctx, cudaMemsetAsync(tmp_l.p, 0, (size_t)2 * M * sizeof(double), s));
-        if (ba->n_obs > 0 && n > 0) {
-            k_backsub_accum<<<obs_grid, kThreads, 0, s>>>(ba->n_obs, chunk, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p,
+        if (ba->lmo_hi > ba->lmo_lo && n > 0) {
+            k_backsub_accum<<<obs_grid, kThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, chunk, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p,
                                                          ba->lm_trig.p, y, tmp_l.p);
             KERNEL_POST(ctx);
         }
-        k_backsub_final<<<div_up(M, 256), 256, 0, s>>>(M, ba->Vinv.p, rhs_l, tmp_l.p, y + 3 * N);
+        k_backsub_final<<<div_up(M, 256), 256, 0, s>>>(M, ba->lm_lo, ba->lm_hi, ba->Vinv.p, rhs_l, tmp_l.p, y + 3 * N);
         KERNEL_POST(ctx);
+        if (ba->part_world > 1 && M > 0) PROPAGATE(ptzba_comm_allreduce_f64(ctx, y + 3 * N, (int64_t)2 * M));
         tr.mark("backsub");
         tr.report("solve");
         return PTZBA_OK;
@@ -641,11 +650,12 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
             CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
             k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, ba->sol2_c.p, nullptr, nullptr, nullptr, ba->scal.p);
             KERNEL_POST(ctx);
-            if (ba->n_obs > 0) {
-                k_jvp_sumsq<<<S.obs_grid, kThreads, 0, s>>>(ba->n_obs, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p,
+            if (ba->lmo_hi > ba->lmo_lo) {
+                k_jvp_sumsq<<<S.obs_grid, kThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p,
                                                            ba->sol2_c.p, ba->sol2_c.p + 3 * N, ba->scal.p + 6);
                 KERNEL_POST(ctx);
             }
+            if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->scal.p + 6, 1));
             // residual at the trial point (trig tables switch to x_trial; restored by the next fused pass)
             PROPAGATE(ba_set_params(ba, xt, d_ref.d));
             PROPAGATE(ba_residual_pass(ba, nullptr, ba->scal.p + 7));
@@ -736,11 +746,12 @@ extern "C" int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, con
     CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
     k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, ba->sol2_c.p, nullptr, nullptr, nullptr, ba->scal.p);
     KERNEL_POST(ctx);
-    if (ba->n_obs > 0) {
-        k_jvp_sumsq<<<S.obs_grid, kThreads, 0, s>>>(ba->n_obs, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p,
+    if (ba->lmo_hi > ba->lmo_lo) {
+        k_jvp_sumsq<<<S.obs_grid, kThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p,
                                                    ba->sol2_c.p, ba->sol2_c.p + 3 * N, ba->scal.p + 6);
         KERNEL_POST(ctx);
     }
+    if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->scal.p + 6, 1));
     PROPAGATE(ba_set_params(ba, xt, d_ref.d));
     PROPAGATE(ba_residual_pass(ba, nullptr, ba->scal.p + 7));
     double h[8];

@@ -60,6 +60,23 @@ def shard_by_keyframe(cam_idx, lm_idx, obs_xy, n_pose, rank, world_size):
     return cam_idx[sel], np.asarray(lm_idx)[sel], np.asarray(obs_xy)[sel], (lo, hi)
 
 
+def solve_partition(lm_idx, n_landmark, world_size):
+    """Work slices of the distributed solve (ptzba_ba_set_partition), one per rank: contiguous landmark ranges balanced by
+    observation count, and equal contiguous slices of the keyframe-major observation list.
+    Returns [((lm_lo, lm_hi), (cm_lo, cm_hi)), ...]; the ranges tile [0, n_landmark) and [0, n_obs)."""
+    lm_idx = np.asarray(lm_idx)
+    n_obs = int(lm_idx.shape[0])
+    counts = np.bincount(lm_idx, minlength=n_landmark).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(counts)])
+    lm_bounds = [0]
+    for r in range(1, world_size):
+        lm_bounds.append(int(np.searchsorted(csum, n_obs * r / world_size, side="left")))
+    lm_bounds.append(n_landmark)
+    lm_bounds = np.maximum.accumulate(np.clip(lm_bounds, 0, n_landmark))
+    cm_bounds = [n_obs * r // world_size for r in range(world_size + 1)]
+    return [((int(lm_bounds[r]), int(lm_bounds[r + 1])), (int(cm_bounds[r]), int(cm_bounds[r + 1]))) for r in range(world_size)]
+
+
 def shard_sequences(n_seq, rank, world_size):
     """Indices of the independent EKF sequences owned by this rank (no collective on this path)."""
     return np.arange(rank, n_seq, world_size)

@@ -52,6 +52,32 @@ def main():
         print("multi_gpu_check OK: world=%d, rank-0 shard keyframes [%d,%d), all-reduced blocks match the oracle" % (world, lo, hi))
     dist.barrier()
     prob.close()
+
+    # ---- distributed SOLVE: replicated data, partitioned work; every rank must end at the single-GPU solution ----
+    full = BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V, ctx=ctx)
+    x_ref, rep_ref = full.solve(fb.x0(), fb.ptz_init[0], ftol=1e-8, xtol=1e-8, gtol=1e-8)
+    full.close()
+    part = BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V, ctx=ctx)
+    lm_range, cm_range = pdist.solve_partition(fb.lm_idx, fb.n_landmark, world)[rank]
+    part.set_partition(rank, world, lm_range, cm_range)
+    x_par, rep = part.solve(fb.x0(), fb.ptz_init[0], ftol=1e-8, xtol=1e-8, gtol=1e-8)
+    part.close()
+    # the all-reduce changes the summation order, so the two runs may stop one tiny step apart: compare at the parity
+    # tolerance of the path (1e-6 rad on angles, 1e-3 px on focal lengths), not iteration counts
+    assert rep["status"] > 0 and rep_ref["status"] > 0, (rep, rep_ref)
+    nc = 3 * (fb.n_pose - 1)
+    d = np.abs(x_par - x_ref)
+    ang = np.concatenate([d[0:nc:3], d[1:nc:3], d[nc:]])
+    assert np.radians(ang.max()) < 1e-6 and d[2:nc:3].max() < 1e-3, (ang.max(), d[2:nc:3].max(), rep, rep_ref)
+    assert abs(rep["cost"] - rep_ref["cost"]) <= 1e-8 * rep_ref["cost"]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, float(np.abs(x_par).sum()))
+    assert max(gathered) - min(gathered) <= 1e-12 * max(gathered), gathered      # identical on every rank
+    if rank == 0:
+        print("multi_gpu_check OK: distributed solve on %d ranks (landmarks %s of %d on rank 0) equals the 1-GPU solve: status %d, nfev %d, "
+              "cost %.6f, max |dx| %.2e" % (world, lm_range, fb.n_landmark, rep["status"], rep["nfev"], rep["cost"],
+                                             float(np.abs(x_par - x_ref).max())))
+    dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
 

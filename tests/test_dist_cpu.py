@@ -46,6 +46,50 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_partition(rank, world, port, out_dir):
+    """Distributed-solve partition (replicated data, partitioned work): landmark slice -> V, g_l, cost; slice of the
+    keyframe-major list -> U, g_c; one all-reduce of the packed blocks reproduces the full normal equations."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fb = synth.make_flat_ba(12, 300, 2400, seed=78)
+    (lm_lo, lm_hi), (cm_lo, cm_hi) = pdist.solve_partition(fb.lm_idx, fb.n_landmark, world)[rank]
+    poses, rays = O.ba_unpack(fb.x0(), fb.n_pose, fb.ptz_init[0])
+    sel_l = (fb.lm_idx >= lm_lo) & (fb.lm_idx < lm_hi)
+    _, _, _, V, gl, cost = O.ba_normal_equations(poses, rays, fb.cam_idx[sel_l], fb.lm_idx[sel_l], fb.obs_xy[sel_l], synth.PP_U, synth.PP_V)
+    order = np.argsort(fb.cam_idx, kind="stable")[cm_lo:cm_hi]          # this rank's slice of the keyframe-major list
+    _, U, gc, _, _, _ = O.ba_normal_equations(poses, rays, fb.cam_idx[order], fb.lm_idx[order], fb.obs_xy[order], synth.PP_U, synth.PP_V)
+    U[0] = 0; gc[0] = 0
+    packed = torch.from_numpy(np.concatenate([[cost], U.ravel(), V.ravel(), gc.ravel(), gl.ravel()]))
+    dist.all_reduce(packed)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "packed_part.npy"), packed.numpy())
+    dist.destroy_process_group()
+
+
+def test_solve_partition_tiles():
+    rng = np.random.default_rng(1)
+    lm = np.sort(rng.integers(0, 700, 20000))
+    for w in (1, 2, 3, 8):
+        parts = pdist.solve_partition(lm, 700, w)
+        assert parts[0][0][0] == 0 and parts[-1][0][1] == 700 and parts[0][1][0] == 0 and parts[-1][1][1] == len(lm)
+        assert all(parts[i][0][1] == parts[i + 1][0][0] and parts[i][1][1] == parts[i + 1][1][0] for i in range(w - 1))
+        counts = [np.sum((lm >= a) & (lm < b)) for (a, b), _ in parts]
+        assert sum(counts) == len(lm) and max(counts) < 1.2 * len(lm) / w + 100
+
+
+def test_world2_partitioned_blocks_sum_to_full(tmp_path):
+    world = 2
+    mp.spawn(_worker_partition, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    packed = np.load(tmp_path / "packed_part.npy")
+    fb = synth.make_flat_ba(12, 300, 2400, seed=78)
+    poses, rays = O.ba_unpack(fb.x0(), fb.n_pose, fb.ptz_init[0])
+    r, U, gc, V, gl, cost = O.ba_normal_equations(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+    U[0] = 0; gc[0] = 0
+    full = np.concatenate([[cost], U.ravel(), V.ravel(), gc.ravel(), gl.ravel()])
+    np.testing.assert_allclose(packed, full, rtol=1e-11, atol=1e-9 * np.abs(full).max())
+
+
 def test_keyframe_ranges_partition():
     rng = np.random.default_rng(0)
     cam = rng.integers(0, 50, 10000)
