@@ -156,12 +156,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def bench_ekf(ctx, n_seq, n_rays, n_frames):
+def bench_ekf(ctx, n_seq, n_rays, n_frames, seed0=2000):
     """Batched independent EKF sequences (BASELINE config 4 recipe at a bounded batch): predict+update per frame."""
     import torch
     from ptz_slam_b200 import synth, _lib
     from ptz_slam_b200.ptz_slam import BatchedEkfTracker
-    seqs = [synth.make_ekf_sequence(n_rays, n_frames + 1, seed=2000 + i) for i in range(n_seq)]
+    seqs = [synth.make_ekf_sequence(n_rays, n_frames + 1, seed=seed0 + i) for i in range(n_seq)]
     max_obs = max(len(i) for q in seqs for i in q.obs_idx)
     trk = BatchedEkfTracker(np.stack([q.rays0 for q in seqs]), np.stack([q.ptz_gt[0] for q in seqs]), synth.PP_U, synth.PP_V,
                             max_obs, synth.IMAGE_H, synth.IMAGE_W, jacobian_mode=_lib.JAC_CENTRAL_FD, ctx=ctx)
@@ -343,10 +343,52 @@ def run_ours(args):
               "solve": {"ftol": 1e-4, "ms": 1e3 * solve_s, "nfev": rep["nfev"], "njev": rep["njev"], "status": rep["status"],
                         "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]}}
 
+    if world > 1 and not args.no_lm:
+        # distributed solve, STRONG scaling of one problem of the named workload: every rank holds the whole observation
+        # list (replicated data) and visits its landmark / keyframe-major slices (partitioned work); partial blocks, the
+        # reduced camera system, right-hand sides and landmark steps are all-reduced inside the library
+        from ptz_slam_b200 import dist as pdist
+        g = make_workload(args.workload, 0)
+        gp = BA.BAProblem(g.n_pose, g.n_landmark, g.cam_idx, g.lm_idx, g.obs_xy, u, v, ctx=ctx)
+        lm_range, cm_range = pdist.solve_partition(g.lm_idx, g.n_landmark, world)[rank]
+        gp.set_partition(rank, world, lm_range, cm_range)
+        gx0, gref = g.x0(), g.ptz_init[0]
+        for _ in range(2):
+            gp.lm_iteration(gx0, gref, alpha=1e-3)
+        barrier()
+        n_lm_it = 10
+        t0 = time.perf_counter()
+        for _ in range(n_lm_it):
+            gp.lm_iteration(gx0, gref, alpha=1e-3)
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / n_lm_it], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lm_s = float(t.item())
+        t0 = time.perf_counter()
+        xs, rep = gp.solve(gx0, gref, ftol=1e-4)
+        solve_s = time.perf_counter() - t0
+        gp.close()
+        lm = {"lm_iters_per_s": 1.0 / lm_s, "ms_per_lm_iter": 1e3 * lm_s, "lm_scaling": "strong",
+              "lm_workload": "%s: ONE problem of %d keyframes x %d landmarks x %d observations solved by %d ranks" %
+                             (args.workload, g.n_pose, g.n_landmark, g.n_obs, world),
+              "solve": {"ftol": 1e-4, "ms": 1e3 * solve_s, "nfev": rep["nfev"], "njev": rep["njev"], "status": rep["status"],
+                        "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]}}
+
     # ---- batched EKF tracking (config 4 shape, bounded batch): sequence-frames/s and matched observations/s ----------
     ekf = None
-    if world == 1 and not args.no_ekf:
-        ekf = bench_ekf(ctx, args.ekf_seqs, args.ekf_rays, args.ekf_frames)
+    if not args.no_ekf:
+        # independent sequences shard over the ranks with no collective; rates add up over the ranks
+        ekf = bench_ekf(ctx, max(1, args.ekf_seqs), args.ekf_rays, args.ekf_frames, seed0=2000 + rank * args.ekf_seqs)
+        if world > 1:
+            t = torch.tensor([ekf["ms_per_frame_batch"], ekf["matched_obs_per_s"] * ekf["ms_per_frame_batch"] * 1e-3],
+                             dtype=torch.float64, device="cuda")          # (ms per frame batch, matched observations per frame batch)
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            ms_ekf = float(tmax[0].item())
+            ekf["workload"] = "%d ranks x (%s), sharded with no collective" % (world, ekf["workload"])
+            ekf["sequence_frames_per_s"] = world * args.ekf_seqs / (ms_ekf * 1e-3)
+            ekf["matched_obs_per_s"] = float(tsum[1].item()) / (ms_ekf * 1e-3)
+            ekf["ms_per_frame_batch"] = ms_ekf
 
     clocks = sampler.stop() if rank == 0 else None
 
