@@ -177,8 +177,13 @@ int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, const double* 
 int ptzba_comm_unique_id(ptzba_ctx* ctx, void* unique_id128);
 int ptzba_comm_init(ptzba_ctx* ctx, const void* unique_id128, int rank, int world_size);
 int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int64_t count);
-/* sums the packed accumulators [cost | U | V | g_c | g_l] of the last fused pass over all ranks (in place, on the stream) */
+/* combines the accumulators of the last fused pass over all ranks (in place, on the stream).  Default: the whole packed
+ * arena [cost | U | V | g_c | g_l] is summed and every rank ends with every block.  After ptzba_ba_setup_exchange (one
+ * all-reduce of a per-landmark touch mask, once per problem) only the cost and the blocks of landmarks observed by MORE THAN
+ * ONE rank travel: blocks of the other landmarks are already complete on the only rank that observes them and each keyframe's
+ * U / g_c is complete on the rank that owns the keyframe (the result is distributed, not replicated). */
 int ptzba_ba_allreduce(ptzba_ba* ba);
+int ptzba_ba_setup_exchange(ptzba_ba* ba, int64_t* n_shared_out);
 /* Second multi-GPU mode - replicated data, partitioned work (the distributed SOLVE): every rank creates its ptzba_ba from
  * the WHOLE observation list and then restricts the per-observation kernels to its slice: landmarks [lm_lo, lm_hi) of the
  * landmark-major list (all observations of a landmark stay on one rank, so landmark blocks, Schur pair products and

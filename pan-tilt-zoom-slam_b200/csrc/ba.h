@@ -51,6 +51,11 @@ struct ptzba_ba {
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int grid_lm_pass = 0, grid_cam_pass = 0;   // one wave of resident CTAs per pass
+    // keyframe-sharded mode: compact exchange of the landmarks observed by more than one rank (ptzba_ba_setup_exchange)
+    bool exchange_ready = false;
+    int64_t n_shared = 0;
+    DevBuf<int32_t> shared_ids;
+    DevBuf<double> shared_buf;
     // work partition (ptzba_ba_set_partition); defaults = everything on this rank
     int part_rank = 0, part_world = 1;
     int lm_lo = 0, lm_hi = 0;                  // landmark slice

@@ -7,6 +7,8 @@
 // torch's bundled NCCL shares that copy (same SONAME).
 #include <dlfcn.h>
 
+#include <vector>
+
 #include "ba.h"
 
 namespace {
@@ -102,8 +104,96 @@ extern "C" int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int6
     return PTZBA_OK;
 }
 
-// sums the accumulators of the last fused pass ([cost | U | V | g_c | g_l]) over all ranks, in place, on the stream
+namespace {
+
+__global__ void k_touch_mask(int n_lm, const int32_t* __restrict__ lm_ptr, double* __restrict__ mask) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n_lm) mask[l] = lm_ptr[l + 1] > lm_ptr[l] ? 1.0 : 0.0;
+}
+
+// shared[l] = 1 when more than one rank observes landmark l; compacted (in ascending id order, identical on every rank)
+__global__ void k_shared_flags(int n_lm, const double* __restrict__ count, int32_t* __restrict__ flag) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n_lm) flag[l] = count[l] > 1.5 ? 1 : 0;
+}
+
+__global__ void k_pack_shared(int n_shared, const int32_t* __restrict__ ids, const double* __restrict__ V, const double* __restrict__ gl,
+                              const double* __restrict__ cost, double* __restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) buf[0] = cost[0];
+    if (i >= n_shared) return;
+    const int l = ids[i];
+    double* b = buf + 1 + 5 * (size_t)i;
+    b[0] = V[3 * (size_t)l]; b[1] = V[3 * (size_t)l + 1]; b[2] = V[3 * (size_t)l + 2];
+    b[3] = gl[2 * (size_t)l]; b[4] = gl[2 * (size_t)l + 1];
+}
+
+__global__ void k_unpack_shared(int n_shared, const int32_t* __restrict__ ids, const double* __restrict__ buf, double* __restrict__ V,
+                                double* __restrict__ gl, double* __restrict__ cost) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) cost[0] = buf[0];
+    if (i >= n_shared) return;
+    const int l = ids[i];
+    const double* b = buf + 1 + 5 * (size_t)i;
+    V[3 * (size_t)l] = b[0]; V[3 * (size_t)l + 1] = b[1]; V[3 * (size_t)l + 2] = b[2];
+    gl[2 * (size_t)l] = b[3]; gl[2 * (size_t)l + 1] = b[4];
+}
+
+}  // namespace
+
+// Keyframe-sharded mode: finds the landmarks that are observed by more than one rank (one all-reduce of a per-landmark
+// 0/1 mask, once per problem).  Afterwards ptzba_ba_allreduce exchanges ONLY the blocks of those shared landmarks (plus the
+// cost): blocks of unshared landmarks are already complete on the only rank that sees them, and every keyframe's U / g_c is
+// complete on the rank that owns the keyframe.  *n_shared_out (may be NULL) receives the number of shared landmarks.
+extern "C" int ptzba_ba_setup_exchange(ptzba_ba* ba, int64_t* n_shared_out) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    cudaStream_t s = ctx->stream;
+    const int M = ba->n_lm;
+    ba->n_shared = 0;
+    ba->exchange_ready = false;
+    if (ctx->world > 1 && M > 0) {
+        DevBuf<double> count;
+        DevBuf<int32_t> flag;
+        CU_CHECK(ctx, count.alloc(M));
+        CU_CHECK(ctx, flag.alloc(M));
+        k_touch_mask<<<div_up(M, 256), 256, 0, s>>>(M, ba->lm_ptr.p, count.p);
+        KERNEL_POST(ctx);
+        PROPAGATE(ptzba_comm_allreduce_f64(ctx, count.p, M));
+        k_shared_flags<<<div_up(M, 256), 256, 0, s>>>(M, count.p, flag.p);
+        KERNEL_POST(ctx);
+        std::vector<int32_t> h(M), ids;
+        CU_CHECK(ctx, cudaMemcpyAsync(h.data(), flag.p, (size_t)M * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        for (int l = 0; l < M; ++l)
+            if (h[l]) ids.push_back(l);
+        ba->n_shared = (int64_t)ids.size();
+        CU_CHECK(ctx, ba->shared_ids.alloc(ids.size() + 1));
+        CU_CHECK(ctx, ba->shared_buf.alloc(1 + 5 * ids.size()));
+        if (!ids.empty())
+            CU_CHECK(ctx, cudaMemcpyAsync(ba->shared_ids.p, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+    }
+    ba->exchange_ready = true;
+    if (n_shared_out) *n_shared_out = ba->n_shared;
+    return PTZBA_OK;
+}
+
+// Combines the accumulators of the last fused pass over all ranks, in place, on the stream.  Without
+// ptzba_ba_setup_exchange: the whole packed arena [cost | U | V | g_c | g_l] is summed (every rank ends with every
+// block).  With it: only the cost and the blocks of landmarks shared between ranks travel (see above).
 extern "C" int ptzba_ba_allreduce(ptzba_ba* ba) {
     if (!ba) return PTZBA_ERR_ARG;
-    return ptzba_comm_allreduce_f64(ba->ctx, ba->acc.base, (int64_t)ba->acc.count);
+    ptzba_ctx* ctx = ba->ctx;
+    if (!ba->exchange_ready) return ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count);
+    if (ctx->world <= 1) return PTZBA_OK;
+    const int ns = (int)ba->n_shared;
+    if (ns == 0) return ptzba_comm_allreduce_f64(ctx, ba->acc.cost, 1);      // nothing shared: only the cost is a sum over ranks
+    cudaStream_t s = ctx->stream;
+    k_pack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->acc.V, ba->acc.gl, ba->acc.cost, ba->shared_buf.p);
+    KERNEL_POST(ctx);
+    PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->shared_buf.p, 1 + 5 * (int64_t)ns));
+    k_unpack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->shared_buf.p, ba->acc.V, ba->acc.gl, ba->acc.cost);
+    KERNEL_POST(ctx);
+    return PTZBA_OK;
 }

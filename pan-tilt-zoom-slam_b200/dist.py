@@ -35,6 +35,13 @@ class Communicator:
         """Sum the accumulators of `problem`'s last fused pass over all ranks (asynchronous on the context stream)."""
         self.ctx.check(self.ctx.lib.ptzba_ba_allreduce(problem.handle))
 
+    def setup_exchange(self, problem):
+        """Keyframe-sharded mode: find the landmarks shared between ranks once; `allreduce_landmark_blocks` then exchanges
+        only their blocks and the cost (the other blocks are complete on the rank that owns them).  Returns their number."""
+        n = ctypes.c_int64(0)
+        self.ctx.check(self.ctx.lib.ptzba_ba_setup_exchange(problem.handle, ctypes.byref(n)))
+        return int(n.value)
+
     def allreduce(self, dev_ptr, count):
         self.ctx.check(self.ctx.lib.ptzba_comm_allreduce_f64(self.ctx.handle, _lib.ptr(int(dev_ptr)), int(count)))
 

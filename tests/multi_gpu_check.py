@@ -4,6 +4,7 @@ Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs; not collecte
 Every rank takes the keyframe shard of ONE global BA problem, runs the CUDA fused pass on it and all-reduces the packed
 blocks with ncclAllReduce (ptzba_ba_allreduce); rank 0 compares the result with the oracle on the full problem.
 """
+import ctypes
 import os
 import sys
 
@@ -35,7 +36,6 @@ def main():
     ctx.synchronize()
     N, M = fb.n_pose, fb.n_landmark
     U, gc, V, gl = np.empty((N, 6)), np.empty((N, 3)), np.empty((M, 3)), np.empty((M, 2))
-    import ctypes
     cost = ctypes.c_double()
     ctx.check(ctx.lib.ptzba_ba_get_blocks(prob.handle, _lib.ptr(U), _lib.ptr(gc), _lib.ptr(V), _lib.ptr(gl), ctypes.byref(cost)))
     ok = True
@@ -50,6 +50,31 @@ def main():
         np.testing.assert_allclose(gl, glo, rtol=1e-8, atol=1e-11 * np.abs(glo).max())
         assert abs(cost.value - costo) < 1e-11 * costo
         print("multi_gpu_check OK: world=%d, rank-0 shard keyframes [%d,%d), all-reduced blocks match the oracle" % (world, lo, hi))
+    dist.barrier()
+
+    # ---- compact exchange: only the blocks of landmarks seen by more than one rank travel; the result is distributed ----
+    n_shared = comm.setup_exchange(prob)
+    prob.normal_equations_device(x.data_ptr(), fb.ptz_init[0])
+    comm.allreduce_landmark_blocks(prob)
+    ctx.synchronize()
+    ctx.check(ctx.lib.ptzba_ba_get_blocks(prob.handle, _lib.ptr(U), _lib.ptr(gc), _lib.ptr(V), _lib.ptr(gl), ctypes.byref(cost)))
+    poses, rays = O.ba_unpack(fb.x0(), N, fb.ptz_init[0])
+    r, Uo, gco, Vo, glo, costo = O.ba_normal_equations(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+    Up = np.stack([Uo[:, 0, 0], Uo[:, 0, 1], Uo[:, 0, 2], Uo[:, 1, 1], Uo[:, 1, 2], Uo[:, 2, 2]], 1)
+    Vp = np.stack([Vo[:, 0, 0], Vo[:, 0, 1], Vo[:, 1, 1]], 1)
+    mine = np.unique(lm)                                   # landmarks this rank observes: complete after the exchange
+    own = np.arange(max(lo, 1), hi)                        # keyframes this rank owns (keyframe 0 is fixed)
+    seen_by = np.zeros(M, int)
+    for r_ in range(world):
+        seen_by[np.unique(pdist.shard_by_keyframe(fb.cam_idx, fb.lm_idx, fb.obs_xy, fb.n_pose, r_, world)[1])] += 1
+    assert n_shared == int((seen_by > 1).sum()) and 0 < n_shared < M, (n_shared, int((seen_by > 1).sum()))
+    np.testing.assert_allclose(V[mine], Vp[mine], rtol=1e-9, atol=1e-12 * np.abs(Vp).max())
+    np.testing.assert_allclose(gl[mine], glo[mine], rtol=1e-8, atol=1e-11 * np.abs(glo).max())
+    np.testing.assert_allclose(U[own], Up[own], rtol=1e-9, atol=1e-12 * np.abs(Up).max())
+    np.testing.assert_allclose(gc[own], gco[own], rtol=1e-8, atol=1e-11 * np.abs(gco).max())
+    assert abs(cost.value - costo) < 1e-11 * costo
+    if rank == 0:
+        print("multi_gpu_check OK: compact exchange of %d shared landmarks (of %d): owned blocks match the oracle" % (n_shared, M))
     dist.barrier()
     prob.close()
 
