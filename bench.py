@@ -196,11 +196,14 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything native libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _lib.get_context(local)
     # an explicit side stream: the legacy default stream has handle 0, which the C-ABI reads as "use the context's own
@@ -421,6 +424,8 @@ def run_ours(args):
             line.update(lm)
         if ekf:
             line["ekf"] = ekf
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     for p in probs:
         p.close()

@@ -32,8 +32,6 @@ struct ptzba_ba {
     DevBuf<int32_t> c_cam, c_lm, c_orig;
     DevBuf<double> c_ox, c_oy;
     // current parameters
-    DevBuf<double> poses;           // [N*3] incl. reference pose at 0
-    DevBuf<double> rays;            // [M*2]
     DevBuf<CamTrig> cam_trig;       // [N]
     DevBuf<LmTrig> lm_trig;         // [M]
     DevBuf<double> accum_store;
@@ -51,6 +49,7 @@ struct ptzba_ba {
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int grid_lm_pass = 0, grid_cam_pass = 0;   // one wave of resident CTAs per pass
+    int touch_cam_lo = 0, touch_cam_hi = 0, touch_lm_lo = 0, touch_lm_hi = 0;   // id ranges the observations touch
     // keyframe-sharded mode: compact exchange of the landmarks observed by more than one rank (ptzba_ba_setup_exchange)
     bool exchange_ready = false;
     int64_t n_shared = 0;
@@ -63,6 +62,7 @@ struct ptzba_ba {
     int64_t cmo_lo = 0, cmo_hi = 0;            // slice of the keyframe-major list
     bool cam_smem = true;           // keyframe trig table fits in shared memory
     bool acc_zeroed = false;        // the arena was cleared by ba_set_params(..., zero_acc = true)
+    bool arena_foreign = false;     // a whole-arena all-reduce wrote blocks outside the touched id ranges
 };
 
 // ---- device-level passes (all pointers device, enqueued on ba->ctx->stream) ----

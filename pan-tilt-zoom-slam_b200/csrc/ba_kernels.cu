@@ -85,33 +85,33 @@ __global__ void k_lm_ptr(int n_lm, int64_t n_obs, const int32_t* __restrict__ s_
 // ZERO: also clears the accumulator arena (this kernel already visits every keyframe and landmark), which saves the
 // separate memset launch in front of the fused pass.
 template <bool ZERO>
-__global__ void k_set_params(int n_pose, int n_lm, const double* __restrict__ x, const double* __restrict__ ref3,
-                             double* __restrict__ poses, double* __restrict__ rays, CamTrig* __restrict__ cam_trig,
-                             LmTrig* __restrict__ lm_trig, double* __restrict__ aCost, double* __restrict__ aU,
-                             double* __restrict__ aGc, double* __restrict__ aV, double* __restrict__ aGl) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ZERO && i == 0) aCost[0] = 0.0;
-    if (i < n_pose) {
-        const double* src = (i == 0) ? ref3 : (x + 3 * (size_t)(i - 1));
-        const double p = src[0], t = src[1], f = src[2];
-        poses[3 * i] = p; poses[3 * i + 1] = t; poses[3 * i + 2] = f;
-        cam_trig[i] = make_cam_trig(p, t, f);
+__global__ void k_set_params(int n_pose, int cam_lo, int cam_hi, int lm_lo, int lm_hi, const double* __restrict__ x,
+                             const double* __restrict__ ref3, CamTrig* __restrict__ cam_trig, LmTrig* __restrict__ lm_trig,
+                             double* __restrict__ aCost, double* __restrict__ aU, double* __restrict__ aGc,
+                             double* __restrict__ aV, double* __restrict__ aGl) {
+    // only the keyframes [cam_lo, cam_hi) and landmarks [lm_lo, lm_hi) that this problem's observations touch are visited
+    // (everything for a whole problem; one pan sector's share in the keyframe-sharded multi-GPU mode)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ZERO && t == 0) aCost[0] = 0.0;
+    const int c = cam_lo + t;
+    if (c < cam_hi) {
+        const double* src = (c == 0) ? ref3 : (x + 3 * (size_t)(c - 1));
+        cam_trig[c] = make_cam_trig(src[0], src[1], src[2]);
         if (ZERO) {
 #pragma unroll
-            for (int e = 0; e < 6; ++e) aU[6 * (size_t)i + e] = 0.0;
+            for (int e = 0; e < 6; ++e) aU[6 * (size_t)c + e] = 0.0;
 #pragma unroll
-            for (int e = 0; e < 3; ++e) aGc[3 * (size_t)i + e] = 0.0;
+            for (int e = 0; e < 3; ++e) aGc[3 * (size_t)c + e] = 0.0;
         }
     }
-    if (i < n_lm) {
+    const int l = lm_lo + t;
+    if (l < lm_hi) {
         // x + 3(N-1) is only 8-byte aligned when N is even: scalar loads
-        const double* lp = x + 3 * (size_t)(n_pose - 1) + 2 * (size_t)i;
-        const double th = lp[0], ph = lp[1];
-        reinterpret_cast<double2*>(rays)[i] = make_double2(th, ph);
-        lm_trig[i] = make_lm_trig(th, ph);
+        const double* lp = x + 3 * (size_t)(n_pose - 1) + 2 * (size_t)l;
+        lm_trig[l] = make_lm_trig(lp[0], lp[1]);
         if (ZERO) {
-            aV[3 * (size_t)i] = 0.0; aV[3 * (size_t)i + 1] = 0.0; aV[3 * (size_t)i + 2] = 0.0;
-            aGl[2 * (size_t)i] = 0.0; aGl[2 * (size_t)i + 1] = 0.0;
+            aV[3 * (size_t)l] = 0.0; aV[3 * (size_t)l + 1] = 0.0; aV[3 * (size_t)l + 2] = 0.0;
+            aGl[2 * (size_t)l] = 0.0; aGl[2 * (size_t)l + 1] = 0.0;
         }
     }
 }
@@ -399,17 +399,20 @@ int stream_grid(ptzba_ctx* ctx, int64_t n, int threads, int per_sm) {
 // ---------------------------------------------------------------------------------------------------------------
 int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3, bool zero_acc) {
     ptzba_ctx* ctx = ba->ctx;
-    const int n = ba->n_pose > ba->n_lm ? ba->n_pose : ba->n_lm;
-    if (zero_acc)
-        k_set_params<true><<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->n_pose, ba->n_lm, d_x, d_ref_pose3, ba->poses.p, ba->rays.p,
-                                                                    ba->cam_trig.p, ba->lm_trig.p, ba->acc.cost, ba->acc.U,
-                                                                    ba->acc.gc, ba->acc.V, ba->acc.gl);
-    else
-        k_set_params<false><<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->n_pose, ba->n_lm, d_x, d_ref_pose3, ba->poses.p, ba->rays.p,
-                                                                     ba->cam_trig.p, ba->lm_trig.p, nullptr, nullptr, nullptr,
-                                                                     nullptr, nullptr);
-    KERNEL_POST(ctx);
-    ba->acc_zeroed = zero_acc;
+    const int nc = ba->touch_cam_hi - ba->touch_cam_lo, nl = ba->touch_lm_hi - ba->touch_lm_lo;
+    const int n = nc > nl ? nc : nl;
+    if (n > 0) {
+        if (zero_acc)
+            k_set_params<true><<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->n_pose, ba->touch_cam_lo, ba->touch_cam_hi, ba->touch_lm_lo,
+                                                                        ba->touch_lm_hi, d_x, d_ref_pose3, ba->cam_trig.p, ba->lm_trig.p,
+                                                                        ba->acc.cost, ba->acc.U, ba->acc.gc, ba->acc.V, ba->acc.gl);
+        else
+            k_set_params<false><<<div_up(n, 256), 256, 0, ctx->stream>>>(ba->n_pose, ba->touch_cam_lo, ba->touch_cam_hi, ba->touch_lm_lo,
+                                                                         ba->touch_lm_hi, d_x, d_ref_pose3, ba->cam_trig.p, ba->lm_trig.p,
+                                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
+        KERNEL_POST(ctx);
+    }
+    ba->acc_zeroed = zero_acc && n > 0;
     return PTZBA_OK;
 }
 
@@ -417,8 +420,10 @@ int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3, bo
 int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     ptzba_ctx* ctx = ba->ctx;
     cudaStream_t s = ctx->stream;
-    if (!ba->acc_zeroed) CU_CHECK(ctx, cudaMemsetAsync(ba->acc.base, 0, ba->acc.count * sizeof(double), s));
+    // (a whole-arena all-reduce also fills blocks this rank's observations never touch: clear everything then)
+    if (!ba->acc_zeroed || ba->arena_foreign) CU_CHECK(ctx, cudaMemsetAsync(ba->acc.base, 0, ba->acc.count * sizeof(double), s));
     ba->acc_zeroed = false;
+    ba->arena_foreign = false;
     if (ba->n_obs == 0) return PTZBA_OK;
     const int32_t* orig = ba->identity_perm ? nullptr : ba->orig.p;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -508,10 +513,10 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     CU_TRY(ba->s_cam.alloc(n_obs + 4)); CU_TRY(ba->s_lm.alloc(n_obs + 4));
     CU_TRY(ba->s_ox.alloc(n_obs + 4)); CU_TRY(ba->s_oy.alloc(n_obs + 4));
     CU_TRY(ba->lm_ptr.alloc((size_t)n_landmark + 1));
-    CU_TRY(ba->poses.alloc((size_t)n_pose * 3)); CU_TRY(ba->rays.alloc((size_t)n_landmark * 2));
     CU_TRY(ba->cam_trig.alloc(n_pose)); CU_TRY(ba->lm_trig.alloc(n_landmark));
     ba->acc.count = 1 + (size_t)n_pose * 9 + (size_t)n_landmark * 5;
     CU_TRY(ba->accum_store.alloc(ba->acc.count));
+    CU_TRY(cudaMemsetAsync(ba->accum_store.p, 0, ba->acc.count * sizeof(double), s));      // untouched blocks stay zero for ever
     ba->acc.base = ba->accum_store.p;
     ba->acc.cost = ba->acc.base;
     // [cost | U | V | gc | gl]: gc and gl are adjacent so that (gc, gl) is the gradient in the solver's full layout
@@ -589,6 +594,17 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         CU_TRY(cudaStreamSynchronize(s));
     }
 
+    // keyframes / landmarks touched by this problem's observations (first and last entry of the two sorted lists)
+    ba->touch_cam_lo = 0; ba->touch_cam_hi = n_pose; ba->touch_lm_lo = 0; ba->touch_lm_hi = n_landmark;
+    if (n_obs > 0) {
+        int32_t e[4];
+        CU_TRY(cudaMemcpyAsync(e + 0, ba->c_cam.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(e + 1, ba->c_cam.p + (n_obs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(e + 2, ba->s_lm.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(e + 3, ba->s_lm.p + (n_obs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        ba->touch_cam_lo = e[0]; ba->touch_cam_hi = e[1] + 1; ba->touch_lm_lo = e[2]; ba->touch_lm_hi = e[3] + 1;
+    }
     // launch geometry of the fused pass: one wave of resident CTAs; keyframe trig table in shared memory when it fits
     {
         const size_t smA = (size_t)n_pose * 6 * sizeof(double);

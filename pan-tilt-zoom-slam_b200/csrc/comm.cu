@@ -185,7 +185,10 @@ extern "C" int ptzba_ba_setup_exchange(ptzba_ba* ba, int64_t* n_shared_out) {
 extern "C" int ptzba_ba_allreduce(ptzba_ba* ba) {
     if (!ba) return PTZBA_ERR_ARG;
     ptzba_ctx* ctx = ba->ctx;
-    if (!ba->exchange_ready) return ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count);
+    if (!ba->exchange_ready) {
+        ba->arena_foreign = ctx->world > 1;
+        return ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count);
+    }
     if (ctx->world <= 1) return PTZBA_OK;
     const int ns = (int)ba->n_shared;
     if (ns == 0) return ptzba_comm_allreduce_f64(ctx, ba->acc.cost, 1);      // nothing shared: only the cost is a sum over ranks
