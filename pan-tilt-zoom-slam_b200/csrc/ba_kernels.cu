@@ -18,6 +18,13 @@
 namespace {
 
 constexpr int kFusedThreads = 256;
+#ifndef PTZBA_LM_MINB
+#define PTZBA_LM_MINB 3
+#endif
+#ifndef PTZBA_CAM_MINB
+#define PTZBA_CAM_MINB 3
+#endif
+constexpr int kLmMinB = PTZBA_LM_MINB, kCamMinB = PTZBA_CAM_MINB;   // resident CTAs per SM the two passes are compiled for
 
 // ---------------------------------------------------------------------------------------------------------------
 // problem set-up kernels
@@ -444,11 +451,11 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         chunkA = (chunkA + 127) / 128 * 128;
         const int gridA = (int)((nA + chunkA - 1) / chunkA);
         if (ba->cam_smem)
-            k_ba_lm_pass4<3, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+            k_ba_lm_pass4<kLmMinB, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
                                                                     ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
                                                                     d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
         else
-            k_ba_lm_pass4<3, false><<<gridA, kFusedThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+            k_ba_lm_pass4<kLmMinB, false><<<gridA, kFusedThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
                                                                    ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
                                                                    d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
@@ -458,7 +465,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         int64_t chunkB = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
         chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
         const int gridB = (int)((nB + chunkB - 1) / chunkB);
-        k_ba_cam_pass<3><<<gridB, kFusedThreads, 0, s>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+        k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, s>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
                                                          ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
         KERNEL_POST(ctx);
     }
@@ -612,12 +619,12 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         int pa = 1, pb = 1;
         if (ba->cam_smem) {
             if (smA > 40 * 1024)
-                CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass4<3, true>, kFusedThreads, smA));
+                CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass4<kLmMinB, true>, kFusedThreads, smA));
         } else {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass4<3, false>, kFusedThreads, 0));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass4<kLmMinB, false>, kFusedThreads, 0));
         }
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<3>, kFusedThreads, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<kCamMinB>, kFusedThreads, 0));
         ba->grid_lm_pass = ctx->sm_count * (pa < 1 ? 1 : pa);
         ba->grid_cam_pass = ctx->sm_count * (pb < 1 ? 1 : pb);
     }

@@ -102,13 +102,25 @@ struct ObsGeom {        // everything one observation needs, in RADIAN derivativ
     double xp, yp;      // d(x,y)/d phi
 };
 
+// 1 / z without the IEEE special-case branch of the compiler's division (z is a homogeneous depth: finite, non-zero, far
+// from the denormal range): hardware seed (>= 20 bits) + two Newton steps in FMA form = full double accuracy (<= 1 ulp),
+// 5 instructions and no BSSY/BSYNC region that would stop the scheduler from interleaving neighbouring observations.
+__device__ __forceinline__ double fast_rcp(double z) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(z));
+    double e = fma(-z, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-z, r, 1.0);
+    return fma(r, e, r);
+}
+
 __device__ __forceinline__ void project_fast(const CamTrig& c, const LmTrig& l, double u, double v, double& x,
                                              double& y) {
     const double sa = l.sth * c.cp - l.cth * c.sp;
     const double ca = l.cth * c.cp + l.sth * c.sp;
     const double Ny = c.st * ca - c.ct * l.T;
     const double z = c.st * l.T + c.ct * ca;
-    const double iz = 1.0 / z;
+    const double iz = fast_rcp(z);
     x = fma(c.f, sa * iz, u);
     y = fma(c.f, Ny * iz, v);
 }
@@ -119,7 +131,7 @@ __device__ __forceinline__ void project_fast_jac(const CamTrig& c, const LmTrig&
     const double ca = l.cth * c.cp + l.sth * c.sp;
     const double Ny = c.st * ca - c.ct * l.T;
     const double z = c.st * l.T + c.ct * ca;
-    const double iz = 1.0 / z;
+    const double iz = fast_rcp(z);
     g.px = sa * iz;
     g.py = Ny * iz;
     x = fma(c.f, g.px, u);
