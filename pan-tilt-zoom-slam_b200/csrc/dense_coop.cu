@@ -253,33 +253,58 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
             HELP_TICK(8);
 #undef HELP_TICK
         } else {
-            // ---- trailing update: lower 64 x 64 tiles, C -= P_i P_j^T (the tile's old values are requested first) ----
+            // ---- trailing update: lower 64 x 64 tiles, C -= P_i P_j^T.  Software pipelined over this CTA's tiles: the panel rows
+            // of the NEXT tile are requested (registers) before the current tile is multiplied, the tile's old values are
+            // requested at its start and only consumed at its end, so no L2 round trip is exposed between tiles ----
             const int m = n - m0;
             const int nt = (m + TS - 1) / TS;
             const int ntiles = nt * (nt + 1) / 2;
-            for (int b = cta; b < ntiles; b += G) {
+            const int tx = tid % 16, ty = tid / 16;
+            auto tile_rc = [&](int b, int& r0, int& c0) {
                 int ti = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
                 while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
                 while (ti * (ti + 1) / 2 > b) --ti;
                 const int tj = b - ti * (ti + 1) / 2;
-                const int r0 = m0 + ti * TS, c0 = m0 + tj * TS;
-                const int tx = tid % 16, ty = tid / 16;
-                double acc[4][4];
+                r0 = m0 + ti * TS; c0 = m0 + tj * TS;
+            };
+            double npi[8], npj[8];                                       // this thread's share of the next tile's panel rows
+            auto load_panels = [&](int b) {
+                int r0, c0;
+                tile_rc(b, r0, c0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = tid + kCoopWorkers * u, rr = e % TS, t = e / TS;
+                    const int gi = r0 + rr, gj = c0 + rr;
+                    npi[u] = gi < n ? __ldcg(A + (size_t)gi + (size_t)(k + t) * lda) : 0.0;
+                    npj[u] = gj < n ? __ldcg(A + (size_t)gj + (size_t)(k + t) * lda) : 0.0;
+                }
+            };
+            if (cta < ntiles) load_panels(cta);
+            for (int b = cta; b < ntiles; b += G) {
+                int r0, c0;
+                tile_rc(b, r0, c0);
+                double cold[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int gi = r0 + tx + 16 * a, gj = c0 + ty + 16 * c;
-                        acc[a][c] = (gi < n && gj < n && gi >= gj) ? __ldcg(A + (size_t)gi + (size_t)gj * lda) : 0.0;
+                        cold[a][c] = (gi < n && gj < n && gi >= gj) ? __ldcg(A + (size_t)gi + (size_t)gj * lda) : 0.0;
                     }
-                worker_sync();
-                for (int e = tid; e < NB * TS; e += kCoopWorkers) {
-                    const int rr = e % TS, t = e / TS;
-                    const int gi = r0 + rr, gj = c0 + rr;
-                    Pi[t][rr] = gi < n ? __ldcg(A + (size_t)gi + (size_t)(k + t) * lda) : 0.0;
-                    Pj[t][rr] = gj < n ? __ldcg(A + (size_t)gj + (size_t)(k + t) * lda) : 0.0;
+                worker_sync();                                           // previous tile's products are done with Pi / Pj
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = tid + kCoopWorkers * u, rr = e % TS, t = e / TS;
+                    Pi[t][rr] = npi[u];
+                    Pj[t][rr] = npj[u];
                 }
                 worker_sync();
+                if (b + G < ntiles) load_panels(b + G);
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
 #pragma unroll 8
                 for (int t = 0; t < NB; ++t) {
                     double pi[4], pj[4];
@@ -288,15 +313,15 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[a][c] = fma(-pi[a], pj[c], acc[a][c]);
+                        for (int c = 0; c < 4; ++c) acc[a][c] = fma(pi[a], pj[c], acc[a][c]);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int gi = r0 + tx + 16 * a, gj = c0 + ty + 16 * c;
-                        // the next diagonal block is private to the look-ahead warps (every CTA updates its own copy)
-                        if (gi < n && gj < n && gi >= gj && !(gi < m0 + NB && gj < m0 + NB)) A[(size_t)gi + (size_t)gj * lda] = acc[a][c];
+                        // the next diagonal block is private to the look-ahead group (every CTA updates its own copy)
+                        if (gi < n && gj < n && gi >= gj && !(gi < m0 + NB && gj < m0 + NB)) A[(size_t)gi + (size_t)gj * lda] = cold[a][c] - acc[a][c];
                     }
             }
         }
