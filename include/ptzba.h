@@ -181,7 +181,8 @@ int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int64_t count);
  * arena [cost | U | V | g_c | g_l] is summed and every rank ends with every block.  After ptzba_ba_setup_exchange (one
  * all-reduce of a per-landmark touch mask, once per problem) only the cost and the blocks of landmarks observed by MORE THAN
  * ONE rank travel: blocks of the other landmarks are already complete on the only rank that observes them and each keyframe's
- * U / g_c is complete on the rank that owns the keyframe (the result is distributed, not replicated). */
+ * U / g_c is complete on the rank that owns the keyframe (the result is distributed, not replicated).  When no landmark is
+ * shared the pass needs no collective at all: the cost is then summed lazily by ptzba_ba_get_blocks (collective in that case). */
 int ptzba_ba_allreduce(ptzba_ba* ba);
 int ptzba_ba_setup_exchange(ptzba_ba* ba, int64_t* n_shared_out);
 /* Second multi-GPU mode - replicated data, partitioned work (the distributed SOLVE): every rank creates its ptzba_ba from

@@ -52,6 +52,7 @@ struct ptzba_ba {
     int touch_cam_lo = 0, touch_cam_hi = 0, touch_lm_lo = 0, touch_lm_hi = 0;   // id ranges the observations touch
     // keyframe-sharded mode: compact exchange of the landmarks observed by more than one rank (ptzba_ba_setup_exchange)
     bool exchange_ready = false;
+    bool cost_partial = false;      // the cost of the last pass has not been summed over the ranks yet
     int64_t n_shared = 0;
     DevBuf<int32_t> shared_ids;
     DevBuf<double> shared_buf;

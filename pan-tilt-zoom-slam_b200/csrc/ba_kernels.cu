@@ -743,6 +743,10 @@ extern "C" int ptzba_ba_get_blocks(ptzba_ba* ba, double* U, double* gc, double* 
     if (V && ba->n_lm) CU_CHECK(ctx, cudaMemcpyAsync(V, ba->acc.V, (size_t)ba->n_lm * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (gl && ba->n_lm) CU_CHECK(ctx, cudaMemcpyAsync(gl, ba->acc.gl, (size_t)ba->n_lm * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     double sumsq = 0;
+    if (cost && ba->cost_partial) {          // exchange mode without shared landmarks: the cost was left as a per-rank partial sum
+        PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->acc.cost, 1));
+        ba->cost_partial = false;
+    }
     if (cost) CU_CHECK(ctx, cudaMemcpyAsync(&sumsq, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, s));
     CU_CHECK(ctx, cudaStreamSynchronize(s));
     if (cost) *cost = 0.5 * sumsq;

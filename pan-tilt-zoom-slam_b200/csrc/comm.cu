@@ -191,7 +191,13 @@ extern "C" int ptzba_ba_allreduce(ptzba_ba* ba) {
     }
     if (ctx->world <= 1) return PTZBA_OK;
     const int ns = (int)ba->n_shared;
-    if (ns == 0) return ptzba_comm_allreduce_f64(ctx, ba->acc.cost, 1);      // nothing shared: only the cost is a sum over ranks
+    if (ns == 0) {
+        // nothing is shared between the ranks: no block travels.  The cost stays a per-rank partial sum until somebody asks
+        // for it (ptzba_ba_get_blocks, a collective call in this mode) - a pass over disjoint shards has no collective at all
+        ba->cost_partial = true;
+        return PTZBA_OK;
+    }
+    ba->cost_partial = false;
     cudaStream_t s = ctx->stream;
     k_pack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->acc.V, ba->acc.gl, ba->acc.cost, ba->shared_buf.p);
     KERNEL_POST(ctx);
