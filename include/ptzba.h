@@ -58,6 +58,11 @@ int64_t ptzba_launch_count(ptzba_ctx* ctx);
 int ptzba_profile_begin(ptzba_ctx* ctx);
 int ptzba_profile_end(ptzba_ctx* ctx, int32_t* n_launches, double* total_ms);
 
+/* dense SPD solve A x = b (host arrays, order n, only the lower triangle of the symmetric A is read) with the cooperative
+ * Cholesky + block-inverse kernels that bundle adjustment uses for its reduced camera system (replaces the dense SVD scipy runs
+ * inside least_squares, bundle_adjustment.py:200-202).  *info = 0, or 1 + the first row of the panel with a non-positive pivot. */
+int ptzba_dense_solve_spd(ptzba_ctx* ctx, int n, const double* A, const double* b, double* x, int* info);
+
 /* ---- A1/A2: projection  (PTZCamera.project_ray ptz_camera.py:191-210, project_rays :212-234,
  *                           TransFunction.from_ray_to_image transformation.py:99-135) ------------------------- */
 /* every camera x every ray.  ptz[n_cam*3] (pan,tilt,f), disp[6] or NULL (lambda_1..6, ptz_camera.py:106-115),

@@ -77,6 +77,7 @@ SIGNATURES = {
     "ptzba_comm_unique_id": (_I, [_P, _P]),
     "ptzba_comm_init": (_I, [_P, _P, _I, _I]),
     "ptzba_comm_allreduce_f64": (_I, [_P, _P, _L]),
+    "ptzba_dense_solve_spd": (_I, [_P, _I, _P, _P, _P, _P]),
     "ptzba_ba_allreduce": (_I, [_P]),
     "ptzba_ba_setup_exchange": (_I, [_P, _P]),
     "ptzba_ba_set_partition": (_I, [_P, _I, _I, _I, _I, _L, _L]),

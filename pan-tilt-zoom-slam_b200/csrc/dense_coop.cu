@@ -169,7 +169,7 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
         helper_sync();
         if (group_potf2(Ls, sInv, sCol, sTri, tid - kCoopWorkers) && tid == kCoopWorkers && cta == 0) atomicMax(info, 1);
     }
-    __syncthreads();
+    grid.sync();        // every CTA has read the first block before CTA 0 overwrites it with its factor (also a CTA barrier)
     COOP_TICK(0);
     for (int kb = 0; kb < nblk; ++kb) {
         const int k = kb * NB;
@@ -557,5 +557,29 @@ int dense_potrs_coop(ptzba_ctx* ctx, const double* L, int n, int lda, const doub
     void* args[] = {&L, &lda, &n, &Dinv_store, &b};
     CU_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_potrs_coop, dim3(grid), dim3(256), args, 0, ctx->stream));
     ctx->launches++;
+    return PTZBA_OK;
+}
+
+// Solves A x = b for a symmetric positive definite A (host arrays, column- or row-major alike, only the lower triangle is read)
+// with the cooperative Cholesky + block-inverse solve that bundle adjustment uses for its reduced camera system.
+// *info = 0, or 1 + the first row of the panel where the factorisation met a non-positive pivot.
+extern "C" int ptzba_dense_solve_spd(ptzba_ctx* ctx, int n, const double* A, const double* b, double* x, int* info) {
+    if (!ctx) return PTZBA_ERR_ARG;
+    ARG_CHECK(ctx, n >= 1 && A && b && x && info);
+    cudaStream_t s = ctx->stream;
+    DevBuf<double> dA, db, dinv;
+    DevBuf<int> dinfo;
+    CU_CHECK(ctx, dA.alloc((size_t)n * n));
+    CU_CHECK(ctx, db.alloc(n));
+    CU_CHECK(ctx, dinv.alloc(dense_coop_dinv_doubles(n)));
+    CU_CHECK(ctx, dinfo.alloc(1));
+    CU_CHECK(ctx, cudaMemcpyAsync(dA.p, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(db.p, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemsetAsync(dinfo.p, 0, sizeof(int), s));
+    PROPAGATE(dense_potrf_coop(ctx, dA.p, n, n, dinfo.p, dinv.p));
+    PROPAGATE(dense_potrs_coop(ctx, dA.p, n, n, dinv.p, db.p));
+    CU_CHECK(ctx, cudaMemcpyAsync(x, db.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
     return PTZBA_OK;
 }

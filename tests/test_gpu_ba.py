@@ -5,7 +5,7 @@ import pytest
 from conftest import load_golden, graph_from_npz
 from oracle import ptz_oracle as O
 import ptz_slam_b200  # noqa: F401
-from ptz_slam_b200 import synth
+from ptz_slam_b200 import synth, _lib
 from ptz_slam_b200 import bundle_adjustment as BA
 
 pytestmark = pytest.mark.gpu
@@ -176,3 +176,35 @@ def test_solve_vs_oracle_trf(n_kf, n_lm, n_obs):
     pe = np.abs(x[:3 * (n_kf - 1)].reshape(-1, 3) - fb.ptz_gt[1:])
     assert pe[:, :2].max() < 0.05 and pe[:, 2].max() < 15.0
     prob.close()
+
+
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 127, 128, 129, 255, 257, 765, 1000])
+def test_dense_spd_solve_matches_numpy(n):
+    """The cooperative Cholesky + block-inverse solve of the reduced camera system on its own, at orders around every block
+    boundary (32-column panels, 64-row tiles, 128-row inverted blocks)."""
+    import ctypes
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n))
+    A = B @ B.T + n * np.eye(n)
+    b = rng.standard_normal(n)
+    ctx = _lib.get_context()
+    x = np.empty(n)
+    info = ctypes.c_int(-1)
+    Ain = np.tril(A) + np.triu(np.full((n, n), np.nan), 1) if n > 1 else A.copy()   # the upper triangle must not be read
+    Acm = np.ascontiguousarray(Ain.T)                  # column-major storage of Ain (kept alive across the call)
+    ctx.check(ctx.lib.ptzba_dense_solve_spd(ctx.handle, n, _lib.ptr(Acm), _lib.ptr(b), _lib.ptr(x), ctypes.byref(info)))
+    assert info.value == 0
+    ref = np.linalg.solve(A, b)
+    np.testing.assert_allclose(x, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+
+
+def test_dense_spd_solve_reports_indefinite():
+    import ctypes
+    n = 70
+    A = np.eye(n)
+    A[40, 40] = -1.0
+    ctx = _lib.get_context()
+    x, b = np.empty(n), np.ones(n)
+    info = ctypes.c_int(0)
+    ctx.check(ctx.lib.ptzba_dense_solve_spd(ctx.handle, n, _lib.ptr(A), _lib.ptr(b), _lib.ptr(x), ctypes.byref(info)))
+    assert info.value == 33          # 1 + first row of the failing 32-column panel
