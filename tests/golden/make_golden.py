@@ -10,6 +10,7 @@ Goldens (reference function -> file):
   PtzSlam.ekf_update + predict lines ptz_slam.py:418-426 (6 frames)               -> ekf.npz
   bundle_adjustment._compute_residual                                             -> ba_residual.npz
   scipy least_squares call of bundle_adjustment.py:200-202 (as-is and tight)      -> ba_solve.npz
+  util.overlap_pan_angle, scene_map.Map.good_new_keyframe                         -> keyframe_map.npz
 """
 import copy
 import io
@@ -202,7 +203,32 @@ def gen_ba():
     np.savez_compressed(os.path.join(OUT, "ba_solve.npz"), **out2)
 
 
+def gen_keyframe_map():
+    """util.overlap_pan_angle (util.py:49-72) and Map.good_new_keyframe (scene_map.py:119-149) on seeded poses."""
+    rng = np.random.default_rng(1011)
+    import util as ref_util
+    from scene_map import Map as RefMap
+    from key_frame import KeyFrame as RefKeyFrame
+    n = 200
+    fl1, fl2 = rng.uniform(1500, 4500, n), rng.uniform(1500, 4500, n)
+    p1 = rng.uniform(30, 90, n)
+    p2 = p1 + rng.uniform(-45, 45, n)
+    ov = np.array([ref_util.overlap_pan_angle(fl1[i], p1[i], fl2[i], p2[i], W) for i in range(n)])
+    kf_ptz = np.stack([np.array([40.0, 52.0, 61.0, 75.0]), rng.uniform(-10, -6, 4), rng.uniform(2000, 4000, 4)], 1)
+    m = RefMap('sift')
+    for i, q in enumerate(kf_ptz):
+        kf = RefKeyFrame(None, i, CC, BASE_ROT, U, V, q[0], q[1], q[2])
+        m.keyframe_list.append(kf)
+    cand = np.stack([rng.uniform(30, 95, 300), rng.uniform(-10, -6, 300), rng.uniform(1800, 4300, 300)], 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        good = np.array([m.good_new_keyframe(c) for c in cand])
+        good_custom = np.array([m.good_new_keyframe(c, 10, 15, W) for c in cand])     # ptz_slam.py:458 thresholds
+    np.savez(os.path.join(OUT, "keyframe_map.npz"), fl1=fl1, fl2=fl2, p1=p1, p2=p2, overlap=ov, kf_ptz=kf_ptz, cand=cand,
+             good=good, good_custom=good_custom, im_width=W)
+
+
 if __name__ == "__main__":
+    gen_keyframe_map()
     gen_projection()
     gen_backprojection()
     gen_h_jacobian()
