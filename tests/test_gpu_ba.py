@@ -151,6 +151,30 @@ def test_bundle_adjustment_core_matches_reference():
     assert len(kfs) == N and kfs[1].landmark_index.dtype == np.int32 and kfs[1].get_feature_num() > 0
 
 
+def test_map_add_keyframe_with_ba():
+    """scene_map.Map.add_keyframe_with_ba (scene_map.py:53-117): the last keyframe joins the map and all keyframes are
+    bundle-adjusted on the GPU; the map is replaced by the result (same landmarks as the direct call)."""
+    from ptz_slam_b200.scene_map import Map
+    from ptz_slam_b200.key_frame import KeyFrame
+    d = load_golden("ba_solve.npz")
+    points, src, dst, lmk, M = graph_from_npz(d)
+    N = len(points)
+    graph = (points, None, points, src, dst, lmk, M)
+    m = Map('sift', build_matching_graph=lambda *a: graph)
+    u, v = d["uv"][0], d["uv"][1]
+    kfs = [KeyFrame(None, i, np.zeros(3), np.eye(3), u, v, *d["ptz_init"][i]) for i in range(N)]
+    m.add_first_keyframe(kfs[0])
+    for kf in kfs[1:-1]:
+        m.add_keyframe_without_ba(kf)
+    landmarks, keyframes = m.add_keyframe_with_ba(kfs[-1], "/tmp")
+    _, ref_landmarks, _ = BA.bundle_adjustment_core(points, src, dst, lmk, M, d["ptz_init"], u, v)
+    np.testing.assert_allclose(landmarks, ref_landmarks, rtol=0, atol=1e-12)
+    assert m.global_ray is landmarks and len(m.keyframe_list) == N and m.last_ba_seconds > 0
+    assert all(kf.get_feature_num() > 0 for kf in m.keyframe_list)
+    x = np.concatenate([np.array([[kf.pan, kf.tilt, kf.f] for kf in m.keyframe_list[1:]]).ravel(), landmarks.ravel()])
+    _assert_params_close(x, d["x_asis"], N)
+
+
 @pytest.mark.parametrize("n_kf,n_lm,n_obs", [(10, 300, 1500), (40, 4000, 40000)])
 def test_solve_vs_oracle_trf(n_kf, n_lm, n_obs):
     """Same trust-region iteration as the scipy restatement (oracle.trf_solve) on a seeded flat problem."""
