@@ -441,6 +441,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         ctx->prof_events.push_back(ev1);
         CU_CHECK(ctx, cudaEventRecord(ev0, s));
     }
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev_fork, s));      // everything before (k_set_params, the arena clear) precedes both passes
     // contiguous chunk per CTA: a multiple of 128 observations (every warp iteration starts on a 32-byte boundary of
     // all four streams), sized so that all resident CTAs of the single wave get the same amount of work.  With a
     // partition (ptzba_ba_set_partition) only this rank's slices of the two sorted lists are visited.
@@ -460,14 +461,23 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
                                                                    d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
     }
+    // the keyframe-major pass touches disjoint accumulators: it runs on the side stream, concurrently with the landmark pass
+    // (each kernel is a single wave; the second one fills the SMs the first one's finishing CTAs leave idle)
     const int64_t nB = ba->cmo_hi - ba->cmo_lo;
+    static const bool concurrent = getenv("PTZBA_SERIAL_PASSES") == nullptr;
     if (nB > 0) {
         int64_t chunkB = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
         chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
         const int gridB = (int)((nB + chunkB - 1) / chunkB);
-        k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, s>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                         ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+        cudaStream_t sb = concurrent ? ctx->side_stream : s;
+        if (concurrent) CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
+        k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                                ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
         KERNEL_POST(ctx);
+        if (concurrent) {
+            CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
+            CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        }
     }
     if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count));
