@@ -162,6 +162,7 @@ k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const in
     double* Wsm = reinterpret_cast<double*>(smem_raw) + (size_t)wid * dmax * 12;
     int* Csm = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)warps * dmax * 12) + (size_t)wid * dmax;
     const int total_warps = gridDim.x * warps;
+    const int q3 = lane / 9, e9 = lane - 9 * q3, sc = e9 / 3, r = e9 - 3 * sc;      // row index fastest: 3 lanes share a 32-byte sector of S
     for (int l = lm_lo + blockIdx.x * warps + wid; l < lm_hi; l += total_warps) {
         const int b = lm_ptr[l], d = lm_ptr[l + 1] - b;
         if (d == 0) continue;
@@ -183,34 +184,27 @@ k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const in
             }
         }
         __syncwarp();
-        const int nval = d * (d + 1) / 2 * 9;
-        for (int pv = lane; pv < nval; pv += 32) {
-            const int p = pv / 9, e = pv - 9 * p;
-            const int sc = e / 3, r = e - 3 * sc;                       // row index fastest
-            int i = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-            while ((i + 1) * (i + 2) / 2 <= p) ++i;
-            while (i * (i + 1) / 2 > p) --i;
-            const int j = p - i * (i + 1) / 2;                          // j <= i
-            const int ci = Csm[i], cj = Csm[j];
-            if (ci <= 0 || cj <= 0) continue;
-            const double* wi = Wsm + i * 12;
-            const double* yi = wi + 6;
-            const double* wj = Wsm + j * 12;
-            // B = Y_i W_j^T ; B[r][s] = yi[2r] wj[2s] + yi[2r+1] wj[2s+1]
-            double val;
-            int cr, cc;
-            if (ci > cj) {
-                val = fma(yi[2 * r], wj[2 * sc], yi[2 * r + 1] * wj[2 * sc + 1]);
-                cr = ci; cc = cj;
-            } else if (ci < cj) {                                        // block (cj, ci) receives B^T
-                val = fma(yi[2 * sc], wj[2 * r], yi[2 * sc + 1] * wj[2 * r + 1]);
-                cr = cj; cc = ci;
-            } else {
-                val = fma(yi[2 * r], wj[2 * sc], yi[2 * r + 1] * wj[2 * sc + 1]);
-                if (i != j) val += fma(yi[2 * sc], wj[2 * r], yi[2 * sc + 1] * wj[2 * r + 1]);   // same keyframe twice: B + B^T
-                cr = cc = ci;
+        // 27 lanes = 3 pairs x 9 block entries per step; a lane's entry (r, sc) never changes, and its pair index advances by 3,
+        // so (i, j) is updated incrementally (no division / square root per entry: the kernel is instruction-issue bound)
+        const int npairs = d * (d + 1) / 2;
+        if (lane < 27) {
+            int i = (q3 == 0) ? 0 : 1, j = (q3 == 2) ? 1 : 0;          // pair q3 of the row-major list (0,0) (1,0) (1,1) (2,0) ...
+            for (int p = q3; p < npairs; p += 3) {
+                const int ci = Csm[i], cj = Csm[j];
+                if (ci > 0 && cj > 0) {
+                    const double* yi = Wsm + i * 12 + 6;
+                    const double* wj = Wsm + j * 12;
+                    // block (max, min) of S receives Y_i W_j^T, transposed when the pair is listed the other way round
+                    const bool sw = ci < cj;
+                    const int a = sw ? sc : r, bb = sw ? r : sc;
+                    double val = fma(yi[2 * a], wj[2 * bb], yi[2 * a + 1] * wj[2 * bb + 1]);
+                    if (ci == cj && i != j) val += fma(yi[2 * sc], wj[2 * r], yi[2 * sc + 1] * wj[2 * r + 1]);   // same keyframe twice: B + B^T
+                    const int cr = sw ? cj : ci, cc = sw ? ci : cj;
+                    atomicAdd(S + (size_t)(3 * (cr - 1) + r) + (size_t)(3 * (cc - 1) + sc) * ld, -val);
+                }
+                j += 3;
+                while (j > i) { j -= i + 1; ++i; }
             }
-            atomicAdd(S + (size_t)(3 * (cr - 1) + r) + (size_t)(3 * (cc - 1) + sc) * ld, -val);
         }
         __syncwarp();
     }
