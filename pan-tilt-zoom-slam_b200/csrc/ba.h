@@ -29,7 +29,7 @@ struct ptzba_ba {
     DevBuf<int32_t> lm_ptr;         // [M+1] CSR offsets into the sorted arrays
     // second copy in keyframe-major order (landmark ascending inside a keyframe) for the keyframe pass of the fused
     // pass: keyframe blocks accumulate in registers there
-    DevBuf<int32_t> c_cam, c_lm, c_orig;
+    DevBuf<int32_t> c_cam, c_lm;
     DevBuf<double> c_ox, c_oy;
     // current parameters
     DevBuf<CamTrig> cam_trig;       // [N]

@@ -53,17 +53,15 @@ __global__ void k_gather_obs(int64_t n, const int32_t* __restrict__ perm, const 
     }
 }
 
-// keyframe-major gather: position k takes landmark-major position perm[k]; c_orig = caller position of the residual
+// keyframe-major gather: position k takes landmark-major position perm[k]
 __global__ void k_gather_cm(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ s_lm,
-                            const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
-                            int32_t* __restrict__ c_lm, double* __restrict__ c_ox, double* __restrict__ c_oy,
-                            int32_t* __restrict__ c_orig) {
+                            const double* __restrict__ s_ox, const double* __restrict__ s_oy, int32_t* __restrict__ c_lm,
+                            double* __restrict__ c_ox, double* __restrict__ c_oy) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const int32_t p = perm[k];
         c_lm[k] = s_lm[p];
         c_ox[k] = s_ox[p];
         c_oy[k] = s_oy[p];
-        c_orig[k] = orig ? orig[p] : p;
     }
 }
 
@@ -593,7 +591,7 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     if (n_obs > 0) {
         DevBuf<int32_t> iota, perm2;
         DevBuf<unsigned char> tmp;
-        CU_TRY(ba->c_cam.alloc(n_obs + 4)); CU_TRY(ba->c_lm.alloc(n_obs + 4)); CU_TRY(ba->c_orig.alloc(n_obs + 4));
+        CU_TRY(ba->c_cam.alloc(n_obs + 4)); CU_TRY(ba->c_lm.alloc(n_obs + 4));
         CU_TRY(ba->c_ox.alloc(n_obs + 4)); CU_TRY(ba->c_oy.alloc(n_obs + 4));
         CU_TRY(iota.alloc(n_obs)); CU_TRY(perm2.alloc(n_obs));
         k_iota<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, iota.p);
@@ -604,9 +602,8 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ba->s_cam.p, ba->c_cam.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
         CU_TRY(tmp.alloc(bytes));
         CU_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ba->s_cam.p, ba->c_cam.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
-        k_gather_cm<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, perm2.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p,
-                                                                    ba->identity_perm ? nullptr : ba->orig.p, ba->c_lm.p,
-                                                                    ba->c_ox.p, ba->c_oy.p, ba->c_orig.p);
+        k_gather_cm<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, perm2.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, ba->c_lm.p,
+                                                                    ba->c_ox.p, ba->c_oy.p);
         ctx->launches++;
         CU_TRY(cudaStreamSynchronize(s));
     }
