@@ -88,7 +88,9 @@ __device__ __forceinline__ CamTrig make_cam_trig(double pan, double tilt, double
 __device__ __forceinline__ LmTrig make_lm_trig(double theta_deg, double phi_deg) {
     LmTrig l;
     sincos(theta_deg * PTZ_DEG2RAD, &l.sth, &l.cth);
-    const double tp = tan(phi_deg * PTZ_DEG2RAD);
+    double sph, cph;
+    sincos(phi_deg * PTZ_DEG2RAD, &sph, &cph);            // tan = sin / cos: one range reduction instead of tan()'s own
+    const double tp = sph / cph;
     const double sg = (l.cth < 0.0) ? -1.0 : 1.0;   // sqrt(tan^2+1) = |sec|  (ptz_camera.py:205)
     l.T = tp * sg;
     l.S = (1.0 + tp * tp) * sg;
