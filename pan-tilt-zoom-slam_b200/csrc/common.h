@@ -26,6 +26,7 @@ struct ptzba_ctx {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
     // optional per-launch event timing of the dominant kernel
+    bool coop_configured = false;      // dynamic shared-memory opt-in of the cooperative Cholesky kernel done on this device
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // start/stop pairs
 };

@@ -516,10 +516,9 @@ size_t dense_coop_dinv_doubles(int n) { return (size_t)((n + IB - 1) / IB) * IB 
 int dense_potrf_coop(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info, double* Dinv_store) {
     if (n <= 0) return PTZBA_OK;
     const size_t smem = (size_t)4 * TS * TS * sizeof(double);      // 128 KB: four 64 x 64 blocks of the doubling level
-    static bool configured = false;
-    if (!configured) {
+    if (!ctx->coop_configured) {            // per context: function attributes belong to the device the context runs on
         CU_CHECK(ctx, cudaFuncSetAttribute(k_potrf_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        ctx->coop_configured = true;
     }
     const int nib = (n + IB - 1) / IB;
     double* Dinv = Dinv_store;
