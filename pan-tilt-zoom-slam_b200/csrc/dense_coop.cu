@@ -27,28 +27,6 @@ constexpr int kCoopWorkers = 256;                  // threads of the panel solve
 constexpr int kCoopHelpers = 128;                  // look-ahead group: updates and factors the NEXT diagonal block during the trailing update
 constexpr int kCoopCta = kCoopWorkers + kCoopHelpers;
 
-// C(32x32 tile at rows r0, cols c0 of an m x m product) helpers are not needed: the doubling levels use this generic
-// small product  Out = -(Bi * (C * Ai))  on square blocks of order h (32 or 64), all operands in shared memory.
-__device__ __forceinline__ void block_inverse_offdiag(int h, const double* __restrict__ Ai, const double* __restrict__ Bi,
-                                                      const double* __restrict__ C, double* __restrict__ T,
-                                                      double* __restrict__ Out) {
-    // T = C * Ai (Ai lower triangular: sum over t >= j), Out = -Bi * T (Bi lower triangular: sum over t <= i); column-major h x h
-    for (int e = threadIdx.x; e < h * h; e += kCoopCta) {
-        const int i = e % h, j = e / h;
-        double s = 0.0;
-        for (int t = j; t < h; ++t) s = fma(C[i + h * t], Ai[t + h * j], s);
-        T[e] = s;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < h * h; e += kCoopCta) {
-        const int i = e % h, j = e / h;
-        double s = 0.0;
-        for (int t = 0; t <= i; ++t) s = fma(Bi[i + h * t], T[t + h * j], s);
-        Out[e] = -s;
-    }
-    __syncthreads();
-}
-
 constexpr int kTri = NB * (NB + 1) / 2;            // entries of a 32 x 32 lower triangle
 
 // column-major list of the lower-triangle positions (i << 8 | c): the entries right of column j are the suffix that starts at
@@ -103,29 +81,6 @@ __device__ __forceinline__ bool group_potf2(double (*Ls)[NB + 1], double* sInv, 
         helper_sync();
     }
     return bad;
-}
-
-// one warp: X = L^-1 for the 32 x 32 lower-triangular block in Ls (diagonal inverses in sInv) by right-looking forward
-// substitution on X = I; lane = column of X, row t is final after step t; 4 rows per lane updated with hoisted loads
-__device__ __forceinline__ void warp_inverse32(double (*Ls)[NB + 1], double (*Li)[NB + 1], const double* sInv, int lane) {
-    for (int i = 0; i < NB; ++i) Li[i][lane] = (i == lane) ? 1.0 : 0.0;
-    __syncwarp();
-    for (int t = 0; t < NB; ++t) {
-        if (lane <= t) {
-            const double xt = Li[t][lane] * sInv[t];
-            Li[t][lane] = xt;
-            for (int i0 = t + 1; i0 < NB; i0 += 4) {
-                double l[4], x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i0 + u < NB) { l[u] = Ls[i0 + u][t]; x[u] = Li[i0 + u][lane]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i0 + u < NB) Li[i0 + u][lane] = fma(-l[u], xt, x[u]);
-            }
-        }
-        __syncwarp();
-    }
 }
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -208,7 +163,7 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
         COOP_TICK(2);
         if (helper) {
             // ---- look-ahead: the next diagonal block, updated with this panel's rows, factored and inverted ----
-            const int k1 = m0, nb1 = (n - k1) < NB ? (n - k1) : NB;
+            const int k1 = m0;
             long long th = dbg ? clock64() : 0;
 #define HELP_TICK(slot)                                                         \
     do {                                                                        \
@@ -219,34 +174,7 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
         }                                                                       \
     } while (0)
             const int hid = tid - kCoopWorkers;
-            {
-                // thread (row = hid & 31, 8 columns): 16 independent loads in flight
-                const int row = hid & 31, j0 = (hid >> 5) * 8;
-                double w[8], d[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = j0 + jj;
-                    w[jj] = row < nb1 ? __ldcg(A + (size_t)(k1 + row) + (size_t)(k + j) * lda) : 0.0;                    // L(k1 + row, k + j)
-                    d[jj] = (row < nb1 && j < nb1 && j <= row) ? __ldcg(A + (size_t)(k1 + row) + (size_t)(k1 + j) * lda) : (row == j ? 1.0 : 0.0);
-                }
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) { Ws[row][j0 + jj] = w[jj]; Ls[row][j0 + jj] = d[jj]; }
-            }
-            helper_sync();
-            HELP_TICK(6);
-            for (int e = hid; e < kTri; e += kCoopHelpers) {    // Ls(i, c) -= sum_t W(i, t) W(c, t), entries spread evenly
-                const int code = sTri[e], i = code >> 8, c = code & 255;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                for (int t = 0; t < NB; t += 4) {
-                    s0 = fma(Ws[i][t], Ws[c][t], s0);
-                    s1 = fma(Ws[i][t + 1], Ws[c][t + 1], s1);
-                    s2 = fma(Ws[i][t + 2], Ws[c][t + 2], s2);
-                    s3 = fma(Ws[i][t + 3], Ws[c][t + 3], s3);
-                }
-                Ls[i][c] -= (s0 + s1) + (s2 + s3);
-            }
-            helper_sync();
+            asm volatile("bar.sync 3, 384;" ::: "memory");      // the workers have loaded and updated the next diagonal block (Ls)
             HELP_TICK(7);
             if (group_potf2(Ls, sInv, sCol, sTri, hid) && hid == 0 && cta == 0) atomicMax(info, k1 + 1);
             if (dbg && blockIdx.x == 0 && threadIdx.x == kCoopWorkers) dbg[16 + kb] = clock64() - th;
@@ -256,6 +184,35 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
             // ---- trailing update: lower 64 x 64 tiles, C -= P_i P_j^T.  Software pipelined over this CTA's tiles: the panel rows
             // of the NEXT tile are requested (registers) before the current tile is multiplied, the tile's old values are
             // requested at its start and only consumed at its end, so no L2 round trip is exposed between tiles ----
+            {
+                // ---- next diagonal block: load it and this panel's rows of it, apply the panel's update, hand it to the look-ahead
+                // group (which factors it while the tiles below are updated); every CTA keeps its own copy ----
+                const int k1 = m0, nb1 = (n - k1) < NB ? (n - k1) : NB;
+                const int row = tid & 31, j0 = (tid >> 5) * 4;
+                double w[4], d[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = j0 + jj;
+                    w[jj] = row < nb1 ? __ldcg(A + (size_t)(k1 + row) + (size_t)(k + j) * lda) : 0.0;                    // L(k1 + row, k + j)
+                    d[jj] = (row < nb1 && j < nb1 && j <= row) ? __ldcg(A + (size_t)(k1 + row) + (size_t)(k1 + j) * lda) : (row == j ? 1.0 : 0.0);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) { Ws[row][j0 + jj] = w[jj]; Ls[row][j0 + jj] = d[jj]; }
+                worker_sync();
+                for (int e = tid; e < kTri; e += kCoopWorkers) {    // Ls(i, c) -= sum_t W(i, t) W(c, t)
+                    const int code = sTri[e], i = code >> 8, c = code & 255;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NB; t += 4) {
+                        s0 = fma(Ws[i][t], Ws[c][t], s0);
+                        s1 = fma(Ws[i][t + 1], Ws[c][t + 1], s1);
+                        s2 = fma(Ws[i][t + 2], Ws[c][t + 2], s2);
+                        s3 = fma(Ws[i][t + 3], Ws[c][t + 3], s3);
+                    }
+                    Ls[i][c] -= (s0 + s1) + (s2 + s3);
+                }
+                asm volatile("bar.arrive 3, 384;" ::: "memory");
+            }
             const int m = n - m0;
             const int nt = (m + TS - 1) / TS;
             const int ntiles = nt * (nt + 1) / 2;
@@ -330,63 +287,85 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
         COOP_TICK(4);
     }
     grid.sync();
-    // ---- inverses of the 32 x 32 diagonal blocks of L (one block per CTA, one warp each) ----
+    // ---- inverses of the 32 x 32 diagonal blocks of L (one block per CTA): right-looking forward substitution on X = I,
+    // all threads of the CTA on the 1024 entries, row t final after step t ----
     for (int b = cta; b < nblk; b += G) {
-        if (tid < 32) {
-            const int k = b * NB, nb = (n - k) < NB ? (n - k) : NB;
-            double d[NB];
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-                d[j] = (lane < nb && j < nb && j <= lane) ? __ldcg(A + (size_t)(k + lane) + (size_t)(k + j) * lda) : (lane == j ? 1.0 : 0.0);
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                Ls[lane][j] = d[j];
-                if (j == lane) sInv[lane] = 1.0 / d[j];
-            }
-            __syncwarp();
-            warp_inverse32(Ls, Li, sInv, lane);
-            for (int i = 0; i < NB; ++i) Dinv32[(size_t)b * NB * NB + i + NB * lane] = Li[i][lane];
+        const int k = b * NB, nb = (n - k) < NB ? (n - k) : NB;
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += kCoopCta) {
+            const int i = e % NB, j = e / NB;
+            Ls[i][j] = (i < nb && j < nb && j <= i) ? __ldcg(A + (size_t)(k + i) + (size_t)(k + j) * lda) : (i == j ? 1.0 : 0.0);
+            Li[i][j] = (i == j) ? 1.0 : 0.0;
         }
         __syncthreads();
+        if (tid < NB) sInv[tid] = 1.0 / Ls[tid][tid];
+        __syncthreads();
+        for (int t = 0; t < NB; ++t) {
+            if (tid <= t) Li[t][tid] *= sInv[t];
+            __syncthreads();
+            for (int e = tid; e < NB * NB; e += kCoopCta) {
+                const int i = e % NB, c = e / NB;
+                if (i > t && c <= t) Li[i][c] = fma(-Ls[i][t], Li[t][c], Li[i][c]);
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < NB * NB; e += kCoopCta) Dinv32[(size_t)b * NB * NB + e] = Li[e % NB][e / NB];
     }
     grid.sync();
     COOP_TICK(9);
-    // ---- inverses of the 128 x 128 diagonal blocks: level 1 (64-blocks from 32-blocks), level 2 (128 from 64) ----
-    // shared memory (doubles) at level h: Ai[h*h] | Bi[h*h] | C[h*h] | T[h*h] ; Dinv block layout: column-major IB x IB
+    // ---- inverses of the 128 x 128 diagonal blocks: level 0 (64-blocks from 32-blocks), level 1 (128 from 64).  One job =
+    // one 16-column slice of one merge  inv [[A 0] [C B]] = [[A^-1 0] [-B^-1 C A^-1  B^-1]] : 24 jobs per level at n = 765.
+    // shared memory (doubles): Bi[h*h] | C[h*h] | Ai slice [h*16] | T slice [h*16]; Dinv block layout: column-major IB x IB ----
     const int nib = (n + IB - 1) / IB;
-    double* sA = sm;
+    constexpr int SL = 16;
     for (int level = 0; level < 2; ++level) {
         const int h = NB << level;                 // order of the inverted halves: 32, then 64
         const int per = IB / (2 * h);              // merges per 128-block: 2, then 1
-        double* sAi = sA; double* sBi = sA + h * h; double* sC = sA + 2 * h * h; double* sT = sA + 3 * h * h;
-        for (int job = cta; job < nib * per; job += G) {
-            const int ib = job / per, q = job - ib * per;
+        const int nsl = h / SL;                    // column slices per merge
+        double* sBi = sm; double* sC = sm + h * h; double* sAi = sm + 2 * h * h; double* sT = sAi + h * SL;
+        for (int job = cta; job < nib * per * nsl; job += G) {
+            const int sl = job % nsl, mq = job / nsl, ib = mq / per, q = mq - ib * per;
             const int o = ib * IB + q * 2 * h;     // first row/col of this merge inside the matrix
+            const int lo = q * 2 * h, j0 = sl * SL; // offset inside the 128-block, first column of the slice
             double* D = Dinv + (size_t)ib * IB * IB;
-            const int lo = q * 2 * h;              // offset inside the 128-block
             __syncthreads();
             for (int e = tid; e < h * h; e += kCoopCta) {
                 const int i = e % h, j = e / h;
                 if (level == 0) {
-                    const int ba = (o >> 5), bb = ba + 1;        // 32-block indices (may lie beyond the matrix: identity)
-                    sAi[e] = ba < nblk ? __ldcg(Dinv32 + (size_t)ba * NB * NB + e) : (i == j ? 1.0 : 0.0);
+                    const int bb = (o >> 5) + 1;                 // 32-block index (may lie beyond the matrix: identity)
                     sBi[e] = bb < nblk ? __ldcg(Dinv32 + (size_t)bb * NB * NB + e) : (i == j ? 1.0 : 0.0);
                 } else {
-                    sAi[e] = __ldcg(D + (size_t)(lo + i) + (size_t)(lo + j) * IB);
                     sBi[e] = __ldcg(D + (size_t)(lo + h + i) + (size_t)(lo + h + j) * IB);
                 }
                 const int gi = o + h + i, gj = o + j;
                 sC[e] = (gi < n && gj < n) ? __ldcg(A + (size_t)gi + (size_t)gj * lda) : 0.0;
             }
+            for (int e = tid; e < h * SL; e += kCoopCta) {
+                const int i = e % h, j = j0 + e / h;
+                if (level == 0) {
+                    const int ba = o >> 5;
+                    sAi[e] = ba < nblk ? __ldcg(Dinv32 + (size_t)ba * NB * NB + i + NB * j) : (i == j ? 1.0 : 0.0);
+                } else {
+                    sAi[e] = __ldcg(D + (size_t)(lo + i) + (size_t)(lo + j) * IB);
+                }
+            }
             __syncthreads();
-            block_inverse_offdiag(h, sAi, sBi, sC, sT, sC);      // sC <- -Bi C Ai
-            for (int e = tid; e < h * h; e += kCoopCta) {
-                const int i = e % h, j = e / h;
-                D[(size_t)(lo + h + i) + (size_t)(lo + j) * IB] = sC[e];
+            for (int e = tid; e < h * SL; e += kCoopCta) {       // T = C * Ai (Ai lower triangular: t >= j)
+                const int i = e % h, jj = e / h, j = j0 + jj;
+                double s0 = 0.0;
+                for (int t = j; t < h; ++t) s0 = fma(sC[i + h * t], sAi[t + h * jj], s0);
+                sT[e] = s0;
+            }
+            __syncthreads();
+            for (int e = tid; e < h * SL; e += kCoopCta) {       // Out = -Bi * T (Bi lower triangular: t <= i)
+                const int i = e % h, jj = e / h, j = j0 + jj;
+                double s0 = 0.0;
+                for (int t = 0; t <= i; ++t) s0 = fma(sBi[i + h * t], sT[t + h * jj], s0);
+                D[(size_t)(lo + h + i) + (size_t)(lo + j) * IB] = -s0;
                 D[(size_t)(lo + i) + (size_t)(lo + h + j) * IB] = 0.0;
                 if (level == 0) {
                     D[(size_t)(lo + i) + (size_t)(lo + j) * IB] = sAi[e];
-                    D[(size_t)(lo + h + i) + (size_t)(lo + h + j) * IB] = sBi[e];
+                    D[(size_t)(lo + h + i) + (size_t)(lo + h + j) * IB] = sBi[i + h * j];
                 }
             }
         }
@@ -537,8 +516,8 @@ int dense_potrf_coop(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info, dou
         long long h[64];
         CU_CHECK(ctx, cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "[ptzba trace] potrf_coop n=%d cycles: first_block=%lld panel=%lld bar=%lld update|lookahead=%lld bar=%lld inv32=%lld blockinv=%lld | helper: loads=%lld update=%lld potf2=%lld\n", n,
-                h[0], h[1], h[2], h[3], h[4], h[9], h[5], h[6], h[7], h[8]);
+        fprintf(stderr, "[ptzba trace] potrf_coop n=%d cycles: first_block=%lld panel=%lld bar=%lld update|lookahead=%lld bar=%lld inv32=%lld blockinv=%lld | helper: wait_for_block=%lld potf2=%lld\n", n,
+                h[0], h[1], h[2], h[3], h[4], h[9], h[5], h[7], h[8]);
         fprintf(stderr, "[ptzba trace] potf2 per panel:");
         for (int i = 0; i < 24; ++i) fprintf(stderr, " %lld", h[16 + i]);
         fprintf(stderr, "\n");
