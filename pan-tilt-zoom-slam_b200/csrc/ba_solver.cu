@@ -191,7 +191,7 @@ k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const in
             int i = (q3 == 0) ? 0 : 1, j = (q3 == 2) ? 1 : 0;          // pair q3 of the row-major list (0,0) (1,0) (1,1) (2,0) ...
             for (int p = q3; p < npairs; p += 3) {
                 const int ci = Csm[i], cj = Csm[j];
-                if (ci > 0 && cj > 0) {
+                if (ci > 0 && cj > 0 && !(i == j && r < sc)) {      // (a diagonal block only needs its lower triangle)
                     const double* yi = Wsm + i * 12 + 6;
                     const double* wj = Wsm + j * 12;
                     // block (max, min) of S receives Y_i W_j^T, transposed when the pair is listed the other way round
