@@ -147,8 +147,10 @@ def run_reference(args):
         "impl": "reference", "metric": "ba_residual_jacobian_normal_eq_obs_per_s", "value": r["value"], "unit": "obs/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload + " keyframe BA: %d keyframes x %d ray landmarks x %d observations" %
-                   (fb.n_pose, fb.n_landmark, fb.n_obs)},
+        "config": {"workload": "%s keyframe BA: %d keyframes x %d ray landmarks x %d observations per GPU" %
+                   (args.workload, fb.n_pose, fb.n_landmark, fb.n_obs),
+                   "parallelism": "host threads (plain-C port of the reference's pass, oracle/ptz_oracle_c.c)",
+                   "step": "one fused residual+Jacobian+normal-equation pass over the whole workload"},
         "cpu_baseline": {"value": r["value"], "unit": "obs/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
