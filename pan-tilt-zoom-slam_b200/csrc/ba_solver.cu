@@ -366,6 +366,7 @@ struct Solver {
     int obs_grid = 0;
     int pair_warps_smem = 0, pair_grid = 0;
     int n_factor = 0;
+    int* h_flags = nullptr;      // pinned host copy of the factorisation verdict (slot 200 of ctx->h_scalars): truly asynchronous
     double *g, *D, *Dc, *Dl;
     DevBuf<int>& flags;      // persistent scratch owned by the problem (no allocation per solve)
     DevBuf<double>&tmp_l, &w_full, &dinv;
@@ -373,6 +374,7 @@ struct Solver {
 
     int init() {
         N = ba->n_pose; M = ba->n_lm; n = 3 * (N - 1); nF = 3 * N + 2 * M;
+        h_flags = reinterpret_cast<int*>(ctx->h_scalars + 200);
         CU_CHECK(ctx, ba->x_cur.alloc(nF)); CU_CHECK(ctx, ba->x_trial.alloc(nF));
         CU_CHECK(ctx, ba->scale_inv.alloc(nF));
         CU_CHECK(ctx, ba->Sred.alloc((size_t)(n > 0 ? n : 1) * (n > 0 ? n : 1)));
@@ -435,10 +437,10 @@ struct Solver {
         }
         tr.report("factor");
         ++n_factor;
-        int h[2];
-        CU_CHECK(ctx, cudaMemcpyAsync(h, flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CU_CHECK(ctx, cudaStreamSynchronize(s));
-        *ok = (h[0] == 0 && h[1] == 0);
+        // the verdict (singular landmark block / non-positive pivot) is read together with the step's scalars in step_at():
+        // one host synchronisation per step instead of two; a solve with a broken factor only produces numbers that are dropped
+        CU_CHECK(ctx, cudaMemcpyAsync(h_flags, flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        *ok = true;
         return PTZBA_OK;
     }
 
@@ -486,7 +488,6 @@ struct Solver {
     // delta = -(A + alpha D^2)^-1 g  -> ba->sol_c ; returns ||D delta||, and (optionally) phi' pieces
     int step_at(double alpha, bool want_derivative, bool* ok, double* p_norm, double* wq) {
         PROPAGATE(factor(alpha, ok));
-        if (!*ok) return PTZBA_OK;
         double* rhs = ba->rhs_c.p;
         k_neg<<<div_up(nF, 256), 256, 0, s>>>(nF, g, rhs);
         KERNEL_POST(ctx);
@@ -502,7 +503,8 @@ struct Solver {
         k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, D, nullptr, ba->sol_c.p, b, c, nullptr, ba->scal.p);
         KERNEL_POST(ctx);
         double h[4];
-        PROPAGATE(read_scalars(h, 4));
+        PROPAGATE(read_scalars(h, 4));                  // synchronises: h_flags of factor() has arrived as well
+        *ok = (h_flags[0] == 0 && h_flags[1] == 0);
         *p_norm = std::sqrt(h[0]);
         if (wq) *wq = h[3];
         if (!std::isfinite(*p_norm)) *ok = false;
@@ -567,31 +569,26 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
     if (opt->verbose) printf("%12s %12s %16s %16s %14s %14s\n", "Iteration", "Total nfev", "Cost", "Cost reduction", "Step norm", "Optimality");
 
     while (true) {
-        // g_norm (inf-norm of the gradient) and ||g_h||^2 = sum (g/D)^2
-        CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
+        // g_norm (inf-norm of the gradient), ||x|| and ||g_h|| = ||g / D|| (sum (D * (g / D^2))^2) in ONE read-back:
+        // the two reductions write to different slots of the scalar block
+        CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 16 * sizeof(double), s));
         k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, S.g, nullptr, nullptr, ba->x_cur.p, ba->scal.p);
         KERNEL_POST(ctx);
-        PROPAGATE(S.read_scalars(h, 6));
-        g_norm = h[5];
-        const double x_norm = std::sqrt(h[4]);
+        k_div_d2<<<div_up(nF, 256), 256, 0, s>>>(nF, S.D, S.g, S.w_full.p);
+        KERNEL_POST(ctx);
+        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, nullptr, S.w_full.p, nullptr, nullptr, nullptr, ba->scal.p + 8);
+        KERNEL_POST(ctx);
+        double h16[16];
+        PROPAGATE(S.read_scalars(h16, 9));
+        g_norm = h16[5];
+        const double x_norm = std::sqrt(h16[4]);
+        const double gh_norm = std::sqrt(h16[8]);
         if (g_norm < gtol) status = 1;
         if (opt->verbose) {
             if (nit == 0) printf("%12d %12d %16.4e %16s %14s %14.2e\n", nit, nfev, cost, "", "", g_norm);
             else printf("%12d %12d %16.4e %16.2e %14.2e %14.2e\n", nit, nfev, cost, actual_reduction, step_norm, g_norm);
         }
         if (status != -1 || nfev >= max_nfev) break;
-
-        // ||g_h||, g_h = g / D:  sum (D * (g / D^2))^2 = sum (g / D)^2
-        double gh_norm;
-        {
-            k_div_d2<<<div_up(nF, 256), 256, 0, s>>>(nF, S.D, S.g, S.w_full.p);
-            KERNEL_POST(ctx);
-            CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
-            k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, nullptr, S.w_full.p, nullptr, nullptr, nullptr, ba->scal.p);
-            KERNEL_POST(ctx);
-            PROPAGATE(S.read_scalars(h, 1));
-            gh_norm = std::sqrt(h[0]);
-        }
 
         actual_reduction = -1;
         double cost_new = cost;
