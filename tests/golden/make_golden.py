@@ -223,8 +223,19 @@ def gen_keyframe_map():
     with contextlib.redirect_stdout(io.StringIO()):
         good = np.array([m.good_new_keyframe(c) for c in cand])
         good_custom = np.array([m.good_new_keyframe(c, 10, 15, W) for c in cand])     # ptz_slam.py:458 thresholds
+    # util.get_overlap_index (util.py:75-96): two-pointer merge of ascending index arrays (ragged / empty / disjoint cases)
+    ov_cases = {}
+    shapes = [(40, 25), (0, 10), (10, 0), (7, 7), (300, 280)]
+    for c, (n1, n2) in enumerate(shapes):
+        a = np.sort(rng.choice(400, n1, replace=False)) if n1 else np.zeros(0, np.int64)
+        b = np.sort(rng.choice(400, n2, replace=False)) if n2 else np.zeros(0, np.int64)
+        if c == 3:
+            b = a + 1000                     # nothing shared
+        i1, i2 = ref_util.get_overlap_index(a, b)
+        ov_cases["ov%d_a" % c], ov_cases["ov%d_b" % c] = a, b
+        ov_cases["ov%d_i1" % c], ov_cases["ov%d_i2" % c] = i1.astype(np.int64), i2.astype(np.int64)
     np.savez(os.path.join(OUT, "keyframe_map.npz"), fl1=fl1, fl2=fl2, p1=p1, p2=p2, overlap=ov, kf_ptz=kf_ptz, cand=cand,
-             good=good, good_custom=good_custom, im_width=W)
+             good=good, good_custom=good_custom, im_width=W, n_overlap_cases=len(shapes), **ov_cases)
 
 
 if __name__ == "__main__":

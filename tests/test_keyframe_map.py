@@ -47,3 +47,12 @@ def test_empty_map_and_argument_checks():
         Map('surf')                                                            # scene_map.py:23
     with pytest.raises(AssertionError):
         m.add_first_keyframe("not a keyframe")
+
+
+def test_get_overlap_index_golden():
+    """util.get_overlap_index (util.py:75-96), the matched-ray index plumbing of ekf_update: ragged, empty and disjoint inputs."""
+    from ptz_slam_b200.util import get_overlap_index
+    for c in range(int(G["n_overlap_cases"])):
+        i1, i2 = get_overlap_index(G["ov%d_a" % c], G["ov%d_b" % c])
+        np.testing.assert_array_equal(i1, G["ov%d_i1" % c])
+        np.testing.assert_array_equal(i2, G["ov%d_i2" % c])
