@@ -1,11 +1,11 @@
-// dense.cu - hand-written dense FP64 factorisation kernels for the Schur-reduced camera system S (order 3(N-1)).
+// dense.cu - hand-written BATCHED dense FP64 Cholesky kernels (the innovation covariances S = H P H^T + R of many independent
+// EKF sequences, ptz_slam.py:256-259; the reference inverts S with numpy's LU).
 //
-// The reference hands the whole problem to scipy's dense SVD (bundle_adjustment.py:200-202 -> _lsq/trf.py); here the
-// reduced system is factorised with a blocked right-looking Cholesky (lower, column-major, in place):
-//     for each 32-wide panel:  potf2 (one warp, registers + shuffles)  ->  trsm (row per thread, L_kk in smem)
-//                              ->  syrk (64x64 tiles, FP64 FMA, lower tiles only)
-// followed by blocked forward / backward substitutions for up to two right-hand sides at once.
-// Bound by the FP64 pipe for large n (n^3/3 flops) and by launch latency for small n.
+// Blocked right-looking Cholesky (lower, column-major, in place), one launch pair per 32-wide panel for the whole batch:
+//     k_potf2_trsm  every CTA factors the 32 x 32 diagonal block redundantly in shared memory, then solves its 128 panel rows
+//     k_syrk_lower  64 x 64 tiles of the trailing matrix, FP64 FMA, lower tiles only
+// and the multi-right-hand-side forward solve Z = L^-1 G on row-major G (k_fwd_diag_rows / k_fwd_update_rows).
+// The single reduced camera system of bundle adjustment uses the cooperative one-kernel path of dense_coop.cu instead.
 #include "common.h"
 #include "dense.h"
 
@@ -13,74 +13,6 @@ namespace {
 
 constexpr int NB = 32;        // panel width
 constexpr int TS = 64;        // syrk tile
-
-// ---- potf2: Cholesky of one NB x NB diagonal block by a single warp; lane = row -----------------------------------
-__global__ void __launch_bounds__(32) k_potf2(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
-                                              int n_fixed, int k, int* __restrict__ info) {
-    const int lane = threadIdx.x;
-    const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
-    if (k >= n) return;
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    double* A = A0 + stride * blockIdx.y;
-    double row[NB];
-    double* blk = A + (size_t)k + (size_t)k * lda;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) row[j] = (lane < nb && j < nb && j <= lane) ? blk[lane + (size_t)j * lda] : 0.0;
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        if (j < nb) {
-            // pivot lives in lane j
-            double piv = __shfl_sync(0xffffffffu, row[j], j);
-            if (!(piv > 0.0)) { bad = true; piv = 1.0; }
-            const double s = sqrt(piv);
-            const double inv = 1.0 / s;
-            if (lane == j) row[j] = s; else if (lane > j) row[j] *= inv;
-            // trailing update: a_ik -= l_ij * l_kj for k in (j, i]
-            const double lij = row[j];
-#pragma unroll
-            for (int c = j + 1; c < NB; ++c) {
-                const double lcj = __shfl_sync(0xffffffffu, row[j], c);
-                if (c < nb && lane >= c) row[c] = fma(-lij, lcj, row[c]);
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-        if (lane < nb && j < nb && j <= lane) blk[lane + (size_t)j * lda] = row[j];
-    if (bad && lane == 0) atomicMax(info, k + 1);
-}
-
-// ---- trsm: rows below the diagonal block, X * L_kk^T = A_panel; one row per thread ------------------------------------
-__global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ A0, int lda, size_t stride,
-                                                    const int* __restrict__ n_arr, int n_fixed, int k) {
-    const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
-    if (k + NB >= n) return;
-    const int nb = NB;
-    double* A = A0 + stride * blockIdx.y;
-    __shared__ double L[NB][NB + 1];
-    for (int e = threadIdx.x; e < NB * NB; e += 128) {
-        const int i = e % NB, j = e / NB;
-        L[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    const int r = k + nb + blockIdx.x * 128 + threadIdx.x;
-    if (r >= n) return;
-    double x[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) x[j] = j < nb ? A[(size_t)r + (size_t)(k + j) * lda] : 0.0;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        double s = x[j];
-#pragma unroll
-        for (int t = 0; t < j; ++t) s = fma(-x[t], L[j][t], s);
-        x[j] = s / L[j][j];
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-        if (j < nb) A[(size_t)r + (size_t)(k + j) * lda] = x[j];
-}
-
 
 // ---- fused panel step: every CTA factors the NB x NB diagonal block redundantly in shared memory (128 threads, rsqrt on the
 // critical path) and then solves its own 128 rows of the panel; CTA 0 also writes the factored diagonal block back.
@@ -195,81 +127,6 @@ __global__ void __launch_bounds__(256) k_syrk_lower(double* __restrict__ A0, int
         }
 }
 
-// ---- triangular solves with NRHS right-hand sides (columns of B, ldb), single CTA, blocked by 32 -----------------
-// forward: L y = b ; backward: L^T x = y.  1024 threads.
-template <int NRHS>
-__global__ void __launch_bounds__(1024) k_trsv_lower(const double* __restrict__ L, int lda, int n, double* __restrict__ B,
-                                                     int ldb, int backward) {
-    __shared__ double xs[NRHS][NB];
-    __shared__ double D[NB][NB + 1];
-    const int tid = threadIdx.x;
-    const int nblk = (n + NB - 1) / NB;
-    for (int bi = 0; bi < nblk; ++bi) {
-        const int blk = backward ? (nblk - 1 - bi) : bi;
-        const int k = blk * NB;
-        const int nb = (n - k) < NB ? (n - k) : NB;
-        // diagonal block into smem
-        for (int e = tid; e < NB * NB; e += 1024) {
-            const int i = e % NB, j = e / NB;
-            D[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : 0.0;
-        }
-        __syncthreads();
-        if (tid < NRHS) {       // one thread per RHS solves the small triangle
-            double x[NB];
-            for (int i = 0; i < nb; ++i) x[i] = B[(size_t)(k + i) + (size_t)tid * ldb];
-            if (!backward) {
-                for (int i = 0; i < nb; ++i) {
-                    double s = x[i];
-                    for (int t = 0; t < i; ++t) s = fma(-D[i][t], x[t], s);
-                    x[i] = s / D[i][i];
-                }
-            } else {
-                for (int i = nb - 1; i >= 0; --i) {
-                    double s = x[i];
-                    for (int t = i + 1; t < nb; ++t) s = fma(-D[t][i], x[t], s);
-                    x[i] = s / D[i][i];
-                }
-            }
-            for (int i = 0; i < nb; ++i) {
-                B[(size_t)(k + i) + (size_t)tid * ldb] = x[i];
-                xs[tid][i] = x[i];
-            }
-            for (int i = nb; i < NB; ++i) xs[tid][i] = 0.0;
-        }
-        __syncthreads();
-        // update the remaining entries with the off-diagonal panel
-        if (!backward) {
-            // b[r] -= sum_j L[r, k+j] x[j]  for r >= k+nb   (thread per row, coalesced over r)
-            for (int r = k + nb + tid; r < n; r += 1024) {
-                double s[NRHS];
-#pragma unroll
-                for (int q = 0; q < NRHS; ++q) s[q] = 0.0;
-                for (int j = 0; j < nb; ++j) {
-                    const double l = L[(size_t)r + (size_t)(k + j) * lda];
-#pragma unroll
-                    for (int q = 0; q < NRHS; ++q) s[q] = fma(l, xs[q][j], s[q]);
-                }
-#pragma unroll
-                for (int q = 0; q < NRHS; ++q) B[(size_t)r + (size_t)q * ldb] -= s[q];
-            }
-        } else {
-            // b[c] -= sum_i L[k+i, c] x[i]  for c < k   (warp per column c, lanes over i -> coalesced over i)
-            const int warp = tid >> 5, lane = tid & 31;
-            for (int c = warp; c < k; c += 32) {
-                const double l = lane < nb ? L[(size_t)(k + lane) + (size_t)c * lda] : 0.0;
-#pragma unroll
-                for (int q = 0; q < NRHS; ++q) {
-                    double s = l * xs[q][lane];
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if (lane == 0) B[(size_t)c + (size_t)q * ldb] -= s;
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 }  // namespace
 
 int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
@@ -284,29 +141,6 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
         const int nt = div_up(m, TS);
         k_syrk_lower<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
         KERNEL_POST(ctx);
-    }
-    return PTZBA_OK;
-}
-
-int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info) {
-    return dense_potrf_lower_batched(ctx, A, lda, 0, nullptr, n, 1, d_info, nullptr);
-}
-
-int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B, int ldb, int nrhs) {
-    cudaStream_t s = ctx->stream;
-    if (n <= 0) return PTZBA_OK;
-    if (nrhs == 1) {
-        k_trsv_lower<1><<<1, 1024, 0, s>>>(L, lda, n, B, ldb, 0);
-        KERNEL_POST(ctx);
-        k_trsv_lower<1><<<1, 1024, 0, s>>>(L, lda, n, B, ldb, 1);
-        KERNEL_POST(ctx);
-    } else if (nrhs == 2) {
-        k_trsv_lower<2><<<1, 1024, 0, s>>>(L, lda, n, B, ldb, 0);
-        KERNEL_POST(ctx);
-        k_trsv_lower<2><<<1, 1024, 0, s>>>(L, lda, n, B, ldb, 1);
-        KERNEL_POST(ctx);
-    } else {
-        return ptzba_fail(ctx, PTZBA_ERR_ARG, "dense_potrs_lower: nrhs must be 1 or 2");
     }
     return PTZBA_OK;
 }
@@ -409,92 +243,5 @@ int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_
                                                                                             d_n_arr, extra_cols, k);
         KERNEL_POST(ctx);
     }
-    return PTZBA_OK;
-}
-
-namespace {
-
-// ---- inverses of the 32 x 32 diagonal blocks of L (one warp per block; lane j solves L x = e_j) ----------------------------
-// Dinv block b is stored column-major: Dinv[b*1024 + i + 32*j] = (L_bb^-1)[i][j]
-__global__ void __launch_bounds__(32) k_diag_inverse(const double* __restrict__ L, int lda, int n, double* __restrict__ Dinv) {
-    __shared__ double T[NB][NB + 1];
-    const int b = blockIdx.x, k = b * NB, lane = threadIdx.x;
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    for (int e = lane; e < NB * NB; e += 32) {
-        const int i = e % NB, j = e / NB;
-        T[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
-    }
-    __syncwarp();
-    double x[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        double s = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int t = 0; t < i; ++t) s = fma(-T[i][t], x[t], s);
-        x[i] = s / T[i][i];
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) Dinv[(size_t)b * NB * NB + i + NB * lane] = x[i];
-}
-
-// ---- single right-hand side solves with the inverted diagonal blocks: every block step is a 32 x 32 mat-vec by one warp
-// followed by a panel update spread over the whole CTA (no sequential triangle solve on the critical path) -----------------
-__global__ void __launch_bounds__(1024) k_trsv_dinv(const double* __restrict__ L, int lda, int n, const double* __restrict__ Dinv,
-                                                    double* __restrict__ bvec, int backward) {
-    __shared__ double xs[NB];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int nblk = (n + NB - 1) / NB;
-    for (int bi = 0; bi < nblk; ++bi) {
-        const int blk = backward ? (nblk - 1 - bi) : bi;
-        const int k = blk * NB;
-        const int nb = (n - k) < NB ? (n - k) : NB;
-        {
-            // x = Dinv * b_k (forward) or Dinv^T * b_k (backward): warp w forms entry w, one product per lane, all loads
-            // independent (1024 threads = 32 x 32 entries of the block)
-            const double* D = Dinv + (size_t)blk * NB * NB;
-            const double bt = lane < nb ? bvec[k + lane] : 0.0;
-            const double d = backward ? D[lane + NB * w] : D[w + NB * lane];
-            double sacc = d * bt;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
-            if (lane == 0) xs[w] = w < nb ? sacc : 0.0;
-        }
-        __syncthreads();
-        if (w == 0 && lane < nb) bvec[k + lane] = xs[lane];
-        if (!backward) {
-            for (int r = k + nb + tid; r < n; r += 1024) {
-                double s = 0.0;
-#pragma unroll 8
-                for (int j = 0; j < NB; ++j) s = fma(j < nb ? L[(size_t)r + (size_t)(k + j) * lda] : 0.0, xs[j], s);
-                bvec[r] -= s;
-            }
-        } else {
-            for (int c = tid; c < k; c += 1024) {
-                const double* col = L + (size_t)k + (size_t)c * lda;
-                double s = 0.0;
-#pragma unroll 8
-                for (int i = 0; i < NB; ++i) s = fma(i < nb ? col[i] : 0.0, xs[i], s);
-                bvec[c] -= s;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-}  // namespace
-
-int dense_diag_inverse(ptzba_ctx* ctx, const double* L, int n, int lda, double* Dinv) {
-    if (n <= 0) return PTZBA_OK;
-    k_diag_inverse<<<div_up(n, NB), 32, 0, ctx->stream>>>(L, lda, n, Dinv);
-    KERNEL_POST(ctx);
-    return PTZBA_OK;
-}
-
-int dense_potrs_dinv(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv, double* b) {
-    if (n <= 0) return PTZBA_OK;
-    k_trsv_dinv<<<1, 1024, 0, ctx->stream>>>(L, lda, n, Dinv, b, 0);
-    KERNEL_POST(ctx);
-    k_trsv_dinv<<<1, 1024, 0, ctx->stream>>>(L, lda, n, Dinv, b, 1);
-    KERNEL_POST(ctx);
     return PTZBA_OK;
 }

@@ -3,12 +3,7 @@
 #pragma once
 #include "common.h"
 
-// in-place Cholesky A = L L^T.  *d_info (device int) = 0 on success, else 1 + first row of the failing panel.
-int dense_potrf_lower(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info);
-// solves L L^T X = B in place for nrhs (1 or 2) right-hand sides stored as columns of B (ldb)
-int dense_potrs_lower(ptzba_ctx* ctx, const double* L, int n, int lda, double* B, int ldb, int nrhs);
-
-// batched variants: matrix b lives at A + b*stride and has order d_n_arr[b] (device array; nullptr = n_max for all)
+// batched in-place Cholesky A_b = L_b L_b^T: matrix b lives at A + b*stride and has order d_n_arr[b] (device array; nullptr = n_max for all)
 // d_info_per_batch (may be nullptr): entry b is set non-zero when matrix b is not positive definite (must be pre-zeroed)
 int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
                               int* d_info, int* d_info_per_batch);
@@ -25,13 +20,8 @@ int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t s
                              const double* B, double* X, int ldg, size_t strideG, const int* d_n_arr, int n_max, int extra_cols,
                              int batch);
 
-// inverses of the 32 x 32 diagonal blocks of a Cholesky factor (Dinv: ceil(n/32) * 1024 doubles) and the single-RHS solve
-// L L^T x = b that uses them (mat-vec per block step instead of a sequential triangle solve)
-int dense_diag_inverse(ptzba_ctx* ctx, const double* L, int n, int lda, double* Dinv);
-int dense_potrs_dinv(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv, double* b);
-
 // ---- single-matrix, latency-optimised path (dense_coop.cu): one persistent cooperative kernel factors A = L L^T and
-// inverts the 128 x 128 diagonal blocks of L into Dinv_store (dense_coop_dinv_doubles(n) doubles).  *d_info as dense_potrf_lower.
+// inverts the 128 x 128 diagonal blocks of L into Dinv_store (dense_coop_dinv_doubles(n) doubles).  *d_info (device int) = 0, or 1 + the first row of the panel with a non-positive pivot.
 size_t dense_coop_dinv_doubles(int n);
 int dense_potrf_coop(ptzba_ctx* ctx, double* A, int n, int lda, int* d_info, double* Dinv_store);
 int dense_potrs_coop(ptzba_ctx* ctx, const double* L, int n, int lda, const double* Dinv_store, double* b);
