@@ -4,6 +4,8 @@ PtzSlam drop-in for the EKF hot path (reference: slam_system/ptz_slam.py).
     PtzSlam.compute_h_jacobian(pan, tilt, focal_length, rays)                    ptz_slam.py:73-138
     PtzSlam.ekf_update(observed_keypoints, observed_keypoint_index, height, width)   ptz_slam.py:210-289
     PtzSlam.predict()  - the predict lines of tracking()                          ptz_slam.py:418-426
+    PtzSlam.remove_rays(index), PtzSlam.add_rays(img, bounding_box, detect)       ptz_slam.py:291-388 (state bookkeeping;
+                                                                                  keypoint detection is an injected callable)
 
 State attributes keep the reference's names and meaning (`rays`, `state_cov`, `cameras`, `current_camera`,
 `velocity`, `observe_var`, `angle_var`, `f_var`).  `ekf_update` mutates them in place like the reference; the
@@ -19,6 +21,23 @@ import ctypes
 import numpy as np
 
 from . import _lib
+
+
+def keypoints_masking(kp, mask):
+    """image_process.py:158-175 (array form): indices of the keypoints whose integer pixel has mask == 1."""
+    kp = np.asarray(kp).reshape(-1, 2)
+    if len(kp) == 0:
+        return np.zeros(0, dtype=np.int32)
+    x, y = kp[:, 0].astype(np.int64), kp[:, 1].astype(np.int64)       # int() truncation, as the reference
+    return np.nonzero(np.asarray(mask)[y, x] == 1)[0].astype(np.int32)
+
+
+def existing_keypoint_mask(keypoints, height, width, half=50):
+    """ptz_slam.py:352-361: 1 everywhere except the 100 x 100 boxes around the keypoints the map already projects to."""
+    mask = np.ones((height, width), np.uint8)
+    for x, y in np.asarray(keypoints).reshape(-1, 2):
+        mask[int(max(0, y - half)):int(min(height, y + half)), int(max(0, x - half)):int(min(width, x + half))] = 0
+    return mask
 
 
 def _params(u, v, disp, observe_var, angle_var, f_var, height, width, jac_mode):
@@ -37,6 +56,7 @@ class PtzSlam:
     def __init__(self):
         # global rays and covariance matrix (ptz_slam.py:29-31)
         self.rays = np.ndarray([0, 2])
+        self.des = np.ndarray([0, 128])
         self.state_cov = np.zeros([3, 3])
         self.current_camera = None
         self.cameras = []
@@ -57,6 +77,49 @@ class PtzSlam:
         self.state_cov[2][2] = self.f_var
         self.cameras = [camera]
         self.current_camera = camera
+
+    # -- ray bookkeeping between frames (ptz_slam.py:291-388; SURVEY.md 8f row N4, host side as in the reference) ----------
+    def remove_rays(self, index):
+        """ptz_slam.py:291-315: drop the rays `index` (RANSAC outliers) with their descriptors and covariance rows / columns."""
+        delete_index = np.asarray(index, dtype=np.int64).reshape(-1)
+        self.rays = np.delete(self.rays, delete_index, axis=0)
+        if len(self.des) > 0:
+            self.des = np.delete(self.des, delete_index, axis=0)
+        p_delete = np.stack([2 * delete_index + 3, 2 * delete_index + 4], axis=1).reshape(-1)
+        self.state_cov = np.delete(np.delete(self.state_cov, p_delete, axis=0), p_delete, axis=1)
+
+    def add_rays(self, img, bounding_box, detect_keypoints):
+        """ptz_slam.py:317-388 with the detector injected: `detect_keypoints(img, keypoint_num) -> (points[n,2], des[n,d] or None)`
+        stands for detect_compute_sift_array (:338).  New keypoints on players (bounding_box == 0) or within 50 px of a keypoint
+        the map already projects to are dropped; the others become rays (back-projection through the current camera on the
+        GPU) with variance angle_var.  Returns (keypoints, keypoints_index) like the reference."""
+        height, width = img.shape[0:2]
+        keypoints, keypoints_index = self.current_camera.project_rays(self.rays, height, width)
+        new_keypoints, new_des = detect_keypoints(img, self.keypoint_num)
+        new_keypoints = np.asarray(new_keypoints, dtype=np.float64).reshape(-1, 2)
+        if bounding_box is not None:
+            keep = keypoints_masking(new_keypoints, bounding_box)
+            new_keypoints = new_keypoints[keep]
+            new_des = None if new_des is None else np.asarray(new_des)[keep]
+        keep = keypoints_masking(new_keypoints, existing_keypoint_mask(keypoints, height, width))
+        new_keypoints = new_keypoints[keep]
+        new_des = None if new_des is None else np.asarray(new_des)[keep]
+        k = len(new_keypoints)
+        if k > 0:
+            new_rays = np.asarray(self.current_camera.back_project_to_rays(new_keypoints), dtype=np.float64).reshape(-1, 2)
+            n_old = len(self.rays)
+            self.rays = np.vstack([np.asarray(self.rays, dtype=np.float64).reshape(-1, 2), new_rays])
+            if new_des is not None:
+                self.des = np.vstack([self.des.reshape(-1, new_des.shape[1]) if len(self.des) else np.zeros((0, new_des.shape[1])), new_des])
+            s_old = self.state_cov.shape[0]
+            cov = np.zeros((s_old + 2 * k, s_old + 2 * k))
+            cov[:s_old, :s_old] = self.state_cov
+            d = np.arange(s_old, s_old + 2 * k)
+            cov[d, d] = self.angle_var
+            self.state_cov = cov
+            keypoints_index = np.append(keypoints_index, np.arange(n_old, n_old + k))
+        keypoints = np.concatenate([np.asarray(keypoints).reshape(-1, 2), new_keypoints], axis=0)
+        return keypoints, keypoints_index
 
     def compute_h_jacobian(self, pan, tilt, focal_length, rays):
         """ptz_slam.py:73-138: dense H [2n, 3+2n]; principal point / displacement come from self.cameras[0] (:92)."""

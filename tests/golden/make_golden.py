@@ -11,12 +11,15 @@ Goldens (reference function -> file):
   bundle_adjustment._compute_residual                                             -> ba_residual.npz
   scipy least_squares call of bundle_adjustment.py:200-202 (as-is and tight)      -> ba_solve.npz
   util.overlap_pan_angle, scene_map.Map.good_new_keyframe                         -> keyframe_map.npz
+  PtzSlam.remove_rays / add_rays (SIFT detector replaced by seeded keypoints),
+  image_process.keypoints_masking                                                 -> ray_bookkeeping.npz
 """
 import copy
 import io
 import os
 import sys
 import contextlib
+import warnings
 
 import numpy as np
 
@@ -238,7 +241,89 @@ def gen_keyframe_map():
              good=good, good_custom=good_custom, im_width=W, n_overlap_cases=len(shapes), **ov_cases)
 
 
+def gen_ray_bookkeeping():
+    """PtzSlam.remove_rays (ptz_slam.py:291-315) and add_rays (:317-388) run on a seeded state.  The only line replaced is
+    the OpenCV SIFT detector (:338, detect_compute_sift_array): it is monkeypatched in the reference module's namespace to
+    return seeded keypoints + descriptors, so every bookkeeping line of the reference executes unmodified.
+    numpy >= 1.19 refuses the float index array remove_rays builds (:309-315) with np.delete; the reference module's
+    np.delete is wrapped for that call so the indices are cast to integers - values unchanged."""
+    import ptz_slam as ref_ptz_slam
+    import image_process as ref_ip
+    rng = np.random.default_rng(1213)
+    out = {"uv": np.array([U, V]), "hw": np.array([H, W])}
+    n_cases, DES = 4, 16                          # the bookkeeping is descriptor-width agnostic; 16 keeps the fixture small
+    for c in range(n_cases):
+        ptz = np.array([rng.uniform(45, 70), rng.uniform(-12, -7), rng.uniform(2200, 3800)])
+        cam = make_camera(ptz, DISP if c == 2 else None)
+        n0 = [16, 0, 10, 24][c]
+        # rays spread wider than the field of view so that some project outside the image
+        fov = np.degrees(np.arctan(W / 2 / ptz[2]))
+        rays0 = np.stack([ptz[0] + rng.uniform(-1.6 * fov, 1.6 * fov, n0), ptz[1] + rng.uniform(-1.2 * fov, 1.2 * fov, n0)], 1)
+        slam = ref.PtzSlam()
+        slam.current_camera = cam
+        slam.cameras = [cam]
+        slam.rays = rays0.copy().reshape(-1, 2)
+        slam.des = rng.uniform(0, 255, (n0, DES)).astype(np.float32)
+        a = rng.normal(size=(3 + 2 * n0, 3 + 2 * n0))
+        slam.state_cov = a @ a.T * 1e-4                     # dense SPD so that every deleted / kept entry is distinguishable
+        out["c%d_ptz" % c], out["c%d_disp" % c] = ptz, (DISP if c == 2 else np.zeros(6))
+        out["c%d_rays0" % c], out["c%d_des0" % c], out["c%d_cov0" % c] = slam.rays.copy(), slam.des.copy(), slam.state_cov.copy()
+        # --- add_rays
+        n_new = [48, 12, 36, 0][c]
+        new_kp = np.stack([rng.uniform(0, W - 1e-3, n_new), rng.uniform(0, H - 1e-3, n_new)], 1).astype(np.float32)
+        new_des = rng.uniform(0, 255, (n_new, DES)).astype(np.float32)
+        bbox = np.ones((H, W), np.uint8)
+        if c != 1:
+            for _ in range(3):
+                x0, y0 = int(rng.uniform(0, W - 200)), int(rng.uniform(0, H - 250))
+                bbox[y0:y0 + 250, x0:x0 + 200] = 0
+        bbox_arg = None if c == 1 else bbox
+        saved = ref_ptz_slam.detect_compute_sift_array
+        ref_ptz_slam.detect_compute_sift_array = lambda img, num, kp=new_kp, de=new_des: (kp.copy(), de.copy())
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                kp, kp_idx = slam.add_rays(np.zeros((H, W, 3), np.uint8), bbox_arg)
+        finally:
+            ref_ptz_slam.detect_compute_sift_array = saved
+        out["c%d_new_kp" % c], out["c%d_new_des" % c] = new_kp, new_des
+        out["c%d_bbox" % c] = np.packbits(bbox)
+        out["c%d_has_bbox" % c] = np.array(bbox_arg is not None)
+        out["c%d_add_kp" % c], out["c%d_add_idx" % c] = np.asarray(kp, np.float64), np.asarray(kp_idx, np.float64)
+        out["c%d_rays1" % c], out["c%d_des1" % c], out["c%d_cov1" % c] = slam.rays.copy(), slam.des.copy(), slam.state_cov.copy()
+        # --- keypoints_masking on its own (image_process.py:158-175)
+        out["c%d_mask_idx" % c] = np.asarray(ref_ip.keypoints_masking(new_kp, bbox), np.int64)
+        # --- remove_rays on the grown state
+        n1 = len(slam.rays)
+        n_del = [5, 3, 0, 9][c]
+        del_idx = rng.choice(n1, min(n_del, n1), replace=False).astype(np.int64)
+        np_delete = np.delete
+
+        class _Np:                                  # np proxy: integer-casts the float index array of ptz_slam.py:309-315
+            def __getattr__(self, k):
+                return getattr(np, k)
+
+            @staticmethod
+            def delete(arr, obj, axis=None):
+                return np_delete(arr, np.asarray(obj).astype(np.int64), axis=axis)
+        ref_ptz_slam.np = _Np()
+        try:
+            slam.remove_rays(del_idx)
+        finally:
+            ref_ptz_slam.np = np
+        out["c%d_del" % c] = del_idx
+        out["c%d_rays2" % c], out["c%d_des2" % c], out["c%d_cov2" % c] = slam.rays.copy(), slam.des.copy(), slam.state_cov.copy()
+        print("ray_bookkeeping case %d: %d rays -> +%d -> -%d -> %d" % (c, n0, n1 - n0, len(del_idx), len(slam.rays)))
+    out["n_cases"] = np.array(n_cases)
+    np.savez_compressed(os.path.join(OUT, "ray_bookkeeping.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                           # regenerate only the named goldens: make_golden.py ray_bookkeeping ...
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
+    gen_ray_bookkeeping()
     gen_keyframe_map()
     gen_projection()
     gen_backprojection()
