@@ -4,7 +4,12 @@ Keyframe map orchestration, image-free (reference: slam_system/scene_map.py:18-1
 `Map` keeps the keyframe list and the global ray landmarks; `add_keyframe_with_ba` re-runs bundle adjustment over all
 keyframes on the GPU (bundle_adjustment.bundle_adjustment -> libptzba) and `good_new_keyframe` is the pan-overlap rule.
 The vision front-end that matches keyframe images is injected (`build_matching_graph`), as in bundle_adjustment().
+
+`RandomForestMap` (scene_map.py:170-244) is the map variant the relocaliser trains from: it bundle-adjusts a sliding window
+of the last 10 keyframes, exports every keyframe as .mat and hands the list to the random-forest builder (C++ `rf_map/`,
+out of scope here: injected as `create_map`).
 """
+import os
 import time
 
 import numpy as np
@@ -77,3 +82,67 @@ class Map:
             print('candidate key frame overlap: ', overlaps)
         max_overlap = max(overlaps)
         return max_overlap > threshold1 and max_overlap < threshold2
+
+    def save_keyframes_to_mat(self, path):
+        """scene_map.py:150-167: index / ptz / center / base_rotation / principal_point of every keyframe."""
+        import scipy.io as sio
+        keyframes = [{'index': kf.img_index, 'ptz': np.array([kf.pan, kf.tilt, kf.f]), 'center': kf.center,
+                      'base_rotation': kf.base_rotation, 'principal_point': np.array([kf.u, kf.v])}
+                     for kf in self.keyframe_list]
+        sio.savemat(path, mdict={'keyframes': keyframes})
+
+
+class RandomForestMap:
+    MAX_BA_FRAME = 10           # scene_map.py:210
+
+    def __init__(self, keyframe_location="./keyframes/", mat_path_file="./train_feature_file.txt", create_map=None,
+                 build_matching_graph=None, bundle_adjustment_fn=None):
+        """scene_map.py:170-180 with the hard-coded Windows paths turned into arguments.  `create_map(mat_path_file)` stands
+        for RFMap.createMap (:197-198); `bundle_adjustment_fn` defaults to the GPU bundle adjustment of this package."""
+        self.keyframe_location = keyframe_location
+        self.mat_path_file = mat_path_file
+        self.create_map = create_map
+        self.build_matching_graph = build_matching_graph
+        self.bundle_adjustment_fn = bundle_adjustment_fn
+        self.keyframe_list = []
+        self.feature_method = 'sift'
+
+    def add_keyframe(self, keyframe):
+        """scene_map.py:182-198: append, re-adjust the window, export every keyframe and rebuild the forest."""
+        self.keyframe_list.append(keyframe)
+        if len(self.keyframe_list) > 1:
+            self.bundle_adjustment_processing()
+        with open(self.mat_path_file, 'w') as f:
+            for frame in self.keyframe_list:
+                mat_path = os.path.join(self.keyframe_location, str(frame.img_index) + ".mat")
+                f.write(mat_path + "\n")
+                frame.save_to_mat(mat_path)
+        if self.create_map is not None:
+            self.create_map(self.mat_path_file)
+
+    def bundle_adjustment_processing(self):
+        """scene_map.py:202-244: bundle-adjust the last MAX_BA_FRAME keyframes (camera constants from the first keyframe of
+        the map); older keyframes are kept as they are, adjusted ones without features are dropped."""
+        ref_frame = self.keyframe_list[0]
+        n = len(self.keyframe_list)
+        first = max(0, n - self.MAX_BA_FRAME)
+        kept, window = self.keyframe_list[:first], self.keyframe_list[first:]
+        initial_ptzs = np.array([[kf.pan, kf.tilt, kf.f] for kf in window])
+        image_indices = [kf.img_index for kf in window]
+        if self.bundle_adjustment_fn is not None:
+            landmarks, keyframes = self.bundle_adjustment_fn([kf.img for kf in window], image_indices, self.feature_method,
+                                                             initial_ptzs, ref_frame.center, ref_frame.base_rotation,
+                                                             ref_frame.u, ref_frame.v, "./bundle_result")
+        else:
+            landmarks, keyframes = bundle_adjustment([kf.img for kf in window], image_indices, self.feature_method,
+                                                     initial_ptzs, ref_frame.center, ref_frame.base_rotation, ref_frame.u,
+                                                     ref_frame.v, "./bundle_result",
+                                                     build_matching_graph=self.build_matching_graph)
+        self.keyframe_list = kept
+        for i, kf in enumerate(keyframes):
+            if kf.get_feature_num() > 0:
+                kf.convert_keypoint_to_array()
+                self.keyframe_list.append(kf)
+            else:
+                print('warning: key frame, %d, image index %d is not included in the map' % (i, image_indices[i]))
+        return landmarks

@@ -13,6 +13,9 @@ Goldens (reference function -> file):
   util.overlap_pan_angle, scene_map.Map.good_new_keyframe                         -> keyframe_map.npz
   PtzSlam.remove_rays / add_rays (SIFT detector replaced by seeded keypoints),
   image_process.keypoints_masking                                                 -> ray_bookkeeping.npz
+  image_process.build_matching_graph steps 4-5 (detector / matcher replaced)      -> match_graph.npz
+  KeyFrame.convert_keypoint_to_array / save_to_mat                                -> keyframe_mat.npz
+  RandomForestMap.bundle_adjustment_processing (BA call replaced by a recorder)   -> sliding_window.npz
 """
 import copy
 import io
@@ -318,12 +321,191 @@ def gen_ray_bookkeeping():
     np.savez_compressed(os.path.join(OUT, "ray_bookkeeping.npz"), **out)
 
 
+class _Kp:
+    """Stand-in for cv2.KeyPoint: build_matching_graph only reads .pt (image_process.py:653-661)."""
+
+    def __init__(self, x, y):
+        self.pt = (float(x), float(y))
+
+
+def synth_match_inputs(seed, n_img=6, n_gt=420):
+    """Seeded front-end output: keypoints per image and raw pair-wise matches (with dropped, wrong and oversized sets)."""
+    rng = np.random.default_rng(seed)
+    see_p = [0.97, 0.96, 0.5, 0.45, 0.5, 0.08][:n_img]
+    kps, gt_of = [], []
+    for i in range(n_img):
+        vis = np.nonzero(rng.uniform(size=n_gt) < see_p[i])[0]
+        rng.shuffle(vis)
+        n_extra = 15                                                 # keypoints that match nothing
+        gt = np.concatenate([vis, -np.ones(n_extra, np.int64)])
+        rng.shuffle(gt)
+        kps.append(np.stack([rng.uniform(1, W - 1, len(gt)), rng.uniform(1, H - 1, len(gt))], 1))
+        gt_of.append(gt)
+    raw = {}
+    for i in range(n_img):
+        for j in range(i + 1, n_img):
+            common = np.intersect1d(gt_of[i][gt_of[i] >= 0], gt_of[j][gt_of[j] >= 0])
+            common = common[rng.uniform(size=len(common)) > (0.05 if (i, j) == (0, 1) else 0.3)]
+            rng.shuffle(common)
+            pos_i = {g: k for k, g in enumerate(gt_of[i])}
+            pos_j = {g: k for k, g in enumerate(gt_of[j])}
+            i1 = [pos_i[g] for g in common]
+            i2 = [pos_j[g] for g in common]
+            for _ in range(4):                                       # wrong matches -> "in-consistent matching" branch
+                i1.append(int(rng.integers(len(gt_of[i]))))
+                i2.append(int(rng.integers(len(gt_of[j]))))
+            raw[(i, j)] = (np.array(i1, np.int64), np.array(i2, np.int64))
+    mask = np.ones((n_img, n_img), np.int64)
+    mask[1, 3] = mask[3, 1] = 0
+    return kps, raw, mask
+
+
+def gen_match_graph():
+    """image_process.build_matching_graph (:510-667) with detect_compute_sift / match_sift_features monkeypatched to a
+    seeded front-end; the mask test, the 20 / 200 match thresholds, random.shuffle thinning and steps 4-5 run unmodified."""
+    import random
+    import image_process as ref_ip
+    out = {}
+    seeds = [2024, 2025]
+    for c, seed in enumerate(seeds):
+        kps, raw, mask = synth_match_inputs(seed, n_img=6 if c == 0 else 4)
+        n = len(kps)
+        key_of = {}
+        images = []
+        for i in range(n):
+            im = np.full((2, 2), i, np.uint8)
+            images.append(im)
+        kp_objs = [[_Kp(x, y) for x, y in kps[i]] for i in range(n)]
+        des = [np.full((len(kps[i]), 4), i, np.float32) for i in range(n)]
+        for i in range(n):
+            key_of[id(kp_objs[i])] = i
+        saved = (ref_ip.detect_compute_sift, ref_ip.match_sift_features)
+        ref_ip.detect_compute_sift = lambda im, nf, verbose=False: (kp_objs[int(im[0, 0])], des[int(im[0, 0])])
+
+        def fake_match(kp1, des1, kp2, des2, verbose=False):
+            i1, i2 = raw[(key_of[id(kp1)], key_of[id(kp2)])]
+            return None, i1.tolist(), None, i2.tolist()
+        ref_ip.match_sift_features = fake_match
+        random.seed(seed)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()) as log:
+                _, _, points, src, dst, lmi, lm_num = ref_ip.build_matching_graph(images, mask.tolist(), 'sift', False)
+        finally:
+            ref_ip.detect_compute_sift, ref_ip.match_sift_features = saved
+        n_warn = log.getvalue().count("in-consistent")
+        out["c%d_seed" % c], out["c%d_n" % c], out["c%d_mask" % c] = np.array(seed), np.array(n), mask[:n, :n]
+        out["c%d_landmark_num" % c], out["c%d_n_inconsistent" % c] = np.array(lm_num), np.array(n_warn)
+        for i in range(n):
+            out["c%d_kp_%d" % (c, i)] = kps[i]
+            np.testing.assert_array_equal(points[i], kps[i])
+            for j in range(n):
+                if i < j:
+                    out["c%d_raw1_%d_%d" % (c, i, j)], out["c%d_raw2_%d_%d" % (c, i, j)] = raw[(i, j)]
+                out["c%d_src_%d_%d" % (c, i, j)] = np.array(src[i][j], np.int64)
+                out["c%d_dst_%d_%d" % (c, i, j)] = np.array(dst[i][j], np.int64)
+                out["c%d_lm_%d_%d" % (c, i, j)] = np.array(lmi[i][j], np.int64)
+        sizes = {k: len(v[0]) for k, v in raw.items()}
+        print("match_graph case %d: %d landmarks, %d inconsistent, raw pair sizes %s" % (c, lm_num, n_warn, sizes))
+    out["n_cases"] = np.array(len(seeds))
+    np.savez_compressed(os.path.join(OUT, "match_graph.npz"), **out)
+
+
+def gen_keyframe_mat():
+    """KeyFrame.convert_keypoint_to_array (key_frame.py:58-73) and save_to_mat (:75-107) of the reference; the written
+    .mat files are read back with scipy and their arrays stored."""
+    import tempfile
+    import scipy.io as sio
+    import cv2
+    from key_frame import KeyFrame as RefKeyFrame
+    rng = np.random.default_rng(1415)
+    out = {}
+    rots = [cv2.Rodrigues(BASE_ROT.reshape(3, 1))[0], BASE_ROT.copy(), np.eye(3),
+            cv2.Rodrigues(np.array([[0.3], [-2.9], [0.8]]))[0]]
+    for c, rot in enumerate(rots):
+        n = [30, 12, 0, 7][c]
+        pts = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1)
+        des = rng.integers(0, 255, (n, 16)).astype(np.float32) + 1
+        ptz = np.array([rng.uniform(40, 70), rng.uniform(-12, -6), rng.uniform(2000, 4000)])
+        kf = RefKeyFrame(None, 100 + c, CC, rot, U, V, ptz[0], ptz[1], ptz[2])
+        as_list = c in (0, 3)
+        kf.feature_pts = [_Kp(x, y) for x, y in pts] if as_list else pts.copy()
+        kf.feature_des = des.copy() if as_list else des.astype(np.float64)
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "kf.mat")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                kf.save_to_mat(path)
+            d = sio.loadmat(path)
+        out["c%d_rot" % c], out["c%d_pts" % c], out["c%d_des" % c], out["c%d_ptz" % c] = rot, pts, des, ptz
+        out["c%d_as_list" % c] = np.array(as_list)
+        out["c%d_im_name" % c] = np.array(str(np.asarray(d['im_name']).ravel()[0]))
+        for k in ("keypoint", "descriptor", "camera", "ptz"):
+            out["c%d_mat_%s" % (c, k)] = d[k]
+        print("keyframe_mat case %d:" % c, {k: d[k].shape for k in ("keypoint", "descriptor", "camera", "ptz")}, d['camera'][3:6].ravel())
+    out["n_cases"] = np.array(len(rots))
+    np.savez_compressed(os.path.join(OUT, "keyframe_mat.npz"), **out)
+
+
+def fake_window_ba(key_frame_cls, seed):
+    """Stand-in for bundle_adjustment() in the sliding-window test: nudges every pose, gives keyframe k 5+k keypoints
+    (none to the third of the window) and records the arguments it was called with."""
+    calls = []
+
+    def run(images, image_indices, feature_method, initial_ptzs, center, rotation, u, v, save_path, *a, **k):
+        rng = np.random.default_rng(seed + len(calls))
+        calls.append((list(image_indices), np.array(initial_ptzs, dtype=np.float64).copy()))
+        kfs = []
+        for i, idx in enumerate(image_indices):
+            kf = key_frame_cls(images[i], idx, center, rotation, u, v, initial_ptzs[i][0] + 0.01 * (i + 1),
+                               initial_ptzs[i][1] - 0.02, initial_ptzs[i][2] + i)
+            n = 0 if i == 2 else 5 + i
+            kf.feature_pts = [_Kp(x, y) for x, y in rng.uniform(0, 700, (n, 2))]
+            kf.feature_des = rng.integers(1, 200, (n, 8)).astype(np.float32)
+            kf.landmark_index = np.arange(n, dtype=np.int32)
+            kfs.append(kf)
+        return rng.uniform(-30, 30, (40, 2)), kfs
+    return run, calls
+
+
+def gen_sliding_window():
+    """RandomForestMap.bundle_adjustment_processing (scene_map.py:202-244) with bundle_adjustment replaced by the fake
+    above: which keyframes enter the window, which survive, and the converted feature arrays."""
+    import scene_map as ref_scene_map
+    from key_frame import KeyFrame as RefKeyFrame
+    out = {}
+    for c, n_kf in enumerate([14, 3, 10]):
+        m = ref_scene_map.RandomForestMap()
+        for k in range(n_kf):
+            m.keyframe_list.append(RefKeyFrame(None, 10 * k + 1, CC, BASE_ROT, U, V, 40.0 + 2 * k, -8.0 - 0.1 * k, 2500.0 + 50 * k))
+        run, calls = fake_window_ba(RefKeyFrame, 500 + c)
+        saved = ref_scene_map.bundle_adjustment
+        ref_scene_map.bundle_adjustment = run
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                m.bundle_adjustment_processing()
+        finally:
+            ref_scene_map.bundle_adjustment = saved
+        out["c%d_n_kf" % c] = np.array(n_kf)
+        out["c%d_call_indices" % c], out["c%d_call_ptzs" % c] = np.array(calls[0][0]), calls[0][1]
+        out["c%d_result_indices" % c] = np.array([kf.img_index for kf in m.keyframe_list])
+        out["c%d_result_ptz" % c] = np.array([[kf.pan, kf.tilt, kf.f] for kf in m.keyframe_list])
+        out["c%d_result_nfeat" % c] = np.array([kf.get_feature_num() for kf in m.keyframe_list])
+        last = m.keyframe_list[-1]
+        out["c%d_last_pts" % c], out["c%d_last_des" % c] = last.feature_pts, last.feature_des
+        print("sliding_window case %d: %d keyframes -> window %s -> %s" % (c, n_kf, calls[0][0], out["c%d_result_indices" % c]))
+    out["n_cases"] = np.array(3)
+    np.savez_compressed(os.path.join(OUT, "sliding_window.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                           # regenerate only the named goldens: make_golden.py ray_bookkeeping ...
         for name in sys.argv[1:]:
             globals()["gen_" + name]()
         sys.exit(0)
     gen_ray_bookkeeping()
+    gen_match_graph()
+    gen_keyframe_mat()
+    gen_sliding_window()
     gen_keyframe_map()
     gen_projection()
     gen_backprojection()

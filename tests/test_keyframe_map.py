@@ -56,3 +56,135 @@ def test_get_overlap_index_golden():
         i1, i2 = get_overlap_index(G["ov%d_a" % c], G["ov%d_b" % c])
         np.testing.assert_array_equal(i1, G["ov%d_i1" % c])
         np.testing.assert_array_equal(i2, G["ov%d_i2" % c])
+
+
+# ---- KeyFrame array conversion and .mat export (key_frame.py:58-107) against files written by the reference ------------------
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "keyframe_mat.npz"))
+
+
+class _Kp:
+    def __init__(self, xy):
+        self.pt = (float(xy[0]), float(xy[1]))
+
+
+def _keyframe_case(c):
+    ptz = GM["c%d_ptz" % c]
+    kf = KeyFrame(None, 100 + c, np.array([13.0099, -14.8109, 6.1790]), GM["c%d_rot" % c], 640.0, 360.0, ptz[0], ptz[1], ptz[2])
+    if bool(GM["c%d_as_list" % c]):
+        kf.feature_pts = [_Kp(p) for p in GM["c%d_pts" % c]]
+        kf.feature_des = GM["c%d_des" % c].copy()
+    else:
+        kf.feature_pts = GM["c%d_pts" % c].copy()
+        kf.feature_des = GM["c%d_des" % c].astype(np.float64)
+    return kf
+
+
+@pytest.mark.parametrize("c", range(int(GM["n_cases"])))
+def test_keyframe_save_to_mat_golden(c, tmp_path):
+    import scipy.io as sio
+    kf = _keyframe_case(c)
+    path = str(tmp_path / "kf.mat")
+    kf.save_to_mat(path)
+    d = sio.loadmat(path)
+    assert str(np.asarray(d["im_name"]).ravel()[0]) == str(GM["c%d_im_name" % c])
+    for k in ("keypoint", "descriptor", "ptz"):
+        assert d[k].shape == GM["c%d_mat_%s" % (c, k)].shape
+        np.testing.assert_allclose(d[k], GM["c%d_mat_%s" % (c, k)], rtol=1e-15, atol=0)
+    # camera = [u, v, f, rodrigues(base_rotation), center]; the rotation vector comes from an arccos/arctan -> 1e-12
+    np.testing.assert_allclose(d["camera"], GM["c%d_mat_camera" % c], rtol=0, atol=1e-12)
+    # and back
+    kf2 = KeyFrame.load_mat(path)
+    assert kf2.img_index == 100 + c and kf2.get_feature_num() == len(GM["c%d_pts" % c])
+    np.testing.assert_allclose([kf2.pan, kf2.tilt, kf2.f], GM["c%d_ptz" % c], rtol=1e-15)
+    rot = GM["c%d_rot" % c]
+    if rot.shape == (3, 3):
+        np.testing.assert_allclose(kf2.base_rotation, rot, atol=1e-12)
+    np.testing.assert_allclose(kf2.feature_pts, GM["c%d_mat_keypoint" % c].reshape(-1, 2), rtol=1e-15)
+
+
+def test_convert_keypoint_to_array_norm():
+    kf = _keyframe_case(0)
+    kf.convert_keypoint_to_array(norm=False)
+    np.testing.assert_array_equal(kf.feature_des, GM["c0_des"].astype(np.float64))
+    assert kf.feature_pts.dtype == np.float64 and kf.feature_pts.shape == (30, 2)
+    kf = _keyframe_case(0)
+    kf.convert_keypoint_to_array()
+    np.testing.assert_allclose(np.linalg.norm(kf.feature_des, axis=1), 1.0, rtol=1e-6)
+    np.testing.assert_allclose(kf.feature_des, GM["c0_mat_descriptor"], rtol=1e-15)
+
+
+# ---- sliding-window bundle adjustment of RandomForestMap (scene_map.py:202-244) ---------------------------------------------
+GS = np.load(os.path.join(os.path.dirname(__file__), "golden", "sliding_window.npz"))
+
+
+def _recording_ba(seed):
+    """Same stand-in for bundle_adjustment() as tests/golden/make_golden.py:fake_window_ba."""
+    calls = []
+
+    def run(images, image_indices, feature_method, initial_ptzs, center, rotation, u, v, save_path, *a, **k):
+        rng = np.random.default_rng(seed + len(calls))
+        calls.append((list(image_indices), np.array(initial_ptzs, dtype=np.float64).copy()))
+        kfs = []
+        for i, idx in enumerate(image_indices):
+            kf = KeyFrame(images[i], idx, center, rotation, u, v, initial_ptzs[i][0] + 0.01 * (i + 1),
+                          initial_ptzs[i][1] - 0.02, initial_ptzs[i][2] + i)
+            n = 0 if i == 2 else 5 + i
+            kf.feature_pts = [_Kp(p) for p in rng.uniform(0, 700, (n, 2))]
+            kf.feature_des = rng.integers(1, 200, (n, 8)).astype(np.float32)
+            kf.landmark_index = np.arange(n, dtype=np.int32)
+            kfs.append(kf)
+        return rng.uniform(-30, 30, (40, 2)), kfs
+    return run, calls
+
+
+@pytest.mark.parametrize("c", range(int(GS["n_cases"])))
+def test_sliding_window_ba_golden(c, capsys):
+    from ptz_slam_b200.scene_map import RandomForestMap
+    run, calls = _recording_ba(500 + c)
+    m = RandomForestMap(bundle_adjustment_fn=run)
+    cc, rot = np.array([13.0099, -14.8109, 6.1790]), np.array([1.5804, -0.1186, 0.1249])
+    for k in range(int(GS["c%d_n_kf" % c])):
+        m.keyframe_list.append(KeyFrame(None, 10 * k + 1, cc, rot, 640.0, 360.0, 40.0 + 2 * k, -8.0 - 0.1 * k, 2500.0 + 50 * k))
+    m.bundle_adjustment_processing()
+    assert len(calls) == 1
+    np.testing.assert_array_equal(calls[0][0], GS["c%d_call_indices" % c])
+    np.testing.assert_array_equal(calls[0][1], GS["c%d_call_ptzs" % c])
+    np.testing.assert_array_equal([kf.img_index for kf in m.keyframe_list], GS["c%d_result_indices" % c])
+    np.testing.assert_array_equal([[kf.pan, kf.tilt, kf.f] for kf in m.keyframe_list], GS["c%d_result_ptz" % c])
+    np.testing.assert_array_equal([kf.get_feature_num() for kf in m.keyframe_list], GS["c%d_result_nfeat" % c])
+    np.testing.assert_array_equal(m.keyframe_list[-1].feature_pts, GS["c%d_last_pts" % c])
+    np.testing.assert_allclose(m.keyframe_list[-1].feature_des, GS["c%d_last_des" % c], rtol=1e-15)
+    assert "is not included in the map" in capsys.readouterr().out
+
+
+def test_random_forest_map_add_keyframe_exports(tmp_path):
+    import scipy.io as sio
+    from ptz_slam_b200.scene_map import RandomForestMap
+    run, calls = _recording_ba(7)
+    built = []
+    m = RandomForestMap(keyframe_location=str(tmp_path), mat_path_file=str(tmp_path / "list.txt"), create_map=built.append,
+                        bundle_adjustment_fn=run)
+    cc, rot = np.zeros(3), np.eye(3)
+    first = KeyFrame(None, 3, cc, rot, 640.0, 360.0, 50.0, -8.0, 3000.0)
+    first.feature_pts, first.feature_des = np.zeros((4, 2)), np.ones((4, 8))
+    m.add_keyframe(first)
+    assert calls == [] and built == [str(tmp_path / "list.txt")]            # one keyframe: no adjustment (scene_map.py:186)
+    second = KeyFrame(None, 9, cc, rot, 640.0, 360.0, 55.0, -8.0, 3000.0)
+    m.add_keyframe(second)
+    assert len(calls) == 1 and calls[0][0] == [3, 9] and len(built) == 2
+    listed = open(str(tmp_path / "list.txt")).read().split()
+    assert [os.path.basename(p) for p in listed] == ["3.mat", "9.mat"]
+    d = sio.loadmat(listed[1])
+    assert d["keypoint"].shape == (6, 2) and d["ptz"].ravel()[0] == pytest.approx(55.02)
+
+
+def test_map_save_keyframes_to_mat(tmp_path):
+    import scipy.io as sio
+    m = _map()
+    path = str(tmp_path / "kfs.mat")
+    m.save_keyframes_to_mat(path)
+    d = sio.loadmat(path)
+    assert d["keyframes"].shape[-1] == len(G["kf_ptz"])
+    rec = d["keyframes"].ravel()[2]
+    np.testing.assert_allclose(rec["ptz"][0, 0].ravel(), G["kf_ptz"][2])
+    assert int(rec["index"][0, 0].ravel()[0]) == 2
