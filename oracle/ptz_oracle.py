@@ -518,3 +518,21 @@ def trf_solve(fun, jac, x0, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=None):
             scale = 1 / scale_inv
         nit += 1
     return dict(x=x, cost=cost, nfev=nfev, njev=njev, status=0 if status is None else status, nit=nit)
+
+
+# ---------------------------------------------------------------------------------------------
+# relocalisation: 3-parameter pose refinement on fixed rays
+# ---------------------------------------------------------------------------------------------
+def reloc_residual(pose, rays, points, u, v):
+    """relocalization.py:22-40 / nearest_neighbor.py:65-85: [2n] (projection - point) through from_ray_to_image."""
+    rays = np.asarray(rays, dtype=np.float64).reshape(-1, 2)
+    points = np.asarray(points, dtype=np.float64).reshape(-1, 2)
+    x, y = from_ray_to_image_vec(u, v, pose[2], pose[0], pose[1], rays[:, 0], rays[:, 1])
+    return np.stack([x - points[:, 0], y - points[:, 1]], axis=1).reshape(-1)
+
+
+def reloc_refine(pose, rays, points, u, v, ftol=1e-4, **kw):
+    """relocalization.py:186-187: scipy least_squares on reloc_residual with the reference's options (2-point Jacobian)."""
+    from scipy.optimize import least_squares
+    return least_squares(reloc_residual, np.asarray(pose, dtype=np.float64), x_scale='jac', ftol=ftol, method='trf',
+                         args=(rays, points, u, v), **kw)

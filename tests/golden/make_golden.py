@@ -16,6 +16,7 @@ Goldens (reference function -> file):
   image_process.build_matching_graph steps 4-5 (detector / matcher replaced)      -> match_graph.npz
   KeyFrame.convert_keypoint_to_array / save_to_mat                                -> keyframe_mat.npz
   RandomForestMap.bundle_adjustment_processing (BA call replaced by a recorder)   -> sliding_window.npz
+  relocalization._compute_residual + its least_squares call (as-is and tight)     -> relocalization.npz
 """
 import copy
 import io
@@ -497,6 +498,34 @@ def gen_sliding_window():
     np.savez_compressed(os.path.join(OUT, "sliding_window.npz"), **out)
 
 
+def gen_relocalization():
+    """relocalization._compute_residual (:22-40) and the least_squares call of :186-187 as the reference makes it
+    (ftol=1e-4) plus a tight run (ftol=xtol=gtol=1e-15 = converged) on seeded ray <-> pixel matches."""
+    import relocalization as ref_reloc
+    rng = np.random.default_rng(1617)
+    out = {"uv": np.array([U, V])}
+    cases = [(60, 0.0, (1.5, -0.8, 150.0)), (200, 0.5, (-2.0, 1.0, -300.0)), (12, 1.0, (0.5, 0.3, 80.0)), (400, 0.3, (4.0, -1.5, 500.0))]
+    for c, (n, noise, dpose) in enumerate(cases):
+        gt = np.array([rng.uniform(45, 70), rng.uniform(-12, -7), rng.uniform(2200, 3800)])
+        pts = np.stack([rng.uniform(20, W - 20, n), rng.uniform(20, H - 20, n)], 1)
+        rays = np.array([ref.TransFunction.from_image_to_ray(U, V, gt[2], gt[0], gt[1], x, y) for x, y in pts])
+        pts_noisy = pts + rng.normal(0, noise, pts.shape) if noise > 0 else pts
+        pose0 = gt + np.array(dpose)
+        r0 = ref_reloc._compute_residual(pose0, rays, pts_noisy, U, V)
+        with contextlib.redirect_stdout(io.StringIO()):
+            asis = ref.least_squares(ref_reloc._compute_residual, pose0, verbose=2, x_scale='jac', ftol=1e-4, method='trf',
+                                     args=(rays, pts_noisy, U, V))
+            tight = ref.least_squares(ref_reloc._compute_residual, pose0, verbose=0, x_scale='jac', ftol=1e-15, xtol=1e-15,
+                                      gtol=1e-15, method='trf', args=(rays, pts_noisy, U, V))
+        out["c%d_gt" % c], out["c%d_pose0" % c], out["c%d_rays" % c], out["c%d_points" % c] = gt, pose0, rays, pts_noisy
+        out["c%d_r0" % c] = r0
+        out["c%d_x_asis" % c], out["c%d_cost_asis" % c], out["c%d_nfev_asis" % c] = asis.x, np.array(asis.cost), np.array(asis.nfev)
+        out["c%d_x_tight" % c], out["c%d_cost_tight" % c] = tight.x, np.array(tight.cost)
+        print("relocalization case %d: n=%d gt=%s asis=%s (nfev %d) tight=%s" % (c, n, gt, asis.x, asis.nfev, tight.x))
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "relocalization.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                           # regenerate only the named goldens: make_golden.py ray_bookkeeping ...
         for name in sys.argv[1:]:
@@ -506,6 +535,7 @@ if __name__ == "__main__":
     gen_match_graph()
     gen_keyframe_mat()
     gen_sliding_window()
+    gen_relocalization()
     gen_keyframe_map()
     gen_projection()
     gen_backprojection()
