@@ -6,12 +6,14 @@ PtzSlam drop-in for the EKF hot path (reference: slam_system/ptz_slam.py).
     PtzSlam.predict()  - the predict lines of tracking()                          ptz_slam.py:418-426
     PtzSlam.remove_rays(index), PtzSlam.add_rays(img, bounding_box, detect)       ptz_slam.py:291-388 (state bookkeeping;
                                                                                   keypoint detection is an injected callable)
+    PtzSlam.init_system / tracking / relocalize / add_keyframe                    ptz_slam.py:140-208, 390-537 (the per-frame
+                                                                                  loop; OpenCV front end injected as `front_end`)
 
 State attributes keep the reference's names and meaning (`rays`, `state_cov`, `cameras`, `current_camera`,
 `velocity`, `observe_var`, `angle_var`, `f_var`).  `ekf_update` mutates them in place like the reference; the
 computation (projection, in-image filter, innovation, central-difference Jacobian, S, Cholesky, gain, covariance
 write-back) runs in csrc/ekf.cu through the C-ABI.  The image front-end of the reference class (SIFT detection,
-optical-flow matching, relocalisation, keyframe maps) is out of scope.
+optical-flow matching, SIFT matching) is out of scope and enters as `front_end` callables.
 
 `BatchedEkfTracker` is the additive batched form for many independent sequences resident on the GPU (config 4).
 """
@@ -53,14 +55,31 @@ def _params(u, v, disp, observe_var, angle_var, f_var, height, width, jac_mode):
 
 
 class PtzSlam:
-    def __init__(self):
+    def __init__(self, front_end=None):
+        """ptz_slam.py:24-71.  `front_end` supplies the OpenCV side that is outside this library, as callables:
+            front_end.detect_keypoints(img, n)                       -> (points[n,2], descriptors[n,d])   (:155, :338)
+            front_end.matching_and_ransac(img1, img2, kp1, kp1_idx)  -> (inlier_kp, inlier_idx, outlier_idx)   (:397)
+            front_end.detect / front_end.match                       -> relocalization.relocalization_camera's pair
+            front_end.build_matching_graph                           -> keyframe bundle adjustment (scene_map.Map)
+        Without it only the image-free members work (init_rays, predict, ekf_update, remove_rays, add_rays(detector))."""
+        self.front_end = front_end
         # global rays and covariance matrix (ptz_slam.py:29-31)
         self.rays = np.ndarray([0, 2])
         self.des = np.ndarray([0, 128])
         self.state_cov = np.zeros([3, 3])
+        # previous frame (ptz_slam.py:34-38)
+        self.previous_img = None
+        self.previous_keypoints = None
+        self.previous_keypoints_index = None
         self.current_camera = None
+        from .scene_map import Map                      # here: scene_map imports bundle_adjustment, which imports nothing of ours
+        self.keyframe_map = Map('sift', build_matching_graph=getattr(front_end, "build_matching_graph", None))
+        self.rf_map = None                              # RandomForestMap / NNBasedMap, set by the caller when used
         self.cameras = []
         self.velocity = np.zeros(3)
+        self.new_keyframe = False                       # state flags (ptz_slam.py:56-63)
+        self.tracking_lost = False
+        self.bad_tracking_cnt = 0
         # hyper parameters (ptz_slam.py:65-71)
         self.keypoint_num = 500
         self.observe_var = 0.1
@@ -78,12 +97,107 @@ class PtzSlam:
         self.cameras = [camera]
         self.current_camera = camera
 
+    def _front(self, name):
+        fn = getattr(self.front_end, name, None)
+        if fn is None:
+            raise NotImplementedError("PtzSlam needs front_end.%s (OpenCV feature detection / matching is outside this "
+                                      "library)" % name)
+        return fn
+
+    def init_system(self, img, camera, bounding_box=None):
+        """ptz_slam.py:140-208: first frame, or the frame after a relocalisation.  Keypoints off the players become the ray
+        landmarks (back-projection through `camera` on the GPU); covariance angle_var * I with f_var for the focal length."""
+        first_img_kp, first_des = self._front("detect_keypoints")(img, self.keypoint_num)
+        first_img_kp = np.asarray(first_img_kp)
+        if bounding_box is not None:
+            masked_index = keypoints_masking(first_img_kp, bounding_box)
+            first_img_kp = first_img_kp[masked_index]
+            first_des = None if first_des is None else np.asarray(first_des)[masked_index]
+        init_rays = camera.back_project_to_rays(first_img_kp)
+        self.rays = np.asarray(init_rays, dtype=np.float64).reshape(-1, 2).copy()
+        self.des = first_des
+        self.state_cov = self.angle_var * np.eye(3 + 2 * len(self.rays))
+        self.state_cov[2][2] = self.f_var
+        self.previous_img = img
+        self.previous_keypoints = first_img_kp
+        self.previous_keypoints_index = np.array([i for i in range(len(self.rays))])
+        self.cameras.append(camera)
+
+    def tracking(self, next_img, bad_tracking_percentage, bounding_box=None):
+        """ptz_slam.py:390-456: one frame.  Optical-flow matches (front end) -> tracking-quality bookkeeping -> predict ->
+        EKF update on the GPU -> drop RANSAC outliers -> detect / add new rays -> keyframe test."""
+        inlier_keypoints, inlier_index, outlier_index = self._front("matching_and_ransac")(
+            self.previous_img, next_img, self.previous_keypoints, self.previous_keypoints_index)
+        tracking_percentage = len(inlier_index) / len(self.previous_keypoints) * 100
+        if tracking_percentage < bad_tracking_percentage:
+            self.bad_tracking_cnt += 1
+        if self.bad_tracking_cnt > 3:
+            self.tracking_lost = True
+            self.bad_tracking_cnt = 0
+        # 1. predict (a lost frame's camera is not appended, :421-422)
+        self.current_camera = copy.deepcopy(self.cameras[-1])
+        self.current_camera.set_ptz(self.current_camera.get_ptz() + self.velocity)
+        if not self.tracking_lost:
+            self.cameras.append(self.current_camera)
+        q_k = 5 * np.diag([self.angle_var, self.angle_var, self.f_var])
+        self.state_cov[0:3, 0:3] = self.state_cov[0:3, 0:3] + q_k
+        # 2. update
+        height, width = next_img.shape[0:2]
+        self.ekf_update(inlier_keypoints, inlier_index, height, width)
+        # 3. delete outliers, 4. add new features and roll the previous frame
+        self.remove_rays(outlier_index)
+        self.previous_img = next_img
+        self.previous_keypoints, self.previous_keypoints_index = self.add_rays(next_img, bounding_box,
+                                                                               self._front("detect_keypoints"))
+        if self.keyframe_map.good_new_keyframe(self.current_camera.get_ptz(), 10, 15):
+            self.new_keyframe = True
+        return tracking_percentage
+
+    def relocalize(self, img, camera, enable_rf=False, bounding_box=None):
+        """ptz_slam.py:458-497: pose of a lost frame from the keyframe map (or from rf_map when enable_rf)."""
+        from .key_frame import KeyFrame
+        from .relocalization import relocalization_camera
+        if enable_rf:
+            pan, tilt, focal_length = camera.pan, camera.tilt, camera.focal_length
+            frame = KeyFrame(img, -1, camera.camera_center, camera.base_rotation, camera.principal_point[0],
+                             camera.principal_point[1], pan, tilt, focal_length)
+            kp, des = self._front("detect_keypoints")(img, 500)
+            if bounding_box is not None:
+                masked_index = keypoints_masking(kp, bounding_box)
+                kp, des = np.asarray(kp)[masked_index], np.asarray(des)[masked_index]
+            frame.feature_pts, frame.feature_des = kp, des
+            camera.set_ptz(self.rf_map.relocalize(frame))
+        elif len(self.keyframe_map.keyframe_list) > 1:
+            lost_pose = camera.pan, camera.tilt, camera.focal_length
+            camera.set_ptz(relocalization_camera(self.keyframe_map, img, lost_pose, detect=self._front("detect"),
+                                                 match=self._front("match")))
+        else:
+            print("Warning: Not enough keyframes for relocalization.")
+        self.tracking_lost = False
+        return camera
+
+    def add_keyframe(self, img, camera, frame_index, enable_rf=False):
+        """ptz_slam.py:499-537: the current frame becomes a keyframe; all keyframes are bundle-adjusted on the GPU."""
+        from .key_frame import KeyFrame
+        new_keyframe = KeyFrame(img, frame_index, camera.camera_center, camera.base_rotation, camera.principal_point[0],
+                                camera.principal_point[1], camera.pan, camera.tilt, camera.focal_length)
+        if enable_rf:
+            new_keyframe.feature_pts = self.previous_keypoints
+            new_keyframe.feature_des = np.asarray(self.des)[np.asarray(self.previous_keypoints_index).astype(np.int64)]
+            self.rf_map.add_keyframe(new_keyframe)
+            self.new_keyframe = False
+        elif frame_index == 0:
+            self.keyframe_map.add_first_keyframe(new_keyframe, verbose=False)
+        else:
+            self.keyframe_map.add_keyframe_with_ba(new_keyframe, "./bundle_result/", verbose=False)
+            self.new_keyframe = False
+
     # -- ray bookkeeping between frames (ptz_slam.py:291-388; SURVEY.md 8f row N4, host side as in the reference) ----------
     def remove_rays(self, index):
         """ptz_slam.py:291-315: drop the rays `index` (RANSAC outliers) with their descriptors and covariance rows / columns."""
         delete_index = np.asarray(index, dtype=np.int64).reshape(-1)
         self.rays = np.delete(self.rays, delete_index, axis=0)
-        if len(self.des) > 0:
+        if self.des is not None and len(self.des) > 0:
             self.des = np.delete(self.des, delete_index, axis=0)
         p_delete = np.stack([2 * delete_index + 3, 2 * delete_index + 4], axis=1).reshape(-1)
         self.state_cov = np.delete(np.delete(self.state_cov, p_delete, axis=0), p_delete, axis=1)

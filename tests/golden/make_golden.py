@@ -17,6 +17,7 @@ Goldens (reference function -> file):
   KeyFrame.convert_keypoint_to_array / save_to_mat                                -> keyframe_mat.npz
   RandomForestMap.bundle_adjustment_processing (BA call replaced by a recorder)   -> sliding_window.npz
   relocalization._compute_residual + its least_squares call (as-is and tight)     -> relocalization.npz
+  PtzSlam.init_system + tracking over a sequence (OpenCV calls replaced)          -> tracking.npz
 """
 import copy
 import io
@@ -526,6 +527,80 @@ def gen_relocalization():
     np.savez_compressed(os.path.join(OUT, "relocalization.npz"), **out)
 
 
+class _IntIndexNp:
+    """np proxy for the reference module: np.delete with the float index arrays ptz_slam.py:309-315 builds (numpy >= 1.19
+    refuses them) and np.row_stack (removed in numpy 2.x; an alias of vstack) - values unchanged."""
+
+    def __getattr__(self, k):
+        return getattr(np, k)
+
+    @staticmethod
+    def delete(arr, obj, axis=None):
+        return np.delete(arr, np.asarray(obj).astype(np.int64), axis=axis)
+
+    @staticmethod
+    def row_stack(a):
+        return np.vstack(a)
+
+
+def cov_probe_vector(n):
+    return np.random.default_rng(n).uniform(0.5, 1.5, n)
+
+
+def gen_tracking():
+    """The per-frame loop of the reference - PtzSlam.init_system (:140-208) and tracking (:390-456: optical-flow
+    bookkeeping, predict, ekf_update, remove_rays, add_rays, keyframe test) - over a seeded sequence, with the two OpenCV
+    calls (detect_compute_sift_array, matching_and_ransac) replaced by tests/synth_front_end.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth_front_end import SyntheticFrontEnd
+    import ptz_slam as ref_ptz_slam
+    from key_frame import KeyFrame as RefKeyFrame
+    out = {}
+    runs = [(31, 11, None), (32, 10, 4)]
+    for c, (seed, n_frames, bad_from) in enumerate(runs):
+        fe = SyntheticFrontEnd(seed, n_frames, bad_from)
+        saved = (ref_ptz_slam.detect_compute_sift_array, ref_ptz_slam.matching_and_ransac, ref_ptz_slam.np)
+        ref_ptz_slam.detect_compute_sift_array = lambda img, n, norm=True: fe.detect_keypoints(img, n)
+        ref_ptz_slam.matching_and_ransac = fe.matching_and_ransac
+        ref_ptz_slam.np = _IntIndexNp()
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                slam = ref.PtzSlam()
+                cam0 = make_camera(fe.gt[0] + np.array([0.02, -0.01, 3.0]))
+                slam.init_system(fe.image(0), cam0, fe.bounding_box)
+                slam.keyframe_map.add_first_keyframe(RefKeyFrame(None, 0, CC, BASE_ROT, U, V, *cam0.get_ptz()))
+                out["c%d_rays_0" % c], out["c%d_cov_diag_0" % c] = slam.rays.copy(), np.diag(slam.state_cov).copy()
+                out["c%d_prev_kp_0" % c] = np.asarray(slam.previous_keypoints, np.float64)
+                for k in range(1, n_frames):
+                    slam.tracking(fe.image(k), 80, fe.bounding_box)
+                    out["c%d_ptz_%d" % (c, k)] = slam.current_camera.get_ptz()
+                    out["c%d_vel_%d" % (c, k)] = np.array(slam.velocity)
+                    out["c%d_rays_%d" % (c, k)] = slam.rays.copy()
+                    if k == n_frames - 1:
+                        out["c%d_des_%d" % (c, k)] = np.asarray(slam.des)
+                    if k == 1 and c == 0:
+                        out["c%d_cov_%d" % (c, k)] = slam.state_cov.copy()
+                    # every frame: the diagonal and a seeded random projection of the full matrix (catches any wrong entry)
+                    out["c%d_cov_diag_%d" % (c, k)] = np.diag(slam.state_cov).copy()
+                    out["c%d_cov_probe_%d" % (c, k)] = slam.state_cov @ cov_probe_vector(slam.state_cov.shape[0])
+                    out["c%d_prev_kp_%d" % (c, k)] = np.asarray(slam.previous_keypoints, np.float64)
+                    out["c%d_prev_idx_%d" % (c, k)] = np.asarray(slam.previous_keypoints_index, np.float64)
+                    out["c%d_flags_%d" % (c, k)] = np.array([slam.new_keyframe, slam.tracking_lost, slam.bad_tracking_cnt,
+                                                             len(slam.cameras)], np.int64)
+        finally:
+            ref_ptz_slam.detect_compute_sift_array, ref_ptz_slam.matching_and_ransac, ref_ptz_slam.np = saved
+        out["c%d_seed" % c], out["c%d_n_frames" % c] = np.array(seed), np.array(n_frames)
+        out["c%d_bad_from" % c] = np.array(-1 if bad_from is None else bad_from)
+        out["c%d_cam0" % c] = cam0.get_ptz() if False else fe.gt[0] + np.array([0.02, -0.01, 3.0])
+        print("tracking run %d: rays per frame %s, flags last %s, ptz err last %s" % (
+            c, [len(out["c%d_rays_%d" % (c, k)]) for k in range(n_frames)], out["c%d_flags_%d" % (c, n_frames - 1)],
+            out["c%d_ptz_%d" % (c, n_frames - 1)] - fe.gt[-1]))
+        print("   flags:", [out["c%d_flags_%d" % (c, k)].tolist() for k in range(1, n_frames)])
+    out["n_runs"] = np.array(len(runs))
+    np.savez_compressed(os.path.join(OUT, "tracking.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                           # regenerate only the named goldens: make_golden.py ray_bookkeeping ...
         for name in sys.argv[1:]:
@@ -536,6 +611,7 @@ if __name__ == "__main__":
     gen_keyframe_mat()
     gen_sliding_window()
     gen_relocalization()
+    gen_tracking()
     gen_keyframe_map()
     gen_projection()
     gen_backprojection()
