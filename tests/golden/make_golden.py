@@ -18,6 +18,7 @@ Goldens (reference function -> file):
   RandomForestMap.bundle_adjustment_processing (BA call replaced by a recorder)   -> sliding_window.npz
   relocalization._compute_residual + its least_squares call (as-is and tight)     -> relocalization.npz
   PtzSlam.init_system + tracking over a sequence (OpenCV calls replaced)          -> tracking.npz
+  util.add_gauss / add_outliers / uniform_point_sample_on_field / compute_error_data  -> util_noise.npz
 """
 import copy
 import io
@@ -601,6 +602,27 @@ def gen_tracking():
     np.savez_compressed(os.path.join(OUT, "tracking.npz"), **out)
 
 
+def gen_util_noise():
+    """util.add_gauss / add_outliers (:99-139, Python `random` seeded), uniform_point_sample_on_field (:186-203),
+    compute_error_data (:301-319)."""
+    import random
+    import util as ref_util
+    rng = np.random.default_rng(1819)
+    pts = np.stack([rng.uniform(-5, W + 5, 80), rng.uniform(-5, H + 5, 80)], 1)
+    pts[0], pts[1], pts[2] = (W + 20, H + 20), (-20, -20), (W - 0.5, 10)          # all four clamps
+    random.seed(4242)
+    g = ref_util.add_gauss(pts, 3.0, W, H)
+    random.seed(4343)
+    o = ref_util.add_outliers(pts, 1.5, W, H, 35)
+    field = ref_util.uniform_point_sample_on_field(118, 70, 7, 5)
+    a = (rng.normal(50, 3, 40), rng.normal(-9, 1, 40), rng.normal(3000, 200, 40))
+    b = (a[0] + rng.normal(0, 0.1, 40), a[1] + rng.normal(0, 0.05, 40), a[2] + rng.normal(0, 9, 40))
+    mean, std = ref_util.compute_error_data(a, b)
+    np.savez(os.path.join(OUT, "util_noise.npz"), pts=pts, gauss=g, outliers=o, field=field, est=np.array(a), gt=np.array(b),
+             err_mean=np.array(mean), err_std=np.array(std))
+    print("util_noise: clamped %d, outliers moved %d" % (((g == 0) | (g[:, :1] == W - 1)).sum(), (np.abs(o - pts) > 20).any(1).sum()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                           # regenerate only the named goldens: make_golden.py ray_bookkeeping ...
         for name in sys.argv[1:]:
@@ -612,6 +634,7 @@ if __name__ == "__main__":
     gen_sliding_window()
     gen_relocalization()
     gen_tracking()
+    gen_util_noise()
     gen_keyframe_map()
     gen_projection()
     gen_backprojection()

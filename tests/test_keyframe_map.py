@@ -188,3 +188,24 @@ def test_map_save_keyframes_to_mat(tmp_path):
     rec = d["keyframes"].ravel()[2]
     np.testing.assert_allclose(rec["ptz"][0, 0].ravel(), G["kf_ptz"][2])
     assert int(rec["index"][0, 0].ravel()[0]) == 2
+
+
+# ---- util.py experiment helpers: noise model, field grid, pose files, error statistics ------------------------------------------
+def test_util_noise_model_and_helpers_golden(tmp_path):
+    import random
+    from ptz_slam_b200 import util
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "util_noise.npz"))
+    W, H = 1280, 720
+    random.seed(4242)
+    np.testing.assert_array_equal(util.add_gauss(d["pts"], 3.0, W, H), d["gauss"])
+    random.seed(4343)
+    np.testing.assert_array_equal(util.add_outliers(d["pts"], 1.5, W, H, 35), d["outliers"])
+    assert d["gauss"].min() == 0 and d["gauss"][:, 0].max() == W - 1 and d["gauss"][:, 1].max() == H - 1     # clamps exercised
+    np.testing.assert_array_equal(util.uniform_point_sample_on_field(118, 70, 7, 5), d["field"])
+    mean, std = util.compute_error_data(tuple(d["est"]), tuple(d["gt"]))
+    np.testing.assert_allclose(mean, d["err_mean"], rtol=1e-15)
+    np.testing.assert_allclose(std, d["err_std"], rtol=1e-14)
+    path = str(tmp_path / "pose.mat")
+    util.save_camera_pose(d["est"][0], d["est"][1], d["est"][2], path)
+    for got, want in zip(util.load_camera_pose(path, separate=True), d["est"]):
+        np.testing.assert_array_equal(got, want)
