@@ -360,6 +360,282 @@ k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENT, opt-in (PTZBA_FUSED_RING=1), NOT the default and not yet timed on hardware: the same two passes with the four
+// observation streams fed by the copy engine (cp.async.bulk + mbarrier) into PER-WARP two-slot shared-memory rings.
+// Motivation: the default kernels are bound by exposed load latency of a few resident warps; register
+// prefetch costs occupancy, and the earlier CTA-wide TMA ring (one __syncthreads per 1024-observation tile) put all warps
+// in lock-step.  Here every warp owns its ring and its mbarriers, so warps stay free-running, the streaming loads cost no
+// registers and no LSU issue slots, and a slot is refilled (by the warp's lane 0) as soon as the warp has copied it to
+// registers - one to two groups of 128 observations ahead of the arithmetic.  Arithmetic, reduction and commit order are
+// those of k_ba_lm_pass4 / k_ba_cam_pass.  Requires lo % 4 == 0 (TMA source alignment); the host falls back otherwise.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGroup = 32 * kQuad;               // observations per warp step
+constexpr int kRing = 2;                         // slots per warp
+constexpr int kWarps = kFusedThreads / 32;
+struct __align__(128) WarpSlot { int cam[kGroup]; int lm[kGroup]; double ox[kGroup]; double oy[kGroup]; };   // 3 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RING_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RING_DONE;\n"
+        "bra RING_WAIT;\n"
+        "RING_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// one lane: start the copies of observations [k0, min(k0 + kGroup, end)) into `slot` (arrays are padded by 4 entries)
+__device__ __forceinline__ void ring_issue(WarpSlot* slot, uint64_t* bar, int64_t k0, int64_t end, const int32_t* cam,
+                                           const int32_t* lm, const double* ox, const double* oy) {
+    int64_t cnt = end - k0;
+    if (cnt > kGroup) cnt = kGroup;
+    const uint32_t c4 = (uint32_t)((cnt + 3) & ~(int64_t)3);
+    mbar_expect_tx(bar, c4 * 24u);
+    tma_load(slot->cam, cam + k0, c4 * 4u, bar);
+    tma_load(slot->lm, lm + k0, c4 * 4u, bar);
+    tma_load(slot->ox, ox + k0, c4 * 8u, bar);
+    tma_load(slot->oy, oy + k0, c4 * 8u, bar);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB)
+k_ba_lm_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+                  const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+                  const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
+                  double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    WarpSlot* slots = reinterpret_cast<WarpSlot*>(dyn);                                              // [kWarps][kRing]
+    double* smem = reinterpret_cast<double*>(dyn + sizeof(WarpSlot) * kWarps * kRing);               // keyframe trig, 48 B each
+    __shared__ uint64_t full[kWarps][kRing];
+    __shared__ double sWarp[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > hi) end = hi;
+    // group j of this warp = observations [begin + (warp + kWarps j) kGroup, + kGroup): the CTA still streams its chunk front to back
+    const int64_t n_groups = end > begin ? (end - begin + kGroup - 1) / kGroup : 0;
+    const int n_mine = n_groups > warp ? (int)((n_groups - warp + kWarps - 1) / kWarps) : 0;
+    WarpSlot* my = slots + warp * kRing;
+    if (lane == 0) {
+        for (int r = 0; r < kRing; ++r) mbar_init(&full[warp][r], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < kRing && j < n_mine; ++j)
+            ring_issue(&my[j], &full[warp][j], begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup, end, s_cam, s_lm, s_ox, s_oy);
+    }
+    for (int i = tid; i < n_pose * 5; i += kFusedThreads) {          // overlaps with the first copies
+        const int c = i / 5, e = i - 5 * c;
+        smem[(size_t)c * 6 + e] = reinterpret_cast<const double*>(cam_trig)[i];
+    }
+    __syncthreads();
+    const double k1 = PTZ_DEG2RAD;
+    double cost = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < n_mine; ++j) {
+        const int r = j % kRing;
+        mbar_wait(&full[warp][r], (uint32_t)((j / kRing) & 1));
+        const WarpSlot& ws = my[r];
+        const int q = lane * kQuad;
+        const int4 c4 = *reinterpret_cast<const int4*>(ws.cam + q);
+        const int4 l4 = *reinterpret_cast<const int4*>(ws.lm + q);
+        const double2 xa = *reinterpret_cast<const double2*>(ws.ox + q), xb = *reinterpret_cast<const double2*>(ws.ox + q + 2);
+        const double2 ya = *reinterpret_cast<const double2*>(ws.oy + q), yb = *reinterpret_cast<const double2*>(ws.oy + q + 2);
+        __syncwarp();                                                // every lane has its copy: the slot may be refilled
+        const int64_t g0 = begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup;
+        if (lane == 0 && j + kRing < n_mine)
+            ring_issue(&my[r], &full[warp][r], g0 + (int64_t)kWarps * kRing * kGroup, end, s_cam, s_lm, s_ox, s_oy);
+        const int64_t k0 = g0 + q;
+        const int cam[kQuad] = {c4.x, c4.y, c4.z, c4.w};
+        int lm[kQuad] = {l4.x, l4.y, l4.z, l4.w};
+        const double ox[kQuad] = {xa.x, xa.y, xb.x, xb.y};
+        const double oy[kQuad] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i)
+            if (k0 + i >= end) lm[i] = -1;
+        double rx[kQuad], ry[kQuad];
+        int cur = -1;
+        LmTrig lt = {0, 1, 0, 1};
+        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            rx[i] = 0.0; ry[i] = 0.0;
+            if (lm[i] < 0) continue;
+            if (lm[i] != cur) {
+                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+                cur = lm[i];
+                lt = lm_trig[cur];
+                vtt = vtp = vpp = glt = glp = 0.0;
+            }
+            const double2* t = reinterpret_cast<const double2*>(smem + (size_t)cam[i] * 6);
+            const double2 pa = t[0], ti = t[1];
+            CamTrig c;
+            c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = smem[(size_t)cam[i] * 6 + 4];
+            double x, y;
+            ObsGeom g;
+            project_fast_jac(c, lt, u, v, x, y, g);
+            rx[i] = x - ox[i];
+            ry[i] = y - oy[i];
+            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
+            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
+            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
+            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
+            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
+            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
+            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
+        }
+        if (resid) {
+            if (!orig && k0 + kQuad <= end) {
+                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
+                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
+                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
+            } else {
+#pragma unroll
+                for (int i = 0; i < kQuad; ++i)
+                    if (lm[i] >= 0) {
+                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
+                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
+                    }
+            }
+        }
+        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
+        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) sWarp[warp] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0;
+        for (int w = 0; w < kWarps; ++w) sum += sWarp[w];
+        atomicAdd(gCost, sum);
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB)
+k_ba_cam_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+                   const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
+                   const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    WarpSlot* slots = reinterpret_cast<WarpSlot*>(dyn);
+    __shared__ uint64_t full[kWarps][kRing];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double k1 = PTZ_DEG2RAD;
+    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > hi) end = hi;
+    const int64_t n_groups = end > begin ? (end - begin + kGroup - 1) / kGroup : 0;
+    const int n_mine = n_groups > warp ? (int)((n_groups - warp + kWarps - 1) / kWarps) : 0;
+    WarpSlot* my = slots + warp * kRing;
+    if (lane == 0) {
+        for (int r = 0; r < kRing; ++r) mbar_init(&full[warp][r], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < kRing && j < n_mine; ++j)
+            ring_issue(&my[j], &full[warp][j], begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup, end, c_cam, c_lm, c_ox, c_oy);
+    }
+    __syncwarp();
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
+    int wcam = -1;
+    CamTrig wc = {0, 1, 0, 1, 1};
+    auto flush = [&]() {
+        if (wcam > 0) {
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
+            if (lane == 0) {
+                double* U = gU + 6 * (size_t)wcam;
+                double* G = gGc + 3 * (size_t)wcam;
+                const double k2 = k1 * k1;
+                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
+                atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
+                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+            }
+        }
+        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
+    };
+    // one step = 32 consecutive observations of a group (4 steps per group).  The streams are read from the warp's slot when
+    // they are needed (shared-memory latency); only the dependent landmark-trig gather of step t + 1 is started before step t
+    // is evaluated.
+    const int n_steps = n_mine * (kGroup / 32);
+    LmTrig lt = {0, 1, 0, 1};
+#pragma unroll 1
+    for (int t = -1; t < n_steps; ++t) {
+        LmTrig nlt = {0, 1, 0, 1};
+        const int tn = t + 1;
+        if (tn < n_steps) {
+            const int jn = tn >> 2, subn = tn & 3, rn = jn % kRing;
+            if (subn == 0) mbar_wait(&full[warp][rn], (uint32_t)((jn / kRing) & 1));
+            const int en = subn * 32 + lane;
+            if (begin + ((int64_t)warp + (int64_t)kWarps * jn) * kGroup + en < end) nlt = lm_trig[my[rn].lm[en]];
+        }
+        if (t >= 0) {
+            const int j = t >> 2, sub = t & 3, r = j % kRing;
+            const int e = sub * 32 + lane;
+            const int64_t g0 = begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup;
+            const bool act = g0 + e < end;
+            const int cam = act ? my[r].cam[e] : -1;
+            const double ox = my[r].ox[e], oy = my[r].oy[e];
+            if (sub == 3) {                                          // last read of this slot: refill it
+                __syncwarp();
+                if (lane == 0 && j + kRing < n_mine)
+                    ring_issue(&my[r], &full[warp][r], g0 + (int64_t)kWarps * kRing * kGroup, end, c_cam, c_lm, c_ox, c_oy);
+            }
+            const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
+            const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
+            const bool uniform = same == 0xffffffffu;
+            if (uniform) {
+                if (cam_lo != wcam) { flush(); wcam = cam_lo; if (wcam >= 0) wc = cam_trig[wcam]; }
+            } else {
+                flush();
+                wcam = -1;
+            }
+            if (act && cam > 0) {
+                const CamTrig c = uniform ? wc : cam_trig[cam];
+                double x, y;
+                ObsGeom g;
+                project_fast_jac(c, lt, u, v, x, y, g);
+                const double rx = x - ox, ry = y - oy;
+                const double upp = fma(g.xa, g.xa, g.ya * g.ya);
+                const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
+                const double upf = -fma(g.xa, g.px, g.ya * g.py);
+                const double utt = fma(g.xt, g.xt, g.yt * g.yt);
+                const double utf = fma(g.xt, g.px, g.yt * g.py);
+                const double uff = fma(g.px, g.px, g.py * g.py);
+                const double gp = -fma(g.xa, rx, g.ya * ry);
+                const double gt = fma(g.xt, rx, g.yt * ry);
+                const double gf = fma(g.px, rx, g.py * ry);
+                if (uniform) {
+                    a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
+                } else {
+                    double* U = gU + 6 * (size_t)cam;
+                    double* G = gGc + 3 * (size_t)cam;
+                    const double k2 = k1 * k1;
+                    atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
+                    atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
+                    atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
+                }
+            }
+        }
+        lt = nlt;
+    }
+    flush();
+}
+
 // residual-only pass (trial points of the trust-region loop, and _compute_residual itself)
 __global__ void __launch_bounds__(kFusedThreads)
 k_ba_residual(int64_t lo, int64_t hi, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
@@ -445,7 +721,31 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     // partition (ptzba_ba_set_partition) only this rank's slices of the two sorted lists are visited.
     const size_t smA = ba->cam_smem ? (size_t)ba->n_pose * 6 * sizeof(double) : 0;
     const int64_t nA = ba->lmo_hi - (ba->lmo_lo & ~(int64_t)3);
-    if (nA > 0) {
+    // opt-in experiment: per-warp copy-engine rings (see k_ba_lm_pass_ring); needs 16-byte aligned slice starts
+    static const bool ring = getenv("PTZBA_FUSED_RING") != nullptr;
+    const size_t smRing = sizeof(WarpSlot) * kWarps * kRing;
+    const bool ringA = ring && ba->cam_smem && ba->lmo_lo % 4 == 0 && smRing + smA <= 200 * 1024;
+    const bool ringB = ring && ba->cmo_lo % 4 == 0;
+    if (ring && ba->grid_lm_ring == 0) {
+        int pa = 1, pb = 1;
+        if (ringA) {
+            CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass_ring<kLmMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smRing + smA)));
+            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass_ring<kLmMinB>, kFusedThreads, smRing + smA));
+        }
+        CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_cam_pass_ring<kCamMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smRing));
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass_ring<kCamMinB>, kFusedThreads, smRing));
+        ba->grid_lm_ring = ctx->sm_count * (pa < 1 ? 1 : pa);
+        ba->grid_cam_ring = ctx->sm_count * (pb < 1 ? 1 : pb);
+    }
+    if (nA > 0 && ringA) {
+        int64_t chunkA = (nA + ba->grid_lm_ring - 1) / ba->grid_lm_ring;
+        chunkA = (chunkA + kGroup - 1) / kGroup * kGroup;
+        const int gridA = (int)((nA + chunkA - 1) / chunkA);
+        k_ba_lm_pass_ring<kLmMinB><<<gridA, kFusedThreads, smRing + smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+                                                                            ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u,
+                                                                            ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        KERNEL_POST(ctx);
+    } else if (nA > 0) {
         int64_t chunkA = (nA + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
         chunkA = (chunkA + 127) / 128 * 128;
         const int gridA = (int)((nA + chunkA - 1) / chunkA);
@@ -469,8 +769,17 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         const int gridB = (int)((nB + chunkB - 1) / chunkB);
         cudaStream_t sb = concurrent ? ctx->side_stream : s;
         if (concurrent) CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
-        k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                                ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+        if (ringB) {
+            int64_t chunkR = (nB + ba->grid_cam_ring - 1) / ba->grid_cam_ring;
+            chunkR = (chunkR + kGroup - 1) / kGroup * kGroup;
+            const int gridR = (int)((nB + chunkR - 1) / chunkR);
+            k_ba_cam_pass_ring<kCamMinB><<<gridR, kFusedThreads, smRing, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkR, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p,
+                                                                             ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v,
+                                                                             ba->acc.U, ba->acc.gc);
+        } else {
+            k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                                    ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
+        }
         KERNEL_POST(ctx);
         if (concurrent) {
             CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
