@@ -49,6 +49,10 @@ struct ptzba_ba {
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int grid_lm_pass = 0, grid_cam_pass = 0;   // one wave of resident CTAs per pass
+    // opt-in experiment (PTZBA_SCHUR_PAIRLIST): keyframe-pair-major list of observation pairs, built at the first solve
+    DevBuf<uint32_t> pl_key, pl_val;
+    long long pl_n = 0;
+    bool pl_ready = false;
     int grid_lm_ring = 0, grid_cam_ring = 0;   // same for the opt-in copy-engine ring variant (PTZBA_FUSED_RING), set on first use
     int touch_cam_lo = 0, touch_cam_hi = 0, touch_lm_lo = 0, touch_lm_hi = 0;   // id ranges the observations touch
     // keyframe-sharded mode: compact exchange of the landmarks observed by more than one rank (ptzba_ba_setup_exchange)

@@ -15,6 +15,8 @@
 #include <utility>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "ba.h"
 #include "dense.h"
 
@@ -210,6 +212,127 @@ k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const in
     }
 }
 
+// ---- EXPERIMENT, opt-in (PTZBA_SCHUR_PAIRLIST=1), off by default and not yet run on hardware -------------------------------
+// k_schur_pairs issues one FP64 RED per block entry per observation pair (189 M at 256 x 100k x 2M) and sits at the L2
+// atomic rate.  The sparsity pattern is static, so the pairs can be listed once per problem, KEYFRAME-PAIR MAJOR:
+//   entry = (key = max_cam << 16 | min_cam, val = landmark | duplicate flag << 31), radix-sorted by key.
+// The runtime kernel then streams the list like the keyframe-major fused pass: a warp keeps the 3x3 block of the current
+// keyframe pair in registers across its whole run and commits it with 9 REDs when the key changes - REDs drop from 9 per
+// entry to 9 per (warp, run), and what is left is FP64 arithmetic (two W evaluations + 30 FMA per entry) on 8 B / entry of
+// streamed data.  W depends only on (keyframe, landmark), so a landmark observed m times from one keyframe contributes m^2
+// times: the position pairs i != j of the same keyframe carry the duplicate flag (weight 2 = B + B^T of k_schur_pairs).
+__global__ void k_pl_count(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const int32_t* __restrict__ s_cam,
+                           long long* __restrict__ counts) {
+    const int l = lm_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lm_hi) return;
+    long long m = 0;
+    for (int k = lm_ptr[l]; k < lm_ptr[l + 1]; ++k) m += s_cam[k] > 0;
+    counts[l - lm_lo] = m * (m + 1) / 2;
+}
+
+__global__ void k_pl_emit(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const int32_t* __restrict__ s_cam,
+                          const long long* __restrict__ offs, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+    const int l = lm_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lm_hi) return;
+    long long o = offs[l - lm_lo];
+    const int b = lm_ptr[l], e = lm_ptr[l + 1];
+    for (int i = b; i < e; ++i) {
+        const int ci = s_cam[i];
+        if (ci <= 0) continue;
+        for (int j = b; j <= i; ++j) {
+            const int cj = s_cam[j];
+            if (cj <= 0) continue;
+            const uint32_t hi = (uint32_t)(ci > cj ? ci : cj), lo = (uint32_t)(ci > cj ? cj : ci);
+            key[o] = hi << 16 | lo;
+            val[o] = (uint32_t)l | ((i != j && ci == cj) ? 0x80000000u : 0u);
+            ++o;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_schur_pairlist(long long n_ent, long long chunk, const uint32_t* __restrict__ key, const uint32_t* __restrict__ val,
+                 const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ Vinv,
+                 double* __restrict__ S, int ld) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long begin = w * chunk;
+    long long end = begin + chunk;
+    if (end > n_ent) end = n_ent;
+    if (begin >= end) return;
+    const uint32_t kNone = 0xffffffffu;
+    double a[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a[q] = 0.0;
+    uint32_t wkey = kNone;
+    CamTrig wr = {0, 1, 0, 1, 1}, wc = {0, 1, 0, 1, 1};
+    auto commit = [&](uint32_t k, const double* b) {              // S(block max,min) -= b, lower triangle only on the diagonal
+        const int cr = (int)(k >> 16), cc = (int)(k & 0xffffu);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int sc = 0; sc < 3; ++sc)
+                if (!(cr == cc && r < sc)) atomicAdd(S + (size_t)(3 * (cr - 1) + r) + (size_t)(3 * (cc - 1) + sc) * ld, -b[r * 3 + sc]);
+    };
+    auto flush = [&]() {
+        if (wkey != kNone) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) a[q] = warp_sum(a[q]);
+            if (lane == 0) commit(wkey, a);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) a[q] = 0.0;
+    };
+    for (long long base = begin; base < end; base += 32) {
+        const long long e = base + lane;
+        const bool act = e < end;
+        const uint32_t k = act ? key[e] : kNone;
+        const uint32_t v = act ? val[e] : 0u;
+        const uint32_t k_lo = __shfl_sync(0xffffffffu, k, 0);                 // lane 0 is always active
+        const bool uniform = __ballot_sync(0xffffffffu, k == k_lo || !act) == 0xffffffffu;
+        if (uniform) {
+            if (k_lo != wkey) {
+                flush();
+                wkey = k_lo;
+                wr = cam_trig[k_lo >> 16];
+                wc = cam_trig[k_lo & 0xffffu];
+            }
+        } else {
+            flush();
+            wkey = kNone;
+        }
+        if (act) {
+            const int l = (int)(v & 0x7fffffffu);
+            const double wt = (v >> 31) ? 2.0 : 1.0;
+            const LmTrig lt = lm_trig[l];
+            const double v00 = wt * Vinv[3 * (size_t)l], v01 = wt * Vinv[3 * (size_t)l + 1], v11 = wt * Vinv[3 * (size_t)l + 2];
+            const int cr = (int)(k >> 16), cc = (int)(k & 0xffffu);
+            double Wr[6], Wc[6];
+            obs_W(uniform ? wr : cam_trig[cr], lt, Wr);
+            if (cr == cc) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) Wc[q] = Wr[q];
+            } else {
+                obs_W(uniform ? wc : cam_trig[cc], lt, Wc);
+            }
+            double b[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double y0 = fma(Wr[2 * r], v00, Wr[2 * r + 1] * v01), y1 = fma(Wr[2 * r], v01, Wr[2 * r + 1] * v11);
+#pragma unroll
+                for (int sc = 0; sc < 3; ++sc) b[r * 3 + sc] = fma(y0, Wc[2 * sc], y1 * Wc[2 * sc + 1]);
+            }
+            if (uniform) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) a[q] += b[q];
+            } else {
+                commit(k, b);           // the warp straddles a key boundary (once per run): commit per lane
+            }
+        }
+    }
+    flush();
+}
+
 // ---- reduced right-hand side: out_c[cam] -= W_i Vinv rhs_l  (keyframe accumulators privatised in shared memory) --------
 __global__ void __launch_bounds__(kThreads)
 k_reduce_rhs(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
@@ -365,6 +488,7 @@ struct Solver {
     int64_t chunk = 0;
     int obs_grid = 0;
     int pair_warps_smem = 0, pair_grid = 0;
+    bool use_pairlist = false;   // opt-in experiment (PTZBA_SCHUR_PAIRLIST): keyframe-pair-major entry list, see k_schur_pairlist
     int n_factor = 0;
     int* h_flags = nullptr;      // pinned host copy of the factorisation verdict (slot 200 of ctx->h_scalars): truly asynchronous
     double *g, *D, *Dc, *Dl;
@@ -408,6 +532,45 @@ struct Solver {
         pair_grid = ctx->sm_count * per_sm;
         const int max_grid = div_up(ba->lm_hi - ba->lm_lo, kThreads / 32);
         if (pair_grid > max_grid) pair_grid = max_grid > 0 ? max_grid : 1;
+        use_pairlist = getenv("PTZBA_SCHUR_PAIRLIST") != nullptr && ba->part_world == 1 && N <= 65535;
+        if (use_pairlist) PROPAGATE(build_pair_list());
+        return PTZBA_OK;
+    }
+
+    // keyframe-pair-major list of all (observation, observation) pairs of every landmark; built once per problem
+    int build_pair_list() {
+        const int nl = ba->lm_hi - ba->lm_lo;
+        if (ba->pl_ready || nl <= 0 || ba->n_obs == 0) return PTZBA_OK;
+        DevBuf<long long> counts, offs;
+        DevBuf<uint32_t> key_in, val_in;
+        DevBuf<unsigned char> tmp;
+        CU_CHECK(ctx, counts.alloc((size_t)nl + 1));
+        CU_CHECK(ctx, offs.alloc((size_t)nl + 1));
+        CU_CHECK(ctx, cudaMemsetAsync(counts.p, 0, ((size_t)nl + 1) * sizeof(long long), s));
+        k_pl_count<<<div_up(nl, 256), 256, 0, s>>>(ba->lm_lo, ba->lm_hi, ba->lm_ptr.p, ba->s_cam.p, counts.p);
+        KERNEL_POST(ctx);
+        size_t bytes = 0;
+        CU_CHECK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.p, offs.p, nl + 1, s));
+        CU_CHECK(ctx, tmp.alloc(bytes));
+        CU_CHECK(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, counts.p, offs.p, nl + 1, s));
+        long long total = 0;
+        CU_CHECK(ctx, cudaMemcpyAsync(&total, offs.p + nl, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        if (total <= 0 || total > 0x7fffffffLL) {      // cub's 32-bit item count; larger lists keep the per-landmark kernel
+            use_pairlist = false;
+            return PTZBA_OK;
+        }
+        CU_CHECK(ctx, key_in.alloc((size_t)total)); CU_CHECK(ctx, val_in.alloc((size_t)total));
+        CU_CHECK(ctx, ba->pl_key.alloc((size_t)total)); CU_CHECK(ctx, ba->pl_val.alloc((size_t)total));
+        k_pl_emit<<<div_up(nl, 256), 256, 0, s>>>(ba->lm_lo, ba->lm_hi, ba->lm_ptr.p, ba->s_cam.p, offs.p, key_in.p, val_in.p);
+        KERNEL_POST(ctx);
+        bytes = 0;
+        CU_CHECK(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in.p, ba->pl_key.p, val_in.p, ba->pl_val.p, (int)total, 0, 32, s));
+        CU_CHECK(ctx, tmp.alloc(bytes));
+        CU_CHECK(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, key_in.p, ba->pl_key.p, val_in.p, ba->pl_val.p, (int)total, 0, 32, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));       // the temporaries go out of scope
+        ba->pl_n = total;
+        ba->pl_ready = true;
         return PTZBA_OK;
     }
 
@@ -425,9 +588,16 @@ struct Solver {
             }
             tr.mark("vinv+memset+diag");
             if (ba->lm_hi > ba->lm_lo && ba->n_obs > 0) {
-                k_schur_pairs<<<pair_grid, kThreads, pair_warps_smem, s>>>(ba->lm_lo, ba->lm_hi, ba->lm_ptr.p, ba->s_cam.p, ba->cam_trig.p,
-                                                                          ba->lm_trig.p, ba->Vinv.p, ba->max_degree,
-                                                                          ba->Sred.p, n);
+                if (use_pairlist && ba->pl_ready) {
+                    const long long per_warp = 1024;              // entries per warp: 32 steps, one or two keyframe pairs
+                    const long long n_warps = (ba->pl_n + per_warp - 1) / per_warp;
+                    k_schur_pairlist<<<(unsigned)((n_warps + kThreads / 32 - 1) / (kThreads / 32)), kThreads, 0, s>>>(
+                        ba->pl_n, per_warp, ba->pl_key.p, ba->pl_val.p, ba->cam_trig.p, ba->lm_trig.p, ba->Vinv.p, ba->Sred.p, n);
+                } else {
+                    k_schur_pairs<<<pair_grid, kThreads, pair_warps_smem, s>>>(ba->lm_lo, ba->lm_hi, ba->lm_ptr.p, ba->s_cam.p, ba->cam_trig.p,
+                                                                              ba->lm_trig.p, ba->Vinv.p, ba->max_degree,
+                                                                              ba->Sred.p, n);
+                }
                 KERNEL_POST(ctx);
             }
             if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->Sred.p, (int64_t)n * n));
