@@ -12,7 +12,7 @@ for spec in "$@"; do
   ( export $envs
     t=$(timeout 900 python -m pytest tests/test_gpu_ba.py tests/test_gpu_configs.py -q -x -m gpu 2>&1 | tail -1)
     timeout 400 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-ekf > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
-    PTZBA_TRACE=1 timeout 200 python tests/lm_trace.py > gpurun_out/trace_$tag.log 2>&1
+    PTZBA_TRACE=1 timeout 200 python scripts/lm_trace.py > gpurun_out/trace_$tag.log 2>&1
     python - "$tag" "$t" <<'PY'
 import json, sys
 tag, t = sys.argv[1], sys.argv[2]

@@ -1,6 +1,9 @@
-import sys, time, numpy as np
-sys.path.insert(0,'/root/repo')
-import ptz_slam_b200
+"""Timing aid (GPU box): Levenberg-Marquardt iterations of the cfg5 problem (1024 keyframes, 20M observations); PTZBA_TRACE=1
+prints the per-phase times.  Not a test."""
+import os, sys, time
+import numpy as np  # noqa: F401
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ptz_slam_b200  # noqa: F401
 from ptz_slam_b200 import synth, bundle_adjustment as BA
 t=time.perf_counter()
 fb=synth.make_flat_ba(1024,1000000,20000000,seed=1005,pan_sweep=40.0)

@@ -5,7 +5,6 @@ on, which walks bad_tracking_cnt to tracking_lost.
 
 CPU: the product's host orchestration with the camera and the EKF update served by the oracle (the checker standing in for the
 device).  GPU: the product end to end (projection, back-projection and EKF update through the C-ABI)."""
-import copy
 import os
 
 import numpy as np
