@@ -51,6 +51,60 @@ class PTZCamera:
         fl, wt = self.focal_length, self.displacement
         return np.array([wt[0] + wt[3] * fl, wt[1] + wt[4] * fl, wt[2] + wt[5] * fl])
 
+    def compute_pan_matrix(self):
+        """ptz_camera.py:83-93."""
+        c, s = np.cos(np.radians(self.pan)), np.sin(np.radians(self.pan))
+        return np.array([[c, 0, -s], [0, 1, 0], [s, 0, c]])
+
+    def compute_tilt_matrix(self):
+        """ptz_camera.py:95-104."""
+        c, s = np.cos(np.radians(self.tilt)), np.sin(np.radians(self.tilt))
+        return np.array([[1, 0, 0], [0, c, s], [0, -s, c]])
+
+    def compute_rotation_matrix(self):
+        """ptz_camera.py:65-81: R_tilt R_pan R_base."""
+        return self.compute_tilt_matrix() @ self.compute_pan_matrix() @ self.base_rotation
+
+    def recompute_matrix(self):
+        """ptz_camera.py:117-141: P = K [I | d] [R 0; 0 1] [I -C; 0 1] (3 x 4), d = displacement of the projection centre."""
+        pose = np.eye(4)
+        pose[0:3, 0:3] = self.compute_rotation_matrix()
+        pose[0:3, 3] = -pose[0:3, 0:3] @ np.asarray(self.camera_center, dtype=np.float64)
+        disp = np.eye(3, 4)
+        disp[:, 3] = self.compute_dispalcement()
+        self.projection_matrix = self.compute_camera_matrix() @ disp @ pose
+        return self.projection_matrix
+
+    # -- world points (the court model); general-camera helpers off the ray path, host algebra as in the reference ------
+    def project_3d_point(self, p):
+        """ptz_camera.py:154-165: world point -> (x, y)."""
+        pts, _ = self.project_3d_points(np.asarray(p, dtype=np.float64).reshape(1, 3))
+        return float(pts[0, 0]), float(pts[0, 1])
+
+    def project_3d_points(self, ps, height=0, width=0):
+        """ptz_camera.py:167-189: (points, index) with the same strict in-image filter as project_rays."""
+        ps = np.asarray(ps, dtype=np.float64).reshape(-1, 3)
+        uvw = np.hstack([ps, np.ones((len(ps), 1))]) @ self.recompute_matrix().T
+        assert np.all(uvw[:, 2] != 0.0)
+        pts = uvw[:, 0:2] / uvw[:, 2:3]
+        if height != 0 and width != 0:
+            keep = (0 < pts[:, 0]) & (pts[:, 0] < width) & (0 < pts[:, 1]) & (pts[:, 1] < height)
+            return pts[keep], np.nonzero(keep)[0].astype(np.float64)
+        return pts, np.ndarray([0])
+
+    def back_project_to_3d_point(self, x, y):
+        """ptz_camera.py:236-273: the point of the ground plane z = 0 seen at pixel (x, y) (displacement ignored, as there)."""
+        return self.back_project_to_3d_points(np.array([[x, y]], dtype=np.float64))[0]
+
+    def back_project_to_3d_points(self, keypoints):
+        """ptz_camera.py:275-285."""
+        kp = np.asarray(keypoints, dtype=np.float64).reshape(-1, 2)
+        inv_mat = np.linalg.inv(self.compute_camera_matrix() @ self.compute_rotation_matrix())
+        center = np.asarray(self.camera_center, dtype=np.float64)
+        rays = np.hstack([kp, np.ones((len(kp), 1))]) @ inv_mat.T
+        coe = (0.0 - center[2]) / rays[:, 2]
+        return rays * coe[:, None] + center
+
     def get_ptz(self):
         return np.array([self.pan, self.tilt, self.focal_length])
 

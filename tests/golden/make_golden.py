@@ -19,6 +19,7 @@ Goldens (reference function -> file):
   relocalization._compute_residual + its least_squares call (as-is and tight)     -> relocalization.npz
   PtzSlam.init_system + tracking over a sequence (OpenCV calls replaced)          -> tracking.npz
   util.add_gauss / add_outliers / uniform_point_sample_on_field / compute_error_data  -> util_noise.npz
+  PTZCamera matrices, project_3d_point(s), back_project_to_3d_point(s)            -> camera_3d.npz
 """
 import copy
 import io
@@ -602,6 +603,30 @@ def gen_tracking():
     np.savez_compressed(os.path.join(OUT, "tracking.npz"), **out)
 
 
+def gen_camera_3d():
+    """PTZCamera matrices and world-point helpers: compute_rotation_matrix (:65-81), recompute_matrix (:117-141),
+    project_3d_point(s) (:154-189), back_project_to_3d_point(s) (:236-285)."""
+    rng = np.random.default_rng(2021)
+    out = {}
+    for c, disp in enumerate([None, DISP]):
+        ptz = np.array([rng.uniform(45, 70), rng.uniform(-12, -7), rng.uniform(2200, 3800)])
+        cam = make_camera(ptz, disp)
+        # world points: the ground points seen at pixels in and around the image, lifted by up to 2 m
+        seed_px = np.stack([rng.uniform(-300, W + 300, 60), rng.uniform(-200, H + 200, 60)], 1)
+        field = cam.back_project_to_3d_points(seed_px) + np.stack([np.zeros(60), np.zeros(60), rng.uniform(0, 2, 60)], 1)
+        cam.recompute_matrix()
+        pts_all, _ = cam.project_3d_points(field)
+        pts_in, idx_in = cam.project_3d_points(field, H, W)
+        px = np.stack([rng.uniform(0, W, 25), rng.uniform(0, H, 25)], 1)
+        out["c%d_ptz" % c], out["c%d_disp" % c] = ptz, (np.zeros(6) if disp is None else disp)
+        out["c%d_R" % c], out["c%d_P" % c] = cam.compute_rotation_matrix(), cam.projection_matrix.copy()
+        out["c%d_pan" % c], out["c%d_tilt" % c] = cam.compute_pan_matrix(), cam.compute_tilt_matrix()
+        out["c%d_field" % c], out["c%d_pts_all" % c], out["c%d_pts_in" % c], out["c%d_idx_in" % c] = field, pts_all, pts_in, idx_in
+        out["c%d_px" % c], out["c%d_ground" % c] = px, cam.back_project_to_3d_points(px)
+        print("camera_3d case %d: %d of %d court points in the image" % (c, len(idx_in), len(field)))
+    np.savez(os.path.join(OUT, "camera_3d.npz"), **out)
+
+
 def gen_util_noise():
     """util.add_gauss / add_outliers (:99-139, Python `random` seeded), uniform_point_sample_on_field (:186-203),
     compute_error_data (:301-319)."""
@@ -635,6 +660,7 @@ if __name__ == "__main__":
     gen_relocalization()
     gen_tracking()
     gen_util_noise()
+    gen_camera_3d()
     gen_keyframe_map()
     gen_projection()
     gen_backprojection()

@@ -209,3 +209,31 @@ def test_util_noise_model_and_helpers_golden(tmp_path):
     util.save_camera_pose(d["est"][0], d["est"][1], d["est"][2], path)
     for got, want in zip(util.load_camera_pose(path, separate=True), d["est"]):
         np.testing.assert_array_equal(got, want)
+
+
+# ---- PTZCamera matrices and world-point helpers (host algebra, ptz_camera.py:65-189, 236-285) ---------------------------------
+def test_ptz_camera_matrices_and_world_points_golden():
+    from ptz_slam_b200.ptz_camera import PTZCamera
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_3d.npz"))
+    cc, base = np.array([13.0099, -14.8109, 6.1790]), np.array([1.5804, -0.1186, 0.1249])
+    for c in range(2):
+        disp = d["c%d_disp" % c]
+        cam = PTZCamera((640.0, 360.0), cc, base, disp if np.any(disp) else None)
+        cam.set_ptz(d["c%d_ptz" % c])
+        np.testing.assert_allclose(cam.compute_pan_matrix(), d["c%d_pan" % c], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(cam.compute_tilt_matrix(), d["c%d_tilt" % c], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(cam.compute_rotation_matrix(), d["c%d_R" % c], rtol=0, atol=1e-12)    # own Rodrigues vs OpenCV's
+        np.testing.assert_allclose(cam.recompute_matrix(), d["c%d_P" % c], rtol=1e-9, atol=1e-8)
+        pts, idx = cam.project_3d_points(d["c%d_field" % c])
+        assert len(idx) == 0
+        np.testing.assert_allclose(pts, d["c%d_pts_all" % c], rtol=1e-9, atol=1e-7)
+        pts, idx = cam.project_3d_points(d["c%d_field" % c], 720, 1280)
+        np.testing.assert_array_equal(idx, d["c%d_idx_in" % c])
+        np.testing.assert_allclose(pts, d["c%d_pts_in" % c], rtol=1e-9, atol=1e-7)
+        assert 0 < len(idx) < len(d["c%d_field" % c])
+        x, y = cam.project_3d_point(d["c%d_field" % c][3])
+        np.testing.assert_allclose([x, y], d["c%d_pts_all" % c][3], rtol=1e-9, atol=1e-7)
+        ground = cam.back_project_to_3d_points(d["c%d_px" % c])
+        np.testing.assert_allclose(ground, d["c%d_ground" % c], rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(cam.back_project_to_3d_point(*d["c%d_px" % c][0]), d["c%d_ground" % c][0], rtol=1e-9, atol=1e-8)
+        assert np.all(np.abs(ground[:, 2]) < 1e-9)
