@@ -45,3 +45,50 @@ class TransFunction:
         ctx.check(ctx.lib.ptzba_backproject(ctx.handle, _lib.HOST, ptz.shape[0], _lib.ptr(ptz), float(u), float(v), None,
                                             points.shape[0], _lib.ptr(points), _lib.ptr(ci), _lib.ptr(out)))
         return out
+
+    # -- world-point helpers ("general slam", transformation.py:23-97, 178-249): a handful of 3-vector products per call,
+    #    host algebra exactly as in the reference (they feed the court-model overlays, not the ray hot path) ---------------
+    @staticmethod
+    def _pan_tilt_rotation(p, t):
+        cp, sp = np.cos(np.radians(p)), np.sin(np.radians(p))
+        ct, st = np.cos(np.radians(t)), np.sin(np.radians(t))
+        return np.array([[1, 0, 0], [0, ct, st], [0, -st, ct]]) @ np.array([[cp, 0, -sp], [0, 1, 0], [sp, 0, cp]])
+
+    @staticmethod
+    def from_3dpoint_to_image(u, v, f, p, t, c, base_r, pos):
+        """transformation.py:23-55: world point -> (x, y) through K R_tilt R_pan R_base (pos - c)."""
+        k = np.array([[f, 0, u], [0, f, v], [0, 0, 1]])
+        q = k @ (TransFunction._pan_tilt_rotation(p, t) @ np.asarray(base_r) @ (np.asarray(pos) - np.asarray(c)))
+        return q[0] / q[2], q[1] / q[2]
+
+    @staticmethod
+    def from_image_to_3dpoint(u, v, f, p, t, c, base_r, point2d):
+        """transformation.py:58-97: the ground-plane (z = 0) point seen at a pixel."""
+        k = np.array([[f, 0, u], [0, f, v], [0, 0, 1]])
+        inv_mat = np.linalg.inv(k @ TransFunction._pan_tilt_rotation(p, t) @ np.asarray(base_r))
+        d = inv_mat @ np.array([point2d[0], point2d[1], 1.0])
+        return d * ((0.0 - c[2]) / d[2]) + np.asarray(c)
+
+    @staticmethod
+    def from_3dpoint_to_ray(proj_center, pos, base_r):
+        """transformation.py:178-191: world point -> (theta, phi) in degrees."""
+        x, y, z = np.asarray(base_r) @ (np.asarray(pos) - np.asarray(proj_center))
+        return float(np.degrees(np.arctan(x / z))), float(np.degrees(np.arctan(-y / np.sqrt(x * x + z * z))))
+
+    @staticmethod
+    def from_ray_to_relative_3dpoint(t, p):
+        """transformation.py:194-205: ray (theta, phi) -> direction [tan theta, -tan phi sqrt(tan^2 theta + 1), 1]."""
+        tt = np.tan(np.radians(t))
+        return np.array([tt, -np.tan(np.radians(p)) * np.sqrt(tt * tt + 1), 1])
+
+    @staticmethod
+    def from_relative_3dpoint_to_image(u, v, f, p, t, pos):
+        """transformation.py:208-236: camera-frame direction -> (x, y) through K R_tilt R_pan."""
+        q = np.array([[f, 0, u], [0, f, v], [0, 0, 1]]) @ (TransFunction._pan_tilt_rotation(p, t) @ np.asarray(pos))
+        return q[0] / q[2], q[1] / q[2]
+
+    @staticmethod
+    def from_3dpoint_to_relative_3dpoint(c, base_r, pos):
+        """transformation.py:239-249: world point -> camera-frame direction with unit depth."""
+        q = np.asarray(base_r) @ (np.asarray(pos) - np.asarray(c))
+        return q / q[2]

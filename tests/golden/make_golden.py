@@ -624,6 +624,28 @@ def gen_camera_3d():
         out["c%d_field" % c], out["c%d_pts_all" % c], out["c%d_pts_in" % c], out["c%d_idx_in" % c] = field, pts_all, pts_in, idx_in
         out["c%d_px" % c], out["c%d_ground" % c] = px, cam.back_project_to_3d_points(px)
         print("camera_3d case %d: %d of %d court points in the image" % (c, len(idx_in), len(field)))
+    # TransFunction world-point helpers (transformation.py:23-97, 178-249)
+    T = ref.TransFunction
+    R0 = make_camera([0, 0, 2000]).base_rotation
+    q = rng.uniform(-1, 1, (20, 8))
+    tf = {k: [] for k in ("to_image", "to_3d", "to_ray", "ray_rel", "rel_image", "to_rel")}
+    tf_in = []
+    for a in q:
+        pan, tilt, f = 55 + 8 * a[0], -9 + 2 * a[1], 3000 + 600 * a[2]
+        px = np.array([640 + 500 * a[3], 360 + 300 * a[4]])
+        world = np.asarray(T.from_image_to_3dpoint(U, V, f, pan, tilt, CC, R0, px)) + np.array([0, 0, 1 + a[5]])
+        theta, phi = pan + 6 * a[6], tilt + 4 * a[7]
+        tf_in.append([pan, tilt, f, px[0], px[1], world[0], world[1], world[2], theta, phi])
+        tf["to_image"].append(T.from_3dpoint_to_image(U, V, f, pan, tilt, CC, R0, world))
+        tf["to_3d"].append(T.from_image_to_3dpoint(U, V, f, pan, tilt, CC, R0, px))
+        tf["to_ray"].append(T.from_3dpoint_to_ray(CC, world, R0))
+        rel = T.from_ray_to_relative_3dpoint(theta, phi)
+        tf["ray_rel"].append(rel)
+        tf["rel_image"].append(T.from_relative_3dpoint_to_image(U, V, f, pan, tilt, rel))
+        tf["to_rel"].append(T.from_3dpoint_to_relative_3dpoint(CC, R0, world))
+    out["tf_in"], out["tf_R0"] = np.array(tf_in), R0
+    for k, vals in tf.items():
+        out["tf_" + k] = np.array(vals, dtype=np.float64)
     np.savez(os.path.join(OUT, "camera_3d.npz"), **out)
 
 

@@ -237,3 +237,19 @@ def test_ptz_camera_matrices_and_world_points_golden():
         np.testing.assert_allclose(ground, d["c%d_ground" % c], rtol=1e-9, atol=1e-8)
         np.testing.assert_allclose(cam.back_project_to_3d_point(*d["c%d_px" % c][0]), d["c%d_ground" % c][0], rtol=1e-9, atol=1e-8)
         assert np.all(np.abs(ground[:, 2]) < 1e-9)
+
+
+def test_transfunction_world_point_helpers_golden():
+    from ptz_slam_b200.transformation import TransFunction as T
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_3d.npz"))
+    cc, R0 = np.array([13.0099, -14.8109, 6.1790]), d["tf_R0"]
+    for k, row in enumerate(d["tf_in"]):
+        pan, tilt, f, px, py, wx, wy, wz, theta, phi = row
+        world = np.array([wx, wy, wz])
+        np.testing.assert_allclose(T.from_3dpoint_to_image(640.0, 360.0, f, pan, tilt, cc, R0, world), d["tf_to_image"][k], rtol=1e-9, atol=1e-7)
+        np.testing.assert_allclose(T.from_image_to_3dpoint(640.0, 360.0, f, pan, tilt, cc, R0, (px, py)), d["tf_to_3d"][k], rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(T.from_3dpoint_to_ray(cc, world, R0), d["tf_to_ray"][k], rtol=1e-12, atol=1e-12)
+        rel = T.from_ray_to_relative_3dpoint(theta, phi)
+        np.testing.assert_allclose(rel, d["tf_ray_rel"][k], rtol=1e-13)
+        np.testing.assert_allclose(T.from_relative_3dpoint_to_image(640.0, 360.0, f, pan, tilt, rel), d["tf_rel_image"][k], rtol=1e-10, atol=1e-8)
+        np.testing.assert_allclose(T.from_3dpoint_to_relative_3dpoint(cc, R0, world), d["tf_to_rel"][k], rtol=1e-12, atol=1e-12)
