@@ -250,7 +250,7 @@ __global__ void k_pl_emit(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_p
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_schur_pairlist(long long n_ent, long long chunk, const uint32_t* __restrict__ key, const uint32_t* __restrict__ val,
                  const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, const double* __restrict__ Vinv,
                  double* __restrict__ S, int ld) {
@@ -283,11 +283,13 @@ k_schur_pairlist(long long n_ent, long long chunk, const uint32_t* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 9; ++q) a[q] = 0.0;
     };
+    uint32_t nk = begin + lane < end ? key[begin + lane] : kNone, nv = begin + lane < end ? val[begin + lane] : 0u;
     for (long long base = begin; base < end; base += 32) {
-        const long long e = base + lane;
-        const bool act = e < end;
-        const uint32_t k = act ? key[e] : kNone;
-        const uint32_t v = act ? val[e] : 0u;
+        const uint32_t k = nk, v = nv;
+        const bool act = base + lane < end;
+        const long long en = base + 32 + lane;                     // next step's entry: in flight during this step's arithmetic
+        nk = en < end ? key[en] : kNone;
+        nv = en < end ? val[en] : 0u;
         const uint32_t k_lo = __shfl_sync(0xffffffffu, k, 0);                 // lane 0 is always active
         const bool uniform = __ballot_sync(0xffffffffu, k == k_lo || !act) == 0xffffffffu;
         if (uniform) {
