@@ -414,7 +414,7 @@ __device__ __forceinline__ void ring_issue(WarpSlot* slot, uint64_t* bar, int64_
     tma_load(slot->oy, oy + k0, c4 * 8u, bar);
 }
 
-template <int MINB>
+template <int MINB, bool DUAL_GATHER>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_lm_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
                   const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
@@ -468,6 +468,13 @@ k_ba_lm_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restri
 #pragma unroll
         for (int i = 0; i < kQuad; ++i)
             if (k0 + i >= end) lm[i] = -1;
+        // the quad's landmark trig rows are gathered up front, both at once (a quad spans at most two landmarks unless a
+        // landmark has fewer than 3 observations): the profile of k_ba_lm_pass4 shows 13 % of all stall samples on the first
+        // use of a gather issued inside the serial loop below
+        // (DUAL_GATHER costs 8 more live registers: 60 bytes of spills at the 80-register cap - to be decided by measurement)
+        const int lmA = lm[0] >= 0 ? lm[0] : 0, lmB = lm[kQuad - 1] >= 0 ? lm[kQuad - 1] : lmA;
+        LmTrig ltA = {0, 1, 0, 1}, ltB = {0, 1, 0, 1};
+        if (DUAL_GATHER) { ltA = lm_trig[lmA]; ltB = lm_trig[lmB]; }
         double rx[kQuad], ry[kQuad];
         int cur = -1;
         LmTrig lt = {0, 1, 0, 1};
@@ -479,7 +486,8 @@ k_ba_lm_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restri
             if (lm[i] != cur) {
                 if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
                 cur = lm[i];
-                lt = lm_trig[cur];
+                if (DUAL_GATHER) lt = cur == lmA ? ltA : cur == lmB ? ltB : lm_trig[cur];
+                else lt = lm_trig[cur];
                 vtt = vtp = vpp = glt = glp = 0.0;
             }
             const double2* t = reinterpret_cast<const double2*>(smem + (size_t)cam[i] * 6);
@@ -722,15 +730,18 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     const size_t smA = ba->cam_smem ? (size_t)ba->n_pose * 6 * sizeof(double) : 0;
     const int64_t nA = ba->lmo_hi - (ba->lmo_lo & ~(int64_t)3);
     // opt-in experiment: per-warp copy-engine rings (see k_ba_lm_pass_ring); needs 16-byte aligned slice starts
-    static const bool ring = getenv("PTZBA_FUSED_RING") != nullptr;
+    static const char* ring_env = getenv("PTZBA_FUSED_RING");          // "1": rings; "2": rings + up-front dual landmark gather
+    static const bool ring = ring_env != nullptr;
+    static const bool ring_dual = ring && ring_env[0] == '2';
     const size_t smRing = sizeof(WarpSlot) * kWarps * kRing;
     const bool ringA = ring && ba->cam_smem && ba->lmo_lo % 4 == 0 && smRing + smA <= 200 * 1024;
     const bool ringB = ring && ba->cmo_lo % 4 == 0;
     if (ring && ba->grid_lm_ring == 0) {
         int pa = 1, pb = 1;
         if (ringA) {
-            CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass_ring<kLmMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smRing + smA)));
-            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass_ring<kLmMinB>, kFusedThreads, smRing + smA));
+            CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass_ring<kLmMinB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smRing + smA)));
+            CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass_ring<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smRing + smA)));
+            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass_ring<kLmMinB, false>, kFusedThreads, smRing + smA));
         }
         CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_cam_pass_ring<kCamMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smRing));
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass_ring<kCamMinB>, kFusedThreads, smRing));
@@ -741,9 +752,16 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         int64_t chunkA = (nA + ba->grid_lm_ring - 1) / ba->grid_lm_ring;
         chunkA = (chunkA + kGroup - 1) / kGroup * kGroup;
         const int gridA = (int)((nA + chunkA - 1) / chunkA);
-        k_ba_lm_pass_ring<kLmMinB><<<gridA, kFusedThreads, smRing + smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
-                                                                            ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u,
-                                                                            ba->v, d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        if (ring_dual)
+            k_ba_lm_pass_ring<kLmMinB, true><<<gridA, kFusedThreads, smRing + smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p,
+                                                                                      ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                                                                                      ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl,
+                                                                                      ba->acc.cost);
+        else
+            k_ba_lm_pass_ring<kLmMinB, false><<<gridA, kFusedThreads, smRing + smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p,
+                                                                                       ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                                                                                       ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl,
+                                                                                       ba->acc.cost);
         KERNEL_POST(ctx);
     } else if (nA > 0) {
         int64_t chunkA = (nA + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
