@@ -158,7 +158,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // L2 REDs, TMA/mbarrier tile rings, one launch with two CTA roles, one pass with a static per-tile keyframe sort) are
 // tabulated in DESIGN.md section 5 with their ncu counters.
 // ---------------------------------------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, bool LOOKAHEAD2 = false>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_cam_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
               const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
@@ -191,13 +191,21 @@ k_ba_cam_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
     double ox = 0, oy = 0;
     LmTrig lt = {0, 1, 0, 1};
     if (k < end) { cam = c_cam[k]; lm = c_lm[k]; ox = c_ox[k]; oy = c_oy[k]; lt = lm_trig[lm]; }
+    // LOOKAHEAD2 (opt-in experiment PTZBA_CAM_LOOKAHEAD, not yet run on hardware): the landmark index is requested TWO steps
+    // ahead, so that the dependent trig gather of the next step can issue at once - 29 % of this kernel's stall samples sit on
+    // that gather's address waiting for an index requested one step earlier (profiles/r1_ncu_fused_source_stalls.txt)
+    int lm_ahead = 0;
+    if (LOOKAHEAD2 && k + kFusedThreads < end) lm_ahead = c_lm[k + kFusedThreads];
     for (int64_t base = begin; base < end; base += kFusedThreads) {
         const bool act = k < end;
         const int64_t kn = k + kFusedThreads;
         int ncam = -1, nlm = 0;
         double nox = 0, noy = 0;
         LmTrig nlt = {0, 1, 0, 1};
-        if (kn < end) { ncam = c_cam[kn]; nlm = c_lm[kn]; nox = c_ox[kn]; noy = c_oy[kn]; nlt = lm_trig[nlm]; }
+        if (LOOKAHEAD2) {
+            if (kn < end) { nlm = lm_ahead; nlt = lm_trig[nlm]; ncam = c_cam[kn]; nox = c_ox[kn]; noy = c_oy[kn]; }
+            if (kn + kFusedThreads < end) lm_ahead = c_lm[kn + kFusedThreads];
+        } else if (kn < end) { ncam = c_cam[kn]; nlm = c_lm[kn]; nox = c_ox[kn]; noy = c_oy[kn]; nlt = lm_trig[nlm]; }
         const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
         const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
         const bool uniform = same == 0xffffffffu;
@@ -781,6 +789,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     // (each kernel is a single wave; the second one fills the SMs the first one's finishing CTAs leave idle)
     const int64_t nB = ba->cmo_hi - ba->cmo_lo;
     static const bool concurrent = getenv("PTZBA_SERIAL_PASSES") == nullptr;
+    static const bool cam_lookahead = getenv("PTZBA_CAM_LOOKAHEAD") != nullptr;
     if (nB > 0) {
         int64_t chunkB = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
         chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
@@ -794,6 +803,10 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
             k_ba_cam_pass_ring<kCamMinB><<<gridR, kFusedThreads, smRing, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkR, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p,
                                                                              ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v,
                                                                              ba->acc.U, ba->acc.gc);
+        } else if (cam_lookahead) {
+            k_ba_cam_pass<kCamMinB, true><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p,
+                                                                          ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U,
+                                                                          ba->acc.gc);
         } else {
             k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
                                                                     ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
