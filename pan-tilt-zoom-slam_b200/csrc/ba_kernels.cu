@@ -381,7 +381,7 @@ k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
 constexpr int kGroup = 32 * kQuad;               // observations per warp step
 constexpr int kRing = 2;                         // slots per warp
 constexpr int kWarps = kFusedThreads / 32;
-struct __align__(128) WarpSlot { int cam[kGroup]; int lm[kGroup]; double ox[kGroup]; double oy[kGroup]; };   // 3 KB
+struct __align__(16) WarpSlot { int cam[kGroup]; int lm[kGroup]; double ox[kGroup]; double oy[kGroup]; };   // 3 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -428,7 +428,7 @@ k_ba_lm_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restri
                   const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
                   const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
                   double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
-    extern __shared__ __align__(128) unsigned char dyn[];
+    extern __shared__ __align__(16) unsigned char dyn[];      // cp.async.bulk needs 16-byte aligned destinations
     WarpSlot* slots = reinterpret_cast<WarpSlot*>(dyn);                                              // [kWarps][kRing]
     double* smem = reinterpret_cast<double*>(dyn + sizeof(WarpSlot) * kWarps * kRing);               // keyframe trig, 48 B each
     __shared__ uint64_t full[kWarps][kRing];
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_cam_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
                    const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
                    const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
-    extern __shared__ __align__(128) unsigned char dyn[];
+    extern __shared__ __align__(16) unsigned char dyn[];      // cp.async.bulk needs 16-byte aligned destinations
     WarpSlot* slots = reinterpret_cast<WarpSlot*>(dyn);
     __shared__ uint64_t full[kWarps][kRing];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
