@@ -259,7 +259,7 @@ __device__ __forceinline__ void commit_lm(double* __restrict__ gV, double* __res
     atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
 }
 
-template <int MINB, bool CAM_SMEM>
+template <int MINB, bool CAM_SMEM, bool IDX_AHEAD = false>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
               const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
@@ -281,13 +281,35 @@ k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
     if (end > hi) end = hi;
     const double k1 = PTZ_DEG2RAD;
     double cost = 0.0;
+    // IDX_AHEAD (opt-in experiment PTZBA_LM_IDX_AHEAD, not yet run on hardware): the two index vectors of the NEXT iteration are
+    // requested one iteration early (8 registers), so that an iteration starts with its indices present and its trig gather /
+    // keyframe rows can go out at once; the observation vectors are still requested at the top and are only needed after the
+    // projection.  19 % of this kernel's stall samples sit on the first use of the streamed indices.
+    int4 c4n = make_int4(0, 0, 0, 0), l4n = make_int4(0, 0, 0, 0);
+    if (IDX_AHEAD) {
+        const int64_t kf = begin + (int64_t)tid * kQuad;
+        if (kf >= lo && kf + kQuad <= end) {
+            c4n = __ldg(reinterpret_cast<const int4*>(s_cam + kf));
+            l4n = __ldg(reinterpret_cast<const int4*>(s_lm + kf));
+        }
+    }
     for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
         const int64_t k0 = base + (int64_t)tid * kQuad;
         int cam[kQuad], lm[kQuad];
         double ox[kQuad], oy[kQuad];
         if (k0 >= lo && k0 + kQuad <= end) {
-            const int4 c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
-            const int4 l4 = __ldg(reinterpret_cast<const int4*>(s_lm + k0));
+            int4 c4, l4;
+            if (IDX_AHEAD) {
+                c4 = c4n; l4 = l4n;
+                const int64_t kn = k0 + (int64_t)kFusedThreads * kQuad;
+                if (kn + kQuad <= end) {
+                    c4n = __ldg(reinterpret_cast<const int4*>(s_cam + kn));
+                    l4n = __ldg(reinterpret_cast<const int4*>(s_lm + kn));
+                }
+            } else {
+                c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
+                l4 = __ldg(reinterpret_cast<const int4*>(s_lm + k0));
+            }
             const D4 x4 = *reinterpret_cast<const D4*>(s_ox + k0);
             const D4 y4 = *reinterpret_cast<const D4*>(s_oy + k0);
             cam[0] = c4.x; cam[1] = c4.y; cam[2] = c4.z; cam[3] = c4.w;
@@ -775,7 +797,15 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         int64_t chunkA = (nA + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
         chunkA = (chunkA + 127) / 128 * 128;
         const int gridA = (int)((nA + chunkA - 1) / chunkA);
-        if (ba->cam_smem)
+        static const bool idx_ahead = getenv("PTZBA_LM_IDX_AHEAD") != nullptr;
+        if (ba->cam_smem && idx_ahead) {
+            if (smA > 40 * 1024)
+                CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass4<kLmMinB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+            k_ba_lm_pass4<kLmMinB, true, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p,
+                                                                                ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
+                                                                                ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl,
+                                                                                ba->acc.cost);
+        } else if (ba->cam_smem)
             k_ba_lm_pass4<kLmMinB, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
                                                                     ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
                                                                     d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
