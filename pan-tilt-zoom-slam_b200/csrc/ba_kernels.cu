@@ -391,7 +391,7 @@ k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENT, opt-in (PTZBA_FUSED_RING=1), NOT the default and not yet timed on hardware: the same two passes with the four
+// EXPERIMENT, opt-in (PTZBA_FUSED_RING=1), NOT the default; parity-green on small problems on a B200, not yet timed: the same two passes with the four
 // observation streams fed by the copy engine (cp.async.bulk + mbarrier) into PER-WARP two-slot shared-memory rings.
 // Motivation: the default kernels are bound by exposed load latency of a few resident warps; register
 // prefetch costs occupancy, and the earlier CTA-wide TMA ring (one __syncthreads per 1024-observation tile) put all warps

@@ -212,7 +212,7 @@ k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const in
     }
 }
 
-// ---- EXPERIMENT, opt-in (PTZBA_SCHUR_PAIRLIST=1), off by default and not yet run on hardware -------------------------------
+// ---- EXPERIMENT, opt-in (PTZBA_SCHUR_PAIRLIST=1), off by default; parity-green on the small solver tests on a B200, not yet timed ----
 // k_schur_pairs issues one FP64 RED per block entry per observation pair (189 M at 256 x 100k x 2M) and sits at the L2
 // atomic rate.  The sparsity pattern is static, so the pairs can be listed once per problem, KEYFRAME-PAIR MAJOR:
 //   entry = (key = max_cam << 16 | min_cam, val = landmark | duplicate flag << 31), radix-sorted by key.
