@@ -16,9 +16,11 @@ Metric (BASELINE.json): residual + Jacobian + normal-equation assembly, OBSERVAT
   cpu_baseline  oracle/ptz_oracle_c.c (plain-C port of the reference algorithm, all host threads) on the same workload.
 
 `--impl reference` times only that CPU port (the reference itself is pure Python and cannot travel to the GPU box).
-Multi-GPU (torchrun, one rank per GPU): observations are sharded by keyframe, every rank runs the fused pass on its
-shard and the landmark blocks are summed with an NCCL all-reduce inside the timed region (weak scaling: each rank
-holds a config-3 sized shard).
+Multi-GPU (torchrun, one rank per GPU): ONE problem of the named workload, its observations sharded by keyframe
+(dist.shard_by_keyframe); every rank runs the fused pass on its shard and the blocks of the landmarks observed by more than
+one rank are summed with ncclAllReduce INSIDE the timed region (strong scaling: `value` = observations of the whole
+problem / max-over-ranks time).  After the timed loop every rank checks its blocks against a single-GPU pass over the whole
+problem (`parity`), and the LM iteration / solve of the same problem is timed with the landmark-partitioned distributed solver.
 """
 import argparse
 import json
@@ -146,9 +148,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "ba_residual_jacobian_normal_eq_obs_per_s", "value": r["value"], "unit": "obs/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s keyframe BA: %d keyframes x %d ray landmarks x %d observations per GPU" %
-                   (args.workload, fb.n_pose, fb.n_landmark, fb.n_obs),
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s keyframe BA: %d keyframes x %d ray landmarks x %d observations%s" %
+                   (args.workload, fb.n_pose, fb.n_landmark, fb.n_obs,
+                    " per GPU" if args.gpus == 1 else ", ONE problem sharded by keyframe over %d GPUs" % args.gpus),
                    "parallelism": "host threads (plain-C port of the reference's pass, oracle/ptz_oracle_c.c)",
                    "step": "one fused residual+Jacobian+normal-equation pass over the whole workload"},
         "cpu_baseline": {"value": r["value"], "unit": "obs/s", "cores": r["cores"], "kind": "port", "sample": sample},
@@ -215,32 +218,28 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
-    fb = make_workload(args.workload, rank)
+    fb_full = make_workload(args.workload, 0)            # the same problem on every rank
     u, v = synth.PP_U, synth.PP_V
+    ref_pose = fb_full.ptz_init[0]
+    x0 = fb_full.x0()
+    kf_range = (0, fb_full.n_pose)
     if world > 1:
-        # weak scaling: ONE global problem made of `world` pan sectors, sharded by keyframe.  Rank r owns keyframes
-        # [r*N, (r+1)*N) and its sector's landmarks [r*M, (r+1)*M); only global keyframe 0 is the fixed reference pose.
-        # The packed blocks of the whole problem (9*N*world + 5*M*world doubles) are all-reduced every pass.
-        N1, M1 = fb.n_pose, fb.n_landmark
-        poses = np.tile(np.array([0.0, 0.0, 2000.0]), (N1 * world, 1))
-        rays = np.zeros((M1 * world, 2))
-        poses[rank * N1:(rank + 1) * N1] = fb.ptz_init
-        rays[rank * M1:(rank + 1) * M1] = fb.rays_init
-        g_ref = poses[0].copy()
-        g_x0 = np.concatenate([poses[1:].ravel(), rays.ravel()])
-        fb = synth.FlatBA((fb.cam_idx + rank * N1).astype(np.int32), (fb.lm_idx + rank * M1).astype(np.int32), fb.obs_xy,
-                          poses, rays, poses, rays)
-        ref_pose, x0 = g_ref, g_x0
+        from ptz_slam_b200 import dist as pdist
+        cam_s, lm_s, xy_s, kf_range = pdist.shard_by_keyframe(fb_full.cam_idx, fb_full.lm_idx, fb_full.obs_xy, fb_full.n_pose, rank, world)
+        fb = synth.FlatBA(cam_s, lm_s, xy_s, fb_full.ptz_gt, fb_full.rays_gt, fb_full.ptz_init, fb_full.rays_init)
     else:
-        ref_pose = fb.ptz_init[0]
-        x0 = fb.x0()
+        fb = fb_full
+    lm_touched = int(np.unique(fb.lm_idx).size)
+    abytes = algorithmic_bytes(fb.n_obs, lm_touched, kf_range[1] - kf_range[0])      # this rank's share of the pass
     R = args.replicas
+    if R <= 0:      # enough replicas of the rank's arrays that a pass never finds them in the 126 MB L2
+        R = max(4, int(np.ceil(2.2 * 126e6 / max(abytes, 1))))
     probs = [BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v, ctx=ctx) for _ in range(R)]
     x_dev = [torch.from_numpy(x0).cuda() for _ in range(R)]
     r_dev = [torch.empty(2 * fb.n_obs, dtype=torch.float64, device="cuda") for _ in range(R)]
     comm = None
+    n_shared = 0
     if world > 1:
-        from ptz_slam_b200 import dist as pdist
         comm = pdist.Communicator(ctx, rank, world)
         n_shared = [comm.setup_exchange(p) for p in probs][0]
 
@@ -281,8 +280,36 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    total_obs = fb.n_obs * world
+    total_obs = fb_full.n_obs
     value = total_obs * args.steps / (ms * 1e-3)
+
+    # ---- parity of the sharded pass: every rank against a single-GPU pass over the WHOLE problem ----------------------
+    parity = None
+    if world > 1:
+        import ctypes as _ct
+        N, M = fb.n_pose, fb.n_landmark
+        device_step(0)
+        U, gc, V, gl = np.empty((N, 6)), np.empty((N, 3)), np.empty((M, 3)), np.empty((M, 2))
+        cst = _ct.c_double()
+        ctx.check(ctx.lib.ptzba_ba_get_blocks(probs[0].handle, _lib.ptr(U), _lib.ptr(gc), _lib.ptr(V), _lib.ptr(gl), _ct.byref(cst)))
+        whole = BA.BAProblem(fb_full.n_pose, fb_full.n_landmark, fb_full.cam_idx, fb_full.lm_idx, fb_full.obs_xy, u, v, ctx=ctx)
+        xw = torch.from_numpy(x0).cuda()
+        whole.normal_equations_device(xw.data_ptr(), ref_pose)
+        U1, gc1, V1, gl1 = np.empty((N, 6)), np.empty((N, 3)), np.empty((M, 3)), np.empty((M, 2))
+        c1 = _ct.c_double()
+        ctx.check(ctx.lib.ptzba_ba_get_blocks(whole.handle, _lib.ptr(U1), _lib.ptr(gc1), _lib.ptr(V1), _lib.ptr(gl1), _ct.byref(c1)))
+        whole.close()
+        own = slice(max(kf_range[0], 1), kf_range[1])
+        mine = np.unique(fb.lm_idx)
+        rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) if a.size else 0.0
+        d = [rel(U[own], U1[own]), rel(gc[own], gc1[own]), rel(V[mine], V1[mine]), rel(gl[mine], gl1[mine]),
+             abs(cst.value - c1.value) / c1.value]
+        t = torch.tensor(d, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        d = [float(q) for q in t.tolist()]
+        parity = {"vs": "single-GPU fused pass over the whole problem, same x", "max_rel_diff": {"U": d[0], "g_c": d[1], "V": d[2], "g_l": d[3], "cost": d[4]},
+                  "tolerance": 1e-9, "checked": "every rank: U/g_c of its keyframes, V/g_l of the landmarks it observes, the cost"}
+        assert max(d) < 1e-9, parity
 
     # ---- kernel-only duration of the fused kernel (events bracketing each launch) -> roofline ----------------------
     import ctypes
@@ -293,7 +320,6 @@ def run_ours(args):
     ctx.check(ctx.lib.ptzba_profile_end(ctx.handle, ctypes.byref(n_l), ctypes.byref(tot)))
     kernel_ms = tot.value / max(n_l.value, 1)
     peaks, peak_kind = measured_peaks()
-    abytes = algorithmic_bytes(fb.n_obs, fb.n_landmark // world, fb.n_pose // world)
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "fused_traffic.json")
@@ -306,7 +332,7 @@ def run_ours(args):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                "kernel": "fused pass (k_ba_lm_pass4 + k_ba_cam_pass)", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
+                "kernel": "fused pass (k_ba_lm_pass + k_ba_cam_pass)", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
 
     # ---- e2e: HOST (pinned) buffers through the C-ABI, copies inside the timed region ------------------------------
     N, M = fb.n_pose, fb.n_landmark
@@ -355,7 +381,7 @@ def run_ours(args):
         # list (replicated data) and visits its landmark / keyframe-major slices (partitioned work); partial blocks, the
         # reduced camera system, right-hand sides and landmark steps are all-reduced inside the library
         from ptz_slam_b200 import dist as pdist
-        g = make_workload(args.workload, 0)
+        g = fb_full
         gp = BA.BAProblem(g.n_pose, g.n_landmark, g.cam_idx, g.lm_idx, g.obs_xy, u, v, ctx=ctx)
         lm_range, cm_range = pdist.solve_partition(g.lm_idx, g.n_landmark, world)[rank]
         gp.set_partition(rank, world, lm_range, cm_range)
@@ -375,11 +401,28 @@ def run_ours(args):
         xs, rep = gp.solve(gx0, gref, ftol=1e-4)
         solve_s = time.perf_counter() - t0
         gp.close()
+        # parity of the distributed solve: the same problem solved on this rank's GPU alone
+        one = BA.BAProblem(g.n_pose, g.n_landmark, g.cam_idx, g.lm_idx, g.obs_xy, u, v, ctx=ctx)
+        x1, rep1 = one.solve(gx0, gref, ftol=1e-4)
+        one.close()
+        nc = 3 * (g.n_pose - 1)
+        dx = np.abs(xs - x1)
+        ang = float(np.radians(max(dx[0:nc:3].max(), dx[1:nc:3].max(), dx[nc:].max())))
+        foc = float(dx[2:nc:3].max())
+        t = torch.tensor([ang, foc, float(np.abs(xs).sum())], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        solve_parity = {"vs": "single-GPU solve of the same problem (ftol 1e-4)", "max_angle_diff_rad": float(tmax[0]), "max_focal_diff_px": float(tmax[1]),
+                        "status": [rep["status"], rep1["status"]], "nfev": [rep["nfev"], rep1["nfev"]],
+                        "x_identical_on_all_ranks": bool(float(tmax[2]) == float(tmin[2])),
+                        "tolerance": "1e-6 rad, 1e-3 px (BASELINE.json)"}
+        assert solve_parity["max_angle_diff_rad"] < 1e-6 and solve_parity["max_focal_diff_px"] < 1e-3 and solve_parity["x_identical_on_all_ranks"], solve_parity
         lm = {"lm_iters_per_s": 1.0 / lm_s, "ms_per_lm_iter": 1e3 * lm_s, "lm_scaling": "strong",
               "lm_workload": "%s: ONE problem of %d keyframes x %d landmarks x %d observations solved by %d ranks" %
                              (args.workload, g.n_pose, g.n_landmark, g.n_obs, world),
               "solve": {"ftol": 1e-4, "ms": 1e3 * solve_s, "nfev": rep["nfev"], "njev": rep["njev"], "status": rep["status"],
-                        "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]}}
+                        "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]},
+              "solve_parity": solve_parity}
 
     # ---- batched EKF tracking (config 4 shape, bounded batch): sequence-frames/s and matched observations/s ----------
     ekf = None
@@ -410,18 +453,23 @@ def run_ours(args):
         line = {
             "metric": "ba_residual_jacobian_normal_eq_obs_per_s", "value": value, "unit": "obs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s keyframe BA: %d keyframes x %d ray landmarks x %d observations per GPU" %
-                       (args.workload, fb.n_pose // world, fb.n_landmark // world, fb.n_obs),
-                       "l2": "rotating over %d replicas of the observation arrays (%.0f MB per pass > 126 MB L2 in total)" %
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s keyframe BA: %d keyframes x %d ray landmarks x %d observations%s" %
+                       (args.workload, fb_full.n_pose, fb_full.n_landmark, fb_full.n_obs,
+                        " per GPU" if world == 1 else ", ONE problem sharded by keyframe over %d GPUs" % world),
+                       "l2": "rotating over %d replicas of the rank's observation arrays (%.0f MB per pass and rank: more than the 126 MB L2 in total)" %
                              (R, abytes / 1e6),
-                       "parallelism": ("keyframe-sharded observations, 1 rank per GPU; every pass ends with one ncclAllReduce of the cost and of the "
-                                       "blocks of the landmarks observed by more than one rank (%d of %d in this problem: the pan sectors are "
-                                       "disjoint); all other blocks are complete on the rank that owns them" %
-                                       (n_shared, fb.n_landmark)) if world > 1 else "1 GPU",
-                       "step": "one fused residual+Jacobian+normal-equation pass (k_set_params + k_ba_lm_pass4 + k_ba_cam_pass)"},
+                       "parallelism": ("keyframe-sharded observations (dist.shard_by_keyframe), 1 rank per GPU; every timed pass ends with one ncclAllReduce "
+                                       "of the cost and of the V/g_l blocks of the landmarks observed by more than one rank (n_shared = %d of %d landmarks, "
+                                       "%.2f MB per rank and pass); U/g_c are complete on the rank that owns the keyframe" %
+                                       (n_shared, fb.n_landmark, (1 + 5 * n_shared) * 8 / 1e6)) if world > 1 else "1 GPU",
+                       "n_shared": int(n_shared),
+                       "step": "one fused residual+Jacobian+normal-equation pass (k_set_params + k_ba_lm_pass + k_ba_cam_pass)%s" %
+                               (" + exchange (k_pack_shared, ncclAllReduce, k_unpack_shared)" if world > 1 else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity:
+            line["parity"] = parity
         if lm:
             line.update(lm)
         if ekf:
@@ -442,7 +490,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--replicas", type=int, default=4)
+    ap.add_argument("--replicas", type=int, default=0, help="problem replicas the passes rotate over (0 = enough to exceed the L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-ekf", action="store_true")

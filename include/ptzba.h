@@ -175,6 +175,16 @@ int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* reference_pos
 int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, const double* reference_pose3, double alpha,
                           double* out_pred_reduction, double* out_cost_trial);
 
+/* tuning knobs of one problem.  PTZBA_OPT_SCHUR_MODE: how the reduced camera system S = U - sum_l W V^-1 W^T is formed -
+ * AUTO (the keyframe-pair-major pair list, built once per problem; falls back to PER_LANDMARK above 65535 keyframes or
+ * 2^31 observation pairs), PER_LANDMARK (one warp per landmark, one FP64 RED per block entry per observation pair; no
+ * extra memory), PAIR_LIST (same as AUTO). */
+#define PTZBA_OPT_SCHUR_MODE 1
+#define PTZBA_SCHUR_AUTO 0
+#define PTZBA_SCHUR_PER_LANDMARK 1
+#define PTZBA_SCHUR_PAIR_LIST 2
+int ptzba_ba_set_option(ptzba_ba* ba, int option, int value);
+
 /* multi-GPU: observations are sharded by keyframe across ranks (each rank creates its ptzba_ba from its shard with
  * the GLOBAL n_pose/n_landmark); landmark blocks and the reduced camera system are summed with ncclAllReduce.
  * unique_id: the 128-byte ncclUniqueId produced by rank 0 (ptzba_comm_unique_id) and distributed by the host

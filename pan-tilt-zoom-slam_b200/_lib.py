@@ -13,8 +13,11 @@ import numpy as np
 
 HOST, DEVICE = 0, 1
 JAC_ANALYTIC, JAC_CENTRAL_FD = 0, 1
+OPT_SCHUR_MODE = 1
+SCHUR_AUTO, SCHUR_PER_LANDMARK, SCHUR_PAIR_LIST = 0, 1, 2
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libptzba.so")
+# PTZBA_LIBRARY names another build of the same library (kernel tuning experiments); it is still this library or nothing
+_LIB_PATH = os.environ.get("PTZBA_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libptzba.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -82,6 +85,7 @@ SIGNATURES = {
     "ptzba_ba_setup_exchange": (_I, [_P, _P]),
     "ptzba_ba_set_partition": (_I, [_P, _I, _I, _I, _I, _L, _L]),
     "ptzba_ba_get_blocks": (_I, [_P, _P, _P, _P, _P, _P]),
+    "ptzba_ba_set_option": (_I, [_P, _I, _I]),
 }
 
 _lock = threading.Lock()

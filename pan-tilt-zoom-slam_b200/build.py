@@ -9,7 +9,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(CSRC, "libptzba.so")
+# PTZBA_BUILD_TAG=<tag> (with PTZBA_EXTRA_NVCC_FLAGS) builds a tuning variant beside the default library:
+# objects in csrc/build_<tag>/, output csrc/libptzba_<tag>.so, selected at run time with PTZBA_LIBRARY=<path>
+TAG = os.environ.get("PTZBA_BUILD_TAG", "")
+OBJDIR = os.path.join(CSRC, "build_" + TAG) if TAG else CSRC
+OUT = os.path.join(CSRC, "libptzba_%s.so" % TAG if TAG else "libptzba.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("PTZBA_EXTRA_NVCC_FLAGS", "").split()
@@ -33,7 +37,8 @@ def _stale(target, deps):
 
 
 def _compile(src, force, verbose):
-    obj = src[:-3] + ".o"
+    os.makedirs(OBJDIR, exist_ok=True)
+    obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
     if not force and not _stale(obj, [src] + headers()):
         return obj, ""
     cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]

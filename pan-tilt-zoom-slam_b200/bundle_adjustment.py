@@ -49,6 +49,10 @@ class BAProblem:
         self.ctx.check(self.ctx.lib.ptzba_ba_set_partition(self.handle, int(rank), int(world_size), int(lm_range[0]),
                                                            int(lm_range[1]), int(cm_range[0]), int(cm_range[1])))
 
+    def set_option(self, option, value):
+        """Tuning knobs (include/ptzba.h: PTZBA_OPT_*), e.g. set_option(_lib.OPT_SCHUR_MODE, _lib.SCHUR_PER_LANDMARK)."""
+        self.ctx.check(self.ctx.lib.ptzba_ba_set_option(self.handle, int(option), int(value)))
+
     def close(self):
         if getattr(self, "handle", None):
             self.ctx.lib.ptzba_ba_destroy(self.handle)

@@ -28,9 +28,12 @@ struct ptzba_ba {
     DevBuf<double> s_ox, s_oy;
     DevBuf<int32_t> lm_ptr;         // [M+1] CSR offsets into the sorted arrays
     // second copy in keyframe-major order (landmark ascending inside a keyframe) for the keyframe pass of the fused
-    // pass: keyframe blocks accumulate in registers there
-    DevBuf<int32_t> c_cam, c_lm;
+    // pass: keyframe blocks accumulate in registers there.
+    // the run of every keyframe starts at a multiple of 128 entries (padding: landmark id -1); iter_cam[it] = keyframe of
+    // entries [128 it, 128 it + 128)
+    DevBuf<int32_t> c_lm, iter_cam;
     DevBuf<double> c_ox, c_oy;
+    int n_cam_iter = 0;
     // current parameters
     DevBuf<CamTrig> cam_trig;       // [N]
     DevBuf<LmTrig> lm_trig;         // [M]
@@ -46,14 +49,16 @@ struct ptzba_ba {
     DevBuf<double> sol_c, sol_l, sol2_c, sol2_l;
     DevBuf<double> Vinv;                    // [M*3] (V + alpha D_l^2)^-1 packed
     DevBuf<double> scal;                    // small device scalar block for reductions
+    DevBuf<double> sums_part;               // per-block partial sums of the deterministic k_sums
+    DevBuf<unsigned> sums_ticket;
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int grid_lm_pass = 0, grid_cam_pass = 0;   // one wave of resident CTAs per pass
-    // opt-in experiment (PTZBA_SCHUR_PAIRLIST): keyframe-pair-major list of observation pairs, built at the first solve
+    // keyframe-pair-major list of observation pairs of this rank's landmark slice, built at the first solve
+    int schur_mode = 0;             // PTZBA_SCHUR_* (ptzba_ba_set_option)
     DevBuf<uint32_t> pl_key, pl_val;
     long long pl_n = 0;
     bool pl_ready = false;
-    int grid_lm_ring = 0, grid_cam_ring = 0;   // same for the opt-in copy-engine ring variant (PTZBA_FUSED_RING), set on first use
     int touch_cam_lo = 0, touch_cam_hi = 0, touch_lm_lo = 0, touch_lm_hi = 0;   // id ranges the observations touch
     // keyframe-sharded mode: compact exchange of the landmarks observed by more than one rank (ptzba_ba_setup_exchange)
     bool exchange_ready = false;
@@ -65,7 +70,7 @@ struct ptzba_ba {
     int part_rank = 0, part_world = 1;
     int lm_lo = 0, lm_hi = 0;                  // landmark slice
     int64_t lmo_lo = 0, lmo_hi = 0;            // its observations in the landmark-major list
-    int64_t cmo_lo = 0, cmo_hi = 0;            // slice of the keyframe-major list
+    int cit_lo = 0, cit_hi = 0;                // slice of the padded keyframe-major list, in iterations of 128 entries
     bool cam_smem = true;           // keyframe trig table fits in shared memory
     bool acc_zeroed = false;        // the arena was cleared by ba_set_params(..., zero_acc = true)
     bool arena_foreign = false;     // a whole-arena all-reduce wrote blocks outside the touched id ranges

@@ -19,10 +19,10 @@ namespace {
 
 constexpr int kFusedThreads = 256;
 #ifndef PTZBA_LM_MINB
-#define PTZBA_LM_MINB 3
+#define PTZBA_LM_MINB 2
 #endif
 #ifndef PTZBA_CAM_MINB
-#define PTZBA_CAM_MINB 3
+#define PTZBA_CAM_MINB 2
 #endif
 constexpr int kLmMinB = PTZBA_LM_MINB, kCamMinB = PTZBA_CAM_MINB;   // resident CTAs per SM the two passes are compiled for
 
@@ -53,15 +53,18 @@ __global__ void k_gather_obs(int64_t n, const int32_t* __restrict__ perm, const 
     }
 }
 
-// keyframe-major gather: position k takes landmark-major position perm[k]
-__global__ void k_gather_cm(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ s_lm,
-                            const double* __restrict__ s_ox, const double* __restrict__ s_oy, int32_t* __restrict__ c_lm,
-                            double* __restrict__ c_ox, double* __restrict__ c_oy) {
+// keyframe-major scatter into the padded layout: sorted position k (keyframe cam[k], landmark-major position perm[k]) goes to
+// pad[cam] + (k - ptr[cam])
+__global__ void k_scatter_cm(int64_t n, const int32_t* __restrict__ perm, const int32_t* __restrict__ cam, const int32_t* __restrict__ ptr,
+                             const int32_t* __restrict__ pad, const int32_t* __restrict__ s_lm, const double* __restrict__ s_ox,
+                             const double* __restrict__ s_oy, int32_t* __restrict__ c_lm, double* __restrict__ c_ox,
+                             double* __restrict__ c_oy) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t p = perm[k];
-        c_lm[k] = s_lm[p];
-        c_ox[k] = s_ox[p];
-        c_oy[k] = s_oy[p];
+        const int32_t p = perm[k], c = cam[k];
+        const int64_t d = (int64_t)pad[c] + (k - ptr[c]);
+        c_lm[d] = s_lm[p];
+        c_ox[d] = s_ox[p];
+        c_oy[d] = s_oy[p];
     }
 }
 
@@ -82,7 +85,7 @@ __global__ void k_lm_ptr(int n_lm, int64_t n_obs, const int32_t* __restrict__ s_
             const int64_t mid = (lo2 + hi2) >> 1;
             if (s_lm[mid] <= l) lo2 = mid + 1; else hi2 = mid;
         }
-        atomicMax(max_degree, (int)(lo2 - lo));
+        if (max_degree) atomicMax(max_degree, (int)(lo2 - lo));
     }
 }
 
@@ -149,26 +152,42 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // The fused pass = two coherent passes; every sum is formed where its operands are adjacent, nothing is scattered.
-//   k_ba_lm_pass4  landmark-major: residual (written), cost, per-landmark V / g_l (thread-serial over 4 consecutive
-//                  observations, then a warp-segmented reduction of each thread's last run)
-//   k_ba_cam_pass  keyframe-major: per-keyframe U / g_c live in registers across the whole chunk
-// Why not one pass: FP64 has no native shared-memory atomic add and L2 REDs cost ~3.9 ns per sector chip-wide, so
-// whichever side is scattered costs more than re-streaming 24 B/observation and re-evaluating the geometry.  The
+//   k_ba_lm_pass   landmark-major: residual (written), cost, per-landmark V / g_l
+//   k_ba_cam_pass  keyframe-major: per-keyframe U / g_c live in registers across a whole run of the keyframe
+// Both kernels give every thread FOUR consecutive observations (one 128-bit index load and one 256-bit load per
+// stream), evaluate the four projections as four independent FP64 chains without a data-dependent branch between
+// them (ILP 4: the round-1 kernels were dependency-latency bound with one serial, branchy chain per thread), issue
+// the four landmark-trig gathers up front, and request the streamed operands of the NEXT iteration before the
+// arithmetic of the current one.
+// Why not one pass: FP64 has no native shared-memory atomic add and L2 REDs cost ~5 ns per entry chip-wide, so
+// whichever side is scattered costs more than re-streaming 20 B/observation and re-evaluating the geometry.  The
 // alternatives that were built, measured and removed (one pass with shared-memory CAS atomics, keyframe-major with
-// L2 REDs, TMA/mbarrier tile rings, one launch with two CTA roles, one pass with a static per-tile keyframe sort) are
-// tabulated in DESIGN.md section 5 with their ncu counters.
+// L2 REDs, CTA-wide and per-warp TMA/mbarrier rings, one launch with two CTA roles, one pass with a static per-tile
+// keyframe sort, serial 4-observation loops with look-ahead index loads) are tabulated in DESIGN.md section 5.
 // ---------------------------------------------------------------------------------------------------------------
-template <int MINB, bool LOOKAHEAD2 = false>
+struct __align__(32) D4 { double a, b, c, d; };
+constexpr int kQuad = 4;
+constexpr int kCamIter = 32 * kQuad;       // observations one warp consumes per iteration of the keyframe-major pass
+
+// Keyframe-major pass.  The keyframe-major copy is stored PADDED: every keyframe's run starts at a multiple of 128
+// entries (padding entries carry landmark id -1), so a warp iteration (32 lanes x 4 observations) never mixes two
+// keyframes, needs no per-observation keyframe id (iter_cam[it], one int per 128 observations, names it) and loads
+// with aligned 128-/256-bit accesses: 20 B per observation are streamed.  A CTA walks a contiguous range of
+// iterations, its warps interleaved; a warp keeps the nine sums of its current keyframe in registers and commits them
+// (warp reduction + 9 REDs) when the keyframe changes - about once per CTA.
+// (Staging the gathered trig rows of the next iteration in shared memory with cp.async was measured: 27.5 us instead of
+// 19.5 us for this kernel, MIO-throttled by the per-lane 16-byte copies; removed.)
+template <int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_cam_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
+k_ba_cam_pass(int it_lo, int it_hi, int iters_per_cta, const int32_t* __restrict__ iter_cam, const int32_t* __restrict__ c_lm,
               const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
               const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const double k1 = PTZ_DEG2RAD;
-    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
-    int64_t end = begin + chunk;
-    if (end > hi) end = hi;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarpsPerCta = kFusedThreads / 32;
+    const int cta_begin = it_lo + blockIdx.x * iters_per_cta;
+    int cta_end = cta_begin + iters_per_cta;
+    if (cta_end > it_hi) cta_end = it_hi;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, signs and scales applied on commit
     int wcam = -1;
     CamTrig wc = {0, 1, 0, 1, 1};
     auto flush = [&]() {
@@ -178,96 +197,143 @@ k_ba_cam_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
             if (lane == 0) {
                 double* U = gU + 6 * (size_t)wcam;
                 double* G = gGc + 3 * (size_t)wcam;
-                const double k2 = k1 * k1;
-                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
+                const double k1 = PTZ_DEG2RAD, k2 = k1 * k1;
+                // d/d pan = -d/d alpha: the pan row / column changes sign
+                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, -a1 * k2); atomicAdd(U + 2, -a2 * k1);
                 atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
-                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
+                atomicAdd(G + 0, -a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
             }
         }
         a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
     };
-    int64_t k = begin + tid;
-    int cam = -1, lm = 0;
-    double ox = 0, oy = 0;
-    LmTrig lt = {0, 1, 0, 1};
-    if (k < end) { cam = c_cam[k]; lm = c_lm[k]; ox = c_ox[k]; oy = c_oy[k]; lt = lm_trig[lm]; }
-    // LOOKAHEAD2 (opt-in experiment PTZBA_CAM_LOOKAHEAD, not yet run on hardware): the landmark index is requested TWO steps
-    // ahead, so that the dependent trig gather of the next step can issue at once - 29 % of this kernel's stall samples sit on
-    // that gather's address waiting for an index requested one step earlier (profiles/r1_ncu_fused_source_stalls.txt)
-    int lm_ahead = 0;
-    if (LOOKAHEAD2 && k + kFusedThreads < end) lm_ahead = c_lm[k + kFusedThreads];
-    for (int64_t base = begin; base < end; base += kFusedThreads) {
-        const bool act = k < end;
-        const int64_t kn = k + kFusedThreads;
-        int ncam = -1, nlm = 0;
-        double nox = 0, noy = 0;
-        LmTrig nlt = {0, 1, 0, 1};
-        if (LOOKAHEAD2) {
-            if (kn < end) { nlm = lm_ahead; nlt = lm_trig[nlm]; ncam = c_cam[kn]; nox = c_ox[kn]; noy = c_oy[kn]; }
-            if (kn + kFusedThreads < end) lm_ahead = c_lm[kn + kFusedThreads];
-        } else if (kn < end) { ncam = c_cam[kn]; nlm = c_lm[kn]; nox = c_ox[kn]; noy = c_oy[kn]; nlt = lm_trig[nlm]; }
-        const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
-        const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
-        const bool uniform = same == 0xffffffffu;
-        if (uniform) {
-            if (cam_lo != wcam) { flush(); wcam = cam_lo; if (wcam >= 0) wc = cam_trig[wcam]; }
-        } else {
-            flush();
-            wcam = -1;
+    int it = cta_begin + warp;
+    int4 nl = make_int4(-1, -1, -1, -1);
+    D4 nx = {0, 0, 0, 0}, ny = {0, 0, 0, 0};
+    int ncam = -1;
+    if (it < cta_end) {
+        const size_t o = (size_t)it * kCamIter + (size_t)lane * kQuad;
+        nl = __ldg(reinterpret_cast<const int4*>(c_lm + o));
+        nx = *reinterpret_cast<const D4*>(c_ox + o);
+        ny = *reinterpret_cast<const D4*>(c_oy + o);
+        ncam = __ldg(iter_cam + it);
+    }
+#pragma unroll 1
+    for (; it < cta_end; it += kWarpsPerCta) {
+        const int lm[kQuad] = {nl.x, nl.y, nl.z, nl.w};
+        const double ox[kQuad] = {nx.a, nx.b, nx.c, nx.d};
+        const double oy[kQuad] = {ny.a, ny.b, ny.c, ny.d};
+        const int cam = ncam;
+        LmTrig lt[kQuad];
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) lt[i] = lm_trig[lm[i] < 0 ? 0 : lm[i]];      // four independent gathers, issued at once
+        const int itn = it + kWarpsPerCta;
+        if (itn < cta_end) {                                                          // next iteration's streams: in flight during the arithmetic
+            const size_t o = (size_t)itn * kCamIter + (size_t)lane * kQuad;
+            nl = __ldg(reinterpret_cast<const int4*>(c_lm + o));
+            nx = *reinterpret_cast<const D4*>(c_ox + o);
+            ny = *reinterpret_cast<const D4*>(c_oy + o);
+            ncam = __ldg(iter_cam + itn);
         }
-        if (act && cam > 0) {
-            const CamTrig c = uniform ? wc : cam_trig[cam];
-            double x, y;
-            ObsGeom g;
-            project_fast_jac(c, lt, u, v, x, y, g);
-            const double rx = x - ox, ry = y - oy;
-            const double upp = fma(g.xa, g.xa, g.ya * g.ya);
-            const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
-            const double upf = -fma(g.xa, g.px, g.ya * g.py);
-            const double utt = fma(g.xt, g.xt, g.yt * g.yt);
-            const double utf = fma(g.xt, g.px, g.yt * g.py);
-            const double uff = fma(g.px, g.px, g.py * g.py);
-            const double gp = -fma(g.xa, rx, g.ya * ry);
-            const double gt = fma(g.xt, rx, g.yt * ry);
-            const double gf = fma(g.px, rx, g.py * ry);
-            if (uniform) {
-                a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
-            } else {   // warp straddles a keyframe boundary (once per keyframe): commit per lane
-                double* U = gU + 6 * (size_t)cam;
-                double* G = gGc + 3 * (size_t)cam;
-                const double k2 = k1 * k1;
-                atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
-                atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
-                atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
+        if (cam != wcam) { flush(); wcam = cam; wc = cam_trig[cam]; }                 // warp-uniform
+        if (cam > 0) {                                                                // keyframe 0 is the fixed reference pose
+#pragma unroll
+            for (int i = 0; i < kQuad; ++i) {
+                double x, y;
+                ObsGeom g;
+                project_fast_jac(wc, lt[i], u, v, x, y, g);
+                const double rx = x - ox[i], ry = y - oy[i];
+                if (lm[i] >= 0) {                                                     // predicated FMAs, no branch
+                    a0 = fma(g.xa, g.xa, fma(g.ya, g.ya, a0));
+                    a1 = fma(g.xa, g.xt, fma(g.ya, g.yt, a1));
+                    a2 = fma(g.xa, g.px, fma(g.ya, g.py, a2));
+                    a3 = fma(g.xt, g.xt, fma(g.yt, g.yt, a3));
+                    a4 = fma(g.xt, g.px, fma(g.yt, g.py, a4));
+                    a5 = fma(g.px, g.px, fma(g.py, g.py, a5));
+                    a6 = fma(g.xa, rx, fma(g.ya, ry, a6));
+                    a7 = fma(g.xt, rx, fma(g.yt, ry, a7));
+                    a8 = fma(g.px, rx, fma(g.py, ry, a8));
+                }
             }
         }
-        cam = ncam; lm = nlm; ox = nox; oy = noy; lt = nlt; k = kn;
     }
     flush();
 }
 
-// 4 consecutive observations per thread: 128-/256-bit loads, quads 32-byte aligned (arrays are padded by 4 entries)
-struct __align__(32) D4 { double a, b, c, d; };
-constexpr int kQuad = 4;
-
+// commit of one landmark's sums (radian units -> per degree)
 __device__ __forceinline__ void commit_lm(double* __restrict__ gV, double* __restrict__ gGl, int lm, double vtt, double vtp,
                                           double vpp, double glt, double glp) {
-    atomicAdd(gV + 3 * (size_t)lm + 0, vtt);
-    atomicAdd(gV + 3 * (size_t)lm + 1, vtp);
-    atomicAdd(gV + 3 * (size_t)lm + 2, vpp);
-    atomicAdd(gGl + 2 * (size_t)lm + 0, glt);
-    atomicAdd(gGl + 2 * (size_t)lm + 1, glp);
+    const double k1 = PTZ_DEG2RAD, k2 = k1 * k1;
+    atomicAdd(gV + 3 * (size_t)lm + 0, vtt * k2);
+    atomicAdd(gV + 3 * (size_t)lm + 1, vtp * k2);
+    atomicAdd(gV + 3 * (size_t)lm + 2, vpp * k2);
+    atomicAdd(gGl + 2 * (size_t)lm + 0, glt * k1);
+    atomicAdd(gGl + 2 * (size_t)lm + 1, glp * k1);
 }
 
-template <int MINB, bool CAM_SMEM, bool IDX_AHEAD = false>
+// 4 consecutive landmark ids k0 .. k0+3 of the landmark-major list restricted to [lo, end): -1 = no observation in this slot
+__device__ __forceinline__ int4 load_lm_ids(int64_t k0, int64_t lo, int64_t end, const int32_t* __restrict__ s_lm) {
+    if (k0 >= lo && k0 + kQuad <= end) return __ldg(reinterpret_cast<const int4*>(s_lm + k0));
+    int4 r;
+    r.x = (k0 >= lo && k0 < end) ? s_lm[k0] : -1;
+    r.y = (k0 + 1 >= lo && k0 + 1 < end) ? s_lm[k0 + 1] : -1;
+    r.z = (k0 + 2 >= lo && k0 + 2 < end) ? s_lm[k0 + 2] : -1;
+    r.w = (k0 + 3 >= lo && k0 + 3 < end) ? s_lm[k0 + 3] : -1;
+    return r;
+}
+
+struct QuadObs {
+    int cam[kQuad];
+    double ox[kQuad], oy[kQuad];
+};
+
+__device__ __forceinline__ void load_quad_obs(QuadObs& q, int64_t k0, int64_t lo, int64_t end, const int32_t* __restrict__ s_cam,
+                                              const double* __restrict__ s_ox, const double* __restrict__ s_oy) {
+    if (k0 >= lo && k0 + kQuad <= end) {
+        const int4 c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
+        const D4 x4 = *reinterpret_cast<const D4*>(s_ox + k0);
+        const D4 y4 = *reinterpret_cast<const D4*>(s_oy + k0);
+        q.cam[0] = c4.x; q.cam[1] = c4.y; q.cam[2] = c4.z; q.cam[3] = c4.w;
+        q.ox[0] = x4.a; q.ox[1] = x4.b; q.ox[2] = x4.c; q.ox[3] = x4.d;
+        q.oy[0] = y4.a; q.oy[1] = y4.b; q.oy[2] = y4.c; q.oy[3] = y4.d;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kQuad; ++i) {
+            const bool in = k0 + i >= lo && k0 + i < end;
+            q.cam[i] = in ? s_cam[k0 + i] : 0;
+            q.ox[i] = in ? s_ox[k0 + i] : 0.0;
+            q.oy[i] = in ? s_oy[k0 + i] : 0.0;
+        }
+    }
+}
+
+// Landmark-major pass.  A quad of 4 consecutive observations spans the tail of one landmark's run and / or the head of
+// the next (landmark ids are non-decreasing): the sums of the observations that share the LAST id of the quad join the
+// warp-segmented reduction (key = that id); the sums of those that share the FIRST id, when it differs, are committed by
+// the thread itself; an id strictly between the two (a landmark with at most two observations) is committed per
+// observation.  All three cases are predicated adds on the same straight-line code.
+// Software pipeline per thread, registers only: landmark ids two iterations ahead, keyframe ids / observed pixels one
+// iteration ahead; the trig rows of the quad's first and last landmark (all a quad needs unless a third landmark sits
+// inside it) are gathered at the top of the iteration.  (Measured and removed: the same rows one iteration ahead in registers
+// - 28.0 instead of 25.5 us, the 16 extra registers spill; - and staged in shared memory by cp.async - 49 us, MIO-throttled.)
+template <int MINB, bool CAM_SMEM>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
-              const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
-              const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
-              double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
+k_ba_lm_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+             const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+             const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
+             double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
     extern __shared__ __align__(16) double smem[];      // keyframe trig, 48 B per keyframe: {sp,cp} {st,ct} {f,-}: two LDS.128 + one LDS.64
     __shared__ double sWarp[kFusedThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // this CTA's observations: [max(begin, lo), end); quads stay aligned to multiples of 4 of the array index
+    const int64_t begin = (lo & ~(int64_t)3) + (int64_t)blockIdx.x * chunk;
+    int64_t end = begin + chunk;
+    if (end > hi) end = hi;
+    constexpr int64_t kStep = (int64_t)kFusedThreads * kQuad;
+    int64_t k0 = begin + (int64_t)tid * kQuad;
+    int4 idA = load_lm_ids(k0, lo, end, s_lm), idB = load_lm_ids(k0 + kStep, lo, end, s_lm);
+    QuadObs qA, qB;
+    load_quad_obs(qA, k0, lo, end, s_cam, s_ox, s_oy);
+    qB = qA;
     if (CAM_SMEM) {
         for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
             const int c = i / 5, e = i - 5 * c;
@@ -275,91 +341,43 @@ k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
         }
         __syncthreads();
     }
-    // this CTA's observations: [max(begin, lo), end); quads stay aligned to multiples of 4 of the array index
-    const int64_t begin = (lo & ~(int64_t)3) + (int64_t)blockIdx.x * chunk;
-    int64_t end = begin + chunk;
-    if (end > hi) end = hi;
-    const double k1 = PTZ_DEG2RAD;
     double cost = 0.0;
-    // IDX_AHEAD (opt-in experiment PTZBA_LM_IDX_AHEAD, not yet run on hardware): the two index vectors of the NEXT iteration are
-    // requested one iteration early (8 registers), so that an iteration starts with its indices present and its trig gather /
-    // keyframe rows can go out at once; the observation vectors are still requested at the top and are only needed after the
-    // projection.  19 % of this kernel's stall samples sit on the first use of the streamed indices.
-    int4 c4n = make_int4(0, 0, 0, 0), l4n = make_int4(0, 0, 0, 0);
-    if (IDX_AHEAD) {
-        const int64_t kf = begin + (int64_t)tid * kQuad;
-        if (kf >= lo && kf + kQuad <= end) {
-            c4n = __ldg(reinterpret_cast<const int4*>(s_cam + kf));
-            l4n = __ldg(reinterpret_cast<const int4*>(s_lm + kf));
-        }
-    }
-    for (int64_t base = begin; base < end; base += kFusedThreads * kQuad) {
-        const int64_t k0 = base + (int64_t)tid * kQuad;
-        int cam[kQuad], lm[kQuad];
-        double ox[kQuad], oy[kQuad];
-        if (k0 >= lo && k0 + kQuad <= end) {
-            int4 c4, l4;
-            if (IDX_AHEAD) {
-                c4 = c4n; l4 = l4n;
-                const int64_t kn = k0 + (int64_t)kFusedThreads * kQuad;
-                if (kn + kQuad <= end) {
-                    c4n = __ldg(reinterpret_cast<const int4*>(s_cam + kn));
-                    l4n = __ldg(reinterpret_cast<const int4*>(s_lm + kn));
-                }
-            } else {
-                c4 = __ldg(reinterpret_cast<const int4*>(s_cam + k0));
-                l4 = __ldg(reinterpret_cast<const int4*>(s_lm + k0));
-            }
-            const D4 x4 = *reinterpret_cast<const D4*>(s_ox + k0);
-            const D4 y4 = *reinterpret_cast<const D4*>(s_oy + k0);
-            cam[0] = c4.x; cam[1] = c4.y; cam[2] = c4.z; cam[3] = c4.w;
-            lm[0] = l4.x; lm[1] = l4.y; lm[2] = l4.z; lm[3] = l4.w;
-            ox[0] = x4.a; ox[1] = x4.b; ox[2] = x4.c; ox[3] = x4.d;
-            oy[0] = y4.a; oy[1] = y4.b; oy[2] = y4.c; oy[3] = y4.d;
-        } else {
-#pragma unroll
-            for (int i = 0; i < kQuad; ++i) {
-                const bool in = k0 + i >= lo && k0 + i < end;
-                cam[i] = in ? s_cam[k0 + i] : 0;
-                lm[i] = in ? s_lm[k0 + i] : -1;
-                ox[i] = in ? s_ox[k0 + i] : 0.0;
-                oy[i] = in ? s_oy[k0 + i] : 0.0;
-            }
-        }
+#pragma unroll 1
+    for (int64_t base = begin; base < end; base += kStep, k0 += kStep) {
+        // this iteration's trig rows; the next iteration's keyframe ids and pixels; the landmark ids of the one after
+        const LmTrig ltF = lm_trig[idA.x < 0 ? 0 : idA.x], ltL = lm_trig[idA.w < 0 ? 0 : idA.w];
+        if (base + kStep < end) load_quad_obs(qB, k0 + kStep, lo, end, s_cam, s_ox, s_oy);
+        const int4 idC = load_lm_ids(k0 + 2 * kStep, lo, end, s_lm);
+        const int lm[kQuad] = {idA.x, idA.y, idA.z, idA.w};
+        const int lm_first = lm[0], lm_last = lm[kQuad - 1];
         double rx[kQuad], ry[kQuad];
-        int cur = -1;
-        LmTrig lt = {0, 1, 0, 1};
-        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
+        double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;      // observations with the quad's last id
+        double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;      // observations with the quad's first id (when it differs)
 #pragma unroll
         for (int i = 0; i < kQuad; ++i) {
-            rx[i] = 0.0; ry[i] = 0.0;
-            if (lm[i] < 0) continue;
-            if (lm[i] != cur) {
-                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);   // run ended inside this thread
-                cur = lm[i];
-                lt = lm_trig[cur];
-                vtt = vtp = vpp = glt = glp = 0.0;
-            }
+            const bool is_last = lm[i] == lm_last, is_first = lm[i] == lm_first;
+            LmTrig lt = is_last ? ltL : ltF;
+            if (!is_last && !is_first) lt = lm_trig[lm[i] < 0 ? 0 : lm[i]];        // a third landmark inside the quad: rare
             CamTrig c;
             if (CAM_SMEM) {
-                const double2* t = reinterpret_cast<const double2*>(smem + (size_t)cam[i] * 6);
+                const double2* t = reinterpret_cast<const double2*>(smem + (size_t)qA.cam[i] * 6);
                 const double2 pa = t[0], ti = t[1];
-                c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = smem[(size_t)cam[i] * 6 + 4];
+                c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = smem[(size_t)qA.cam[i] * 6 + 4];
             } else {
-                c = cam_trig[cam[i]];
+                c = cam_trig[qA.cam[i]];
             }
             double x, y;
             ObsGeom g;
             project_fast_jac(c, lt, u, v, x, y, g);
-            rx[i] = x - ox[i];
-            ry[i] = y - oy[i];
+            const bool valid = lm[i] >= 0;
+            rx[i] = valid ? x - qA.ox[i] : 0.0;
+            ry[i] = valid ? y - qA.oy[i] : 0.0;
             cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
-            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
-            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
-            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
-            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
-            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
-            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
+            const double vtt = fma(g.xa, g.xa, g.ya * g.ya), vtp = fma(g.xa, g.xp, g.ya * g.yp), vpp = fma(g.xp, g.xp, g.yp * g.yp);
+            const double glt = fma(g.xa, rx[i], g.ya * ry[i]), glp = fma(g.xp, rx[i], g.yp * ry[i]);
+            if (is_last) { t0 += vtt; t1 += vtp; t2 += vpp; t3 += glt; t4 += glp; }
+            else if (is_first) { h0 += vtt; h1 += vtp; h2 += vpp; h3 += glt; h4 += glp; }
+            else if (valid) commit_lm(gV, gGl, lm[i], vtt, vtp, vpp, glt, glp);        // only i = 1, 2 can get here
         }
         if (resid) {
             if (!orig && k0 >= lo && k0 + kQuad <= end) {
@@ -375,303 +393,21 @@ k_ba_lm_pass4(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__
                     }
             }
         }
+        if (lm_first != lm_last && lm_first >= 0) commit_lm(gV, gGl, lm_first, h0, h1, h2, h3, h4);   // run ended inside this thread
         // the thread's last run joins the warp-segmented reduction (keys non-decreasing across lanes, -1 = none)
-        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
-        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
-        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
+        seg_reduce5(lm_last, lane, t0, t1, t2, t3, t4);
+        const int prev = __shfl_up_sync(0xffffffffu, lm_last, 1);
+        if (lm_last >= 0 && (lane == 0 || prev != lm_last)) commit_lm(gV, gGl, lm_last, t0, t1, t2, t3, t4);
+        idA = idB; idB = idC; qA = qB;
     }
     cost = warp_sum(cost);
-    if (lane == 0) sWarp[tid >> 5] = cost;
+    if (lane == 0) sWarp[warp] = cost;
     __syncthreads();
     if (tid == 0) {
         double s = 0;
         for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
         atomicAdd(gCost, s);
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENT, opt-in (PTZBA_FUSED_RING=1), NOT the default; parity-green on small problems on a B200, not yet timed: the same two passes with the four
-// observation streams fed by the copy engine (cp.async.bulk + mbarrier) into PER-WARP two-slot shared-memory rings.
-// Motivation: the default kernels are bound by exposed load latency of a few resident warps; register
-// prefetch costs occupancy, and the earlier CTA-wide TMA ring (one __syncthreads per 1024-observation tile) put all warps
-// in lock-step.  Here every warp owns its ring and its mbarriers, so warps stay free-running, the streaming loads cost no
-// registers and no LSU issue slots, and a slot is refilled (by the warp's lane 0) as soon as the warp has copied it to
-// registers - one to two groups of 128 observations ahead of the arithmetic.  Arithmetic, reduction and commit order are
-// those of k_ba_lm_pass4 / k_ba_cam_pass.  Requires lo % 4 == 0 (TMA source alignment); the host falls back otherwise.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kGroup = 32 * kQuad;               // observations per warp step
-constexpr int kRing = 2;                         // slots per warp
-constexpr int kWarps = kFusedThreads / 32;
-struct __align__(16) WarpSlot { int cam[kGroup]; int lm[kGroup]; double ox[kGroup]; double oy[kGroup]; };   // 3 KB
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "RING_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra RING_DONE;\n"
-        "bra RING_WAIT;\n"
-        "RING_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-// one lane: start the copies of observations [k0, min(k0 + kGroup, end)) into `slot` (arrays are padded by 4 entries)
-__device__ __forceinline__ void ring_issue(WarpSlot* slot, uint64_t* bar, int64_t k0, int64_t end, const int32_t* cam,
-                                           const int32_t* lm, const double* ox, const double* oy) {
-    int64_t cnt = end - k0;
-    if (cnt > kGroup) cnt = kGroup;
-    const uint32_t c4 = (uint32_t)((cnt + 3) & ~(int64_t)3);
-    mbar_expect_tx(bar, c4 * 24u);
-    tma_load(slot->cam, cam + k0, c4 * 4u, bar);
-    tma_load(slot->lm, lm + k0, c4 * 4u, bar);
-    tma_load(slot->ox, ox + k0, c4 * 8u, bar);
-    tma_load(slot->oy, oy + k0, c4 * 8u, bar);
-}
-
-template <int MINB, bool DUAL_GATHER>
-__global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_lm_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
-                  const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
-                  const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
-                  double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
-    extern __shared__ __align__(16) unsigned char dyn[];      // cp.async.bulk needs 16-byte aligned destinations
-    WarpSlot* slots = reinterpret_cast<WarpSlot*>(dyn);                                              // [kWarps][kRing]
-    double* smem = reinterpret_cast<double*>(dyn + sizeof(WarpSlot) * kWarps * kRing);               // keyframe trig, 48 B each
-    __shared__ uint64_t full[kWarps][kRing];
-    __shared__ double sWarp[kWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
-    int64_t end = begin + chunk;
-    if (end > hi) end = hi;
-    // group j of this warp = observations [begin + (warp + kWarps j) kGroup, + kGroup): the CTA still streams its chunk front to back
-    const int64_t n_groups = end > begin ? (end - begin + kGroup - 1) / kGroup : 0;
-    const int n_mine = n_groups > warp ? (int)((n_groups - warp + kWarps - 1) / kWarps) : 0;
-    WarpSlot* my = slots + warp * kRing;
-    if (lane == 0) {
-        for (int r = 0; r < kRing; ++r) mbar_init(&full[warp][r], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int j = 0; j < kRing && j < n_mine; ++j)
-            ring_issue(&my[j], &full[warp][j], begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup, end, s_cam, s_lm, s_ox, s_oy);
-    }
-    for (int i = tid; i < n_pose * 5; i += kFusedThreads) {          // overlaps with the first copies
-        const int c = i / 5, e = i - 5 * c;
-        smem[(size_t)c * 6 + e] = reinterpret_cast<const double*>(cam_trig)[i];
-    }
-    __syncthreads();
-    const double k1 = PTZ_DEG2RAD;
-    double cost = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < n_mine; ++j) {
-        const int r = j % kRing;
-        mbar_wait(&full[warp][r], (uint32_t)((j / kRing) & 1));
-        const WarpSlot& ws = my[r];
-        const int q = lane * kQuad;
-        const int4 c4 = *reinterpret_cast<const int4*>(ws.cam + q);
-        const int4 l4 = *reinterpret_cast<const int4*>(ws.lm + q);
-        const double2 xa = *reinterpret_cast<const double2*>(ws.ox + q), xb = *reinterpret_cast<const double2*>(ws.ox + q + 2);
-        const double2 ya = *reinterpret_cast<const double2*>(ws.oy + q), yb = *reinterpret_cast<const double2*>(ws.oy + q + 2);
-        __syncwarp();                                                // every lane has its copy: the slot may be refilled
-        const int64_t g0 = begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup;
-        if (lane == 0 && j + kRing < n_mine)
-            ring_issue(&my[r], &full[warp][r], g0 + (int64_t)kWarps * kRing * kGroup, end, s_cam, s_lm, s_ox, s_oy);
-        const int64_t k0 = g0 + q;
-        const int cam[kQuad] = {c4.x, c4.y, c4.z, c4.w};
-        int lm[kQuad] = {l4.x, l4.y, l4.z, l4.w};
-        const double ox[kQuad] = {xa.x, xa.y, xb.x, xb.y};
-        const double oy[kQuad] = {ya.x, ya.y, yb.x, yb.y};
-#pragma unroll
-        for (int i = 0; i < kQuad; ++i)
-            if (k0 + i >= end) lm[i] = -1;
-        // the quad's landmark trig rows are gathered up front, both at once (a quad spans at most two landmarks unless a
-        // landmark has fewer than 3 observations): the profile of k_ba_lm_pass4 shows 13 % of all stall samples on the first
-        // use of a gather issued inside the serial loop below
-        // (DUAL_GATHER costs 8 more live registers: 60 bytes of spills at the 80-register cap - to be decided by measurement)
-        const int lmA = lm[0] >= 0 ? lm[0] : 0, lmB = lm[kQuad - 1] >= 0 ? lm[kQuad - 1] : lmA;
-        LmTrig ltA = {0, 1, 0, 1}, ltB = {0, 1, 0, 1};
-        if (DUAL_GATHER) { ltA = lm_trig[lmA]; ltB = lm_trig[lmB]; }
-        double rx[kQuad], ry[kQuad];
-        int cur = -1;
-        LmTrig lt = {0, 1, 0, 1};
-        double vtt = 0, vtp = 0, vpp = 0, glt = 0, glp = 0;
-#pragma unroll
-        for (int i = 0; i < kQuad; ++i) {
-            rx[i] = 0.0; ry[i] = 0.0;
-            if (lm[i] < 0) continue;
-            if (lm[i] != cur) {
-                if (cur >= 0) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
-                cur = lm[i];
-                if (DUAL_GATHER) lt = cur == lmA ? ltA : cur == lmB ? ltB : lm_trig[cur];
-                else lt = lm_trig[cur];
-                vtt = vtp = vpp = glt = glp = 0.0;
-            }
-            const double2* t = reinterpret_cast<const double2*>(smem + (size_t)cam[i] * 6);
-            const double2 pa = t[0], ti = t[1];
-            CamTrig c;
-            c.sp = pa.x; c.cp = pa.y; c.st = ti.x; c.ct = ti.y; c.f = smem[(size_t)cam[i] * 6 + 4];
-            double x, y;
-            ObsGeom g;
-            project_fast_jac(c, lt, u, v, x, y, g);
-            rx[i] = x - ox[i];
-            ry[i] = y - oy[i];
-            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
-            const double kxa = k1 * g.xa, kya = k1 * g.ya, kxp = k1 * g.xp, kyp = k1 * g.yp;
-            vtt = fma(kxa, kxa, fma(kya, kya, vtt));
-            vtp = fma(kxa, kxp, fma(kya, kyp, vtp));
-            vpp = fma(kxp, kxp, fma(kyp, kyp, vpp));
-            glt = fma(kxa, rx[i], fma(kya, ry[i], glt));
-            glp = fma(kxp, rx[i], fma(kyp, ry[i], glp));
-        }
-        if (resid) {
-            if (!orig && k0 + kQuad <= end) {
-                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
-                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
-                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
-            } else {
-#pragma unroll
-                for (int i = 0; i < kQuad; ++i)
-                    if (lm[i] >= 0) {
-                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
-                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
-                    }
-            }
-        }
-        seg_reduce5(cur, lane, vtt, vtp, vpp, glt, glp);
-        const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
-        if (cur >= 0 && (lane == 0 || prev != cur)) commit_lm(gV, gGl, cur, vtt, vtp, vpp, glt, glp);
-    }
-    cost = warp_sum(cost);
-    if (lane == 0) sWarp[warp] = cost;
-    __syncthreads();
-    if (tid == 0) {
-        double sum = 0;
-        for (int w = 0; w < kWarps; ++w) sum += sWarp[w];
-        atomicAdd(gCost, sum);
-    }
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_cam_pass_ring(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ c_cam, const int32_t* __restrict__ c_lm,
-                   const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
-                   const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
-    extern __shared__ __align__(16) unsigned char dyn[];      // cp.async.bulk needs 16-byte aligned destinations
-    WarpSlot* slots = reinterpret_cast<WarpSlot*>(dyn);
-    __shared__ uint64_t full[kWarps][kRing];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double k1 = PTZ_DEG2RAD;
-    const int64_t begin = lo + (int64_t)blockIdx.x * chunk;
-    int64_t end = begin + chunk;
-    if (end > hi) end = hi;
-    const int64_t n_groups = end > begin ? (end - begin + kGroup - 1) / kGroup : 0;
-    const int n_mine = n_groups > warp ? (int)((n_groups - warp + kWarps - 1) / kWarps) : 0;
-    WarpSlot* my = slots + warp * kRing;
-    if (lane == 0) {
-        for (int r = 0; r < kRing; ++r) mbar_init(&full[warp][r], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int j = 0; j < kRing && j < n_mine; ++j)
-            ring_issue(&my[j], &full[warp][j], begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup, end, c_cam, c_lm, c_ox, c_oy);
-    }
-    __syncwarp();
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, scaled on commit
-    int wcam = -1;
-    CamTrig wc = {0, 1, 0, 1, 1};
-    auto flush = [&]() {
-        if (wcam > 0) {
-            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
-            a5 = warp_sum(a5); a6 = warp_sum(a6); a7 = warp_sum(a7); a8 = warp_sum(a8);
-            if (lane == 0) {
-                double* U = gU + 6 * (size_t)wcam;
-                double* G = gGc + 3 * (size_t)wcam;
-                const double k2 = k1 * k1;
-                atomicAdd(U + 0, a0 * k2); atomicAdd(U + 1, a1 * k2); atomicAdd(U + 2, a2 * k1);
-                atomicAdd(U + 3, a3 * k2); atomicAdd(U + 4, a4 * k1); atomicAdd(U + 5, a5);
-                atomicAdd(G + 0, a6 * k1); atomicAdd(G + 1, a7 * k1); atomicAdd(G + 2, a8);
-            }
-        }
-        a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
-    };
-    // one step = 32 consecutive observations of a group (4 steps per group).  The streams are read from the warp's slot when
-    // they are needed (shared-memory latency); only the dependent landmark-trig gather of step t + 1 is started before step t
-    // is evaluated.
-    const int n_steps = n_mine * (kGroup / 32);
-    LmTrig lt = {0, 1, 0, 1};
-#pragma unroll 1
-    for (int t = -1; t < n_steps; ++t) {
-        LmTrig nlt = {0, 1, 0, 1};
-        const int tn = t + 1;
-        if (tn < n_steps) {
-            const int jn = tn >> 2, subn = tn & 3, rn = jn % kRing;
-            if (subn == 0) mbar_wait(&full[warp][rn], (uint32_t)((jn / kRing) & 1));
-            const int en = subn * 32 + lane;
-            if (begin + ((int64_t)warp + (int64_t)kWarps * jn) * kGroup + en < end) nlt = lm_trig[my[rn].lm[en]];
-        }
-        if (t >= 0) {
-            const int j = t >> 2, sub = t & 3, r = j % kRing;
-            const int e = sub * 32 + lane;
-            const int64_t g0 = begin + ((int64_t)warp + (int64_t)kWarps * j) * kGroup;
-            const bool act = g0 + e < end;
-            const int cam = act ? my[r].cam[e] : -1;
-            const double ox = my[r].ox[e], oy = my[r].oy[e];
-            if (sub == 3) {                                          // last read of this slot: refill it
-                __syncwarp();
-                if (lane == 0 && j + kRing < n_mine)
-                    ring_issue(&my[r], &full[warp][r], g0 + (int64_t)kWarps * kRing * kGroup, end, c_cam, c_lm, c_ox, c_oy);
-            }
-            const int cam_lo = __shfl_sync(0xffffffffu, cam, 0);
-            const unsigned same = __ballot_sync(0xffffffffu, cam == cam_lo || !act);
-            const bool uniform = same == 0xffffffffu;
-            if (uniform) {
-                if (cam_lo != wcam) { flush(); wcam = cam_lo; if (wcam >= 0) wc = cam_trig[wcam]; }
-            } else {
-                flush();
-                wcam = -1;
-            }
-            if (act && cam > 0) {
-                const CamTrig c = uniform ? wc : cam_trig[cam];
-                double x, y;
-                ObsGeom g;
-                project_fast_jac(c, lt, u, v, x, y, g);
-                const double rx = x - ox, ry = y - oy;
-                const double upp = fma(g.xa, g.xa, g.ya * g.ya);
-                const double upt = -fma(g.xa, g.xt, g.ya * g.yt);
-                const double upf = -fma(g.xa, g.px, g.ya * g.py);
-                const double utt = fma(g.xt, g.xt, g.yt * g.yt);
-                const double utf = fma(g.xt, g.px, g.yt * g.py);
-                const double uff = fma(g.px, g.px, g.py * g.py);
-                const double gp = -fma(g.xa, rx, g.ya * ry);
-                const double gt = fma(g.xt, rx, g.yt * ry);
-                const double gf = fma(g.px, rx, g.py * ry);
-                if (uniform) {
-                    a0 += upp; a1 += upt; a2 += upf; a3 += utt; a4 += utf; a5 += uff; a6 += gp; a7 += gt; a8 += gf;
-                } else {
-                    double* U = gU + 6 * (size_t)cam;
-                    double* G = gGc + 3 * (size_t)cam;
-                    const double k2 = k1 * k1;
-                    atomicAdd(U + 0, upp * k2); atomicAdd(U + 1, upt * k2); atomicAdd(U + 2, upf * k1);
-                    atomicAdd(U + 3, utt * k2); atomicAdd(U + 4, utf * k1); atomicAdd(U + 5, uff);
-                    atomicAdd(G + 0, gp * k1); atomicAdd(G + 1, gt * k1); atomicAdd(G + 2, gf);
-                }
-            }
-        }
-        lt = nlt;
-    }
-    flush();
 }
 
 // residual-only pass (trial points of the trust-region loop, and _compute_residual itself)
@@ -759,93 +495,34 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     // partition (ptzba_ba_set_partition) only this rank's slices of the two sorted lists are visited.
     const size_t smA = ba->cam_smem ? (size_t)ba->n_pose * 6 * sizeof(double) : 0;
     const int64_t nA = ba->lmo_hi - (ba->lmo_lo & ~(int64_t)3);
-    // opt-in experiment: per-warp copy-engine rings (see k_ba_lm_pass_ring); needs 16-byte aligned slice starts
-    static const char* ring_env = getenv("PTZBA_FUSED_RING");          // "1": rings; "2": rings + up-front dual landmark gather
-    static const bool ring = ring_env != nullptr;
-    static const bool ring_dual = ring && ring_env[0] == '2';
-    const size_t smRing = sizeof(WarpSlot) * kWarps * kRing;
-    const bool ringA = ring && ba->cam_smem && ba->lmo_lo % 4 == 0 && smRing + smA <= 200 * 1024;
-    const bool ringB = ring && ba->cmo_lo % 4 == 0;
-    if (ring && ba->grid_lm_ring == 0) {
-        int pa = 1, pb = 1;
-        if (ringA) {
-            CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass_ring<kLmMinB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smRing + smA)));
-            CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass_ring<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smRing + smA)));
-            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass_ring<kLmMinB, false>, kFusedThreads, smRing + smA));
-        }
-        CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_cam_pass_ring<kCamMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smRing));
-        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass_ring<kCamMinB>, kFusedThreads, smRing));
-        ba->grid_lm_ring = ctx->sm_count * (pa < 1 ? 1 : pa);
-        ba->grid_cam_ring = ctx->sm_count * (pb < 1 ? 1 : pb);
-    }
-    if (nA > 0 && ringA) {
-        int64_t chunkA = (nA + ba->grid_lm_ring - 1) / ba->grid_lm_ring;
-        chunkA = (chunkA + kGroup - 1) / kGroup * kGroup;
-        const int gridA = (int)((nA + chunkA - 1) / chunkA);
-        if (ring_dual)
-            k_ba_lm_pass_ring<kLmMinB, true><<<gridA, kFusedThreads, smRing + smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p,
-                                                                                      ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                                                                                      ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl,
-                                                                                      ba->acc.cost);
-        else
-            k_ba_lm_pass_ring<kLmMinB, false><<<gridA, kFusedThreads, smRing + smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p,
-                                                                                       ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                                                                                       ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl,
-                                                                                       ba->acc.cost);
-        KERNEL_POST(ctx);
-    } else if (nA > 0) {
+    if (nA > 0) {
         int64_t chunkA = (nA + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
         chunkA = (chunkA + 127) / 128 * 128;
         const int gridA = (int)((nA + chunkA - 1) / chunkA);
-        static const bool idx_ahead = getenv("PTZBA_LM_IDX_AHEAD") != nullptr;
-        if (ba->cam_smem && idx_ahead) {
-            if (smA > 40 * 1024)
-                CU_CHECK(ctx, cudaFuncSetAttribute(k_ba_lm_pass4<kLmMinB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-            k_ba_lm_pass4<kLmMinB, true, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p,
-                                                                                ba->s_ox.p, ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p,
-                                                                                ba->n_pose, ba->u, ba->v, d_resid, ba->acc.V, ba->acc.gl,
-                                                                                ba->acc.cost);
-        } else if (ba->cam_smem)
-            k_ba_lm_pass4<kLmMinB, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
-                                                                    ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
-                                                                    d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
-        else
-            k_ba_lm_pass4<kLmMinB, false><<<gridA, kFusedThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+        if (ba->cam_smem)
+            k_ba_lm_pass<kLmMinB, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
                                                                    ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
                                                                    d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
+        else
+            k_ba_lm_pass<kLmMinB, false><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
+                                                                  ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
+                                                                  d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
         KERNEL_POST(ctx);
     }
     // the keyframe-major pass touches disjoint accumulators: it runs on the side stream, concurrently with the landmark pass
     // (each kernel is a single wave; the second one fills the SMs the first one's finishing CTAs leave idle)
-    const int64_t nB = ba->cmo_hi - ba->cmo_lo;
-    static const bool concurrent = getenv("PTZBA_SERIAL_PASSES") == nullptr;
-    static const bool cam_lookahead = getenv("PTZBA_CAM_LOOKAHEAD") != nullptr;
+    const int nB = ba->cit_hi - ba->cit_lo;                 // iterations of 128 padded keyframe-major entries
     if (nB > 0) {
-        int64_t chunkB = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
-        chunkB = (chunkB + kFusedThreads - 1) / kFusedThreads * kFusedThreads;
-        const int gridB = (int)((nB + chunkB - 1) / chunkB);
-        cudaStream_t sb = concurrent ? ctx->side_stream : s;
-        if (concurrent) CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
-        if (ringB) {
-            int64_t chunkR = (nB + ba->grid_cam_ring - 1) / ba->grid_cam_ring;
-            chunkR = (chunkR + kGroup - 1) / kGroup * kGroup;
-            const int gridR = (int)((nB + chunkR - 1) / chunkR);
-            k_ba_cam_pass_ring<kCamMinB><<<gridR, kFusedThreads, smRing, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkR, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p,
-                                                                             ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v,
-                                                                             ba->acc.U, ba->acc.gc);
-        } else if (cam_lookahead) {
-            k_ba_cam_pass<kCamMinB, true><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p,
-                                                                          ba->c_oy.p, ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U,
-                                                                          ba->acc.gc);
-        } else {
-            k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cmo_lo, ba->cmo_hi, chunkB, ba->c_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                                    ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
-        }
+        int per_cta = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
+        if (per_cta < 1) per_cta = 1;
+        const int gridB = (nB + per_cta - 1) / per_cta;
+        cudaStream_t sb = ctx->side_stream;
+        CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
+        k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cit_lo, ba->cit_hi, per_cta, ba->iter_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
+                                                                ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
         KERNEL_POST(ctx);
-        if (concurrent) {
-            CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
-            CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
-        }
+        CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
+        CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
     if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count));
@@ -881,7 +558,7 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     cudaStream_t s = ctx->stream;
     ptzba_ba* ba = new ptzba_ba();
     ba->ctx = ctx; ba->n_pose = n_pose; ba->n_lm = n_landmark; ba->n_obs = n_obs; ba->u = u; ba->v = v;
-    ba->lm_hi = n_landmark; ba->lmo_hi = n_obs; ba->cmo_hi = n_obs;
+    ba->lm_hi = n_landmark; ba->lmo_hi = n_obs;
     auto fail = [&](int code) { delete ba; return code; };
 #define CU_TRY(expr)                                                                                   \
     do {                                                                                               \
@@ -957,49 +634,72 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
     CU_TRY(cudaGetLastError());
     ba->max_degree = h_flags[1];
 
-    // keyframe-major copy: stable sort of the landmark-major list by keyframe id
+    // keyframe-major copy: stable sort of the landmark-major list by keyframe id, then every keyframe's run is moved to a
+    // start that is a multiple of 128 entries (padding entries: landmark id -1); iter_cam names the keyframe of every
+    // group of 128 entries.  touch_* = keyframes / landmarks touched by this problem's observations.
+    ba->touch_cam_lo = 0; ba->touch_cam_hi = n_pose; ba->touch_lm_lo = 0; ba->touch_lm_hi = n_landmark;
+    ba->n_cam_iter = 0;
     if (n_obs > 0) {
-        DevBuf<int32_t> iota, perm2;
+        DevBuf<int32_t> iota, perm2, cam_sorted, d_ptr, d_pad;
         DevBuf<unsigned char> tmp;
-        CU_TRY(ba->c_cam.alloc(n_obs + 4)); CU_TRY(ba->c_lm.alloc(n_obs + 4));
-        CU_TRY(ba->c_ox.alloc(n_obs + 4)); CU_TRY(ba->c_oy.alloc(n_obs + 4));
-        CU_TRY(iota.alloc(n_obs)); CU_TRY(perm2.alloc(n_obs));
+        CU_TRY(iota.alloc(n_obs)); CU_TRY(perm2.alloc(n_obs)); CU_TRY(cam_sorted.alloc(n_obs));
         k_iota<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, iota.p);
         ctx->launches++;
         size_t bytes = 0;
         int end_bit = 1;
         while ((1ll << end_bit) < (long long)n_pose && end_bit < 31) ++end_bit;
-        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ba->s_cam.p, ba->c_cam.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ba->s_cam.p, cam_sorted.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
         CU_TRY(tmp.alloc(bytes));
-        CU_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ba->s_cam.p, ba->c_cam.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
-        k_gather_cm<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, perm2.p, ba->s_lm.p, ba->s_ox.p, ba->s_oy.p, ba->c_lm.p,
-                                                                    ba->c_ox.p, ba->c_oy.p);
+        CU_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, ba->s_cam.p, cam_sorted.p, iota.p, perm2.p, (int)n_obs, 0, end_bit, s));
+        // run offsets of the keyframes in the sorted list (binary search per keyframe), padded offsets on the host
+        CU_TRY(d_ptr.alloc((size_t)n_pose + 1)); CU_TRY(d_pad.alloc((size_t)n_pose + 1));
+        k_lm_ptr<<<div_up(n_pose + 1, 256), 256, 0, s>>>(n_pose, n_obs, cam_sorted.p, d_ptr.p, nullptr);
         ctx->launches++;
+        std::vector<int32_t> h_ptr((size_t)n_pose + 1), h_pad((size_t)n_pose + 1);
+        CU_TRY(cudaMemcpyAsync(h_ptr.data(), d_ptr.p, ((size_t)n_pose + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaStreamSynchronize(s));
+        int64_t padded = 0;
+        for (int c = 0; c < n_pose; ++c) {
+            h_pad[c] = (int32_t)padded;
+            padded += ((int64_t)(h_ptr[c + 1] - h_ptr[c]) + kCamIter - 1) / kCamIter * kCamIter;
+            if (padded > (int64_t)2147483000) return fail(ptzba_fail(ctx, PTZBA_ERR_ARG, "padded keyframe-major list exceeds 2^31 entries"));
+        }
+        h_pad[n_pose] = (int32_t)padded;
+        ba->n_cam_iter = (int)(padded / kCamIter);
+        std::vector<int32_t> h_iter((size_t)ba->n_cam_iter);
+        int first_cam = -1, last_cam = -1;
+        for (int c = 0; c < n_pose; ++c) {
+            if (h_ptr[c + 1] > h_ptr[c]) { if (first_cam < 0) first_cam = c; last_cam = c; }
+            for (int it = h_pad[c] / kCamIter; it < h_pad[c + 1] / kCamIter; ++it) h_iter[it] = c;
+        }
+        CU_TRY(ba->c_lm.alloc(padded + 4)); CU_TRY(ba->c_ox.alloc(padded + 4)); CU_TRY(ba->c_oy.alloc(padded + 4));
+        CU_TRY(ba->iter_cam.alloc((size_t)ba->n_cam_iter + 1));
+        CU_TRY(cudaMemsetAsync(ba->c_lm.p, 0xff, (size_t)(padded + 4) * sizeof(int32_t), s));
+        CU_TRY(cudaMemsetAsync(ba->c_ox.p, 0, (size_t)(padded + 4) * sizeof(double), s));
+        CU_TRY(cudaMemsetAsync(ba->c_oy.p, 0, (size_t)(padded + 4) * sizeof(double), s));
+        CU_TRY(cudaMemcpyAsync(d_pad.p, h_pad.data(), ((size_t)n_pose + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(ba->iter_cam.p, h_iter.data(), (size_t)ba->n_cam_iter * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        k_scatter_cm<<<stream_grid(ctx, n_obs, 256, 8), 256, 0, s>>>(n_obs, perm2.p, cam_sorted.p, d_ptr.p, d_pad.p, ba->s_lm.p, ba->s_ox.p,
+                                                                     ba->s_oy.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p);
+        ctx->launches++;
+        int32_t e[2];
+        CU_TRY(cudaMemcpyAsync(e + 0, ba->s_lm.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(e + 1, ba->s_lm.p + (n_obs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));     // the host vectors and temporaries go out of scope
+        ba->touch_cam_lo = first_cam; ba->touch_cam_hi = last_cam + 1; ba->touch_lm_lo = e[0]; ba->touch_lm_hi = e[1] + 1;
     }
-
-    // keyframes / landmarks touched by this problem's observations (first and last entry of the two sorted lists)
-    ba->touch_cam_lo = 0; ba->touch_cam_hi = n_pose; ba->touch_lm_lo = 0; ba->touch_lm_hi = n_landmark;
-    if (n_obs > 0) {
-        int32_t e[4];
-        CU_TRY(cudaMemcpyAsync(e + 0, ba->c_cam.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(e + 1, ba->c_cam.p + (n_obs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(e + 2, ba->s_lm.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(e + 3, ba->s_lm.p + (n_obs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaStreamSynchronize(s));
-        ba->touch_cam_lo = e[0]; ba->touch_cam_hi = e[1] + 1; ba->touch_lm_lo = e[2]; ba->touch_lm_hi = e[3] + 1;
-    }
+    ba->cit_lo = 0; ba->cit_hi = ba->n_cam_iter;
     // launch geometry of the fused pass: one wave of resident CTAs; keyframe trig table in shared memory when it fits
     {
-        const size_t smA = (size_t)n_pose * 6 * sizeof(double);
-        ba->cam_smem = smA <= 200 * 1024;
+        const size_t smTab = (size_t)n_pose * 6 * sizeof(double);
+        ba->cam_smem = smTab <= 100 * 1024;            // two CTAs per SM
+        const size_t smA = ba->cam_smem ? smTab : 0;
         int pa = 1, pb = 1;
         if (ba->cam_smem) {
-            if (smA > 40 * 1024)
-                CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass4<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass4<kLmMinB, true>, kFusedThreads, smA));
+            CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass<kLmMinB, true>, kFusedThreads, smA));
         } else {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass4<kLmMinB, false>, kFusedThreads, 0));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass<kLmMinB, false>, kFusedThreads, smA));
         }
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<kCamMinB>, kFusedThreads, 0));
         ba->grid_lm_pass = ctx->sm_count * (pa < 1 ? 1 : pa);
@@ -1027,10 +727,26 @@ extern "C" int ptzba_ba_set_partition(ptzba_ba* ba, int rank, int world_size, in
     CU_CHECK(ctx, cudaMemcpyAsync(&ends[1], ba->lm_ptr.p + lm_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ba->part_rank = rank; ba->part_world = world_size;
+    ba->pl_ready = false;            // the pair list covers the rank's landmark slice: rebuilt at the next solve
     ba->lm_lo = lm_lo; ba->lm_hi = lm_hi;
     ba->lmo_lo = ends[0]; ba->lmo_hi = ends[1];
-    ba->cmo_lo = cm_lo; ba->cmo_hi = cm_hi;
+    // the keyframe-major slice, given in observation positions, becomes a range of 128-entry iterations of the padded list
+    ba->cit_lo = ba->n_obs > 0 ? (int)((cm_lo * (int64_t)ba->n_cam_iter) / ba->n_obs) : 0;
+    ba->cit_hi = ba->n_obs > 0 ? (int)((cm_hi * (int64_t)ba->n_cam_iter) / ba->n_obs) : 0;
     return PTZBA_OK;
+}
+
+extern "C" int ptzba_ba_set_option(ptzba_ba* ba, int option, int value) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    switch (option) {
+        case PTZBA_OPT_SCHUR_MODE:
+            ARG_CHECK(ctx, value == PTZBA_SCHUR_AUTO || value == PTZBA_SCHUR_PER_LANDMARK || value == PTZBA_SCHUR_PAIR_LIST);
+            ba->schur_mode = value;
+            return PTZBA_OK;
+        default:
+            return ptzba_fail(ctx, PTZBA_ERR_ARG, "unknown option %d", option);
+    }
 }
 
 extern "C" void ptzba_ba_destroy(ptzba_ba* ba) {
@@ -1070,6 +786,8 @@ extern "C" int ptzba_ba_residual(ptzba_ba* ba, int mem, const double* x, const d
         CU_CHECK(ctx, ba->resid.alloc(2 * (size_t)ba->n_obs));
         d_r = ba->resid.p;
     }
+    // with a work partition only this rank's landmark slice is written: the other entries read as zero
+    if (ba->part_world > 1 && ba->n_obs) CU_CHECK(ctx, cudaMemsetAsync(d_r, 0, 2 * (size_t)ba->n_obs * sizeof(double), s));
     PROPAGATE(ba_set_params(ba, d_x, ba->ref_stage.p));
     PROPAGATE(ba_residual_pass(ba, d_r, nullptr));
     if (mem == PTZBA_HOST) {
@@ -1092,6 +810,7 @@ extern "C" int ptzba_ba_normal_equations(ptzba_ba* ba, int mem, const double* x,
         CU_CHECK(ctx, ba->resid.alloc(2 * (size_t)ba->n_obs));
         d_r = ba->resid.p;
     }
+    if (ba->part_world > 1 && d_r && ba->n_obs) CU_CHECK(ctx, cudaMemsetAsync(d_r, 0, 2 * (size_t)ba->n_obs * sizeof(double), s));
     PROPAGATE(ba_set_params(ba, d_x, ba->ref_stage.p, true));
     PROPAGATE(ba_fused_pass(ba, d_r));
     const cudaMemcpyKind kind = mem == PTZBA_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;

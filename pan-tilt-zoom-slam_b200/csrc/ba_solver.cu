@@ -90,10 +90,17 @@ __global__ void k_axpy_packed(int n, const double* __restrict__ x, const double*
     }
 }
 // sums: out[0] += sum (D a)^2 ; out[1] += sum g a ; out[2] += sum a^2 ; out[3] += sum b c ; out[4] += sum x^2 (packed)
-// out[5] = max |g|   (as double bits via atomicMax on non-negative values)
-__global__ void k_sums(int nF, const double* __restrict__ D, const double* __restrict__ g, const double* __restrict__ a,
-                       const double* __restrict__ b, const double* __restrict__ c, const double* __restrict__ xfull,
-                       double* __restrict__ out) {
+// out[5] = max(out[5], max |g|)
+// DETERMINISTIC (fixed summation order, no floating-point atomics): in the partitioned multi-GPU solve every rank runs this
+// kernel on bit-identical replicated vectors and branches on the results (trust-region radius, secular iteration, termination
+// tests); a last-bit difference between ranks would let them issue different sequences of collectives.  Blocks write their
+// partial sums to `part`, the block that takes the last ticket adds them up in a fixed order.
+__global__ void __launch_bounds__(256)
+k_sums(int nF, const double* __restrict__ D, const double* __restrict__ g, const double* __restrict__ a,
+       const double* __restrict__ b, const double* __restrict__ c, const double* __restrict__ xfull,
+       double* __restrict__ part, unsigned* __restrict__ ticket, double* __restrict__ out) {
+    __shared__ double sw[8][6];
+    __shared__ bool last;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, mx = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nF; i += gridDim.x * blockDim.x) {
         if (i < 3) continue;
@@ -103,13 +110,40 @@ __global__ void k_sums(int nF, const double* __restrict__ D, const double* __res
         if (b) s3 = fma(b[i], c[i], s3);
         if (xfull) s4 = fma(xfull[i], xfull[i], s4);
     }
-    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3); s4 = warp_sum(s4);
+    auto reduce6 = [&](double& v0, double& v1, double& v2, double& v3, double& v4, double& vm) {
+        v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(out + 0, s0); atomicAdd(out + 1, s1); atomicAdd(out + 2, s2); atomicAdd(out + 3, s3);
-        atomicAdd(out + 4, s4);
-        atomicMax(reinterpret_cast<unsigned long long*>(out + 5), (unsigned long long)__double_as_longlong(mx));
+        for (int off = 16; off > 0; off >>= 1) vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, off));
+    };
+    reduce6(s0, s1, s2, s3, s4, mx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sw[warp][0] = s0; sw[warp][1] = s1; sw[warp][2] = s2; sw[warp][3] = s3; sw[warp][4] = s4; sw[warp][5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (int w = 0; w < 8; ++w) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) t[j] += sw[w][j];
+            t[5] = fmax(t[5], sw[w][5]);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) part[6 * (size_t)blockIdx.x + j] = t[j];
+        __threadfence();
+        last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;       // wraps to 0: ready for the next launch
+    }
+    __syncthreads();
+    if (!last || warp != 0) return;
+    __threadfence();
+    const volatile double* vp = part;
+    s0 = s1 = s2 = s3 = s4 = mx = 0.0;
+    for (int blk = lane; blk < (int)gridDim.x; blk += 32) {
+        s0 += vp[6 * blk]; s1 += vp[6 * blk + 1]; s2 += vp[6 * blk + 2]; s3 += vp[6 * blk + 3]; s4 += vp[6 * blk + 4];
+        mx = fmax(mx, vp[6 * blk + 5]);
+    }
+    reduce6(s0, s1, s2, s3, s4, mx);
+    if (lane == 0) {
+        out[0] += s0; out[1] += s1; out[2] += s2; out[3] += s3; out[4] += s4;
+        out[5] = fmax(out[5], mx);
     }
 }
 
@@ -212,9 +246,10 @@ k_schur_pairs(int lm_lo, int lm_hi, const int32_t* __restrict__ lm_ptr, const in
     }
 }
 
-// ---- EXPERIMENT, opt-in (PTZBA_SCHUR_PAIRLIST=1), off by default; parity-green on the small solver tests on a B200, not yet timed ----
+// ---- default Schur formation: keyframe-pair-major pair list (k_schur_pairs is the fallback for > 65535 keyframes or > 2^31 pairs) ----
 // k_schur_pairs issues one FP64 RED per block entry per observation pair (189 M at 256 x 100k x 2M) and sits at the L2
-// atomic rate.  The sparsity pattern is static, so the pairs can be listed once per problem, KEYFRAME-PAIR MAJOR:
+// atomic rate (0.97 ms at cfg3; this kernel: 0.46 ms).  The sparsity pattern is static, so the pairs are listed once per
+// problem, KEYFRAME-PAIR MAJOR:
 //   entry = (key = max_cam << 16 | min_cam, val = landmark | duplicate flag << 31), radix-sorted by key.
 // The runtime kernel then streams the list like the keyframe-major fused pass: a warp keeps the 3x3 block of the current
 // keyframe pair in registers across its whole run and commits it with 9 REDs when the key changes - REDs drop from 9 per
@@ -490,7 +525,7 @@ struct Solver {
     int64_t chunk = 0;
     int obs_grid = 0;
     int pair_warps_smem = 0, pair_grid = 0;
-    bool use_pairlist = false;   // opt-in experiment (PTZBA_SCHUR_PAIRLIST): keyframe-pair-major entry list, see k_schur_pairlist
+    bool use_pairlist = false;   // keyframe-pair-major entry list (k_schur_pairlist) unless the problem is too large for its keys
     int n_factor = 0;
     int* h_flags = nullptr;      // pinned host copy of the factorisation verdict (slot 200 of ctx->h_scalars): truly asynchronous
     double *g, *D, *Dc, *Dl;
@@ -509,6 +544,11 @@ struct Solver {
         CU_CHECK(ctx, ba->Vinv.alloc((size_t)M * 3));
         CU_CHECK(ctx, flags.alloc(4)); CU_CHECK(ctx, tmp_l.alloc((size_t)2 * M)); CU_CHECK(ctx, w_full.alloc(nF));
         CU_CHECK(ctx, dinv.alloc(dense_coop_dinv_doubles(n > 0 ? n : 1)));
+        if (!ba->sums_ticket.p) {
+            CU_CHECK(ctx, ba->sums_part.alloc((size_t)6 * ctx->sm_count));
+            CU_CHECK(ctx, ba->sums_ticket.alloc(1));
+            CU_CHECK(ctx, cudaMemsetAsync(ba->sums_ticket.p, 0, sizeof(unsigned), s));
+        }
 
         g = ba->acc.gc;           // gc | gl contiguous = full layout
         D = ba->scale_inv.p; Dc = D; Dl = D + 3 * N;
@@ -534,7 +574,7 @@ struct Solver {
         pair_grid = ctx->sm_count * per_sm;
         const int max_grid = div_up(ba->lm_hi - ba->lm_lo, kThreads / 32);
         if (pair_grid > max_grid) pair_grid = max_grid > 0 ? max_grid : 1;
-        use_pairlist = getenv("PTZBA_SCHUR_PAIRLIST") != nullptr && ba->part_world == 1 && N <= 65535;
+        use_pairlist = ba->schur_mode != PTZBA_SCHUR_PER_LANDMARK && N <= 65535;
         if (use_pairlist) PROPAGATE(build_pair_list());
         return PTZBA_OK;
     }
@@ -672,7 +712,7 @@ struct Solver {
             PROPAGATE(solve(w_full.p, ba->sol2_c.p));
             b = w_full.p; c = ba->sol2_c.p;
         }
-        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, D, nullptr, ba->sol_c.p, b, c, nullptr, ba->scal.p);
+        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, D, nullptr, ba->sol_c.p, b, c, nullptr, ba->sums_part.p, ba->sums_ticket.p, ba->scal.p);
         KERNEL_POST(ctx);
         double h[4];
         PROPAGATE(read_scalars(h, 4));                  // synchronises: h_flags of factor() has arrived as well
@@ -729,7 +769,7 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
     // Delta = ||x0 * scale_inv||  ; g_norm, ||g_h|| etc. come from k_sums
     double h[8];
     CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
-    k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, nullptr, ba->x_cur.p, nullptr, nullptr, nullptr, ba->scal.p);
+    k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, nullptr, ba->x_cur.p, nullptr, nullptr, nullptr, ba->sums_part.p, ba->sums_ticket.p, ba->scal.p);
     KERNEL_POST(ctx);
     PROPAGATE(S.read_scalars(h, 1));
     double Delta = std::sqrt(h[0]);
@@ -744,11 +784,11 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
         // g_norm (inf-norm of the gradient), ||x|| and ||g_h|| = ||g / D|| (sum (D * (g / D^2))^2) in ONE read-back:
         // the two reductions write to different slots of the scalar block
         CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 16 * sizeof(double), s));
-        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, S.g, nullptr, nullptr, ba->x_cur.p, ba->scal.p);
+        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, S.g, nullptr, nullptr, ba->x_cur.p, ba->sums_part.p, ba->sums_ticket.p, ba->scal.p);
         KERNEL_POST(ctx);
         k_div_d2<<<div_up(nF, 256), 256, 0, s>>>(nF, S.D, S.g, S.w_full.p);
         KERNEL_POST(ctx);
-        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, nullptr, S.w_full.p, nullptr, nullptr, nullptr, ba->scal.p + 8);
+        k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, nullptr, S.w_full.p, nullptr, nullptr, nullptr, ba->sums_part.p, ba->sums_ticket.p, ba->scal.p + 8);
         KERNEL_POST(ctx);
         double h16[16];
         PROPAGATE(S.read_scalars(h16, 9));
@@ -811,7 +851,7 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
             KERNEL_POST(ctx);
             CU_CHECK(ctx, cudaMemsetAsync(ba->sol2_c.p, 0, 3 * sizeof(double), s));
             CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
-            k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, ba->sol2_c.p, nullptr, nullptr, nullptr, ba->scal.p);
+            k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, ba->sol2_c.p, nullptr, nullptr, nullptr, ba->sums_part.p, ba->sums_ticket.p, ba->scal.p);
             KERNEL_POST(ctx);
             if (ba->lmo_hi > ba->lmo_lo) {
                 k_jvp_sumsq<<<S.obs_grid, kThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p,
@@ -907,7 +947,7 @@ extern "C" int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, con
     KERNEL_POST(ctx);
     CU_CHECK(ctx, cudaMemsetAsync(ba->sol2_c.p, 0, 3 * sizeof(double), s));
     CU_CHECK(ctx, cudaMemsetAsync(ba->scal.p, 0, 8 * sizeof(double), s));
-    k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, ba->sol2_c.p, nullptr, nullptr, nullptr, ba->scal.p);
+    k_sums<<<ctx->sm_count, 256, 0, s>>>(nF, S.D, S.g, ba->sol2_c.p, nullptr, nullptr, nullptr, ba->sums_part.p, ba->sums_ticket.p, ba->scal.p);
     KERNEL_POST(ctx);
     if (ba->lmo_hi > ba->lmo_lo) {
         k_jvp_sumsq<<<S.obs_grid, kThreads, 0, s>>>(ba->lmo_lo, ba->lmo_hi, ba->s_cam.p, ba->s_lm.p, ba->cam_trig.p, ba->lm_trig.p,

@@ -117,23 +117,31 @@ __global__ void k_shared_flags(int n_lm, const double* __restrict__ count, int32
     if (l < n_lm) flag[l] = count[l] > 1.5 ? 1 : 0;
 }
 
-__global__ void k_pack_shared(int n_shared, const int32_t* __restrict__ ids, const double* __restrict__ V, const double* __restrict__ gl,
-                              const double* __restrict__ cost, double* __restrict__ buf) {
+// Only the shared landmarks THIS rank observes are packed (zeros otherwise) and unpacked: a landmark this rank never observes
+// may lie outside the id range k_set_params clears, so writing the global sum into the arena would be re-added by the next
+// pass's pack (stale blocks on every pass after the first with >= 3 ranks).
+__global__ void k_pack_shared(int n_shared, const int32_t* __restrict__ ids, const int32_t* __restrict__ lm_ptr, const double* __restrict__ V,
+                              const double* __restrict__ gl, const double* __restrict__ cost, double* __restrict__ buf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) buf[0] = cost[0];
     if (i >= n_shared) return;
     const int l = ids[i];
     double* b = buf + 1 + 5 * (size_t)i;
-    b[0] = V[3 * (size_t)l]; b[1] = V[3 * (size_t)l + 1]; b[2] = V[3 * (size_t)l + 2];
-    b[3] = gl[2 * (size_t)l]; b[4] = gl[2 * (size_t)l + 1];
+    if (lm_ptr[l + 1] > lm_ptr[l]) {
+        b[0] = V[3 * (size_t)l]; b[1] = V[3 * (size_t)l + 1]; b[2] = V[3 * (size_t)l + 2];
+        b[3] = gl[2 * (size_t)l]; b[4] = gl[2 * (size_t)l + 1];
+    } else {
+        b[0] = b[1] = b[2] = b[3] = b[4] = 0.0;
+    }
 }
 
-__global__ void k_unpack_shared(int n_shared, const int32_t* __restrict__ ids, const double* __restrict__ buf, double* __restrict__ V,
-                                double* __restrict__ gl, double* __restrict__ cost) {
+__global__ void k_unpack_shared(int n_shared, const int32_t* __restrict__ ids, const int32_t* __restrict__ lm_ptr, const double* __restrict__ buf,
+                                double* __restrict__ V, double* __restrict__ gl, double* __restrict__ cost) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) cost[0] = buf[0];
     if (i >= n_shared) return;
     const int l = ids[i];
+    if (lm_ptr[l + 1] <= lm_ptr[l]) return;
     const double* b = buf + 1 + 5 * (size_t)i;
     V[3 * (size_t)l] = b[0]; V[3 * (size_t)l + 1] = b[1]; V[3 * (size_t)l + 2] = b[2];
     gl[2 * (size_t)l] = b[3]; gl[2 * (size_t)l + 1] = b[4];
@@ -199,10 +207,10 @@ extern "C" int ptzba_ba_allreduce(ptzba_ba* ba) {
     }
     ba->cost_partial = false;
     cudaStream_t s = ctx->stream;
-    k_pack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->acc.V, ba->acc.gl, ba->acc.cost, ba->shared_buf.p);
+    k_pack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->lm_ptr.p, ba->acc.V, ba->acc.gl, ba->acc.cost, ba->shared_buf.p);
     KERNEL_POST(ctx);
     PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->shared_buf.p, 1 + 5 * (int64_t)ns));
-    k_unpack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->shared_buf.p, ba->acc.V, ba->acc.gl, ba->acc.cost);
+    k_unpack_shared<<<div_up(ns > 0 ? ns : 1, 256), 256, 0, s>>>(ns, ba->shared_ids.p, ba->lm_ptr.p, ba->shared_buf.p, ba->acc.V, ba->acc.gl, ba->acc.cost);
     KERNEL_POST(ctx);
     return PTZBA_OK;
 }

@@ -38,48 +38,36 @@ __device__ __forceinline__ void warp_build_tri(unsigned short* tab, int lane) {
     __syncwarp();
 }
 
-__device__ __forceinline__ void helper_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-
-// look-ahead group (128 threads): Cholesky of the 32 x 32 block held in Ls (lower, identity padded); 1 / L_jj into sInv.
-// Thread h owns the triangle entries e = h, h + 128, ... of the column-major list (<= 5 entries) in REGISTERS for the whole
-// factorisation; per column only the column itself travels through shared memory (col[]): owners publish it unscaled, every
-// thread reads the pivot and the two column entries each of its trailing entries needs (all loads issued before any use).
-constexpr int kOwn = (kTri + kCoopHelpers - 1) / kCoopHelpers;             // 5
-__device__ __forceinline__ bool group_potf2(double (*Ls)[NB + 1], double* sInv, double* col, const unsigned short* tab, int hid) {
-    int ii[kOwn], cc[kOwn];
-    double v[kOwn];
+// look-ahead group: Cholesky of the 32 x 32 block held in Ls (lower, identity padded); 1 / L_jj into sInv.
+// ONE warp, lane = row, right-looking, warp-synchronous (no named barrier): per column the pivot is a broadcast read, every lane
+// scales its entry of the column, then updates its own row right of it - (31 - j) independent read-modify-writes whose partner
+// L(c, j) is a broadcast read.  The round-1 version (128 threads, entries in registers, two bar.sync per column) needed 610
+// cycles per column (19.5 k per panel, the critical path of the whole factorisation at n = 765).
+__device__ __forceinline__ bool warp_potf2(double (*Ls)[NB + 1], double* sInv, double (*col)[NB], int lane) {
+    // lane = row, the row lives in registers (fully unrolled: 496 FMAs, ~1.6 k instructions); only the scaled column travels
+    // through shared memory (double buffered: one __syncwarp per column).  Entries right of the diagonal hold garbage that is
+    // never read.
+    double a[NB];
 #pragma unroll
-    for (int u = 0; u < kOwn; ++u) {
-        const int e = hid + kCoopHelpers * u;
-        const int code = e < kTri ? tab[e] : 0xff00;          // padding entry: column 255 > any j, never published
-        ii[u] = e < kTri ? (code >> 8) : 0;
-        cc[u] = e < kTri ? (code & 255) : 255;
-        v[u] = e < kTri ? Ls[ii[u]][cc[u]] : 0.0;
-    }
+    for (int c = 0; c < NB; ++c) a[c] = Ls[lane][c];
     bool bad = false;
+#pragma unroll
     for (int j = 0; j < NB; ++j) {
-#pragma unroll
-        for (int u = 0; u < kOwn; ++u)
-            if (cc[u] == j) col[ii[u]] = v[u];
-        helper_sync();
-        double piv = col[j];
+        double piv = __shfl_sync(0xffffffffu, a[j], j);
         if (!(piv > 0.0)) { bad = true; piv = 1.0; }
-        double ci[kOwn], cj[kOwn];
-#pragma unroll
-        for (int u = 0; u < kOwn; ++u) { ci[u] = col[ii[u]]; cj[u] = col[cc[u] & 31]; }
         const double inv = rsqrt(piv);
-        const double rp = inv * inv;
-        if (hid == 0) sInv[j] = inv;
+        const double lij = (lane == j) ? piv * inv : a[j] * inv;
+        a[j] = lij;
+        col[j & 1][lane] = lij;
+        if (lane == 0) sInv[j] = inv;
+        __syncwarp();
 #pragma unroll
-        for (int u = 0; u < kOwn; ++u) {
-            const bool own = cc[u] == j, trail = cc[u] > j && cc[u] < NB;
-            const double upd = fma(-(ci[u] * rp), cj[u], v[u]);
-            const double fin = (ii[u] == j) ? piv * inv : v[u] * inv;
-            v[u] = own ? fin : (trail ? upd : v[u]);
-            if (own) Ls[ii[u]][j] = v[u];
-        }
-        helper_sync();
+        for (int c = j + 1; c < NB; ++c) a[c] = fma(-lij, col[j & 1][c], a[c]);
     }
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+        if (c <= lane) Ls[lane][c] = a[c];
+    __syncwarp();
     return bad;
 }
 
@@ -108,7 +96,7 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
     double (*Ws)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + 2 * NB * (NB + 1) + 2 * NB * (TS + 1));
     __shared__ double sInv[NB];
     __shared__ unsigned short sTri[kTri];
-    __shared__ double sCol[NB];
+    __shared__ double sCol[2][NB];
     const int tid = threadIdx.x, lane = tid & 31;
     const bool helper = tid >= kCoopWorkers;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -119,10 +107,9 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
         Ls[i][j] = (i < n && j < n && j <= i) ? A[(size_t)i + (size_t)j * lda] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
-    if (helper) {
-        if (tid < kCoopWorkers + 32) warp_build_tri(sTri, lane);
-        helper_sync();
-        if (group_potf2(Ls, sInv, sCol, sTri, tid - kCoopWorkers) && tid == kCoopWorkers && cta == 0) atomicMax(info, 1);
+    if (tid >= kCoopWorkers && tid < kCoopWorkers + 32) {
+        warp_build_tri(sTri, lane);
+        if (warp_potf2(Ls, sInv, sCol, lane) && lane == 0 && cta == 0) atomicMax(info, 1);
     }
     grid.sync();        // every CTA has read the first block before CTA 0 overwrites it with its factor (also a CTA barrier)
     COOP_TICK(0);
@@ -176,7 +163,7 @@ k_potrf_coop(double* __restrict__ A, int n, int lda, int* __restrict__ info, dou
             const int hid = tid - kCoopWorkers;
             asm volatile("bar.sync 3, 384;" ::: "memory");      // the workers have loaded and updated the next diagonal block (Ls)
             HELP_TICK(7);
-            if (group_potf2(Ls, sInv, sCol, sTri, hid) && hid == 0 && cta == 0) atomicMax(info, k1 + 1);
+            if (hid < 32 && warp_potf2(Ls, sInv, sCol, lane) && hid == 0 && cta == 0) atomicMax(info, k1 + 1);
             if (dbg && blockIdx.x == 0 && threadIdx.x == kCoopWorkers) dbg[16 + kb] = clock64() - th;
             HELP_TICK(8);
 #undef HELP_TICK

@@ -116,31 +116,39 @@ __device__ __forceinline__ double fast_rcp(double z) {
     return fma(r, e, r);
 }
 
+// shared front end of project_fast / project_fast_jac.  Every product that feeds an addition is written as an explicit
+// __dmul_rn / fma, so that the compiler's FMA contraction cannot differ between kernels: the residual-only pass and the
+// fused pass return bit-identical residuals (the trust-region loop compares costs computed by the two).
+struct ProjCore { double sa, ca, Ny, iz, px, py; };
+__device__ __forceinline__ ProjCore project_core(const CamTrig& c, const LmTrig& l) {
+    ProjCore p;
+    p.sa = fma(l.sth, c.cp, -__dmul_rn(l.cth, c.sp));
+    p.ca = fma(l.cth, c.cp, __dmul_rn(l.sth, c.sp));
+    p.Ny = fma(c.st, p.ca, -__dmul_rn(c.ct, l.T));
+    const double z = fma(c.st, l.T, __dmul_rn(c.ct, p.ca));
+    p.iz = fast_rcp(z);
+    p.px = __dmul_rn(p.sa, p.iz);
+    p.py = __dmul_rn(p.Ny, p.iz);
+    return p;
+}
+
 __device__ __forceinline__ void project_fast(const CamTrig& c, const LmTrig& l, double u, double v, double& x,
                                              double& y) {
-    const double sa = l.sth * c.cp - l.cth * c.sp;
-    const double ca = l.cth * c.cp + l.sth * c.sp;
-    const double Ny = c.st * ca - c.ct * l.T;
-    const double z = c.st * l.T + c.ct * ca;
-    const double iz = fast_rcp(z);
-    x = fma(c.f, sa * iz, u);
-    y = fma(c.f, Ny * iz, v);
+    const ProjCore p = project_core(c, l);
+    x = fma(c.f, p.px, u);
+    y = fma(c.f, p.py, v);
 }
 
 __device__ __forceinline__ void project_fast_jac(const CamTrig& c, const LmTrig& l, double u, double v, double& x,
                                                  double& y, ObsGeom& g) {
-    const double sa = l.sth * c.cp - l.cth * c.sp;
-    const double ca = l.cth * c.cp + l.sth * c.sp;
-    const double Ny = c.st * ca - c.ct * l.T;
-    const double z = c.st * l.T + c.ct * ca;
-    const double iz = fast_rcp(z);
-    g.px = sa * iz;
-    g.py = Ny * iz;
+    const ProjCore p = project_core(c, l);
+    g.px = p.px;
+    g.py = p.py;
     x = fma(c.f, g.px, u);
     y = fma(c.f, g.py, v);
-    const double fz = c.f * iz;
-    g.xa = fz * fma(c.ct * sa, g.px, ca);            // f (ca z + ct sa^2) / z^2
-    g.ya = fz * sa * fma(c.ct, g.py, -c.st);         // f sa (-st z + ct Ny) / z^2
+    const double fz = c.f * p.iz;
+    g.xa = fz * fma(c.ct * p.sa, g.px, p.ca);        // f (ca z + ct sa^2) / z^2
+    g.ya = fz * p.sa * fma(c.ct, g.py, -c.st);       // f sa (-st z + ct Ny) / z^2
     g.xt = c.f * g.px * g.py;                        // f Nx Ny / z^2
     g.yt = fma(c.f * g.py, g.py, c.f);               // f (1 + Ny^2/z^2)
     const double fzS = -fz * l.S;

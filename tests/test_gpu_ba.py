@@ -4,6 +4,7 @@ import pytest
 
 from conftest import load_golden, graph_from_npz
 from oracle import ptz_oracle as O
+from oracle import c_port
 import ptz_slam_b200  # noqa: F401
 from ptz_slam_b200 import synth, _lib
 from ptz_slam_b200 import bundle_adjustment as BA
@@ -45,6 +46,23 @@ def _check_normal_equations(fb, x, ref_pose, u, v):
     np.testing.assert_allclose(out["V"], V, rtol=RTOL, atol=1e-12 * np.abs(V).max())
     np.testing.assert_allclose(out["gl"], gl, rtol=1e-8, atol=1e-11 * np.abs(gl).max())
     prob.close()
+
+
+def check_against_c_port(out, fb, x, ref_pose, u, v):
+    """ALL of residual, U, g_c, V, g_l and the cost against the plain-C restatement (oracle/ptz_oracle_c.c), which handles the
+    full-size configs in well under a second on the host threads; the C port itself is pinned to the numpy oracle and the
+    reference goldens by tests/test_oracle_c.py."""
+    poses, rays = O.ba_unpack(x, fb.n_pose, ref_pose)
+    r, U, gc, V, gl, cost = c_port.ba_fused(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v)
+    np.testing.assert_allclose(out["residual"], r.ravel(), rtol=RTOL, atol=ATOL)
+    assert abs(out["cost"] - cost) <= 1e-11 * cost
+    Up = np.stack([out["U"][:, 0, 0], out["U"][:, 0, 1], out["U"][:, 0, 2], out["U"][:, 1, 1], out["U"][:, 1, 2], out["U"][:, 2, 2]], 1)
+    Vp = np.stack([out["V"][:, 0, 0], out["V"][:, 0, 1], out["V"][:, 1, 1]], 1)
+    np.testing.assert_allclose(Up[1:], U[1:], rtol=RTOL, atol=1e-12 * np.abs(U[1:]).max())
+    np.testing.assert_allclose(out["gc"][1:], gc[1:], rtol=1e-8, atol=1e-11 * np.abs(gc[1:]).max())
+    np.testing.assert_allclose(Vp, V, rtol=RTOL, atol=1e-12 * np.abs(V).max())
+    np.testing.assert_allclose(out["gl"], gl, rtol=1e-8, atol=1e-11 * np.abs(gl).max())
+    assert np.all(out["U"][0] == 0) and np.all(out["gc"][0] == 0)
 
 
 def test_normal_equations_small_unsorted():
@@ -100,6 +118,8 @@ def test_full_size_cfg3_properties():
     sub = slice(0, 200000)
     ro = O.ba_residual_flat(poses, rays, fb.cam_idx[sub], fb.lm_idx[sub], fb.obs_xy[sub], synth.PP_U, synth.PP_V)
     np.testing.assert_allclose(out["residual"][:400000], ro.ravel(), rtol=RTOL, atol=ATOL)
+    # (5) every block and every residual of the full-size problem against the C port
+    check_against_c_port(out, fb, x, fb.ptz_init[0], synth.PP_U, synth.PP_V)
     prob.close()
 
 

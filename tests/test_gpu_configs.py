@@ -89,4 +89,7 @@ def test_cfg5_full_size_properties():
     rhs = out["V"][:, 0, 0].sum() - np.sum(Jr0[:, :, 0] ** 2)
     assert abs(lhs - rhs) <= 1e-9 * rhs
     assert np.all(out["U"][0] == 0)
+    # every block and every residual of the full-size problem against the C port of the reference's pass
+    from test_gpu_ba import check_against_c_port
+    check_against_c_port(out, fb, x, fb.ptz_init[0], synth.PP_U, synth.PP_V)
     prob.close()
