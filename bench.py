@@ -232,8 +232,9 @@ def run_ours(args):
     lm_touched = int(np.unique(fb.lm_idx).size)
     abytes = algorithmic_bytes(fb.n_obs, lm_touched, kf_range[1] - kf_range[0])      # this rank's share of the pass
     R = args.replicas
-    if R <= 0:      # enough replicas of the rank's arrays that a pass never finds them in the 126 MB L2
-        R = max(4, int(np.ceil(2.2 * 126e6 / max(abytes, 1))))
+    if R <= 0:      # enough replicas of the rank's arrays that a pass never finds them in the 126 MB L2; the SAME number on every
+        # rank (the shards differ slightly in size, and setting up a replica's exchange is a collective)
+        R = max(4, int(np.ceil(2.2 * 126e6 * world / algorithmic_bytes(fb_full.n_obs, fb_full.n_landmark, fb_full.n_pose))))
     probs = [BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v, ctx=ctx) for _ in range(R)]
     x_dev = [torch.from_numpy(x0).cuda() for _ in range(R)]
     r_dev = [torch.empty(2 * fb.n_obs, dtype=torch.float64, device="cuda") for _ in range(R)]

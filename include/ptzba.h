@@ -130,8 +130,25 @@ int ptzba_ekf_batch_set(ptzba_ekf_batch* b, int seq, const double* ptz3, const d
                         const double* state_cov);
 /* copy state back to host: ptz[n_seq*3], velocity[n_seq*3], rays[n_seq*n_ray*2] (any may be NULL) */
 int ptzba_ekf_batch_get(ptzba_ekf_batch* b, double* ptz, double* velocity, double* rays);
-/* dense covariance of one sequence, (3+2 n_ray)^2 row-major, host */
+/* dense covariance of one sequence, (3+2 n_active)^2 row-major, host */
 int ptzba_ekf_batch_get_cov(ptzba_ekf_batch* b, int seq, double* state_cov);
+/* ---- N4: ray bookkeeping between frames on the RESIDENT state (PtzSlam.remove_rays / add_rays, ptz_slam.py:291-388).
+ * n_ray of ptzba_ekf_batch_create is the initial ray count of every sequence AND the initial capacity (stride) of the per-sequence
+ * arrays; afterwards every sequence has its own active count, the first n_active rays of its slot.  ptzba_ekf_batch_set /
+ * _get_cov / _get_rays address the active part of one sequence (dense, no padding); ptzba_ekf_batch_get keeps returning rays
+ * with the capacity as stride. */
+int ptzba_ekf_batch_n_rays(ptzba_ekf_batch* b, int seq, int32_t* n_active, int32_t* capacity);
+int ptzba_ekf_batch_get_rays(ptzba_ekf_batch* b, int seq, double* rays /*[n_active*2] host*/);
+/* the rays delete_index[0..n_del) (host, any order) leave sequence `seq` with their covariance rows / columns; order of the others kept */
+int ptzba_ekf_batch_remove_rays(ptzba_ekf_batch* b, int seq, int n_del, const int32_t* delete_index);
+/* k rays (host [k*2]) are appended to sequence `seq`: variance angle_var, no correlation; the capacity grows when needed */
+int ptzba_ekf_batch_add_rays(ptzba_ekf_batch* b, int seq, int k, const double* new_rays);
+/* covariance part of the predict step alone: P[0:3,0:3] += 5 diag(angle_var, angle_var, f_var) for every sequence (ptz_slam.py:425-426) */
+int ptzba_ekf_batch_predict_cov(ptzba_ekf_batch* b);
+/* current observation capacity per step: obs_xy / obs_index of the step calls are [n_seq * max_obs * 2] / [n_seq * max_obs] */
+int ptzba_ekf_batch_max_obs(ptzba_ekf_batch* b, int32_t* max_obs);
+/* grow the ray capacity per sequence and / or the observation capacity per step (max_obs) ahead of time */
+int ptzba_ekf_batch_reserve(ptzba_ekf_batch* b, int ray_capacity, int max_obs);
 
 /* ---- A6/A7: bundle adjustment  (bundle_adjustment._compute_residual bundle_adjustment.py:25-106,
  *             steps 2-3 :167-208, scipy least_squares(method='trf', x_scale='jac') call :200-202;

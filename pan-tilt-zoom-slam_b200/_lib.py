@@ -71,6 +71,13 @@ SIGNATURES = {
     "ptzba_ekf_batch_set": (_I, [_P, _I, _P, _P, _P, _P]),
     "ptzba_ekf_batch_get": (_I, [_P, _P, _P, _P]),
     "ptzba_ekf_batch_get_cov": (_I, [_P, _I, _P]),
+    "ptzba_ekf_batch_n_rays": (_I, [_P, _I, _P, _P]),
+    "ptzba_ekf_batch_get_rays": (_I, [_P, _I, _P]),
+    "ptzba_ekf_batch_remove_rays": (_I, [_P, _I, _I, _P]),
+    "ptzba_ekf_batch_add_rays": (_I, [_P, _I, _I, _P]),
+    "ptzba_ekf_batch_reserve": (_I, [_P, _I, _I]),
+    "ptzba_ekf_batch_predict_cov": (_I, [_P]),
+    "ptzba_ekf_batch_max_obs": (_I, [_P, _P]),
     "ptzba_ba_create": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _D, _D, ctypes.POINTER(_P)]),
     "ptzba_ba_destroy": (None, [_P]),
     "ptzba_ba_residual": (_I, [_P, _I, _P, _P, _P]),

@@ -1,18 +1,21 @@
 // dense.cu - hand-written BATCHED dense FP64 Cholesky kernels (the innovation covariances S = H P H^T + R of many independent
 // EKF sequences, ptz_slam.py:256-259; the reference inverts S with numpy's LU).
 //
-// Blocked right-looking Cholesky (lower, column-major, in place), one launch pair per 32-wide panel for the whole batch:
-//     k_potf2_trsm  every CTA factors the 32 x 32 diagonal block redundantly in shared memory, then solves its 128 panel rows
-//     k_syrk_lower  64 x 64 tiles of the trailing matrix, FP64 FMA, lower tiles only
-// and the multi-right-hand-side forward solve Z = L^-1 G on row-major G (k_fwd_diag_rows / k_fwd_update_rows).
+// Blocked LEFT-looking Cholesky (lower, column-major, in place), one launch pair per 32-wide panel for the whole batch:
+//     k_chol_ll_update  64 x 32 tiles of block column k: C -= L[:, 0:k] L[k:k+32, 0:k]^T  - one DMMA product over the whole K
+//                       range, so every entry of the matrix is read and written ONCE (the right-looking rank-32 updates of
+//                       round 1 re-streamed the trailing matrix for every panel: ~1.3 FMA per byte)
+//     k_potf2_trsm      every CTA factors the 32 x 32 diagonal block redundantly in shared memory, then solves its 128 panel rows
+// and the multi-right-hand-side forward solve Z = L^-1 G on row-major G, left-looking as well (k_fwd_ll_update: 32 x 64 tiles of
+// block row k, K = k; k_fwd_diag_rows).  The tile products run on the FP64 tensor cores (dense_mma.cuh).
 // The single reduced camera system of bundle adjustment uses the cooperative one-kernel path of dense_coop.cu instead.
 #include "common.h"
 #include "dense.h"
+#include "dense_mma.cuh"
 
 namespace {
 
 constexpr int NB = 32;        // panel width
-constexpr int TS = 64;        // syrk tile
 
 // ---- fused panel step: every CTA factors the NB x NB diagonal block redundantly in shared memory (128 threads, rsqrt on the
 // critical path) and then solves its own 128 rows of the panel; CTA 0 also writes the factored diagonal block back.
@@ -73,58 +76,25 @@ __global__ void __launch_bounds__(128) k_potf2_trsm(double* __restrict__ A0, int
     for (int j = 0; j < NB; ++j) A[(size_t)r + (size_t)(k + j) * lda] = x[j];
 }
 
-// ---- syrk: C -= P P^T on the lower tiles of the trailing matrix; 256 threads, 4x4 outputs each -----------------------
-__global__ void __launch_bounds__(256) k_syrk_lower(double* __restrict__ A0, int lda, size_t stride,
-                                                    const int* __restrict__ n_arr, int n_fixed, int k) {
+// ---- left-looking update of block column k (32 columns): rows r0 .. r0+63 of it, C -= L[r0.., 0:k] * L[k..k+31, 0:k]^T ----------
+__global__ void __launch_bounds__(dmma::kThreads) k_chol_ll_update(double* __restrict__ A0, int lda, size_t stride,
+                                                                  const int* __restrict__ n_arr, int n_fixed, int k) {
+    using T = dmma::Tile<64, 32>;
+    __shared__ __align__(16) double sm[T::kSmemDoubles];
     const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
-    if (k + NB >= n) return;
-    const int nb = NB;
+    const int r0 = k + blockIdx.x * 64;
+    if (k >= n || r0 >= n) return;
     double* A = A0 + stride * blockIdx.y;
-    // tile pair (ti >= tj) from the linear block index
-    const int t0 = k + nb;
-    const int m = n - t0;
-    const int nt = (m + TS - 1) / TS;
-    int b = blockIdx.x, ti = 0;
-    // rows of the lower-triangular tile grid have 1,2,3,... tiles
-    ti = (int)((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
-    while (ti * (ti + 1) / 2 > b) --ti;
-    const int tj = b - ti * (ti + 1) / 2;
-    if (ti >= nt) return;
-    __shared__ double Pi[NB][TS + 1];
-    __shared__ double Pj[NB][TS + 1];
-    const int tid = threadIdx.x;
-    const int r0 = t0 + ti * TS, c0 = t0 + tj * TS;
-    for (int e = tid; e < NB * TS; e += 256) {
-        const int rr = e % TS, t = e / TS;
-        const int gi = r0 + rr, gj = c0 + rr;
-        Pi[t][rr] = (gi < n && t < nb) ? A[(size_t)gi + (size_t)(k + t) * lda] : 0.0;
-        Pj[t][rr] = (gj < n && t < nb) ? A[(size_t)gj + (size_t)(k + t) * lda] : 0.0;
-    }
-    __syncthreads();
-    const int tx = tid % 16, ty = tid / 16;      // rows tx + 16*a, cols ty + 16*b  (coalesced along rows)
-    double acc[4][4];
+    double acc[T::RM][T::RN][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < T::RM; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < NB; ++t) {
-        double pi[4], pj[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { pi[a] = Pi[t][tx + 16 * a]; pj[a] = Pj[t][ty + 16 * a]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = fma(pi[a], pj[c], acc[a][c]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int gi = r0 + tx + 16 * a, gj = c0 + ty + 16 * c;
-            if (gi < n && gj < n && gi >= gj) A[(size_t)gi + (size_t)gj * lda] -= acc[a][c];
-        }
+        for (int b = 0; b < T::RN; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    T::accumulate(A + r0, (size_t)lda, n - r0, A + k, (size_t)lda, n - k, k, acc, sm);
+    T::for_each(acc, [&](int i, int j, double v) {
+        const int gi = r0 + i, gj = k + j;
+        if (gi < n && gj < n && gi >= gj) A[(size_t)gi + (size_t)gj * lda] -= v;
+    });
 }
 
 }  // namespace
@@ -134,12 +104,12 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
     cudaStream_t s = ctx->stream;
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
     for (int k = 0; k < n_max; k += NB) {
+        if (k > 0) {
+            k_chol_ll_update<<<dim3(div_up(n_max - k, 64), batch), dmma::kThreads, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
+            KERNEL_POST(ctx);
+        }
         const int m = n_max - k - NB;
         k_potf2_trsm<<<dim3(m > 0 ? div_up(m, 128) : 1, batch), 128, 0, s>>>(A, lda, stride, d_n_arr, n_max, k, d_info, d_info_per_batch);
-        KERNEL_POST(ctx);
-        if (m <= 0) break;
-        const int nt = div_up(m, TS);
-        k_syrk_lower<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;
@@ -181,50 +151,28 @@ __global__ void __launch_bounds__(128) k_fwd_diag_rows(const double* __restrict_
         if (i < nb) G[(size_t)(k + i) * ldg + c] = x[i];
 }
 
-// trailing rows: G[r, c] -= sum_t L[r, k+t] * G[k+t, c]   for r >= k+NB ; 64 x 64 tiles, 4x4 per thread
-__global__ void __launch_bounds__(256) k_fwd_update_rows(const double* __restrict__ L0, int lda, size_t strideL,
-                                                         double* __restrict__ G0, int ldg, size_t strideG,
-                                                         const int* __restrict__ n_arr, int extra_cols, int k) {
-    const int n = n_arr[blockIdx.z];
-    const int r0 = k + NB + blockIdx.y * TS;
-    if (r0 >= n) return;
+// block row k (32 rows) of G, columns c0 .. c0+63:  G[k+i, c] -= sum_{t<k} L[k+i, t] * Z[t, c]   (left-looking, K = k)
+__global__ void __launch_bounds__(dmma::kThreads) k_fwd_ll_update(const double* __restrict__ L0, int lda, size_t strideL,
+                                                                 double* __restrict__ G0, int ldg, size_t strideG,
+                                                                 const int* __restrict__ n_arr, int extra_cols, int k) {
+    using T = dmma::Tile<32, 64>;
+    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    const int n = n_arr[blockIdx.y];
+    if (k >= n) return;
     const int ncols = n + extra_cols;
-    const int c0 = blockIdx.x * TS;
+    const int c0 = blockIdx.x * 64;
     if (c0 >= ncols) return;
-    const double* L = L0 + strideL * blockIdx.z;
-    double* G = G0 + strideG * blockIdx.z;
-    __shared__ double Lp[NB][TS + 1];   // Lp[t][r]
-    __shared__ double Zk[NB][TS + 1];   // Zk[t][c]
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NB * TS; e += 256) {
-        const int rr = e % TS, t = e / TS;
-        Lp[t][rr] = (r0 + rr < n) ? L[(size_t)(r0 + rr) + (size_t)(k + t) * lda] : 0.0;
-        Zk[t][rr] = (c0 + rr < ncols) ? G[(size_t)(k + t) * ldg + c0 + rr] : 0.0;
-    }
-    __syncthreads();
-    const int tx = tid % 16, ty = tid / 16;   // cols tx + 16*b (coalesced), rows ty + 16*a
-    double acc[4][4];
+    const double* L = L0 + strideL * blockIdx.y;
+    double* G = G0 + strideG * blockIdx.y;
+    double acc[T::RM][T::RN][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < T::RM; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < NB; ++t) {
-        double lr[4], zc[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { lr[a] = Lp[t][ty + 16 * a]; zc[a] = Zk[t][tx + 16 * a]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(lr[a], zc[b], acc[a][b]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int r = r0 + ty + 16 * a, c = c0 + tx + 16 * b;
-            if (r < n && c < ncols) G[(size_t)r * ldg + c] -= acc[a][b];
-        }
+        for (int b = 0; b < T::RN; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    T::accumulate(L + k, (size_t)lda, n - k, G + c0, (size_t)ldg, ncols - c0, k, acc, sm);
+    T::for_each(acc, [&](int i, int j, double v) {
+        if (k + i < n && c0 + j < ncols) G[(size_t)(k + i) * ldg + c0 + j] -= v;
+    });
 }
 
 }  // namespace
@@ -235,12 +183,11 @@ int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_
     cudaStream_t s = ctx->stream;
     const int ncols_max = n_max + extra_cols;
     for (int k = 0; k < n_max; k += NB) {
+        if (k > 0) {
+            k_fwd_ll_update<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, 0, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
+            KERNEL_POST(ctx);
+        }
         k_fwd_diag_rows<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
-        KERNEL_POST(ctx);
-        const int m = n_max - k - NB;
-        if (m <= 0) break;
-        k_fwd_update_rows<<<dim3(div_up(ncols_max, TS), div_up(m, TS), batch), 256, 0, s>>>(L, lda, strideL, G, ldg, strideG,
-                                                                                            d_n_arr, extra_cols, k);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;

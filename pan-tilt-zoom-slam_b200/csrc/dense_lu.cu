@@ -7,10 +7,13 @@
 // getrf's behaviour on those matrices.
 //
 // Layout: A column-major (lda), matrix b of the batch at A + b*stride, order n_arr[b] (device array).  Right-looking,
-// panel width 32:  panel (one CTA per matrix: pivot search, swap, scale, rank-1 inside the panel) -> laswp on the
-// other columns -> U12 = L11^-1 A12 -> A22 -= L21 U12 (64x64 tiles).  Right-hand sides are ROW-major [n x ncols].
+// panel width 32:  panel (one CTA per matrix; the panel is factored in sub-panels of W columns that live in SHARED memory
+// for their whole pivot search / swap / scale / rank-1 sequence) -> laswp on the other columns -> U12 = L11^-1 A12 ->
+// A22 -= L21 U12 (64x64 tiles on the FP64 tensor cores).  Right-hand sides are ROW-major [n x ncols]; the two triangular
+// solves are left-looking (one DMMA product over the whole K range per block row, dense_mma.cuh).
 #include "common.h"
 #include "dense.h"
+#include "dense_mma.cuh"
 
 namespace {
 
@@ -18,8 +21,15 @@ constexpr int NB = 32;
 constexpr int TS = 64;
 constexpr int PT = 512;     // threads of the panel kernel
 
+// One CTA per matrix factors the 32-column panel k0 in sub-panels of W columns.  A sub-panel (rows j0 .. n-1, W columns) is
+// copied to shared memory once, goes through its W pivot searches / swaps / scalings / rank-1 updates there, is written back,
+// and is then applied to the panel columns right of it (W x w triangular solve + rank-W update through L2).  The round-1
+// kernel did every rank-1 update of the whole 32-column panel through global memory: 265 us per panel at n = 1150.
+// Shared memory: W * (n - k0) doubles (+ small); W is chosen by the host so that it fits.
+template <int W>
 __global__ void __launch_bounds__(PT) k_lu_panel(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
                                                  int k0, int* __restrict__ ipiv0, int ld_ipiv, int* __restrict__ info) {
+    extern __shared__ __align__(16) double Sp[];     // [W][mp]: column c of the sub-panel at Sp + c * mp
     const int b = blockIdx.x;
     const int n = n_arr[b];
     if (k0 >= n) return;
@@ -30,57 +40,116 @@ __global__ void __launch_bounds__(PT) k_lu_panel(double* __restrict__ A0, int ld
     __shared__ int s_idx[PT / 32];
     __shared__ int s_piv;
     __shared__ double s_row[NB];
+    __shared__ double s_U[W][NB];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int jj = 0; jj < nb; ++jj) {
-        const int j = k0 + jj;
-        // (1) pivot search in column j, rows j..n-1 (first index of the maximum magnitude, like idamax)
-        double best = -1.0;
-        int bi = j;
-        const double* col = A + (size_t)j * lda;
-        for (int r = j + tid; r < n; r += PT) {
-            const double a = fabs(col[r]);
-            if (a > best) { best = a; bi = r; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (lane == 0) { s_val[w] = best; s_idx[w] = bi; }
+    for (int q0 = 0; q0 < nb; q0 += W) {
+        const int j0 = k0 + q0;                       // first column / row of the sub-panel
+        const int wq = (nb - q0) < W ? (nb - q0) : W;
+        const int mp = n - j0;                        // its rows j0 .. n-1
+        for (int c = 0; c < wq; ++c)
+            for (int r = tid; r < mp; r += PT) Sp[(size_t)c * mp + r] = A[(size_t)(j0 + c) * lda + j0 + r];
         __syncthreads();
-        if (w == 0) {
-            best = lane < PT / 32 ? s_val[lane] : -1.0;
-            bi = lane < PT / 32 ? s_idx[lane] : 0x7fffffff;
+        for (int jj = 0; jj < wq; ++jj) {
+            const int j = j0 + jj;
+            // (1) pivot search in column jj of the sub-panel, local rows jj .. mp-1 (first index of the maximum magnitude, like idamax)
+            double best = -1.0;
+            int bi = jj;
+            const double* col = Sp + (size_t)jj * mp;
+            for (int r = jj + tid; r < mp; r += PT) {
+                const double a = fabs(col[r]);
+                if (a > best) { best = a; bi = r; }
+            }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, off);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            if (lane == 0) {
-                s_piv = bi;
-                ipiv[j] = bi;
-                if (!(best > 0.0)) atomicMax(info, j + 1);
+            if (lane == 0) { s_val[w] = best; s_idx[w] = bi; }
+            __syncthreads();
+            if (w == 0) {
+                best = lane < PT / 32 ? s_val[lane] : -1.0;
+                bi = lane < PT / 32 ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) {
+                    s_piv = bi;
+                    ipiv[j] = j0 + bi;
+                    if (!(best > 0.0)) atomicMax(info, j + 1);
+                }
             }
+            __syncthreads();
+            const int pl = s_piv;                      // local pivot row
+            // (2) swap rows jj and pl: inside the sub-panel (shared memory) and in the other columns of the panel (global memory);
+            // publish the pivot row of the sub-panel
+            if (tid < nb) {
+                const int c = tid - q0;                // column relative to the sub-panel
+                if (c >= 0 && c < wq) {
+                    double* cc = Sp + (size_t)c * mp;
+                    const double vj = cc[jj], vp = cc[pl];
+                    if (pl != jj) { cc[jj] = vp; cc[pl] = vj; }
+                    s_row[c] = vp;
+                } else if (pl != jj) {
+                    double* cg = A + (size_t)(k0 + tid) * lda + j0;
+                    const double vj = cg[jj], vp = cg[pl];
+                    cg[jj] = vp; cg[pl] = vj;
+                }
+            }
+            __syncthreads();
+            const double piv = s_row[jj];
+            const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+            // (3) scale the column and rank-1 update of the remaining sub-panel columns, all in shared memory
+            for (int r = jj + 1 + tid; r < mp; r += PT) {
+                const double l = Sp[(size_t)jj * mp + r] * inv;
+                Sp[(size_t)jj * mp + r] = l;
+#pragma unroll
+                for (int c = 0; c < W; ++c)
+                    if (c > jj && c < wq) Sp[(size_t)c * mp + r] = fma(-l, s_row[c], Sp[(size_t)c * mp + r]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const int p = s_piv;
-        // (2) swap rows j and p inside the panel, publish the pivot row
-        if (tid < nb) {
-            double* cj = A + (size_t)(k0 + tid) * lda;
-            const double vj = cj[j], vp = cj[p];
-            if (p != j) { cj[j] = vp; cj[p] = vj; }
-            s_row[tid] = vp;
-        }
-        __syncthreads();
-        const double piv = s_row[jj];
-        const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
-        // (3) scale the column and rank-1 update of the remaining panel columns
-        for (int r = j + 1 + tid; r < n; r += PT) {
-            const double l = A[(size_t)j * lda + r] * inv;
-            A[(size_t)j * lda + r] = l;
-            for (int c = jj + 1; c < nb; ++c) A[(size_t)(k0 + c) * lda + r] = fma(-l, s_row[c], A[(size_t)(k0 + c) * lda + r]);
+        // (4) write the factored sub-panel back
+        for (int c = 0; c < wq; ++c)
+            for (int r = tid; r < mp; r += PT) A[(size_t)(j0 + c) * lda + j0 + r] = Sp[(size_t)c * mp + r];
+        // (5) apply it to the panel columns right of it: U = L11^-1 A12 (unit lower W x W), then A22 -= L21 U
+        const int wr = nb - q0 - wq;                   // columns to the right, inside the panel
+        if (wr > 0) {
+            __syncthreads();                           // the row swaps of those columns (global memory) are visible
+            if (tid < wr) {
+                double* cg = A + (size_t)(j0 + wq + tid) * lda + j0;
+                double x[W];
+#pragma unroll
+                for (int i = 0; i < W; ++i) x[i] = i < wq ? cg[i] : 0.0;
+#pragma unroll
+                for (int i = 1; i < W; ++i) {
+                    double sacc = x[i];
+#pragma unroll
+                    for (int t = 0; t < i; ++t) sacc = fma(-Sp[(size_t)t * mp + i], x[t], sacc);
+                    x[i] = sacc;
+                }
+#pragma unroll
+                for (int i = 0; i < W; ++i) {
+                    if (i < wq) cg[i] = x[i];
+                    s_U[i][tid] = x[i];
+                }
+            }
+            __syncthreads();
+            for (int r = wq + tid; r < mp; r += PT) {
+                double l[W];
+#pragma unroll
+                for (int t = 0; t < W; ++t) l[t] = t < wq ? Sp[(size_t)t * mp + r] : 0.0;
+                for (int c = 0; c < wr; ++c) {
+                    double* dst = A + (size_t)(j0 + wq + c) * lda + j0 + r;
+                    double v = *dst;
+#pragma unroll
+                    for (int t = 0; t < W; ++t) v = fma(-l[t], s_U[t][c], v);
+                    *dst = v;
+                }
+            }
         }
         __syncthreads();
     }
@@ -133,50 +202,27 @@ __global__ void __launch_bounds__(128) k_lu_trsm_u12(double* __restrict__ A0, in
     for (int i = 0; i < NB; ++i) col[i] = x[i];
 }
 
-// A22 -= L21 U12 ; 64x64 tiles, 4x4 per thread
-__global__ void __launch_bounds__(256) k_lu_gemm(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
-                                                 int k0) {
+// A22 -= L21 U12 ; 64x64 tiles on the FP64 tensor cores (K = 32)
+__global__ void __launch_bounds__(dmma::kThreads) k_lu_gemm(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
+                                                           int k0) {
+    using T = dmma::Tile<64, 64>;
+    __shared__ __align__(16) double sm[T::kSmemDoubles];
     const int b = blockIdx.z;
     const int n = n_arr[b];
     const int t0 = k0 + NB;
     const int r0 = t0 + blockIdx.x * TS, c0 = t0 + blockIdx.y * TS;
     if (r0 >= n || c0 >= n) return;
     double* A = A0 + stride * b;
-    __shared__ double Lp[NB][TS + 1];   // Lp[t][r] = A[r0+r][k0+t]
-    __shared__ double Uk[NB][TS + 1];   // Uk[t][c] = A[k0+t][c0+c]
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NB * TS; e += 256) {
-        const int rr = e % TS, t = e / TS;
-        Lp[t][rr] = (r0 + rr < n) ? A[(size_t)(r0 + rr) + (size_t)(k0 + t) * lda] : 0.0;
-    }
-    for (int e = tid; e < NB * TS; e += 256) {
-        const int t = e % NB, cc = e / NB;
-        Uk[t][cc] = (c0 + cc < n) ? A[(size_t)(k0 + t) + (size_t)(c0 + cc) * lda] : 0.0;
-    }
-    __syncthreads();
-    const int tx = tid % 16, ty = tid / 16;   // rows tx + 16a (coalesced), cols ty + 16c
-    double acc[4][4];
+    double acc[T::RM][T::RN][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < T::RM; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < NB; ++t) {
-        double lr[4], uc[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { lr[a] = Lp[t][tx + 16 * a]; uc[a] = Uk[t][ty + 16 * a]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = fma(lr[a], uc[c], acc[a][c]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int r = r0 + tx + 16 * a, cc = c0 + ty + 16 * c;
-            if (r < n && cc < n) A[(size_t)r + (size_t)cc * lda] -= acc[a][c];
-        }
+        for (int c = 0; c < T::RN; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+    // L21(i, t) = A[r0 + i, k0 + t] (i contiguous); U12(t, j) = A[k0 + t, c0 + j] (t contiguous)
+    T::accumulate<true>(A + r0 + (size_t)k0 * lda, (size_t)lda, n - r0, A + k0 + (size_t)c0 * lda, (size_t)lda, n - c0, NB, acc, sm);
+    T::for_each(acc, [&](int i, int j, double v) {
+        if (r0 + i < n && c0 + j < n) A[(size_t)(r0 + i) + (size_t)(c0 + j) * lda] -= v;
+    });
 }
 
 // perm[i] = source row of row i after all interchanges (one thread per matrix; n is a few thousand)
@@ -271,54 +317,33 @@ __global__ void __launch_bounds__(128) k_lu_bwd_diag(const double* __restrict__ 
         if (i < nb) X[(size_t)(k + i) * ldg + c] = x[i];
 }
 
-// X[r][c] -= sum_t M[r][k+t] X[k+t][c]  for the rows r in [lo, hi) : forward (r > panel, M = L) and backward (r < panel, M = U)
-__global__ void __launch_bounds__(256) k_lu_update_rows(const double* __restrict__ A0, int lda, size_t stride,
-                                                        double* __restrict__ X0, int ldg, size_t strideG,
-                                                        const int* __restrict__ n_arr, int extra_cols, int k, int backward) {
-    const int b = blockIdx.z;
+// block row k (32 rows) of X, columns c0 .. c0+63, LEFT-looking:  X[k+i, c] -= sum_{t in [t_lo, t_hi)} M[k+i, t] * X[t, c]
+// forward solve with the unit-lower factor: t in [0, k); backward solve with U: t in [k + 32, n).  One DMMA product over the
+// whole K range: every entry of X is updated once (the right-looking rank-32 updates of round 1 re-streamed X per panel).
+__global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __restrict__ A0, int lda, size_t stride,
+                                                              double* __restrict__ X0, int ldg, size_t strideG,
+                                                              const int* __restrict__ n_arr, int extra_cols, int k, int backward) {
+    using T = dmma::Tile<32, 64>;
+    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    const int b = blockIdx.y;
     const int n = n_arr[b];
     if (k >= n) return;
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    const int lo = backward ? 0 : k + NB, hi = backward ? k : n;
-    const int r0 = lo + blockIdx.y * TS;
-    if (r0 >= hi) return;
     const int ncols = n + extra_cols;
-    const int c0 = blockIdx.x * TS;
+    const int c0 = blockIdx.x * 64;
     if (c0 >= ncols) return;
+    const int t_lo = backward ? k + NB : 0, t_hi = backward ? n : k;
+    if (t_hi <= t_lo) return;
     const double* A = A0 + stride * b;
     double* X = X0 + strideG * b;
-    __shared__ double Mp[NB][TS + 1];
-    __shared__ double Xk[NB][TS + 1];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NB * TS; e += 256) {
-        const int rr = e % TS, t = e / TS;
-        Mp[t][rr] = (r0 + rr < hi && t < nb) ? A[(size_t)(r0 + rr) + (size_t)(k + t) * lda] : 0.0;
-        Xk[t][rr] = (c0 + rr < ncols && t < nb) ? X[(size_t)(k + t) * ldg + c0 + rr] : 0.0;
-    }
-    __syncthreads();
-    const int tx = tid % 16, ty = tid / 16;
-    double acc[4][4];
+    double acc[T::RM][T::RN][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < T::RM; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < NB; ++t) {
-        double mr[4], xc[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { mr[a] = Mp[t][ty + 16 * a]; xc[a] = Xk[t][tx + 16 * a]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = fma(mr[a], xc[c], acc[a][c]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int r = r0 + ty + 16 * a, cc = c0 + tx + 16 * c;
-            if (r < hi && cc < ncols) X[(size_t)r * ldg + cc] -= acc[a][c];
-        }
+        for (int c = 0; c < T::RN; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+    T::accumulate(A + k + (size_t)t_lo * lda, (size_t)lda, n - k, X + (size_t)t_lo * ldg + c0, (size_t)ldg, ncols - c0, t_hi - t_lo, acc, sm);
+    T::for_each(acc, [&](int i, int j, double v) {
+        if (i < NB && k + i < n && c0 + j < ncols) X[(size_t)(k + i) * ldg + c0 + j] -= v;
+    });
 }
 
 }  // namespace
@@ -328,7 +353,28 @@ int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const
     cudaStream_t s = ctx->stream;
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
     for (int k0 = 0; k0 < n_max; k0 += NB) {
-        k_lu_panel<<<batch, PT, 0, s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
+        // widest sub-panel whose rows fit in shared memory
+        const size_t rows = (size_t)(n_max - k0);
+        const size_t lim = 200 * 1024;
+        if (rows * 8 * sizeof(double) <= lim) {
+            static bool cfg8 = false;
+            if (!cfg8) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg8 = true; }
+            k_lu_panel<8><<<batch, PT, rows * 8 * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
+        } else if (rows * 4 * sizeof(double) <= lim) {
+            static bool cfg4 = false;
+            if (!cfg4) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg4 = true; }
+            k_lu_panel<4><<<batch, PT, rows * 4 * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
+        } else if (rows * 2 * sizeof(double) <= lim) {
+            static bool cfg2 = false;
+            if (!cfg2) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg2 = true; }
+            k_lu_panel<2><<<batch, PT, rows * 2 * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
+        } else {
+            if (rows * sizeof(double) > lim)
+                return ptzba_fail(ctx, PTZBA_ERR_ARG, "LU panel of %zu rows exceeds the shared-memory sub-panel", rows);
+            static bool cfg1 = false;
+            if (!cfg1) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg1 = true; }
+            k_lu_panel<1><<<batch, PT, rows * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
+        }
         KERNEL_POST(ctx);
         k_lu_laswp<<<dim3(div_up(n_max, 256), batch), 256, 0, s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv);
         KERNEL_POST(ctx);
@@ -336,7 +382,7 @@ int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const
         if (m <= 0) break;
         k_lu_trsm_u12<<<dim3(div_up(m, 128), batch), 128, 0, s>>>(A, lda, stride, d_n_arr, k0);
         KERNEL_POST(ctx);
-        k_lu_gemm<<<dim3(div_up(m, TS), div_up(m, TS), batch), 256, 0, s>>>(A, lda, stride, d_n_arr, k0);
+        k_lu_gemm<<<dim3(div_up(m, TS), div_up(m, TS), batch), dmma::kThreads, 0, s>>>(A, lda, stride, d_n_arr, k0);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;
@@ -353,21 +399,19 @@ int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t s
     k_lu_gather_rows<<<dim3(div_up(ncols_max, 256), n_max, batch), 256, 0, s>>>(B, X, ldg, strideG, d_n_arr, extra_cols, d_perm, ld_ipiv);
     KERNEL_POST(ctx);
     for (int k = 0; k < n_max; k += NB) {
+        if (k > 0) {
+            k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 0);
+            KERNEL_POST(ctx);
+        }
         k_lu_fwd_diag<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k);
-        KERNEL_POST(ctx);
-        const int m = n_max - k - NB;
-        if (m <= 0) break;
-        k_lu_update_rows<<<dim3(div_up(ncols_max, TS), div_up(m, TS), batch), 256, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr,
-                                                                                          extra_cols, k, 0);
         KERNEL_POST(ctx);
     }
     const int last = (n_max - 1) / NB * NB;
     for (int k = last; k >= 0; k -= NB) {
-        k_lu_bwd_diag<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k);
+        // (sequences shorter than n_max skip the block rows beyond their order; within a sequence the rows right of block k are final)
+        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 1);
         KERNEL_POST(ctx);
-        if (k == 0) break;
-        k_lu_update_rows<<<dim3(div_up(ncols_max, TS), div_up(k, TS), batch), 256, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr,
-                                                                                          extra_cols, k, 1);
+        k_lu_bwd_diag<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;

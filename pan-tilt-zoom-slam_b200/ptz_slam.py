@@ -15,6 +15,12 @@ computation (projection, in-image filter, innovation, central-difference Jacobia
 write-back) runs in csrc/ekf.cu through the C-ABI.  The image front-end of the reference class (SIFT detection,
 optical-flow matching, SIFT matching) is out of scope and enters as `front_end` callables.
 
+The filter state is RESIDENT on the GPU between frames (a one-sequence ptzba_ekf_batch): `ekf_update`, `predict`, `remove_rays`
+and `add_rays` work on the device copy and per frame only the observations go in and the pose / velocity come back.  `rays` and
+`state_cov` stay the reference's public attributes: reading them downloads the device copy when it is newer, ASSIGNING them
+(`slam.rays = ...`) makes the host copy the truth again.  Code that mutates the returned arrays in place must call
+`slam.invalidate_device()` afterwards (the reference's own methods never do that outside the ones mirrored here).
+
 `BatchedEkfTracker` is the additive batched form for many independent sequences resident on the GPU (config 4).
 """
 import copy
@@ -63,6 +69,12 @@ class PtzSlam:
             front_end.build_matching_graph                           -> keyframe bundle adjustment (scene_map.Map)
         Without it only the image-free members work (init_rays, predict, ekf_update, remove_rays, add_rays(detector))."""
         self.front_end = front_end
+        # device-resident filter state (see the module docstring): handle, what is current where
+        self._dev = None                # ctypes handle of the one-sequence ptzba_ekf_batch
+        self._dev_valid = False         # the device copy is the current state
+        self._rays_stale = False        # the host copy of rays / state_cov is older than the device copy
+        self._cov_stale = False
+        self._dev_prm = None
         # global rays and covariance matrix (ptz_slam.py:29-31)
         self.rays = np.ndarray([0, 2])
         self.des = np.ndarray([0, 128])
@@ -87,6 +99,100 @@ class PtzSlam:
         self.f_var = 1
         # PTZBA_JAC_CENTRAL_FD reproduces the reference's central differences; JAC_ANALYTIC is the closed form
         self.jacobian_mode = _lib.JAC_CENTRAL_FD
+
+    # -- rays / state_cov: host attributes backed by the device-resident copy ---------------------------------------
+    @property
+    def rays(self):
+        if self._rays_stale:
+            n = self._dev_n_rays()
+            self._rays = np.empty((n, 2), np.float64)
+            ctx = _lib.get_context()
+            ctx.check(ctx.lib.ptzba_ekf_batch_get_rays(self._dev, 0, _lib.ptr(self._rays)))
+            self._rays_stale = False
+        return self._rays
+
+    @rays.setter
+    def rays(self, value):
+        self._sync_other("rays")
+        self._rays = value
+        self._rays_stale = False
+        self._dev_valid = False
+
+    @property
+    def state_cov(self):
+        if self._cov_stale:
+            s_ = 3 + 2 * self._dev_n_rays()
+            self._cov = np.empty((s_, s_), np.float64)
+            ctx = _lib.get_context()
+            ctx.check(ctx.lib.ptzba_ekf_batch_get_cov(self._dev, 0, _lib.ptr(self._cov)))
+            self._cov_stale = False
+        return self._cov
+
+    @state_cov.setter
+    def state_cov(self, value):
+        self._sync_other("cov")
+        self._cov = value
+        self._cov_stale = False
+        self._dev_valid = False
+
+    def _sync_other(self, which):
+        """Assigning one of the two attributes invalidates the device copy: fetch the other one first if only the device has it."""
+        if which == "rays" and getattr(self, "_cov_stale", False):
+            _ = self.state_cov
+        if which == "cov" and getattr(self, "_rays_stale", False):
+            _ = self.rays
+
+    def invalidate_device(self):
+        """Call after mutating `rays` / `state_cov` IN PLACE: the host copies become the truth again."""
+        _ = self.rays, self.state_cov
+        self._dev_valid = False
+
+    def _dev_n_rays(self):
+        ctx = _lib.get_context()
+        n = ctypes.c_int32(0)
+        ctx.check(ctx.lib.ptzba_ekf_batch_n_rays(self._dev, 0, ctypes.byref(n), None))
+        return int(n.value)
+
+    def _dev_release(self):
+        if self._dev is not None:
+            _ = self.rays, self.state_cov            # keep whatever only the device has
+            _lib.get_context().lib.ptzba_ekf_batch_destroy(self._dev)
+            self._dev = None
+        self._dev_valid = False
+
+    def __del__(self):
+        try:
+            if self._dev is not None:
+                _lib.get_context().lib.ptzba_ekf_batch_destroy(self._dev)
+                self._dev = None
+        except Exception:
+            pass
+
+    def _dev_ensure(self, prm_key, prm, max_obs):
+        """Make the device copy current (upload only when the host copy is the truth) with room for max_obs observations."""
+        ctx = _lib.get_context()
+        if self._dev is not None and (self._dev_prm != prm_key):
+            self._dev_release()
+        if not self._dev_valid:
+            rays = _lib.f64(self._rays).reshape(-1, 2)
+            cov = _lib.f64(self._cov)
+            n = rays.shape[0]
+            assert cov.shape == (3 + 2 * n, 3 + 2 * n)
+            if self._dev is not None and self._dev_n_rays() != n:
+                lib = ctx.lib
+                lib.ptzba_ekf_batch_destroy(self._dev)
+                self._dev = None
+            if self._dev is None:
+                h = ctypes.c_void_p()
+                ptz0 = np.zeros(3)
+                ctx.check(ctx.lib.ptzba_ekf_batch_create(ctx.handle, ctypes.byref(prm), 1, n, int(min(max(max_obs, 1), max(n, 1))),
+                                                         _lib.ptr(rays), _lib.ptr(ptz0), ctypes.byref(h)))
+                self._dev = h
+                self._dev_prm = prm_key
+            ctx.check(ctx.lib.ptzba_ekf_batch_set(self._dev, 0, None, None, _lib.ptr(rays), _lib.ptr(cov)))
+            self._dev_valid = True
+            self._rays_stale = self._cov_stale = False
+        ctx.check(ctx.lib.ptzba_ekf_batch_reserve(self._dev, 0, int(max_obs)))
 
     # -- state initialisation without images (ptz_slam.py:186-208 minus keypoint detection) ----------------------
     def init_rays(self, rays, camera):
@@ -139,8 +245,7 @@ class PtzSlam:
         self.current_camera.set_ptz(self.current_camera.get_ptz() + self.velocity)
         if not self.tracking_lost:
             self.cameras.append(self.current_camera)
-        q_k = 5 * np.diag([self.angle_var, self.angle_var, self.f_var])
-        self.state_cov[0:3, 0:3] = self.state_cov[0:3, 0:3] + q_k
+        self._predict_cov()
         # 2. update
         height, width = next_img.shape[0:2]
         self.ekf_update(inlier_keypoints, inlier_index, height, width)
@@ -196,9 +301,17 @@ class PtzSlam:
     def remove_rays(self, index):
         """ptz_slam.py:291-315: drop the rays `index` (RANSAC outliers) with their descriptors and covariance rows / columns."""
         delete_index = np.asarray(index, dtype=np.int64).reshape(-1)
-        self.rays = np.delete(self.rays, delete_index, axis=0)
         if self.des is not None and len(self.des) > 0:
             self.des = np.delete(self.des, delete_index, axis=0)
+        if self._dev_valid:
+            # resident state: rows / columns are compacted on the GPU (csrc/ekf.cu:ptzba_ekf_batch_remove_rays)
+            if len(delete_index):
+                ctx = _lib.get_context()
+                di = _lib.i32(np.unique(delete_index))
+                ctx.check(ctx.lib.ptzba_ekf_batch_remove_rays(self._dev, 0, int(di.shape[0]), _lib.ptr(di)))
+                self._rays_stale = self._cov_stale = True
+            return
+        self.rays = np.delete(self.rays, delete_index, axis=0)
         p_delete = np.stack([2 * delete_index + 3, 2 * delete_index + 4], axis=1).reshape(-1)
         self.state_cov = np.delete(np.delete(self.state_cov, p_delete, axis=0), p_delete, axis=1)
 
@@ -222,15 +335,22 @@ class PtzSlam:
         if k > 0:
             new_rays = np.asarray(self.current_camera.back_project_to_rays(new_keypoints), dtype=np.float64).reshape(-1, 2)
             n_old = len(self.rays)
-            self.rays = np.vstack([np.asarray(self.rays, dtype=np.float64).reshape(-1, 2), new_rays])
             if new_des is not None:
                 self.des = np.vstack([self.des.reshape(-1, new_des.shape[1]) if len(self.des) else np.zeros((0, new_des.shape[1])), new_des])
-            s_old = self.state_cov.shape[0]
-            cov = np.zeros((s_old + 2 * k, s_old + 2 * k))
-            cov[:s_old, :s_old] = self.state_cov
-            d = np.arange(s_old, s_old + 2 * k)
-            cov[d, d] = self.angle_var
-            self.state_cov = cov
+            if self._dev_valid:
+                # resident state: the new rays and their covariance rows / columns are appended on the GPU
+                ctx = _lib.get_context()
+                nr = _lib.f64(new_rays)
+                ctx.check(ctx.lib.ptzba_ekf_batch_add_rays(self._dev, 0, int(k), _lib.ptr(nr)))
+                self._rays_stale = self._cov_stale = True
+            else:
+                self.rays = np.vstack([np.asarray(self.rays, dtype=np.float64).reshape(-1, 2), new_rays])
+                s_old = self.state_cov.shape[0]
+                cov = np.zeros((s_old + 2 * k, s_old + 2 * k))
+                cov[:s_old, :s_old] = self.state_cov
+                d = np.arange(s_old, s_old + 2 * k)
+                cov[d, d] = self.angle_var
+                self.state_cov = cov
             keypoints_index = np.append(keypoints_index, np.arange(n_old, n_old + k))
         keypoints = np.concatenate([np.asarray(keypoints).reshape(-1, 2), new_keypoints], axis=0)
         return keypoints, keypoints_index
@@ -255,36 +375,56 @@ class PtzSlam:
         self.current_camera = copy.deepcopy(self.cameras[-1])
         self.current_camera.set_ptz(self.current_camera.get_ptz() + self.velocity)
         self.cameras.append(self.current_camera)
-        q_k = 5 * np.diag([self.angle_var, self.angle_var, self.f_var])
-        self.state_cov[0:3, 0:3] = self.state_cov[0:3, 0:3] + q_k
+        self._predict_cov()
+
+    def _predict_cov(self):
+        """P[0:3, 0:3] += 5 diag(angle_var, angle_var, f_var) (ptz_slam.py:425-426), on whichever copy is current."""
+        if self._dev_valid:
+            ctx = _lib.get_context()
+            ctx.check(ctx.lib.ptzba_ekf_batch_predict_cov(self._dev))
+            self._cov_stale = True
+        else:
+            q_k = 5 * np.diag([self.angle_var, self.angle_var, self.f_var])
+            cov = self.state_cov
+            cov[0:3, 0:3] = cov[0:3, 0:3] + q_k
+            self.state_cov = cov
 
     def ekf_update(self, observed_keypoints, observed_keypoint_index, height, width):
         """ptz_slam.py:210-289.  Mutates rays, state_cov, current_camera (pan/tilt/focal_length) and velocity."""
         ctx = _lib.get_context()
         cam = self.current_camera
         ref = self.cameras[0]
-        n_total = len(self.rays)
         obs = _lib.f64(observed_keypoints).reshape(-1, 2)
         idx = _lib.i32(np.asarray(observed_keypoint_index).astype(np.int64))
         m = obs.shape[0]
         assert idx.shape[0] == m
+        disp = None if ref.displacement is None else tuple(np.asarray(ref.displacement, dtype=np.float64).ravel())
+        prm_key = (float(ref.principal_point[0]), float(ref.principal_point[1]), disp, float(self.observe_var), float(self.angle_var),
+                   float(self.f_var), float(height), float(width), int(self.jacobian_mode))
         prm = _params(ref.principal_point[0], ref.principal_point[1], ref.displacement, self.observe_var, self.angle_var,
                       self.f_var, height, width, self.jacobian_mode)
-        if not (self.rays.flags.c_contiguous and self.rays.dtype == np.float64):
-            self.rays = _lib.f64(self.rays)
-        if not (self.state_cov.flags.c_contiguous and self.state_cov.dtype == np.float64):
-            self.state_cov = _lib.f64(self.state_cov)
-        assert self.state_cov.shape == (3 + 2 * n_total, 3 + 2 * n_total)
+        self._dev_ensure(prm_key, prm, m)
         ptz = _lib.f64([cam.pan, cam.tilt, cam.focal_length])
+        ctx.check(ctx.lib.ptzba_ekf_batch_set(self._dev, 0, _lib.ptr(ptz), None, None, None))
+        cnt = np.array([m], np.int32)
+        matched = np.zeros(1, np.int32)
+        cap = ctypes.c_int32(0)
+        ctx.check(ctx.lib.ptzba_ekf_batch_max_obs(self._dev, ctypes.byref(cap)))
+        # the batch call takes observation arrays padded to its max_obs
+        if m < cap.value:
+            obs_p = np.zeros((cap.value, 2)); obs_p[:m] = obs
+            idx_p = np.zeros(cap.value, np.int32); idx_p[:m] = idx
+        else:
+            obs_p, idx_p = obs, idx
+        ctx.check(ctx.lib.ptzba_ekf_batch_update_only(self._dev, _lib.HOST, _lib.ptr(obs_p), _lib.ptr(idx_p), _lib.ptr(cnt),
+                                                      _lib.ptr(matched)))
         vel = np.zeros(3)
-        matched = ctypes.c_int32(0)
-        ctx.check(ctx.lib.ptzba_ekf_update(ctx.handle, ctypes.byref(prm), n_total, _lib.ptr(self.rays),
-                                           _lib.ptr(self.state_cov), _lib.ptr(ptz), _lib.ptr(vel), m, _lib.ptr(obs),
-                                           _lib.ptr(idx), ctypes.byref(matched)))
+        ctx.check(ctx.lib.ptzba_ekf_batch_get(self._dev, _lib.ptr(ptz), _lib.ptr(vel), None))
+        self._rays_stale = self._cov_stale = True
         cam.pan, cam.tilt, cam.focal_length = float(ptz[0]), float(ptz[1]), float(ptz[2])
         self.current_camera = cam
         self.velocity = vel
-        return int(matched.value)
+        return int(matched[0])
 
 
 class BatchedEkfTracker:

@@ -76,6 +76,20 @@ def main():
     if rank == 0:
         print("multi_gpu_check OK: compact exchange of %d shared landmarks (of %d): owned blocks match the oracle" % (n_shared, M))
     dist.barrier()
+    # two MORE consecutive pass + exchange rounds: with >= 3 ranks a shared landmark this rank never observes used to be written into
+    # its arena by the unpack and re-added by the next pack (round-1 advisor finding); every round must give the same blocks
+    for rnd in range(2):
+        prob.normal_equations_device(x.data_ptr(), fb.ptz_init[0])
+        comm.allreduce_landmark_blocks(prob)
+        ctx.synchronize()
+        ctx.check(ctx.lib.ptzba_ba_get_blocks(prob.handle, _lib.ptr(U), _lib.ptr(gc), _lib.ptr(V), _lib.ptr(gl), ctypes.byref(cost)))
+        np.testing.assert_allclose(V[mine], Vp[mine], rtol=1e-9, atol=1e-12 * np.abs(Vp).max())
+        np.testing.assert_allclose(gl[mine], glo[mine], rtol=1e-8, atol=1e-11 * np.abs(glo).max())
+        np.testing.assert_allclose(U[own], Up[own], rtol=1e-9, atol=1e-12 * np.abs(Up).max())
+        assert abs(cost.value - costo) < 1e-11 * costo
+    if rank == 0:
+        print("multi_gpu_check OK: three consecutive pass + exchange rounds give the same blocks (world=%d)" % world)
+    dist.barrier()
     prob.close()
 
     # ---- disjoint shards (the weak-scaling benchmark's shape): nothing shared, no collective per pass, the cost is summed lazily ----
