@@ -161,6 +161,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def fp64_peak():
+    """Measured FP64 peaks of this pool's B200 (scripts/fp64_peak.cu, profiles/r2_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure."""
+    p = os.path.join(ROOT, "profiles", "r2_fp64_peak.json")
+    try:
+        j = json.load(open(p))
+        return {"dfma_tflops": j["dfma_tflops"], "dmma_tflops": j["dmma_m8n8k4_tflops"], "source": "profiles/r2_fp64_peak.json (measured)"}
+    except Exception:
+        return {"dfma_tflops": 34.0, "dmma_tflops": 37.0, "source": "fallback (round-2 measurement)"}
+
+
+def ekf_flops(n_matched, lu_route):
+    """Algorithmic FP64 flops of one EKF update with n matched rays (m = 2n rows, s = 3 + 2n state columns), BASELINE.md section 4:
+    Cholesky route m^3/3 + m^2 (s+1) + 2 n^2 m (+ 2 m s); pivoted-LU route 2 m^3/3 + 2 m^2 (s+1) + 2 n^2 m (+ 2 m s)."""
+    n = np.asarray(n_matched, dtype=np.float64)
+    m, s_ = 2 * n, 3 + 2 * n
+    chol = m ** 3 / 3 + m * m * (s_ + 1) + 2 * n * n * m + 2 * m * s_
+    lu = 2 * m ** 3 / 3 + 2 * m * m * (s_ + 1) + 2 * n * n * m + 2 * m * s_
+    return np.where(np.asarray(lu_route) != 0, lu, chol)
+
+
 def bench_ekf(ctx, n_seq, n_rays, n_frames, seed0=2000):
     """Batched independent EKF sequences (BASELINE config 4 recipe at a bounded batch): predict+update per frame."""
     import torch
@@ -175,17 +195,68 @@ def bench_ekf(ctx, n_seq, n_rays, n_frames, seed0=2000):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     tot = 0
+    flops = 0.0
     for k in range(1, n_frames):
         m = trk.step(*packed[k])
         tot += int(m.sum())
+        flops += float(ekf_flops(m, trk.route()).sum())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    n_lu = int(trk.route().sum())
     trk.close()
     frames = n_frames - 1
+    pk = fp64_peak()
+    ach = flops / dt / 1e12
     return {"workload": "%d independent sequences x %d rays, %d timed frames, host observations in / matched counts out" %
                         (n_seq, n_rays, frames),
             "sequence_frames_per_s": n_seq * frames / dt, "matched_obs_per_s": tot / dt,
-            "mean_matched_rays": tot / (n_seq * frames), "ms_per_frame_batch": 1e3 * dt / frames}
+            "mean_matched_rays": tot / (n_seq * frames), "ms_per_frame_batch": 1e3 * dt / frames,
+            "sequences_on_lu_route_at_end": n_lu,
+            "roofline": {"bound": "fp64", "achieved": ach, "peak": pk["dfma_tflops"], "unit": "TFLOP/s", "frac": ach / pk["dfma_tflops"],
+                         "peak_kind": pk["source"], "peak_dmma": pk["dmma_tflops"],
+                         "flops": "algorithmic: factorisation of S + triangular solves of [G | y] + covariance down-date, per route (bench.py:ekf_flops)"}}
+
+
+def bench_cfg2(ctx, n_rays=3000, n_frames=20):
+    """BASELINE config 2 shape: ONE sequence over the 3 000-ray soccer cloud through the drop-in PtzSlam (filter state resident on the
+    GPU; per frame the observations go in and the pose comes back).  The first 20 frames of the 300: the reference's recursion
+    itself diverges on noisy synthetic data after ~25 frames (its covariance write-back), later frames would
+    time a filter that has lost track.  cpu_baseline: the numpy restatement of the reference's ekf_update (oracle) on 3 frames."""
+    import torch
+    from ptz_slam_b200 import synth
+    from ptz_slam_b200.ptz_camera import PTZCamera
+    from ptz_slam_b200.ptz_slam import PtzSlam
+    seq = synth.make_ekf_sequence(n_rays, n_frames + 2, seed=1002, keep_prob=1.0)
+    cam = PTZCamera((synth.PP_U, synth.PP_V), np.zeros(3), np.eye(3))
+    cam.set_ptz(seq.ptz_gt[0])
+    slam = PtzSlam()
+    slam.init_rays(seq.rays0, cam)
+    slam.predict()
+    slam.ekf_update(seq.obs_xy[1], seq.obs_idx[1], synth.IMAGE_H, synth.IMAGE_W)      # warm-up frame (uploads the state once)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tot = 0
+    for k in range(2, n_frames + 2):
+        slam.predict()
+        tot += slam.ekf_update(seq.obs_xy[k], seq.obs_idx[k], synth.IMAGE_H, synth.IMAGE_W)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    err = np.abs(slam.current_camera.get_ptz() - seq.ptz_gt[n_frames + 1])
+    out = {"workload": "1 sequence x %d rays, %d timed frames, PtzSlam.predict + ekf_update on the resident state" % (n_rays, n_frames),
+           "frames_per_s": n_frames / dt, "matched_obs_per_s": tot / dt, "mean_matched_rays": tot / n_frames, "ms_per_frame": 1e3 * dt / n_frames,
+           "final_pose_error_vs_ground_truth": [float(e) for e in err]}
+    from oracle import ptz_oracle as O
+    s = O.EkfState(seq.rays0, seq.ptz_gt[0], synth.PP_U, synth.PP_V)
+    O.ekf_predict(s)
+    O.ekf_update(s, seq.obs_xy[1], seq.obs_idx[1], synth.IMAGE_H, synth.IMAGE_W)
+    t0 = time.perf_counter()
+    for k in range(2, 5):
+        O.ekf_predict(s)
+        O.ekf_update(s, seq.obs_xy[k], seq.obs_idx[k], synth.IMAGE_H, synth.IMAGE_W)
+    cdt = (time.perf_counter() - t0) / 3
+    out["cpu_baseline"] = {"value": 1.0 / cdt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                           "sample": "3 frames of the same sequence through oracle.ekf_update (numpy restatement of ptz_slam.py:210-289, BLAS threads)"}
+    return out
 
 
 # -------------------------------------------------------------------------------------------------------------------
@@ -336,27 +407,71 @@ def run_ours(args):
                 "kernel": "fused pass (k_ba_lm_pass + k_ba_cam_pass)", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
 
     # ---- e2e: HOST (pinned) buffers through the C-ABI, copies inside the timed region ------------------------------
+    # The call a user of the normal equations makes: x in; the U/g_c blocks of the rank's keyframes, the V/g_l blocks of the
+    # landmarks it observes and the cost out (the residual VECTOR is not an input of any solver step: it is opt-in and timed
+    # separately below).  ptzba_ba_normal_equations_begin / ptzba_ba_wait pipeline the copies of one problem replica against the
+    # kernels of the next (up to 3 passes in flight); every step still moves its own x in and its own blocks out.
+    import ctypes as _ct2
     N, M = fb.n_pose, fb.n_landmark
-    pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()
-    hx = pin(len(x0)); hx[:] = x0
-    hr, hU, hgc, hV, hgl = pin(2 * fb.n_obs), pin(N * 6), pin(N * 3), pin(M * 3), pin(M * 2)
-    e2e_steps = max(3, min(args.steps, 50))
-    for i in range(min(args.warmup, 3)):
-        probs[i % R].normal_equations_into(hx, ref_pose, hr, hU, hgc, hV, hgl)
+    lm_lo, lm_hi = (int(fb.lm_idx.min()), int(fb.lm_idx.max()) + 1) if fb.n_obs else (0, 0)
+    nk, nl = kf_range[1] - kf_range[0], lm_hi - lm_lo
+    pin = lambda n: torch.empty(max(n, 1), dtype=torch.float64).pin_memory().numpy()
+    hx = [pin(len(x0)) for _ in range(R)]
+    for h in hx:
+        h[:] = x0
+    hU, hgc, hV, hgl = [pin(nk * 6) for _ in range(R)], [pin(nk * 3) for _ in range(R)], [pin(nl * 3) for _ in range(R)], [pin(nl * 2) for _ in range(R)]
+    costs = [_ct2.c_double(0.0) for _ in range(R)]
+    e2e_steps = max(3, min(args.steps, 100))
+
+    depth = min(3, R)          # passes in flight: H2D of one, kernels of the next, D2H of the one before
+
+    def e2e_loop(n):
+        for i in range(n):
+            r_ = i % R
+            if i >= depth:
+                probs[(i - depth) % R].wait()
+            probs[r_].normal_equations_begin(hx[r_], ref_pose, kf_range, (lm_lo, lm_hi), hU[r_], hgc[r_], hV[r_], hgl[r_], costs[r_])
+        for i in range(max(0, n - depth), n):
+            probs[i % R].wait()
+
+    e2e_loop(min(args.warmup, 4))
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        cost = probs[i % R].normal_equations_into(hx, ref_pose, hr, hU, hgc, hV, hgl)
-    torch.cuda.synchronize()
+    e2e_loop(e2e_steps)
     e2e_s = time.perf_counter() - t0
+    # the device-resident pass of the same problem must give the same blocks
+    chkU = np.empty((N, 6)); chkV = np.empty((M, 3)); chkc = _ct2.c_double()
+    device_step(0)
+    ctx.check(ctx.lib.ptzba_ba_get_blocks(probs[0].handle, _lib.ptr(chkU), None, _lib.ptr(chkV), None, _ct2.byref(chkc)))
+    assert np.array_equal(hU[0].reshape(-1, 6)[:nk], chkU[kf_range[0]:kf_range[1]]) or np.allclose(hU[0].reshape(-1, 6)[:nk], chkU[kf_range[0]:kf_range[1]], rtol=1e-12)
+    assert np.allclose(hV[0].reshape(-1, 3)[:nl], chkV[lm_lo:lm_hi], rtol=1e-12, atol=0) and abs(costs[0].value - chkc.value) <= 1e-12 * chkc.value
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = {"value": total_obs * e2e_steps / e2e_s, "unit": "obs/s", "h2d_bytes_per_step": int(8 * (len(x0) + 3)),
-           "d2h_bytes_per_step": int(8 * (2 * fb.n_obs + N * 9 + M * 5 + 1)), "steps": e2e_steps,
+           "d2h_bytes_per_step": int(8 * (nk * 9 + nl * 5 + 1)), "steps": e2e_steps,
            "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "call": "ptzba_ba_normal_equations(mem=HOST): x in; residual, U, g_c, V, g_l, cost out (pinned buffers)"}
+           "call": "ptzba_ba_normal_equations_begin / ptzba_ba_wait (pinned host buffers, copies of one replica overlap the kernels of the "
+                   "next): x in; U, g_c of the rank's keyframes, V, g_l of its landmarks, cost out"}
+    # the same pass with the residual vector requested as well (synchronous call, 16 B per observation more to download)
+    hr = pin(2 * fb.n_obs)
+    fU, fgc, fV, fgl = pin(N * 6), pin(N * 3), pin(M * 3), pin(M * 2)
+    n_r = max(3, min(args.steps, 20))
+    probs[0].normal_equations_into(hx[0], ref_pose, hr, fU, fgc, fV, fgl)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_r):
+        probs[i % R].normal_equations_into(hx[0], ref_pose, hr, fU, fgc, fV, fgl)
+    torch.cuda.synchronize()
+    er_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([er_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        er_s = float(t.item())
+    e2e["with_residual_vector"] = {"value": total_obs * n_r / er_s, "unit": "obs/s", "ms_per_step": 1e3 * er_s / n_r,
+                                   "d2h_bytes_per_step": int(8 * (2 * fb.n_obs + N * 9 + M * 5 + 1)),
+                                   "call": "ptzba_ba_normal_equations(mem=HOST) with the residual vector (synchronous)"}
 
     # ---- BA LM iterations/s (fused pass + Schur + Cholesky + back-substitution + trial residual pass) --------------
     lm = None
@@ -441,6 +556,10 @@ def run_ours(args):
             ekf["matched_obs_per_s"] = float(tsum[1].item()) / (ms_ekf * 1e-3)
             ekf["ms_per_frame_batch"] = ms_ekf
 
+    cfg2 = None
+    if rank == 0 and not args.no_ekf:
+        cfg2 = bench_cfg2(ctx)
+
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -475,6 +594,8 @@ def run_ours(args):
             line.update(lm)
         if ekf:
             line["ekf"] = ekf
+        if cfg2:
+            line["ekf_cfg2"] = cfg2
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -147,6 +147,9 @@ int ptzba_ekf_batch_add_rays(ptzba_ekf_batch* b, int seq, int k, const double* n
 int ptzba_ekf_batch_predict_cov(ptzba_ekf_batch* b);
 /* current observation capacity per step: obs_xy / obs_index of the step calls are [n_seq * max_obs * 2] / [n_seq * max_obs] */
 int ptzba_ekf_batch_max_obs(ptzba_ekf_batch* b, int32_t* max_obs);
+/* factorisation route of every sequence (host int32[n_seq]): 0 = Cholesky of the innovation covariance, 1 = pivoted LU (S was
+ * indefinite once - the reference's covariance write-back, ptz_slam.py:281-289, makes P indefinite - and stays on that route) */
+int ptzba_ekf_batch_route(ptzba_ekf_batch* b, int32_t* route);
 /* grow the ray capacity per sequence and / or the observation capacity per step (max_obs) ahead of time */
 int ptzba_ekf_batch_reserve(ptzba_ekf_batch* b, int ray_capacity, int max_obs);
 
@@ -167,6 +170,14 @@ int ptzba_ba_residual(ptzba_ba* ba, int mem, const double* x, const double* refe
  *   gl[n_landmark*2]; cost (host double) = 0.5 * sum r^2.  Keyframe 0's U/gc are zero (fixed pose). */
 int ptzba_ba_normal_equations(ptzba_ba* ba, int mem, const double* x, const double* reference_pose3,
                               double* residual, double* U, double* gc, double* V, double* gl, double* cost);
+
+/* pipelined form of the host-buffer pass (no residual vector): `begin` enqueues H2D of x on the problem's own copy stream, the fused
+ * pass on the context stream and D2H of the block ranges U/gc[kf_lo, kf_hi) and V/gl[lm_lo, lm_hi) (packed as above, any pointer may
+ * be NULL) on the copy stream, and returns at once; `wait` blocks until they have landed and stores the cost.  Host buffers should
+ * be pinned.  With several problems in rotation the copies of one overlap the kernels of the next. */
+int ptzba_ba_normal_equations_begin(ptzba_ba* ba, const double* x, const double* reference_pose3, int kf_lo, int kf_hi, int lm_lo,
+                                    int lm_hi, double* U, double* gc, double* V, double* gl, double* cost);
+int ptzba_ba_wait(ptzba_ba* ba);
 
 typedef struct ptzba_ba_options {
     double ftol, xtol, gtol;   /* scipy least_squares tolerances; the reference passes ftol=1e-4 (others default 1e-8) */

@@ -78,6 +78,7 @@ SIGNATURES = {
     "ptzba_ekf_batch_reserve": (_I, [_P, _I, _I]),
     "ptzba_ekf_batch_predict_cov": (_I, [_P]),
     "ptzba_ekf_batch_max_obs": (_I, [_P, _P]),
+    "ptzba_ekf_batch_route": (_I, [_P, _P]),
     "ptzba_ba_create": (_I, [_P, _I, _I, _I, _L, _P, _P, _P, _D, _D, ctypes.POINTER(_P)]),
     "ptzba_ba_destroy": (None, [_P]),
     "ptzba_ba_residual": (_I, [_P, _I, _P, _P, _P]),
@@ -93,6 +94,8 @@ SIGNATURES = {
     "ptzba_ba_set_partition": (_I, [_P, _I, _I, _I, _I, _L, _L]),
     "ptzba_ba_get_blocks": (_I, [_P, _P, _P, _P, _P, _P]),
     "ptzba_ba_set_option": (_I, [_P, _I, _I]),
+    "ptzba_ba_normal_equations_begin": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ptzba_ba_wait": (_I, [_P]),
 }
 
 _lock = threading.Lock()

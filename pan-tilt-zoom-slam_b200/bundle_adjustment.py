@@ -111,6 +111,17 @@ class BAProblem:
                                                               _lib.ptr(gl), ctypes.byref(cost)))
         return cost.value
 
+    def normal_equations_begin(self, x, reference_pose, kf_range, lm_range, Up, gc, Vp, gl, cost_out):
+        """Pipelined host-buffer pass: enqueue H2D(x) -> fused pass -> D2H of U/gc[kf_range) and V/gl[lm_range) into the caller's
+        (pinned) buffers and return at once; `wait()` blocks until they have landed.  cost_out: ctypes.c_double."""
+        ref = _lib.f64(reference_pose)
+        self.ctx.check(self.ctx.lib.ptzba_ba_normal_equations_begin(
+            self.handle, _lib.ptr(x), _lib.ptr(ref), int(kf_range[0]), int(kf_range[1]), int(lm_range[0]), int(lm_range[1]),
+            _lib.ptr(Up), _lib.ptr(gc), _lib.ptr(Vp), _lib.ptr(gl), ctypes.cast(ctypes.byref(cost_out), ctypes.c_void_p)))
+
+    def wait(self):
+        self.ctx.check(self.ctx.lib.ptzba_ba_wait(self.handle))
+
     def lm_iteration(self, x, reference_pose, alpha=0.0):
         """One LM iteration's device work at fixed damping (benchmark unit); returns (predicted_reduction, trial_cost)."""
         x = _lib.f64(x)

@@ -41,6 +41,20 @@ struct ptzba_ba {
     BaAccum acc;
     DevBuf<double> resid;           // [2*n_obs] caller order, staging for host-side residual requests
     DevBuf<double> x_stage, ref_stage;   // persistent H2D staging of x and the reference pose
+    // pipelined host-buffer pass (ptzba_ba_normal_equations_begin / ptzba_ba_wait): own copy stream, the events that order it
+    // against the compute stream
+    cudaStream_t cp_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_pass = nullptr, ev_out = nullptr;
+    bool async_pending = false;
+    double* async_cost_dst = nullptr;
+    double* h_cost = nullptr;            // pinned
+    ~ptzba_ba() {
+        if (cp_stream) cudaStreamDestroy(cp_stream);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_pass) cudaEventDestroy(ev_pass);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (h_cost) cudaFreeHost(h_cost);
+    }
     // ---- solver workspace (allocated on first solve) ----
     DevBuf<double> x_cur, x_trial;          // [3(N-1)+2M] packed parameter vectors
     DevBuf<double> scale_inv;               // [3N + 2M] (camera part incl. slot for pose 0, then landmarks)

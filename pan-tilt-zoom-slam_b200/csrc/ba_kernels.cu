@@ -830,6 +830,65 @@ extern "C" int ptzba_ba_normal_equations(ptzba_ba* ba, int mem, const double* x,
     return PTZBA_OK;
 }
 
+// ---- pipelined host-buffer pass --------------------------------------------------------------------------------------------------
+// begin: x (host, ideally pinned) travels on the problem's own copy stream, the fused pass runs on the context stream once it has
+// arrived, and the requested block ranges travel back on the copy stream once the pass is done; the call returns at once.
+// wait: blocks until the outputs of the last begin have landed and stores the cost.  With several problems in rotation the copies
+// of one problem overlap the kernels of the next (the e2e figure of bench.py); a second begin on the SAME problem first waits,
+// on the device, for the previous download of its accumulators.
+extern "C" int ptzba_ba_normal_equations_begin(ptzba_ba* ba, const double* x, const double* reference_pose3, int kf_lo, int kf_hi,
+                                               int lm_lo, int lm_hi, double* U, double* gc, double* V, double* gl, double* cost) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    ARG_CHECK(ctx, x && reference_pose3 && kf_lo >= 0 && kf_lo <= kf_hi && kf_hi <= ba->n_pose && lm_lo >= 0 && lm_lo <= lm_hi && lm_hi <= ba->n_lm);
+    if (ba->async_pending) return ptzba_fail(ctx, PTZBA_ERR_STATE, "ptzba_ba_wait must follow ptzba_ba_normal_equations_begin");
+    if (!ba->cp_stream) {
+        CU_CHECK(ctx, cudaStreamCreateWithFlags(&ba->cp_stream, cudaStreamNonBlocking));
+        CU_CHECK(ctx, cudaEventCreateWithFlags(&ba->ev_in, cudaEventDisableTiming));
+        CU_CHECK(ctx, cudaEventCreateWithFlags(&ba->ev_pass, cudaEventDisableTiming));
+        CU_CHECK(ctx, cudaEventCreateWithFlags(&ba->ev_out, cudaEventDisableTiming));
+        CU_CHECK(ctx, cudaMallocHost((void**)&ba->h_cost, 4 * sizeof(double)));
+        CU_CHECK(ctx, cudaEventRecord(ba->ev_out, ba->cp_stream));
+    }
+    cudaStream_t s = ctx->stream, c = ba->cp_stream;
+    const size_t nx = 3 * (size_t)(ba->n_pose - 1) + 2 * (size_t)ba->n_lm;
+    CU_CHECK(ctx, ba->ref_stage.alloc(4));
+    CU_CHECK(ctx, ba->x_stage.alloc(nx + 2));
+    // (the staging buffers are free: the previous pass on this problem was waited for)
+    ba->h_cost[1] = reference_pose3[0]; ba->h_cost[2] = reference_pose3[1]; ba->h_cost[3] = reference_pose3[2];
+    CU_CHECK(ctx, cudaMemcpyAsync(ba->ref_stage.p, ba->h_cost + 1, 3 * sizeof(double), cudaMemcpyHostToDevice, c));
+    if (nx) CU_CHECK(ctx, cudaMemcpyAsync(ba->x_stage.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, c));
+    CU_CHECK(ctx, cudaEventRecord(ba->ev_in, c));
+    CU_CHECK(ctx, cudaStreamWaitEvent(s, ba->ev_in, 0));
+    CU_CHECK(ctx, cudaStreamWaitEvent(s, ba->ev_out, 0));          // the accumulators are no longer being downloaded
+    PROPAGATE(ba_set_params(ba, ba->x_stage.p, ba->ref_stage.p, true));
+    PROPAGATE(ba_fused_pass(ba, nullptr));
+    // keyframe-sharded mode with the compact exchange set up: the blocks of the shared landmarks are summed before they travel
+    if (ba->exchange_ready && ctx->world > 1) PROPAGATE(ptzba_ba_allreduce(ba));
+    CU_CHECK(ctx, cudaEventRecord(ba->ev_pass, s));
+    CU_CHECK(ctx, cudaStreamWaitEvent(c, ba->ev_pass, 0));
+    const int nk = kf_hi - kf_lo, nl = lm_hi - lm_lo;
+    if (U && nk) CU_CHECK(ctx, cudaMemcpyAsync(U, ba->acc.U + 6 * (size_t)kf_lo, (size_t)nk * 6 * sizeof(double), cudaMemcpyDeviceToHost, c));
+    if (gc && nk) CU_CHECK(ctx, cudaMemcpyAsync(gc, ba->acc.gc + 3 * (size_t)kf_lo, (size_t)nk * 3 * sizeof(double), cudaMemcpyDeviceToHost, c));
+    if (V && nl) CU_CHECK(ctx, cudaMemcpyAsync(V, ba->acc.V + 3 * (size_t)lm_lo, (size_t)nl * 3 * sizeof(double), cudaMemcpyDeviceToHost, c));
+    if (gl && nl) CU_CHECK(ctx, cudaMemcpyAsync(gl, ba->acc.gl + 2 * (size_t)lm_lo, (size_t)nl * 2 * sizeof(double), cudaMemcpyDeviceToHost, c));
+    CU_CHECK(ctx, cudaMemcpyAsync(ba->h_cost, ba->acc.cost, sizeof(double), cudaMemcpyDeviceToHost, c));
+    CU_CHECK(ctx, cudaEventRecord(ba->ev_out, c));
+    ba->async_pending = true;
+    ba->async_cost_dst = cost;
+    return PTZBA_OK;
+}
+
+extern "C" int ptzba_ba_wait(ptzba_ba* ba) {
+    if (!ba) return PTZBA_ERR_ARG;
+    ptzba_ctx* ctx = ba->ctx;
+    if (!ba->async_pending) return PTZBA_OK;
+    CU_CHECK(ctx, cudaEventSynchronize(ba->ev_out));
+    if (ba->async_cost_dst) *ba->async_cost_dst = 0.5 * ba->h_cost[0];
+    ba->async_pending = false;
+    return PTZBA_OK;
+}
+
 extern "C" int ptzba_ba_get_blocks(ptzba_ba* ba, double* U, double* gc, double* V, double* gl, double* cost) {
     if (!ba) return PTZBA_ERR_ARG;
     ptzba_ctx* ctx = ba->ctx;

@@ -33,6 +33,9 @@ struct ptzba_ekf_batch {
     bool has_disp = false;
     std::vector<int32_t> h_n_act;
     DevBuf<int32_t> n_act;
+    // sequences whose innovation covariance was indefinite once go straight to the pivoted-LU route afterwards (P stays indefinite)
+    std::vector<char> h_use_lu;
+    DevBuf<int32_t> use_lu;
     DevBuf<double> rays, P, ptz, vel, disp;
     // observations of the current step
     DevBuf<double> obs_xy;
@@ -338,17 +341,31 @@ __global__ void __launch_bounds__(dmma::kThreads) k_ekf_pp_blocks(int b0, int ma
 }
 
 
-// path selection after the Cholesky attempt: sequences whose S was positive definite finish on the Cholesky path, the others
-// are redone with pivoted LU (their n is zero on the other path, which makes every batched kernel skip them)
-__global__ void k_ekf_split(int n_seq, const int32_t* __restrict__ fail, const int32_t* __restrict__ n_mat,
+// path selection BEFORE the factorisation: sequences flagged use_lu skip the Cholesky attempt (n = 0 on that path, which
+// makes every batched kernel skip them)
+__global__ void k_ekf_route(int n_seq, const int32_t* __restrict__ use_lu, const int32_t* __restrict__ n_mat,
                             int32_t* __restrict__ nm_chol, int32_t* __restrict__ n2_chol, int32_t* __restrict__ nm_lu,
                             int32_t* __restrict__ n2_lu) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_seq) return;
     const int n = n_mat[b];
-    const bool f = fail[b] != 0;
+    const bool f = use_lu[b] != 0;
     nm_chol[b] = f ? 0 : n; n2_chol[b] = f ? 0 : 2 * n;
     nm_lu[b] = f ? n : 0;   n2_lu[b] = f ? 2 * n : 0;
+}
+
+// path selection AFTER the Cholesky attempt: sequences whose S was positive definite finish on the Cholesky path, the others
+// are redone with pivoted LU and keep that route in later frames
+__global__ void k_ekf_split(int n_seq, const int32_t* __restrict__ fail, const int32_t* __restrict__ n_mat,
+                            int32_t* __restrict__ nm_chol, int32_t* __restrict__ n2_chol, int32_t* __restrict__ nm_lu,
+                            int32_t* __restrict__ n2_lu, int32_t* __restrict__ use_lu) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_seq) return;
+    if (fail[b] == 0) return;
+    const int n = n_mat[b];
+    nm_chol[b] = 0; n2_chol[b] = 0;
+    nm_lu[b] = n;   n2_lu[b] = 2 * n;
+    use_lu[b] = 1;
 }
 
 // X = G for the rows / columns in use (row-major, n2 rows, n2 + extra columns)
@@ -472,20 +489,28 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched, const in
         const int wb = std::min(B->wave, n_seq - b0);
         int n_max = 0;                                   // upper bound of the matched rays of any sequence of the wave
         for (int q = 0; q < wb; ++q) n_max = std::max(n_max, h_obs_count ? std::min((int)h_obs_count[b0 + q], max_obs) : max_obs);
+        bool any_chol = false, any_lu = false;
+        for (int q = 0; q < wb; ++q) { any_chol = any_chol || !B->h_use_lu[b0 + q]; any_lu = any_lu || B->h_use_lu[b0 + q]; }
         if (n_max > 0) {
             const int s_max = 3 + 2 * n_max;
+            k_ekf_route<<<div_up(wb, 128), 128, 0, s>>>(wb, B->use_lu.p + b0, B->n_mat.p + b0, B->nm_chol.p + b0, B->n2_chol.p + b0,
+                                                       B->nm_lu.p + b0, B->n2_lu.p + b0);
+            KERNEL_POST(ctx);
             k_ekf_G<<<dim3(div_up(s_max + 1, 128), n_max, wb), 128, 0, s>>>(b0, max_obs, s_tot, B->P.p, strideP, B->n_mat.p, B->m_ray.p,
                                                                            B->Jc.p, B->Jr.p, B->y.p, B->G.p, B->ldg, strideG);
             KERNEL_POST(ctx);
-            k_ekf_S<<<dim3(div_up(n_max, 128), 2 * n_max, wb), 128, 0, s>>>(b0, max_obs, B->n_mat.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
+            CU_CHECK(ctx, cudaMemsetAsync(B->chol_fail.p + b0, 0, (size_t)wb * sizeof(int32_t), s));
+        }
+        if (n_max > 0 && any_chol) {
+            const int s_max = 3 + 2 * n_max;
+            k_ekf_S<<<dim3(div_up(n_max, 128), 2 * n_max, wb), 128, 0, s>>>(b0, max_obs, B->nm_chol.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
                                                                            strideG, B->S.p, B->lds, strideS, B->prm.observe_var);
             KERNEL_POST(ctx);
-            // ---- Cholesky first: S is positive definite for most sequence-frames; pivoted LU only where it breaks down ----
-            CU_CHECK(ctx, cudaMemsetAsync(B->chol_fail.p + b0, 0, (size_t)wb * sizeof(int32_t), s));
-            PROPAGATE(dense_potrf_lower_batched(ctx, B->S.p, B->lds, strideS, B->n2.p + b0, 2 * n_max, wb, B->flags.p + 3,
+            // ---- Cholesky first: S is positive definite in the first frames of a sequence; pivoted LU where it breaks down ----
+            PROPAGATE(dense_potrf_lower_batched(ctx, B->S.p, B->lds, strideS, B->n2_chol.p + b0, 2 * n_max, wb, B->flags.p + 3,
                                                 B->chol_fail.p + b0));
             k_ekf_split<<<div_up(wb, 128), 128, 0, s>>>(wb, B->chol_fail.p + b0, B->n_mat.p + b0, B->nm_chol.p + b0, B->n2_chol.p + b0,
-                                                       B->nm_lu.p + b0, B->n2_lu.p + b0);
+                                                       B->nm_lu.p + b0, B->n2_lu.p + b0, B->use_lu.p + b0);
             KERNEL_POST(ctx);
             // Z = L^-1 [G | y] in X ; delta = Z^T z_y ; P+ = P - Z^T Z   (same kernels with G := X := Z); sequences whose Cholesky
             // broke down have n = 0 on this path and are skipped by every kernel
@@ -505,20 +530,16 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched, const in
             k_ekf_pp_blocks<<<dim3(ntc * (ntc + 1) / 2, 2, wb), dmma::kThreads, 0, s>>>(b0, max_obs, B->nm_chol.p, B->m_ray.p, B->X.p, B->X.p, B->ldg,
                                                                                        strideG, B->P.p, strideP, s_tot);
             KERNEL_POST(ctx);
+            // the Cholesky verdicts decide whether this wave needs the LU route at all: one extra synchronisation, only while
+            // some sequence of the wave is still on the Cholesky route
+            CU_CHECK(ctx, cudaMemcpyAsync(h_fail + b0, B->chol_fail.p + b0, (size_t)wb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CU_CHECK(ctx, cudaStreamSynchronize(s));
+            for (int q = 0; q < wb; ++q)
+                if (h_fail[b0 + q]) { B->h_use_lu[b0 + q] = 1; any_lu = true; }
         }
-        // ---- the wave's only host synchronisation: matched counts, Cholesky verdicts, argument flags ----
-        CU_CHECK(ctx, cudaMemcpyAsync(h_n + b0, B->n_mat.p + b0, (size_t)wb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_CHECK(ctx, cudaMemcpyAsync(h_fail + b0, B->chol_fail.p + b0, (size_t)wb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_CHECK(ctx, cudaMemcpyAsync(h_flags, B->flags.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_CHECK(ctx, cudaStreamSynchronize(s));
-        if (h_flags[0] & 2) return ptzba_fail(ctx, PTZBA_ERR_ARG, "observed ray index out of range");
-        if (h_flags[0] & 1) return ptzba_fail(ctx, PTZBA_ERR_ARG, "observation count exceeds max_obs");
-        int n_max_lu = 0;
-        for (int q = 0; q < wb; ++q)
-            if (n_max > 0 && h_fail[b0 + q]) n_max_lu = std::max(n_max_lu, (int)h_n[b0 + q]);
-        if (n_max_lu > 0) {
-            // indefinite S (the reference's write-back made P indefinite): rebuild S and take the getrf route for those sequences
-            const int sm = 3 + 2 * n_max_lu;
+        if (n_max > 0 && any_lu) {
+            // indefinite S (the reference's write-back made P indefinite): the getrf route; n_max bounds the order of every sequence
+            const int n_max_lu = n_max, sm = 3 + 2 * n_max_lu;
             k_ekf_S<<<dim3(div_up(n_max_lu, 128), 2 * n_max_lu, wb), 128, 0, s>>>(b0, max_obs, B->nm_lu.p, B->Jc.p, B->Jr.p, B->G.p, B->ldg,
                                                                                  strideG, B->S.p, B->lds, strideS, B->prm.observe_var);
             KERNEL_POST(ctx);
@@ -538,11 +559,15 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched, const in
                                                                                        strideG, B->P.p, strideP, s_tot);
             KERNEL_POST(ctx);
             B->n_lu_total += 1;
-            CU_CHECK(ctx, cudaMemcpyAsync(h_flags, B->flags.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-            CU_CHECK(ctx, cudaStreamSynchronize(s));
-            if (h_flags[2] != 0)
-                return ptzba_fail(ctx, PTZBA_ERR_NUMERIC, "innovation covariance is singular (zero pivot in column %d)", h_flags[2] - 1);
         }
+        // ---- the wave's closing host synchronisation: matched counts, argument flags, LU verdict ----
+        CU_CHECK(ctx, cudaMemcpyAsync(h_n + b0, B->n_mat.p + b0, (size_t)wb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaMemcpyAsync(h_flags, B->flags.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+        if (h_flags[0] & 2) return ptzba_fail(ctx, PTZBA_ERR_ARG, "observed ray index out of range");
+        if (h_flags[0] & 1) return ptzba_fail(ctx, PTZBA_ERR_ARG, "observation count exceeds max_obs");
+        if (h_flags[2] != 0)
+            return ptzba_fail(ctx, PTZBA_ERR_NUMERIC, "innovation covariance is singular (zero pivot in column %d)", h_flags[2] - 1);
     }
     if (out_matched) memcpy(out_matched, h_n, (size_t)n_seq * sizeof(int32_t));
     return PTZBA_OK;
@@ -562,6 +587,7 @@ extern "C" int ptzba_ekf_batch_create(ptzba_ctx* ctx, const ptzba_ekf_params* pr
     if (max_obs > n_ray) max_obs = n_ray;
     B->max_obs = max_obs; B->s_tot = 3 + 2 * n_ray;
     B->h_n_act.assign(n_seq, n_ray);
+    B->h_use_lu.assign(n_seq, 0);
     for (int e = 0; e < 6; ++e) B->has_disp = B->has_disp || prm->disp[e] != 0.0;
     const size_t strideP = (size_t)B->s_tot * B->s_tot;
     auto fail = [&](int code) { delete B; return code; };
@@ -576,6 +602,8 @@ extern "C" int ptzba_ekf_batch_create(ptzba_ctx* ctx, const ptzba_ekf_params* pr
     CU_TRY(B->ptz.alloc((size_t)n_seq * 3)); CU_TRY(B->vel.alloc((size_t)n_seq * 3)); CU_TRY(B->disp.alloc(6));
     CU_TRY(B->obs_cnt.alloc(n_seq)); CU_TRY(B->n_mat.alloc(n_seq)); CU_TRY(B->n2.alloc(n_seq)); CU_TRY(B->n_act.alloc(n_seq));
     CU_TRY(B->flags.alloc(8));
+    CU_TRY(B->use_lu.alloc(n_seq));
+    CU_TRY(cudaMemsetAsync(B->use_lu.p, 0, (size_t)n_seq * sizeof(int32_t), s));
     CU_TRY(B->chol_fail.alloc(n_seq)); CU_TRY(B->nm_chol.alloc(n_seq)); CU_TRY(B->n2_chol.alloc(n_seq));
     CU_TRY(B->nm_lu.alloc(n_seq)); CU_TRY(B->n2_lu.alloc(n_seq));
     CU_TRY(cudaMallocHost((void**)&B->h_back, (2 * (size_t)n_seq + 8) * sizeof(int32_t)));
@@ -655,9 +683,12 @@ extern "C" int ptzba_ekf_batch_set(ptzba_ekf_batch* B, int seq, const double* pt
     if (rays && na)
         CU_CHECK(ctx, cudaMemcpyAsync(B->rays.p + 2 * (size_t)B->n_ray * seq, rays, (size_t)na * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     // state_cov: dense (3 + 2 n_active)^2 row-major, placed with the batch's leading dimension
-    if (state_cov)
+    if (state_cov) {
         CU_CHECK(ctx, cudaMemcpy2DAsync(B->P.p + strideP * seq, (size_t)B->s_tot * sizeof(double), state_cov, (size_t)sa * sizeof(double),
                                         (size_t)sa * sizeof(double), sa, cudaMemcpyHostToDevice, s));
+        B->h_use_lu[seq] = 0;                       // a new covariance gets a new Cholesky attempt
+        CU_CHECK(ctx, cudaMemsetAsync(B->use_lu.p + seq, 0, sizeof(int32_t), s));
+    }
     CU_CHECK(ctx, cudaStreamSynchronize(s));
     return PTZBA_OK;
 }
@@ -769,6 +800,13 @@ extern "C" int ptzba_ekf_batch_predict_cov(ptzba_ekf_batch* B) {
 extern "C" int ptzba_ekf_batch_max_obs(ptzba_ekf_batch* B, int32_t* max_obs) {
     if (!B || !max_obs) return PTZBA_ERR_ARG;
     *max_obs = B->max_obs;
+    return PTZBA_OK;
+}
+
+// which factorisation route every sequence is on: route[b] = 0 Cholesky, 1 pivoted LU (its innovation covariance was indefinite once)
+extern "C" int ptzba_ekf_batch_route(ptzba_ekf_batch* B, int32_t* route) {
+    if (!B || !route) return PTZBA_ERR_ARG;
+    for (int b = 0; b < B->n_seq; ++b) route[b] = B->h_use_lu[b];
     return PTZBA_OK;
 }
 

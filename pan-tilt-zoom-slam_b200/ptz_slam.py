@@ -478,6 +478,12 @@ class BatchedEkfTracker:
         self.ctx.check(fn(self.handle, mem, _lib.ptr(obs_xy), _lib.ptr(obs_idx), _lib.ptr(obs_cnt), _lib.ptr(matched)))
         return matched
 
+    def route(self):
+        """0 = Cholesky route, 1 = pivoted-LU route (indefinite innovation covariance), per sequence."""
+        r = np.zeros(self.n_seq, np.int32)
+        self.ctx.check(self.ctx.lib.ptzba_ekf_batch_route(self.handle, _lib.ptr(r)))
+        return r
+
     def get_state(self, want_rays=True):
         ptz = np.empty((self.n_seq, 3)); vel = np.empty((self.n_seq, 3))
         rays = np.empty((self.n_seq, self.n_ray, 2)) if want_rays else None

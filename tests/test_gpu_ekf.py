@@ -152,9 +152,12 @@ def test_resident_state_ray_bookkeeping_matches_host_path():
             if which == 0:
                 assert s_._dev_valid and s_._rays_stale          # nothing was downloaded for the bookkeeping itself except rays
         alive = np.concatenate([np.delete(alive, drop), -np.arange(1, len(slams[0].rays) - (len(alive) - 7) + 1) - 1000 * k])
-        np.testing.assert_array_equal(slams[0].rays, slams[1].rays)
-        np.testing.assert_array_equal(slams[0].state_cov, slams[1].state_cov)
-        np.testing.assert_array_equal(slams[0].current_camera.get_ptz(), slams[1].current_camera.get_ptz())
+        # (not bit for bit: the resident sequence stays on the pivoted-LU route once its S was indefinite, the re-uploaded twin
+        # gets a fresh Cholesky attempt every frame - same mathematics, different rounding)
+        np.testing.assert_allclose(slams[0].rays, slams[1].rays, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(slams[0].state_cov, slams[1].state_cov, rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(slams[0].current_camera.get_ptz(), slams[1].current_camera.get_ptz(), rtol=1e-9, atol=1e-9)
+        assert slams[0].state_cov.shape == slams[1].state_cov.shape
     assert len(slams[0].rays) > n_global                                   # the device capacity had to grow
 
 
