@@ -93,5 +93,5 @@ struct ptzba_ba {
 // ---- device-level passes (all pointers device, enqueued on ba->ctx->stream) ----
 int ba_set_params(ptzba_ba* ba, const double* d_x, const double* d_ref_pose3, bool zero_acc = false);   // unpack + trig tables (+ clear ba->acc)
 int ba_fused_pass(ptzba_ba* ba, double* d_resid_or_null);                            // -> ba->acc
-int ba_residual_pass(ptzba_ba* ba, double* d_resid_or_null, double* d_sumsq);        // r (caller order) and sum r^2
+int ba_residual_pass(ptzba_ba* ba, double* d_resid_or_null, double* d_sumsq, bool reduce = true);   // r (caller order) and sum r^2 (summed over the ranks of a partition unless !reduce)
 extern "C" int ptzba_comm_allreduce_f64(ptzba_ctx* ctx, double* device_buf, int64_t count);

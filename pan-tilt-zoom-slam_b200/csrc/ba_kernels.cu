@@ -529,7 +529,7 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     return PTZBA_OK;
 }
 
-int ba_residual_pass(ptzba_ba* ba, double* d_resid, double* d_sumsq) {
+int ba_residual_pass(ptzba_ba* ba, double* d_resid, double* d_sumsq, bool reduce) {
     ptzba_ctx* ctx = ba->ctx;
     cudaStream_t s = ctx->stream;
     if (d_sumsq) CU_CHECK(ctx, cudaMemsetAsync(d_sumsq, 0, sizeof(double), s));
@@ -541,7 +541,7 @@ int ba_residual_pass(ptzba_ba* ba, double* d_resid, double* d_sumsq) {
             d_resid, d_sumsq);
         KERNEL_POST(ctx);
     }
-    if (ba->part_world > 1 && d_sumsq) PROPAGATE(ptzba_comm_allreduce_f64(ctx, d_sumsq, 1));
+    if (reduce && ba->part_world > 1 && d_sumsq) PROPAGATE(ptzba_comm_allreduce_f64(ctx, d_sumsq, 1));
     return PTZBA_OK;
 }
 

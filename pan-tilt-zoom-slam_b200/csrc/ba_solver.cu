@@ -858,10 +858,11 @@ extern "C" int ptzba_ba_solve(ptzba_ba* ba, int mem, double* x, const double* re
                                                            ba->sol2_c.p, ba->sol2_c.p + 3 * N, ba->scal.p + 6);
                 KERNEL_POST(ctx);
             }
-            if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->scal.p + 6, 1));
             // residual at the trial point (trig tables switch to x_trial; restored by the next fused pass)
             PROPAGATE(ba_set_params(ba, xt, d_ref.d));
-            PROPAGATE(ba_residual_pass(ba, nullptr, ba->scal.p + 7));
+            PROPAGATE(ba_residual_pass(ba, nullptr, ba->scal.p + 7, /*reduce=*/false));
+            // ||J delta||^2 and the trial sum of squares are partial sums over this rank's slice: ONE all-reduce for both
+            if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->scal.p + 6, 2));
             PROPAGATE(S.read_scalars(h, 8));
             ++nfev;
             const double g_dot_step = h[1], step_sq = h[2], Js_sq = h[6];
@@ -954,9 +955,9 @@ extern "C" int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, con
                                                    ba->sol2_c.p, ba->sol2_c.p + 3 * N, ba->scal.p + 6);
         KERNEL_POST(ctx);
     }
-    if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->scal.p + 6, 1));
     PROPAGATE(ba_set_params(ba, xt, d_ref.d));
-    PROPAGATE(ba_residual_pass(ba, nullptr, ba->scal.p + 7));
+    PROPAGATE(ba_residual_pass(ba, nullptr, ba->scal.p + 7, /*reduce=*/false));
+    if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->scal.p + 6, 2));
     double h[8];
     PROPAGATE(S.read_scalars(h, 8));
     if (out_pred_reduction) *out_pred_reduction = -(0.5 * h[6] + h[1]);

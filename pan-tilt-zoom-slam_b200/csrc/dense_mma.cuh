@@ -4,8 +4,10 @@
 // One CTA (256 threads = 8 warps) accumulates   acc += A[TM x K] * B[K x TN]   for one TM x TN output tile:
 //   A(i, t) = A0[i + t * sAt]   (i contiguous in memory, i < mA else 0)
 //   B(t, j) = B0[j + t * sBt]   (j contiguous in memory, j < nB else 0)        [B_TCONTIG: B0[t + j * sBt], t contiguous]
-// K runs over [0, K) in slabs of 16 that are staged through shared memory (register-staged double buffer, one
-// __syncthreads per slab).  Each warp owns (TM/8/WM) x (TN/8/WN) m8n8 accumulator tiles; per k-step of 4 it loads one A
+// K runs over [0, K) in slabs of 32 that are staged through shared memory: the next slab is requested into registers
+// before the current one is multiplied (one shared-memory buffer, two __syncthreads per slab).  (Slabs of 16 with two
+// shared-memory buffers were measured first: with few CTAs per SM the K loop is bound by the load latency per slab, so
+// fewer, larger slabs win.)  Each warp owns (TM/8/WM) x (TN/8/WN) m8n8 accumulator tiles; per k-step of 4 it loads one A
 // fragment per tile row and one B fragment per tile column (conflict-free: the slab row stride is 4 mod 16 doubles) and
 // issues one DMMA per tile.  Measured DMMA peak on this B200: 37.1 TFLOP/s (profiles/r2_fp64_peak.json; DFMA: 34.1).
 // FP64 has no tcgen05 kind: mma.sync (SASS DMMA.8x8x4) IS the FP64 tensor path of sm_100a.
@@ -15,7 +17,7 @@
 namespace dmma {
 
 constexpr int kThreads = 256;
-constexpr int KS = 16;                      // K slab staged per step
+constexpr int KS = 32;                      // K slab staged per step
 
 __device__ __forceinline__ void mma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -27,7 +29,7 @@ struct Tile {
     static constexpr int WM = (TM >= 64) ? 4 : 2, WN = 8 / WM;          // warp grid
     static constexpr int RM = MB / WM, RN = NBK / WN;                    // m8n8 tiles per warp
     static constexpr int SA = TM + 4, SB = TN + 4;                       // slab row strides (doubles): 4 mod 16
-    static constexpr int kSmemDoubles = 2 * KS * (SA + SB);
+    static constexpr int kSmemDoubles = KS * (SA + SB);
     static constexpr int LA = KS * TM / kThreads, LB = KS * TN / kThreads;   // doubles per thread and slab
     static_assert(RM >= 1 && RN >= 1 && LA >= 1 && LB >= 1, "tile too small for 8 warps");
 
@@ -38,8 +40,8 @@ struct Tile {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int wm = warp % WM, wn = warp / WM;
         const int g = lane >> 2, t4 = lane & 3;
-        double* As = sm;                          // [2][KS][SA]
-        double* Bs = sm + 2 * KS * SA;            // [2][KS][SB]
+        double* As = sm;                          // [KS][SA]
+        double* Bs = sm + KS * SA;                // [KS][SB]
         double ra[LA], rb[LB];
         auto gload = [&](int k0) {
 #pragma unroll
@@ -59,42 +61,41 @@ struct Tile {
                 }
             }
         };
-        auto sstore = [&](int buf) {
+        auto sstore = [&]() {
 #pragma unroll
             for (int q = 0; q < LA; ++q) {
                 const int e = tid + kThreads * q, i = e % TM, t = e / TM;
-                As[(buf * KS + t) * SA + i] = ra[q];
+                As[t * SA + i] = ra[q];
             }
 #pragma unroll
             for (int q = 0; q < LB; ++q) {
                 const int e = tid + kThreads * q;
                 const int j = B_TCONTIG ? e / KS : e % TN, t = B_TCONTIG ? e % KS : e / TN;
-                Bs[(buf * KS + t) * SB + j] = rb[q];
+                Bs[t * SB + j] = rb[q];
             }
         };
         if (K <= 0) return;
         gload(0);
-        sstore(0);
-        __syncthreads();
         const int nslab = (K + KS - 1) / KS;
         for (int s = 0; s < nslab; ++s) {
-            const int buf = s & 1;
+            __syncthreads();                      // the previous slab has been consumed
+            sstore();
+            __syncthreads();
             if (s + 1 < nslab) gload((s + 1) * KS);
 #pragma unroll
             for (int ks = 0; ks < KS / 4; ++ks) {
                 double fa[RM], fb[RN];
 #pragma unroll
-                for (int rm = 0; rm < RM; ++rm) fa[rm] = As[(buf * KS + ks * 4 + t4) * SA + (wm * RM + rm) * 8 + g];
+                for (int rm = 0; rm < RM; ++rm) fa[rm] = As[(ks * 4 + t4) * SA + (wm * RM + rm) * 8 + g];
 #pragma unroll
-                for (int rn = 0; rn < RN; ++rn) fb[rn] = Bs[(buf * KS + ks * 4 + t4) * SB + (wn * RN + rn) * 8 + g];
+                for (int rn = 0; rn < RN; ++rn) fb[rn] = Bs[(ks * 4 + t4) * SB + (wn * RN + rn) * 8 + g];
 #pragma unroll
                 for (int rm = 0; rm < RM; ++rm)
 #pragma unroll
                     for (int rn = 0; rn < RN; ++rn) mma884(acc[rm][rn][0], acc[rm][rn][1], fa[rm], fb[rn]);
             }
-            if (s + 1 < nslab) sstore(buf ^ 1);
-            __syncthreads();
         }
+        __syncthreads();                          // callers reuse the shared-memory buffer
     }
 
     // visits every accumulator element: f(row in tile, column in tile, value)
