@@ -93,6 +93,21 @@ int ptzba_h_jacobian_blocks(ptzba_ctx* ctx, int mem, const double* ptz3, double 
 int ptzba_h_jacobian_dense(ptzba_ctx* ctx, int mem, const double* ptz3, double u, double v, const double* disp,
                            int n_ray, const double* rays, int mode, double* H);
 
+/* ---- N2: pose estimation on fixed ray <-> pixel matches, batched over hypotheses (relocalization.py:22-40, :186-187;
+ *            rf_map/util/ptz_pose_estimation.cpp:95-239 preemptive RANSAC: score the hypotheses on a sample of matches, keep the
+ *            better half, re-optimise the survivors on their inliers).  rays[n*2] (theta, phi), points[n*2] pixels, sel[n_sel]
+ *            indices of the sampled matches (NULL = all n), ptz[n_hyp*3].  One CTA per hypothesis. -------------------------------- */
+/* outliers[h] = number of selected matches whose pixel distance under hypothesis h exceeds `threshold`; mean_err may be NULL */
+int ptzba_pose_score(ptzba_ctx* ctx, int mem, int n_hyp, const double* ptz, double u, double v, int n, const double* rays,
+                     const double* points, int n_sel, const int32_t* sel, double threshold, int32_t* out_outliers, double* out_mean_err);
+/* Levenberg-Marquardt on (pan, tilt, f) of every hypothesis over the selected matches that are inliers of its incoming pose
+ * (threshold <= 0: all selected matches), analytic Jacobian; a hypothesis with at most min_used inliers is left unchanged
+ * (the reference uses 4).  Stops when an accepted step reduces the cost by less than ftol * cost, or after max_iter cost
+ * evaluations.  ptz in/out; out_cost = 0.5 sum r^2 over the used matches, out_n_used, out_iters: [n_hyp], any may be NULL. */
+int ptzba_pose_refine(ptzba_ctx* ctx, int mem, int n_hyp, double* ptz, double u, double v, int n, const double* rays,
+                      const double* points, int n_sel, const int32_t* sel, double threshold, int min_used, int max_iter, double ftol,
+                      double* out_cost, int32_t* out_n_used, int32_t* out_iters);
+
 /* ---- A5: EKF update  (PtzSlam.ekf_update ptz_slam.py:210-289, predict lines :418-426) ---------------------- */
 typedef struct ptzba_ekf_params {
     double u, v;            /* principal point */

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ptzba_backproject": (_I, [_P, _I, _I, _P, _D, _D, _P, _L, _P, _P, _P]),
     "ptzba_h_jacobian_blocks": (_I, [_P, _I, _P, _D, _D, _P, _I, _P, _I, _P, _P]),
     "ptzba_h_jacobian_dense": (_I, [_P, _I, _P, _D, _D, _P, _I, _P, _I, _P]),
+    "ptzba_pose_score": (_I, [_P, _I, _I, _P, _D, _D, _I, _P, _P, _I, _P, _D, _P, _P]),
+    "ptzba_pose_refine": (_I, [_P, _I, _I, _P, _D, _D, _I, _P, _P, _I, _P, _D, _I, _I, _D, _P, _P, _P]),
     "ptzba_ekf_update": (_I, [_P, ctypes.POINTER(EkfParams), _I, _P, _P, _P, _P, _I, _P, _P, _P]),
     "ptzba_ekf_batch_create": (_I, [_P, ctypes.POINTER(EkfParams), _I, _I, _I, _P, _P, ctypes.POINTER(_P)]),
     "ptzba_ekf_batch_destroy": (None, [_P]),

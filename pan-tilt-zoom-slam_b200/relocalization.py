@@ -12,6 +12,11 @@ least_squares with the reference's settings (method='trf', x_scale='jac', ftol=1
     refine_pose(pose, rays, points, u, v)            relocalization.py:186-187 / nearest_neighbor.py:98-99
     score_hypotheses(ptzs, rays, points, u, v, thr)  inlier count of H candidate poses in one launch
                                                      (rf_map/util/ptz_pose_estimation.cpp:95-239 scores hypotheses one by one)
+    refine_poses_batched(ptzs, rays, points, ...)    Levenberg-Marquardt on (pan, tilt, f) of H poses at once on the GPU
+    ptz_from_two_points(...)                         the two-point minimal solver that seeds the hypotheses
+                                                     (rf_map/util/eigen_geometry_util.cpp:126-167)
+    preemptive_ransac(rays, points, u, v, ...)       ptz_pose_estimation.cpp:95-239 with scoring and refinement of ALL hypotheses of
+                                                     a round in one launch each
     relocalization_camera(map, img, pose, ...)       relocalization.py:96-189, OpenCV front-end injected
     NNBasedMap                                       nearest_neighbor.py:18-101, exact nearest neighbour instead of FLANN
 """
@@ -54,14 +59,97 @@ def refine_pose(pose, rays, points, u, v, ftol=1e-4, verbose=0):
                          x_scale='jac', ftol=ftol, method='trf', args=(rays, points, u, v))
 
 
-def score_hypotheses(ptzs, rays, points, u, v, threshold=2.0):
-    """Reprojection of all rays under H candidate poses in one device call; returns (inlier_count[H], mean_error[H])
-    with inlier = pixel distance < threshold (the preemptive-RANSAC score of ptz_pose_estimation.cpp)."""
+def score_hypotheses(ptzs, rays, points, u, v, threshold=2.0, sel=None):
+    """Reprojection of the (selected) rays under H candidate poses in one device call (one CTA per hypothesis); returns
+    (inlier_count[H], mean_error[H]) with inlier = pixel distance <= threshold (the preemptive-RANSAC score of
+    ptz_pose_estimation.cpp:163-195, which counts the complement as its loss)."""
+    ctx = _lib.get_context()
     ptzs = _lib.f64(ptzs).reshape(-1, 3)
-    points = np.asarray(points, dtype=np.float64).reshape(-1, 2)
-    xy = TransFunction.from_rays_to_image_batch(u, v, ptzs, rays)
-    dist = np.sqrt(((xy - points[None]) ** 2).sum(axis=2))
-    return (dist < threshold).sum(axis=1), dist.mean(axis=1) if dist.shape[1] else np.zeros(len(ptzs))
+    rays = _lib.f64(rays).reshape(-1, 2)
+    points = _lib.f64(points).reshape(-1, 2)
+    n, H = rays.shape[0], ptzs.shape[0]
+    sel_a = None if sel is None else _lib.i32(sel)
+    n_sel = n if sel_a is None else int(sel_a.shape[0])
+    outl = np.zeros(H, np.int32)
+    err = np.zeros(H, np.float64)
+    ctx.check(ctx.lib.ptzba_pose_score(ctx.handle, _lib.HOST, H, _lib.ptr(ptzs), float(u), float(v), n, _lib.ptr(rays), _lib.ptr(points),
+                                       n_sel, _lib.ptr(sel_a), float(threshold), _lib.ptr(outl), _lib.ptr(err)))
+    return n_sel - outl, err
+
+
+def refine_poses_batched(ptzs, rays, points, u, v, sel=None, threshold=0.0, min_used=4, max_iter=30, ftol=1e-10):
+    """Levenberg-Marquardt on (pan, tilt, f) of H poses at once (one CTA per pose, analytic Jacobian, csrc/pose_refine.cu): the
+    batched device form of refine_pose / optimizePTZ.  threshold > 0 restricts every pose to the selected matches that are inliers
+    of its incoming value.  Returns (ptzs[H,3], cost[H] = 0.5 sum r^2 over the used matches, n_used[H], iterations[H])."""
+    ctx = _lib.get_context()
+    out = _lib.f64(ptzs).reshape(-1, 3).copy()
+    rays = _lib.f64(rays).reshape(-1, 2)
+    points = _lib.f64(points).reshape(-1, 2)
+    n, H = rays.shape[0], out.shape[0]
+    sel_a = None if sel is None else _lib.i32(sel)
+    n_sel = n if sel_a is None else int(sel_a.shape[0])
+    cost = np.zeros(H); used = np.zeros(H, np.int32); iters = np.zeros(H, np.int32)
+    ctx.check(ctx.lib.ptzba_pose_refine(ctx.handle, _lib.HOST, H, _lib.ptr(out), float(u), float(v), n, _lib.ptr(rays), _lib.ptr(points),
+                                        n_sel, _lib.ptr(sel_a), float(threshold), int(min_used), int(max_iter), float(ftol),
+                                        _lib.ptr(cost), _lib.ptr(used), _lib.ptr(iters)))
+    return out, cost, used, iters
+
+
+def ptz_from_two_points(pan_tilt1, pan_tilt2, point1, point2, pp):
+    """Two-point minimal solver (rf_map/util/eigen_geometry_util.cpp:126-167), vectorised over H samples: the focal length from the
+    angle between the two rays against the pixel vectors (cos = (p1.p2 + f^2) / (|(p1,f)| |(p2,f)|), a quadratic in f^2), then pan
+    and tilt as the mean of what either match implies.  Arrays [H,2]; returns (ptz[H,3], valid[H])."""
+    pt1 = np.asarray(pan_tilt1, dtype=np.float64).reshape(-1, 2)
+    pt2 = np.asarray(pan_tilt2, dtype=np.float64).reshape(-1, 2)
+    p1 = np.asarray(point1, dtype=np.float64).reshape(-1, 2) - np.asarray(pp, dtype=np.float64)
+    p2 = np.asarray(point2, dtype=np.float64).reshape(-1, 2) - np.asarray(pp, dtype=np.float64)
+    a, b, c = (p1 * p1).sum(1), (p2 * p2).sum(1), (p1 * p2).sum(1)
+    # z axis rotated by the pan / tilt differences: its z component is the cosine of the angle between the two rays
+    dp, dt = np.radians(pt2[:, 0] - pt1[:, 0]), np.radians(pt2[:, 1] - pt1[:, 1])
+    d = np.cos(dp) * np.cos(dt)
+    d2 = d * d
+    # d^2 (a + F)(b + F) = (c + F)^2,  F = f^2
+    qa, qb, qc = d2 - 1.0, d2 * (a + b) - 2.0 * c, d2 * a * b - c * c
+    disc = qb * qb - 4.0 * qa * qc
+    valid = (disc >= 0.0) & (np.abs(qa) > 1e-14)
+    sq = np.sqrt(np.where(valid, disc, 0.0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r1, r2 = (-qb + sq) / (2.0 * qa), (-qb - sq) / (2.0 * qa)
+    # the root that is positive and consistent with the sign of the cosine: (c + F) has the sign of d
+    ok1 = (r1 > 0) & ((c + r1) * d > 0)
+    ok2 = (r2 > 0) & ((c + r2) * d > 0)
+    F = np.where(ok1, r1, np.where(ok2, r2, np.nan))
+    valid &= np.isfinite(F)
+    f = np.sqrt(np.where(valid, F, 1.0))
+    pan = 0.5 * ((pt1[:, 0] - np.degrees(np.arctan2(p1[:, 0], f))) + (pt2[:, 0] - np.degrees(np.arctan2(p2[:, 0], f))))
+    tilt = 0.5 * ((pt1[:, 1] + np.degrees(np.arctan2(p1[:, 1], f))) + (pt2[:, 1] + np.degrees(np.arctan2(p2[:, 1], f))))
+    return np.stack([pan, tilt, f], 1), valid
+
+
+def preemptive_ransac(rays, points, u, v, init_ptz, threshold=2.0, sample_number=32, n_iteration=1024, n_keep=512, seed=0,
+                      max_iter=20, ftol=1e-8):
+    """Preemptive RANSAC over (pan, tilt, f) hypotheses (ptz_pose_estimation.cpp:95-239): hypotheses from two-point samples
+    (plus the initial pose); per round a random sample of `sample_number` matches is scored under every hypothesis, the better half
+    survives and is re-optimised on its inliers; until one is left.  Scoring and refinement of a round are ONE launch each over all
+    hypotheses.  Returns (ptz[3] or None when there are at most 12 matches, like the reference)."""
+    rays = _lib.f64(rays).reshape(-1, 2)
+    points = _lib.f64(points).reshape(-1, 2)
+    n = rays.shape[0]
+    if n <= 12:
+        return None
+    rng = np.random.default_rng(seed)
+    k1 = rng.integers(0, n, n_iteration)
+    k2 = rng.integers(0, n, n_iteration)
+    keep = k1 != k2
+    cand, valid = ptz_from_two_points(rays[k1[keep]], rays[k2[keep]], points[k1[keep]], points[k2[keep]], (u, v))
+    hyp = np.vstack([np.asarray(init_ptz, dtype=np.float64).reshape(1, 3), cand[valid]])[:n_keep + 1]
+    while len(hyp) > 1:
+        sel = rng.integers(0, n, sample_number).astype(np.int32)
+        inl, _ = score_hypotheses(hyp, rays, points, u, v, threshold, sel=sel)
+        order = np.argsort(-inl, kind="stable")                    # loss = outliers: fewest first, ties keep their order
+        hyp = hyp[order[:max(len(hyp) // 2, 1)]]
+        hyp, _, _, _ = refine_poses_batched(hyp, rays, points, u, v, sel=sel, threshold=threshold, min_used=4, max_iter=max_iter, ftol=ftol)
+    return hyp[0]
 
 
 def select_nearest_keyframe(match_counts):

@@ -252,3 +252,20 @@ def test_dense_spd_solve_reports_indefinite():
     info = ctypes.c_int(0)
     ctx.check(ctx.lib.ptzba_dense_solve_spd(ctx.handle, n, _lib.ptr(A), _lib.ptr(b), _lib.ptr(x), ctypes.byref(info)))
     assert info.value == 33          # 1 + first row of the failing 32-column panel
+
+
+def test_schur_per_landmark_route_equals_pair_list():
+    """PTZBA_OPT_SCHUR_MODE: the per-landmark Schur formation (k_schur_pairs, the fallback above 65535 keyframes / 2^31 observation
+    pairs) and the default keyframe-pair-major list (k_schur_pairlist) form the same reduced camera system: identical status and
+    iteration counts, parameters equal far below the parity tolerance."""
+    fb = synth.make_flat_ba(24, 1500, 18000, seed=11)
+    res = []
+    for mode in (_lib.SCHUR_PAIR_LIST, _lib.SCHUR_PER_LANDMARK):
+        prob = BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+        prob.set_option(_lib.OPT_SCHUR_MODE, mode)
+        x, rep = prob.solve(fb.x0(), fb.ptz_init[0], ftol=1e-10, xtol=1e-10, gtol=1e-10)
+        res.append((x, rep))
+        prob.close()
+    assert res[0][1]["status"] == res[1][1]["status"] and res[0][1]["nfev"] == res[1][1]["nfev"]
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-10, atol=1e-9)
+    assert abs(res[0][1]["cost"] - res[1][1]["cost"]) <= 1e-10 * res[0][1]["cost"]
