@@ -112,7 +112,8 @@ def make_workload(name, rank=0):
     import ptz_slam_b200  # noqa: F401
     from ptz_slam_b200 import synth
     w = WORKLOADS[name]
-    return synth.make_flat_ba(w["n_kf"], w["n_lm"], w["n_obs"], seed=w["seed"] + 17 * rank, pan_sweep=w["pan_sweep"])
+    return synth.make_flat_ba(w["n_kf"], w["n_lm"], w["n_obs"], seed=w["seed"] + 17 * rank, pan_sweep=w["pan_sweep"],
+                              id_order=os.environ.get("PTZBA_BENCH_ID_ORDER", "first_keyframe"))
 
 
 # -------------------------------------------------------------------------------------------------------------------
@@ -307,6 +308,11 @@ def run_ours(args):
         # rank (the shards differ slightly in size, and setting up a replica's exchange is a collective)
         R = max(4, int(np.ceil(2.2 * 126e6 * world / algorithmic_bytes(fb_full.n_obs, fb_full.n_landmark, fb_full.n_pose))))
     probs = [BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v, ctx=ctx) for _ in range(R)]
+    for p_ in probs:      # kernel tuning knobs (include/ptzba.h PTZBA_OPT_*); the defaults are the measured best
+        if args.fused_launch is not None:
+            p_.set_option(_lib.OPT_FUSED_LAUNCH, args.fused_launch)
+        if args.lm_share is not None:
+            p_.set_option(_lib.OPT_FUSED_LM_SHARE, args.lm_share)
     x_dev = [torch.from_numpy(x0).cuda() for _ in range(R)]
     r_dev = [torch.empty(2 * fb.n_obs, dtype=torch.float64, device="cuda") for _ in range(R)]
     comm = None
@@ -613,6 +619,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--replicas", type=int, default=0, help="problem replicas the passes rotate over (0 = enough to exceed the L2)")
+    ap.add_argument("--fused-launch", type=int, default=None, help="tuning: 0 one launch with two CTA roles, 1 two launches")
+    ap.add_argument("--lm-share", type=int, default=None, help="tuning: per cent of the fused pass's CTA budget for the landmark-major role")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-ekf", action="store_true")

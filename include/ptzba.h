@@ -223,10 +223,24 @@ int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, const double* 
  * 2^31 observation pairs), PER_LANDMARK (one warp per landmark, one FP64 RED per block entry per observation pair; no
  * extra memory), PAIR_LIST (same as AUTO). */
 #define PTZBA_OPT_SCHUR_MODE 1
+/* PTZBA_OPT_FUSED_LAUNCH: 0 (default) the two passes of the fused pass are ONE launch with two interleaved CTA roles; 1 two launches
+ * on two streams.  PTZBA_OPT_FUSED_LM_SHARE: per cent (1..99, default 57) of the CTAs' work budget given to the landmark-major role. */
+#define PTZBA_OPT_FUSED_LAUNCH 2
+#define PTZBA_OPT_FUSED_LM_SHARE 3
 #define PTZBA_SCHUR_AUTO 0
 #define PTZBA_SCHUR_PER_LANDMARK 1
 #define PTZBA_SCHUR_PAIR_LIST 2
 int ptzba_ba_set_option(ptzba_ba* ba, int option, int value);
+
+/* ---- N3: match graph -> observation list (image_process.py:612-650 landmark ids; bundle_adjustment.py:67-98 residual order).
+ * Keypoints of all images are numbered globally ("nodes": node_img[n_node] = image of the node, node_xy[n_node*2] = its pixel);
+ * matches are edges (edge_a[k] in image i, edge_b[k] in image j > i) in the reference's visiting order.  out_label[n_node] receives
+ * the landmark id of every keypoint (-1: unmatched) exactly as the reference's sequential propagation assigns it, *out_n_landmark
+ * their number; out_cam / out_lm [2*n_edge] and out_xy [4*n_edge] (all three or none) the flat observation list that
+ * ptzba_ba_create consumes.  Arrays live in `mem`; the two counts are host memory. */
+int ptzba_match_graph_to_observations(ptzba_ctx* ctx, int mem, int n_node, const int32_t* node_img, const double* node_xy, int n_edge,
+                                      const int32_t* edge_a, const int32_t* edge_b, int32_t* out_label, int32_t* out_n_landmark,
+                                      int32_t* out_cam, int32_t* out_lm, double* out_xy);
 
 /* multi-GPU: observations are sharded by keyframe across ranks (each rank creates its ptzba_ba from its shard with
  * the GLOBAL n_pose/n_landmark); landmark blocks and the reduced camera system are summed with ncclAllReduce.

@@ -14,6 +14,7 @@ import numpy as np
 HOST, DEVICE = 0, 1
 JAC_ANALYTIC, JAC_CENTRAL_FD = 0, 1
 OPT_SCHUR_MODE = 1
+OPT_FUSED_LAUNCH, OPT_FUSED_LM_SHARE = 2, 3
 SCHUR_AUTO, SCHUR_PER_LANDMARK, SCHUR_PAIR_LIST = 0, 1, 2
 
 # PTZBA_LIBRARY names another build of the same library (kernel tuning experiments); it is still this library or nothing
@@ -63,6 +64,7 @@ SIGNATURES = {
     "ptzba_backproject": (_I, [_P, _I, _I, _P, _D, _D, _P, _L, _P, _P, _P]),
     "ptzba_h_jacobian_blocks": (_I, [_P, _I, _P, _D, _D, _P, _I, _P, _I, _P, _P]),
     "ptzba_h_jacobian_dense": (_I, [_P, _I, _P, _D, _D, _P, _I, _P, _I, _P]),
+    "ptzba_match_graph_to_observations": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "ptzba_pose_score": (_I, [_P, _I, _I, _P, _D, _D, _I, _P, _P, _I, _P, _D, _P, _P]),
     "ptzba_pose_refine": (_I, [_P, _I, _I, _P, _D, _D, _I, _P, _P, _I, _P, _D, _I, _I, _D, _P, _P, _P]),
     "ptzba_ekf_update": (_I, [_P, ctypes.POINTER(EkfParams), _I, _P, _P, _P, _P, _I, _P, _P, _P]),

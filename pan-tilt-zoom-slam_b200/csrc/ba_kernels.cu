@@ -166,6 +166,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // keyframe sort, serial 4-observation loops with look-ahead index loads) are tabulated in DESIGN.md section 5.
 // ---------------------------------------------------------------------------------------------------------------
 struct __align__(32) D4 { double a, b, c, d; };
+
 constexpr int kQuad = 4;
 constexpr int kCamIter = 32 * kQuad;       // observations one warp consumes per iteration of the keyframe-major pass
 
@@ -175,16 +176,16 @@ constexpr int kCamIter = 32 * kQuad;       // observations one warp consumes per
 // with aligned 128-/256-bit accesses: 20 B per observation are streamed.  A CTA walks a contiguous range of
 // iterations, its warps interleaved; a warp keeps the nine sums of its current keyframe in registers and commits them
 // (warp reduction + 9 REDs) when the keyframe changes - about once per CTA.
-// (Staging the gathered trig rows of the next iteration in shared memory with cp.async was measured: 27.5 us instead of
-// 19.5 us for this kernel, MIO-throttled by the per-lane 16-byte copies; removed.)
-template <int MINB>
-__global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_cam_pass(int it_lo, int it_hi, int iters_per_cta, const int32_t* __restrict__ iter_cam, const int32_t* __restrict__ c_lm,
-              const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
-              const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
+// (Measured and removed: staging the gathered trig rows of the next iteration in shared memory with cp.async - 27.5 us instead of
+// 19.5 us for this role alone, MIO-throttled by the per-lane 16-byte copies; requesting them into L1 one iteration ahead with
+// prefetch.global.L1 - 48.6 instead of 42.2 us for the whole pass - or with dummy loads - 42.1 us, no gain.)
+__device__ __forceinline__ void
+cam_role(int cta, int it_lo, int it_hi, int iters_per_cta, const int32_t* __restrict__ iter_cam, const int32_t* __restrict__ c_lm,
+         const double* __restrict__ c_ox, const double* __restrict__ c_oy, const CamTrig* __restrict__ cam_trig,
+         const LmTrig* __restrict__ lm_trig, double u, double v, double* __restrict__ gU, double* __restrict__ gGc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarpsPerCta = kFusedThreads / 32;
-    const int cta_begin = it_lo + blockIdx.x * iters_per_cta;
+    const int cta_begin = it_lo + cta * iters_per_cta;
     int cta_end = cta_begin + iters_per_cta;
     if (cta_end > it_hi) cta_end = it_hi;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;   // radian units, signs and scales applied on commit
@@ -206,55 +207,66 @@ k_ba_cam_pass(int it_lo, int it_hi, int iters_per_cta, const int32_t* __restrict
         }
         a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = 0.0;
     };
+    // Rolling software pipeline at half-iteration granularity, registers only: while the first two observations of an iteration
+    // are evaluated the trig rows of its last two are in flight, and while those are evaluated the rows of the NEXT iteration's
+    // first two are - the gather (an L2 round trip, the top stall of the round-2 profile: 15 % of all samples on its first use)
+    // always has two observations' worth of arithmetic to hide behind, at the register cost of the four rows held before.
+    // Landmark ids are loaded two iterations ahead, observed pixels one.
     int it = cta_begin + warp;
-    int4 nl = make_int4(-1, -1, -1, -1);
-    D4 nx = {0, 0, 0, 0}, ny = {0, 0, 0, 0};
-    int ncam = -1;
-    if (it < cta_end) {
+    if (it >= cta_end) return;
+    auto ld_ids = [&](int i) { return __ldg(reinterpret_cast<const int4*>(c_lm + (size_t)i * kCamIter + (size_t)lane * kQuad)); };
+    auto row = [&](int l) { return lm_trig[l < 0 ? 0 : l]; };
+    int4 idA = ld_ids(it), idB = make_int4(-1, -1, -1, -1);
+    D4 oxA, oyA, oxB = {0, 0, 0, 0}, oyB = {0, 0, 0, 0};
+    int camA = __ldg(iter_cam + it), camB = -1;
+    {
         const size_t o = (size_t)it * kCamIter + (size_t)lane * kQuad;
-        nl = __ldg(reinterpret_cast<const int4*>(c_lm + o));
-        nx = *reinterpret_cast<const D4*>(c_ox + o);
-        ny = *reinterpret_cast<const D4*>(c_oy + o);
-        ncam = __ldg(iter_cam + it);
+        oxA = *reinterpret_cast<const D4*>(c_ox + o);
+        oyA = *reinterpret_cast<const D4*>(c_oy + o);
     }
+    if (it + kWarpsPerCta < cta_end) idB = ld_ids(it + kWarpsPerCta);
+    LmTrig p0 = row(idA.x), p1 = row(idA.y);                  // rows of the first two observations of the current iteration
+    auto accumulate = [&](const LmTrig& lt, double ox, double oy, bool valid) {
+        double x, y;
+        ObsGeom g;
+        project_fast_jac(wc, lt, u, v, x, y, g);
+        const double rx = x - ox, ry = y - oy;
+        if (valid) {                                          // predicated FMAs, no branch
+            a0 = fma(g.xa, g.xa, fma(g.ya, g.ya, a0));
+            a1 = fma(g.xa, g.xt, fma(g.ya, g.yt, a1));
+            a2 = fma(g.xa, g.px, fma(g.ya, g.py, a2));
+            a3 = fma(g.xt, g.xt, fma(g.yt, g.yt, a3));
+            a4 = fma(g.xt, g.px, fma(g.yt, g.py, a4));
+            a5 = fma(g.px, g.px, fma(g.py, g.py, a5));
+            a6 = fma(g.xa, rx, fma(g.ya, ry, a6));
+            a7 = fma(g.xt, rx, fma(g.yt, ry, a7));
+            a8 = fma(g.px, rx, fma(g.py, ry, a8));
+        }
+    };
 #pragma unroll 1
     for (; it < cta_end; it += kWarpsPerCta) {
-        const int lm[kQuad] = {nl.x, nl.y, nl.z, nl.w};
-        const double ox[kQuad] = {nx.a, nx.b, nx.c, nx.d};
-        const double oy[kQuad] = {ny.a, ny.b, ny.c, ny.d};
-        const int cam = ncam;
-        LmTrig lt[kQuad];
-#pragma unroll
-        for (int i = 0; i < kQuad; ++i) lt[i] = lm_trig[lm[i] < 0 ? 0 : lm[i]];      // four independent gathers, issued at once
         const int itn = it + kWarpsPerCta;
-        if (itn < cta_end) {                                                          // next iteration's streams: in flight during the arithmetic
+        const LmTrig q0 = row(idA.z), q1 = row(idA.w);        // rows of this iteration's last two observations: in flight during the first two
+        int4 idC = make_int4(-1, -1, -1, -1);
+        if (itn < cta_end) {                                  // next iteration's pixels, the ids of the one after
             const size_t o = (size_t)itn * kCamIter + (size_t)lane * kQuad;
-            nl = __ldg(reinterpret_cast<const int4*>(c_lm + o));
-            nx = *reinterpret_cast<const D4*>(c_ox + o);
-            ny = *reinterpret_cast<const D4*>(c_oy + o);
-            ncam = __ldg(iter_cam + itn);
+            oxB = *reinterpret_cast<const D4*>(c_ox + o);
+            oyB = *reinterpret_cast<const D4*>(c_oy + o);
+            camB = __ldg(iter_cam + itn);
+            if (itn + kWarpsPerCta < cta_end) idC = ld_ids(itn + kWarpsPerCta);
         }
-        if (cam != wcam) { flush(); wcam = cam; wc = cam_trig[cam]; }                 // warp-uniform
-        if (cam > 0) {                                                                // keyframe 0 is the fixed reference pose
-#pragma unroll
-            for (int i = 0; i < kQuad; ++i) {
-                double x, y;
-                ObsGeom g;
-                project_fast_jac(wc, lt[i], u, v, x, y, g);
-                const double rx = x - ox[i], ry = y - oy[i];
-                if (lm[i] >= 0) {                                                     // predicated FMAs, no branch
-                    a0 = fma(g.xa, g.xa, fma(g.ya, g.ya, a0));
-                    a1 = fma(g.xa, g.xt, fma(g.ya, g.yt, a1));
-                    a2 = fma(g.xa, g.px, fma(g.ya, g.py, a2));
-                    a3 = fma(g.xt, g.xt, fma(g.yt, g.yt, a3));
-                    a4 = fma(g.xt, g.px, fma(g.yt, g.py, a4));
-                    a5 = fma(g.px, g.px, fma(g.py, g.py, a5));
-                    a6 = fma(g.xa, rx, fma(g.ya, ry, a6));
-                    a7 = fma(g.xt, rx, fma(g.yt, ry, a7));
-                    a8 = fma(g.px, rx, fma(g.py, ry, a8));
-                }
-            }
+        if (camA != wcam) { flush(); wcam = camA; wc = cam_trig[camA]; }              // warp-uniform
+        const bool on = camA > 0;                                                     // keyframe 0 is the fixed reference pose
+        if (on) {
+            accumulate(p0, oxA.a, oyA.a, idA.x >= 0);
+            accumulate(p1, oxA.b, oyA.b, idA.y >= 0);
         }
+        p0 = row(idB.x); p1 = row(idB.y);                     // rows of the next iteration's first two: in flight during the last two
+        if (on) {
+            accumulate(q0, oxA.c, oyA.c, idA.z >= 0);
+            accumulate(q1, oxA.d, oyA.d, idA.w >= 0);
+        }
+        idA = idB; idB = idC; oxA = oxB; oyA = oyB; camA = camB;
     }
     flush();
 }
@@ -313,19 +325,20 @@ __device__ __forceinline__ void load_quad_obs(QuadObs& q, int64_t k0, int64_t lo
 // observation.  All three cases are predicated adds on the same straight-line code.
 // Software pipeline per thread, registers only: landmark ids two iterations ahead, keyframe ids / observed pixels one
 // iteration ahead; the trig rows of the quad's first and last landmark (all a quad needs unless a third landmark sits
-// inside it) are gathered at the top of the iteration.  (Measured and removed: the same rows one iteration ahead in registers
-// - 28.0 instead of 25.5 us, the 16 extra registers spill; - and staged in shared memory by cp.async - 49 us, MIO-throttled.)
-template <int MINB, bool CAM_SMEM>
-__global__ void __launch_bounds__(kFusedThreads, MINB)
-k_ba_lm_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
-             const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
-             const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
-             double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost) {
-    extern __shared__ __align__(16) double smem[];      // keyframe trig, 48 B per keyframe: {sp,cp} {st,ct} {f,-}: two LDS.128 + one LDS.64
-    __shared__ double sWarp[kFusedThreads / 32];
+// inside it) roll half an iteration ahead of their use (see the loop).  (Measured and removed: both rows a whole iteration
+// ahead in registers - 28.0 instead of 25.5 us, the 16 extra registers spill; - and staged in shared memory by cp.async -
+// 49 us, MIO-throttled.)
+template <bool CAM_SMEM>
+__device__ __forceinline__ void
+lm_role(int cta, int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_lm,
+        const double* __restrict__ s_ox, const double* __restrict__ s_oy, const int32_t* __restrict__ orig,
+        const CamTrig* __restrict__ cam_trig, const LmTrig* __restrict__ lm_trig, int n_pose, double u, double v,
+        double* __restrict__ resid, double* __restrict__ gV, double* __restrict__ gGl, double* __restrict__ gCost,
+        double* __restrict__ smem, double* __restrict__ sWarp) {
+    // smem: keyframe trig, 48 B per keyframe: {sp,cp} {st,ct} {f,-}: two LDS.128 + one LDS.64
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // this CTA's observations: [max(begin, lo), end); quads stay aligned to multiples of 4 of the array index
-    const int64_t begin = (lo & ~(int64_t)3) + (int64_t)blockIdx.x * chunk;
+    const int64_t begin = (lo & ~(int64_t)3) + (int64_t)cta * chunk;
     int64_t end = begin + chunk;
     if (end > hi) end = hi;
     constexpr int64_t kStep = (int64_t)kFusedThreads * kQuad;
@@ -334,6 +347,8 @@ k_ba_lm_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ 
     QuadObs qA, qB;
     load_quad_obs(qA, k0, lo, end, s_cam, s_ox, s_oy);
     qB = qA;
+    auto row = [&](int l) { return lm_trig[l < 0 ? 0 : l]; };
+    LmTrig ltF = row(idA.x);                    // trig row of the quad's first landmark
     if (CAM_SMEM) {
         for (int i = tid; i < n_pose * 5; i += kFusedThreads) {
             const int c = i / 5, e = i - 5 * c;
@@ -344,20 +359,20 @@ k_ba_lm_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ 
     double cost = 0.0;
 #pragma unroll 1
     for (int64_t base = begin; base < end; base += kStep, k0 += kStep) {
-        // this iteration's trig rows; the next iteration's keyframe ids and pixels; the landmark ids of the one after
-        const LmTrig ltF = lm_trig[idA.x < 0 ? 0 : idA.x], ltL = lm_trig[idA.w < 0 ? 0 : idA.w];
+        // rolling pipeline, registers only: the row of the quad's LAST landmark travels while observation 0 (which always
+        // belongs to the first landmark) is evaluated; the first row of the NEXT quad travels during observations 2 and 3
+        const LmTrig ltL = row(idA.w);
         if (base + kStep < end) load_quad_obs(qB, k0 + kStep, lo, end, s_cam, s_ox, s_oy);
         const int4 idC = load_lm_ids(k0 + 2 * kStep, lo, end, s_lm);
         const int lm[kQuad] = {idA.x, idA.y, idA.z, idA.w};
         const int lm_first = lm[0], lm_last = lm[kQuad - 1];
-        double rx[kQuad], ry[kQuad];
+        const bool direct = resid && !orig && k0 >= lo && k0 + kQuad <= end;
         double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;      // observations with the quad's last id
         double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;      // observations with the quad's first id (when it differs)
-#pragma unroll
-        for (int i = 0; i < kQuad; ++i) {
+        auto one = [&](int i, double& rx, double& ry) {
             const bool is_last = lm[i] == lm_last, is_first = lm[i] == lm_first;
-            LmTrig lt = is_last ? ltL : ltF;
-            if (!is_last && !is_first) lt = lm_trig[lm[i] < 0 ? 0 : lm[i]];        // a third landmark inside the quad: rare
+            LmTrig lt = (i == 0) ? ltF : (i == kQuad - 1 ? ltL : (is_last ? ltL : ltF));
+            if (i != 0 && i != kQuad - 1 && !is_last && !is_first) lt = row(lm[i]);   // a third landmark inside the quad: rare
             CamTrig c;
             if (CAM_SMEM) {
                 const double2* t = reinterpret_cast<const double2*>(smem + (size_t)qA.cam[i] * 6);
@@ -370,35 +385,33 @@ k_ba_lm_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ 
             ObsGeom g;
             project_fast_jac(c, lt, u, v, x, y, g);
             const bool valid = lm[i] >= 0;
-            rx[i] = valid ? x - qA.ox[i] : 0.0;
-            ry[i] = valid ? y - qA.oy[i] : 0.0;
-            cost = fma(rx[i], rx[i], fma(ry[i], ry[i], cost));
+            rx = valid ? x - qA.ox[i] : 0.0;
+            ry = valid ? y - qA.oy[i] : 0.0;
+            cost = fma(rx, rx, fma(ry, ry, cost));
             const double vtt = fma(g.xa, g.xa, g.ya * g.ya), vtp = fma(g.xa, g.xp, g.ya * g.yp), vpp = fma(g.xp, g.xp, g.yp * g.yp);
-            const double glt = fma(g.xa, rx[i], g.ya * ry[i]), glp = fma(g.xp, rx[i], g.yp * ry[i]);
+            const double glt = fma(g.xa, rx, g.ya * ry), glp = fma(g.xp, rx, g.yp * ry);
             if (is_last) { t0 += vtt; t1 += vtp; t2 += vpp; t3 += glt; t4 += glp; }
             else if (is_first) { h0 += vtt; h1 += vtp; h2 += vpp; h3 += glt; h4 += glp; }
             else if (valid) commit_lm(gV, gGl, lm[i], vtt, vtp, vpp, glt, glp);        // only i = 1, 2 can get here
-        }
-        if (resid) {
-            if (!orig && k0 >= lo && k0 + kQuad <= end) {
-                D4* dst = reinterpret_cast<D4*>(resid + 2 * k0);
-                dst[0] = D4{rx[0], ry[0], rx[1], ry[1]};
-                dst[1] = D4{rx[2], ry[2], rx[3], ry[3]};
-            } else {
-#pragma unroll
-                for (int i = 0; i < kQuad; ++i)
-                    if (lm[i] >= 0) {
-                        const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
-                        reinterpret_cast<double2*>(resid)[o] = make_double2(rx[i], ry[i]);
-                    }
+            if (resid && !direct && valid) {
+                const int64_t o = orig ? (int64_t)orig[k0 + i] : k0 + i;
+                reinterpret_cast<double2*>(resid)[o] = make_double2(rx, ry);
             }
-        }
+        };
+        double ra, rb, rc, rd;
+        one(0, ra, rb);
+        one(1, rc, rd);
+        if (direct) *reinterpret_cast<D4*>(resid + 2 * k0) = D4{ra, rb, rc, rd};
+        const LmTrig nF = row(idB.x);               // first row of the next quad: in flight during observations 2 and 3
+        one(2, ra, rb);
+        one(3, rc, rd);
+        if (direct) *reinterpret_cast<D4*>(resid + 2 * k0 + 4) = D4{ra, rb, rc, rd};
         if (lm_first != lm_last && lm_first >= 0) commit_lm(gV, gGl, lm_first, h0, h1, h2, h3, h4);   // run ended inside this thread
         // the thread's last run joins the warp-segmented reduction (keys non-decreasing across lanes, -1 = none)
         seg_reduce5(lm_last, lane, t0, t1, t2, t3, t4);
         const int prev = __shfl_up_sync(0xffffffffu, lm_last, 1);
         if (lm_last >= 0 && (lane == 0 || prev != lm_last)) commit_lm(gV, gGl, lm_last, t0, t1, t2, t3, t4);
-        idA = idB; idB = idC; qA = qB;
+        idA = idB; idB = idC; qA = qB; ltF = nF;
     }
     cost = warp_sum(cost);
     if (lane == 0) sWarp[warp] = cost;
@@ -408,6 +421,57 @@ k_ba_lm_pass(int64_t lo, int64_t hi, int64_t chunk, const int32_t* __restrict__ 
         for (int w = 0; w < kFusedThreads / 32; ++w) s += sWarp[w];
         atomicAdd(gCost, s);
     }
+}
+
+struct FusedArgs {
+    // landmark-major role
+    int64_t lo, hi, chunk;
+    const int32_t *s_cam, *s_lm, *orig;
+    const double *s_ox, *s_oy;
+    double *resid, *gV, *gGl, *gCost;
+    // keyframe-major role
+    int it_lo, it_hi, iters_per_cta;
+    const int32_t *iter_cam, *c_lm;
+    const double *c_ox, *c_oy;
+    double *gU, *gGc;
+    // shared
+    const CamTrig* cam_trig;
+    const LmTrig* lm_trig;
+    int n_pose;
+    double u, v;
+    int n_lm_cta, n_cam_cta;      // CTAs per role
+};
+
+// ONE launch for both passes: CTA b takes the landmark-major role iff floor((b+1) G_lm / G) > floor(b G_lm / G) (the two roles
+// are interleaved evenly in launch order, so that every SM hosts CTAs of both kinds from the first to the last cycle: the
+// landmark-major role is bound by the LSU / shared-memory pipe, the keyframe-major role by L2 gathers and the FP64 pipe).  The
+// two-launch form (two streams, fork / join events) paid ~2 x 3 us of event latency and only overlapped the tail of one kernel
+// with the head of the other.
+template <int MINB, bool CAM_SMEM>
+__global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_fused(const FusedArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double sWarp[kFusedThreads / 32];
+    const int G = a.n_lm_cta + a.n_cam_cta, b = blockIdx.x;
+    const int before = (int)(((int64_t)b * a.n_lm_cta) / G), after = (int)(((int64_t)(b + 1) * a.n_lm_cta) / G);
+    if (after > before)
+        lm_role<CAM_SMEM>(before, a.lo, a.hi, a.chunk, a.s_cam, a.s_lm, a.s_ox, a.s_oy, a.orig, a.cam_trig, a.lm_trig, a.n_pose, a.u, a.v,
+                          a.resid, a.gV, a.gGl, a.gCost, smem, sWarp);
+    else
+        cam_role(b - before, a.it_lo, a.it_hi, a.iters_per_cta, a.iter_cam, a.c_lm, a.c_ox, a.c_oy, a.cam_trig, a.lm_trig, a.u, a.v, a.gU,
+                 a.gGc);
+}
+
+// the two roles as separate launches (PTZBA_OPT_FUSED_LAUNCH = 1: two streams)
+template <int MINB, bool CAM_SMEM>
+__global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_lm_pass(const FusedArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double sWarp[kFusedThreads / 32];
+    lm_role<CAM_SMEM>(blockIdx.x, a.lo, a.hi, a.chunk, a.s_cam, a.s_lm, a.s_ox, a.s_oy, a.orig, a.cam_trig, a.lm_trig, a.n_pose, a.u, a.v,
+                      a.resid, a.gV, a.gGl, a.gCost, smem, sWarp);
+}
+template <int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_cam_pass(const FusedArgs a) {
+    cam_role(blockIdx.x, a.it_lo, a.it_hi, a.iters_per_cta, a.iter_cam, a.c_lm, a.c_ox, a.c_oy, a.cam_trig, a.lm_trig, a.u, a.v, a.gU, a.gGc);
 }
 
 // residual-only pass (trial points of the trust-region loop, and _compute_residual itself)
@@ -489,40 +553,60 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
         ctx->prof_events.push_back(ev1);
         CU_CHECK(ctx, cudaEventRecord(ev0, s));
     }
-    CU_CHECK(ctx, cudaEventRecord(ctx->ev_fork, s));      // everything before (k_set_params, the arena clear) precedes both passes
-    // contiguous chunk per CTA: a multiple of 128 observations (every warp iteration starts on a 32-byte boundary of
-    // all four streams), sized so that all resident CTAs of the single wave get the same amount of work.  With a
-    // partition (ptzba_ba_set_partition) only this rank's slices of the two sorted lists are visited.
+    // work split.  Landmark-major role: contiguous chunks that are multiples of 1024 observations (every thread of every CTA
+    // iteration owns an aligned quad); keyframe-major role: contiguous ranges of 128-entry iterations.  With a partition
+    // (ptzba_ba_set_partition) only this rank's slices of the two sorted lists are visited.
     const size_t smA = ba->cam_smem ? (size_t)ba->n_pose * 6 * sizeof(double) : 0;
     const int64_t nA = ba->lmo_hi - (ba->lmo_lo & ~(int64_t)3);
-    if (nA > 0) {
-        int64_t chunkA = (nA + ba->grid_lm_pass - 1) / ba->grid_lm_pass;
-        chunkA = (chunkA + 127) / 128 * 128;
-        const int gridA = (int)((nA + chunkA - 1) / chunkA);
-        if (ba->cam_smem)
-            k_ba_lm_pass<kLmMinB, true><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
-                                                                   ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
-                                                                   d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
-        else
-            k_ba_lm_pass<kLmMinB, false><<<gridA, kFusedThreads, smA, s>>>(ba->lmo_lo, ba->lmo_hi, chunkA, ba->s_cam.p, ba->s_lm.p, ba->s_ox.p,
-                                                                  ba->s_oy.p, orig, ba->cam_trig.p, ba->lm_trig.p, ba->n_pose, ba->u, ba->v,
-                                                                  d_resid, ba->acc.V, ba->acc.gl, ba->acc.cost);
-        KERNEL_POST(ctx);
-    }
-    // the keyframe-major pass touches disjoint accumulators: it runs on the side stream, concurrently with the landmark pass
-    // (each kernel is a single wave; the second one fills the SMs the first one's finishing CTAs leave idle)
     const int nB = ba->cit_hi - ba->cit_lo;                 // iterations of 128 padded keyframe-major entries
-    if (nB > 0) {
-        int per_cta = (nB + ba->grid_cam_pass - 1) / ba->grid_cam_pass;
-        if (per_cta < 1) per_cta = 1;
-        const int gridB = (nB + per_cta - 1) / per_cta;
-        cudaStream_t sb = ctx->side_stream;
-        CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
-        k_ba_cam_pass<kCamMinB><<<gridB, kFusedThreads, 0, sb>>>(ba->cit_lo, ba->cit_hi, per_cta, ba->iter_cam.p, ba->c_lm.p, ba->c_ox.p, ba->c_oy.p,
-                                                                ba->cam_trig.p, ba->lm_trig.p, ba->u, ba->v, ba->acc.U, ba->acc.gc);
-        KERNEL_POST(ctx);
-        CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
-        CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    FusedArgs a;
+    a.lo = ba->lmo_lo; a.hi = ba->lmo_hi; a.s_cam = ba->s_cam.p; a.s_lm = ba->s_lm.p; a.orig = orig; a.s_ox = ba->s_ox.p; a.s_oy = ba->s_oy.p;
+    a.resid = d_resid; a.gV = ba->acc.V; a.gGl = ba->acc.gl; a.gCost = ba->acc.cost;
+    a.it_lo = ba->cit_lo; a.it_hi = ba->cit_hi; a.iter_cam = ba->iter_cam.p; a.c_lm = ba->c_lm.p; a.c_ox = ba->c_ox.p; a.c_oy = ba->c_oy.p;
+    a.gU = ba->acc.U; a.gGc = ba->acc.gc;
+    a.cam_trig = ba->cam_trig.p; a.lm_trig = ba->lm_trig.p; a.n_pose = ba->n_pose; a.u = ba->u; a.v = ba->v;
+    const int G = ba->grid_fused;                           // one wave of resident CTAs
+    const double wA = nA > 0 ? (double)nA * ba->fused_lm_share : 0.0, wB = (double)nB * kCamIter * (100.0 - ba->fused_lm_share);
+    auto split_chunks = [&](int g_lm, int g_cam) {
+        a.n_lm_cta = g_lm; a.n_cam_cta = g_cam;
+        a.chunk = 1024; a.iters_per_cta = 1;
+        if (g_lm > 0) {
+            a.chunk = ((nA + g_lm - 1) / g_lm + 1023) / 1024 * 1024;
+            a.n_lm_cta = (int)((nA + a.chunk - 1) / a.chunk);
+        }
+        if (g_cam > 0) {
+            a.iters_per_cta = (nB + g_cam - 1) / g_cam;
+            a.n_cam_cta = (nB + a.iters_per_cta - 1) / a.iters_per_cta;
+        }
+    };
+    if (ba->fused_launch == 0) {
+        int g_lm = (nA > 0) ? (int)(G * wA / (wA + wB) + 0.5) : 0;
+        if (nA > 0 && g_lm < 1) g_lm = 1;
+        if (nB > 0 && g_lm > G - 1) g_lm = G - 1;
+        if (nB <= 0) g_lm = nA > 0 ? G : 0;
+        split_chunks(g_lm, nB > 0 ? G - g_lm : 0);
+        if (a.n_lm_cta + a.n_cam_cta > 0) {
+            if (ba->cam_smem) k_ba_fused<kLmMinB, true><<<a.n_lm_cta + a.n_cam_cta, kFusedThreads, smA, s>>>(a);
+            else k_ba_fused<kLmMinB, false><<<a.n_lm_cta + a.n_cam_cta, kFusedThreads, 0, s>>>(a);
+            KERNEL_POST(ctx);
+        }
+    } else {
+        // two launches; the keyframe-major one on the side stream, concurrently with the landmark-major one
+        split_chunks(nA > 0 ? G : 0, nB > 0 ? G : 0);
+        CU_CHECK(ctx, cudaEventRecord(ctx->ev_fork, s));
+        if (a.n_lm_cta > 0) {
+            if (ba->cam_smem) k_ba_lm_pass<kLmMinB, true><<<a.n_lm_cta, kFusedThreads, smA, s>>>(a);
+            else k_ba_lm_pass<kLmMinB, false><<<a.n_lm_cta, kFusedThreads, 0, s>>>(a);
+            KERNEL_POST(ctx);
+        }
+        if (a.n_cam_cta > 0) {
+            cudaStream_t sb = ctx->side_stream;
+            CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
+            k_ba_cam_pass<kCamMinB><<<a.n_cam_cta, kFusedThreads, 0, sb>>>(a);
+            KERNEL_POST(ctx);
+            CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
+            CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        }
     }
     if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count));
@@ -694,16 +778,15 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         const size_t smTab = (size_t)n_pose * 6 * sizeof(double);
         ba->cam_smem = smTab <= 100 * 1024;            // two CTAs per SM
         const size_t smA = ba->cam_smem ? smTab : 0;
-        int pa = 1, pb = 1;
+        int pa = 1;
         if (ba->cam_smem) {
+            CU_TRY(cudaFuncSetAttribute(k_ba_fused<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
             CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass<kLmMinB, true>, kFusedThreads, smA));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_fused<kLmMinB, true>, kFusedThreads, smA));
         } else {
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_lm_pass<kLmMinB, false>, kFusedThreads, smA));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_fused<kLmMinB, false>, kFusedThreads, 0));
         }
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, k_ba_cam_pass<kCamMinB>, kFusedThreads, 0));
-        ba->grid_lm_pass = ctx->sm_count * (pa < 1 ? 1 : pa);
-        ba->grid_cam_pass = ctx->sm_count * (pb < 1 ? 1 : pb);
+        ba->grid_fused = ctx->sm_count * (pa < 1 ? 1 : pa);
     }
 #undef CU_TRY
     *out = ba;
@@ -743,6 +826,14 @@ extern "C" int ptzba_ba_set_option(ptzba_ba* ba, int option, int value) {
         case PTZBA_OPT_SCHUR_MODE:
             ARG_CHECK(ctx, value == PTZBA_SCHUR_AUTO || value == PTZBA_SCHUR_PER_LANDMARK || value == PTZBA_SCHUR_PAIR_LIST);
             ba->schur_mode = value;
+            return PTZBA_OK;
+        case PTZBA_OPT_FUSED_LAUNCH:
+            ARG_CHECK(ctx, value == 0 || value == 1);
+            ba->fused_launch = value;
+            return PTZBA_OK;
+        case PTZBA_OPT_FUSED_LM_SHARE:
+            ARG_CHECK(ctx, value >= 1 && value <= 99);
+            ba->fused_lm_share = value;
             return PTZBA_OK;
         default:
             return ptzba_fail(ctx, PTZBA_ERR_ARG, "unknown option %d", option);

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) k_potf2_trsm(double* __restrict__ A0, int
 __global__ void __launch_bounds__(dmma::kThreads) k_chol_ll_update(double* __restrict__ A0, int lda, size_t stride,
                                                                   const int* __restrict__ n_arr, int n_fixed, int k) {
     using T = dmma::Tile<64, 32>;
-    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    extern __shared__ __align__(16) double sm[];
     const int n = n_arr ? n_arr[blockIdx.y] : n_fixed;
     const int r0 = k + blockIdx.x * 64;
     if (k >= n || r0 >= n) return;
@@ -102,10 +102,12 @@ __global__ void __launch_bounds__(dmma::kThreads) k_chol_ll_update(double* __res
 int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch,
                               int* d_info, int* d_info_per_batch) {
     cudaStream_t s = ctx->stream;
+    static bool cfg = false;
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_chol_ll_update, dmma::Tile<64, 32>::kSmemBytes)); cfg = true; }
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
     for (int k = 0; k < n_max; k += NB) {
         if (k > 0) {
-            k_chol_ll_update<<<dim3(div_up(n_max - k, 64), batch), dmma::kThreads, 0, s>>>(A, lda, stride, d_n_arr, n_max, k);
+            k_chol_ll_update<<<dim3(div_up(n_max - k, 64), batch), dmma::kThreads, dmma::Tile<64, 32>::kSmemBytes, s>>>(A, lda, stride, d_n_arr, n_max, k);
             KERNEL_POST(ctx);
         }
         const int m = n_max - k - NB;
@@ -117,46 +119,13 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
 
 namespace {
 
-// block row k of  L Z = G  (L column-major lower, G row-major [n x ncols], ld = ldg): solve the NB x NB triangle for every
-// column; one thread per column (coalesced along columns).
-__global__ void __launch_bounds__(128) k_fwd_diag_rows(const double* __restrict__ L0, int lda, size_t strideL,
-                                                       double* __restrict__ G0, int ldg, size_t strideG,
-                                                       const int* __restrict__ n_arr, int extra_cols, int k) {
-    const int n = n_arr[blockIdx.y];
-    if (k >= n) return;
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    const int ncols = n + extra_cols;
-    const double* L = L0 + strideL * blockIdx.y;
-    double* G = G0 + strideG * blockIdx.y;
-    __shared__ double D[NB][NB + 1];
-    for (int e = threadIdx.x; e < NB * NB; e += 128) {
-        const int i = e % NB, j = e / NB;
-        D[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= ncols) return;
-    double x[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) x[i] = i < nb ? G[(size_t)(k + i) * ldg + c] : 0.0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        double s = x[i];
-#pragma unroll
-        for (int t = 0; t < i; ++t) s = fma(-D[i][t], x[t], s);
-        x[i] = s / D[i][i];
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-        if (i < nb) G[(size_t)(k + i) * ldg + c] = x[i];
-}
-
-// block row k (32 rows) of G, columns c0 .. c0+63:  G[k+i, c] -= sum_{t<k} L[k+i, t] * Z[t, c]   (left-looking, K = k)
+// block row k (32 rows) of  L Z = G  (L column-major lower, G row-major [n x ncols], ld = ldg), columns c0 .. c0+63:
+//   G[k+i, c] -= sum_{t<k} L[k+i, t] * Z[t, c]   (left-looking, K = k; FP64 tensor cores), then the 32 x 32 triangle
 __global__ void __launch_bounds__(dmma::kThreads) k_fwd_ll_update(const double* __restrict__ L0, int lda, size_t strideL,
                                                                  double* __restrict__ G0, int ldg, size_t strideG,
                                                                  const int* __restrict__ n_arr, int extra_cols, int k) {
     using T = dmma::Tile<32, 64>;
-    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    extern __shared__ __align__(16) double sm[];
     const int n = n_arr[blockIdx.y];
     if (k >= n) return;
     const int ncols = n + extra_cols;
@@ -173,6 +142,29 @@ __global__ void __launch_bounds__(dmma::kThreads) k_fwd_ll_update(const double* 
     T::for_each(acc, [&](int i, int j, double v) {
         if (k + i < n && c0 + j < ncols) G[(size_t)(k + i) * ldg + c0 + j] -= v;
     });
+    // ... and the triangle of block row k for the same 64 columns (one thread per column), so that a block row is ONE launch
+    const int nb = (n - k) < NB ? (n - k) : NB;
+    double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    __syncthreads();                                   // the updated rows are visible to the CTA; the ring buffer is free
+    for (int e = threadIdx.x; e < NB * NB; e += dmma::kThreads) {
+        const int i = e % NB, j = e / NB;
+        D[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // the 32 values of a column live in shared memory (not in registers: the tile product's occupancy decides this kernel's speed)
+    double (*xs)[65] = reinterpret_cast<double (*)[65]>(sm + NB * (NB + 1));
+    const int c = c0 + threadIdx.x;
+    if (threadIdx.x >= 64 || c >= ncols) return;
+    const int tc = threadIdx.x;
+    for (int i = 0; i < nb; ++i) xs[i][tc] = G[(size_t)(k + i) * ldg + c];
+    for (int i = 0; i < nb; ++i) {
+        double sacc = xs[i][tc];
+#pragma unroll 4
+        for (int tt = 0; tt < i; ++tt) sacc = fma(-D[i][tt], xs[tt][tc], sacc);
+        sacc /= D[i][i];
+        xs[i][tc] = sacc;
+        G[(size_t)(k + i) * ldg + c] = sacc;
+    }
 }
 
 }  // namespace
@@ -181,13 +173,11 @@ __global__ void __launch_bounds__(dmma::kThreads) k_fwd_ll_update(const double* 
 int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_t strideL, double* G, int ldg, size_t strideG,
                                  const int* d_n_arr, int n_max, int extra_cols, int batch) {
     cudaStream_t s = ctx->stream;
+    static bool cfg = false;
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_fwd_ll_update, dmma::Tile<32, 64>::kSmemBytes)); cfg = true; }
     const int ncols_max = n_max + extra_cols;
     for (int k = 0; k < n_max; k += NB) {
-        if (k > 0) {
-            k_fwd_ll_update<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, 0, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
-            KERNEL_POST(ctx);
-        }
-        k_fwd_diag_rows<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
+        k_fwd_ll_update<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<32, 64>::kSmemBytes, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) k_lu_trsm_u12(double* __restrict__ A0, in
 __global__ void __launch_bounds__(dmma::kThreads) k_lu_gemm(double* __restrict__ A0, int lda, size_t stride, const int* __restrict__ n_arr,
                                                            int k0) {
     using T = dmma::Tile<64, 64>;
-    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.z;
     const int n = n_arr[b];
     const int t0 = k0 + NB;
@@ -253,78 +253,15 @@ __global__ void __launch_bounds__(256) k_lu_gather_rows(const double* __restrict
     X0[strideG * b + (size_t)i * ldg + c] = B0[strideG * b + (size_t)src * ldg + c];
 }
 
-// block row k of the unit-lower forward solve: triangle for every column (one thread per column)
-__global__ void __launch_bounds__(128) k_lu_fwd_diag(const double* __restrict__ A0, int lda, size_t stride, double* __restrict__ X0,
-                                                     int ldg, size_t strideG, const int* __restrict__ n_arr, int extra_cols, int k) {
-    const int b = blockIdx.y;
-    const int n = n_arr[b];
-    if (k >= n) return;
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    const double* A = A0 + stride * b;
-    double* X = X0 + strideG * b;
-    __shared__ double D[NB][NB + 1];
-    for (int e = threadIdx.x; e < NB * NB; e += 128) {
-        const int i = e % NB, j = e / NB;
-        D[i][j] = (i < nb && j < i) ? A[(size_t)(k + i) + (size_t)(k + j) * lda] : 0.0;
-    }
-    __syncthreads();
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= n + extra_cols) return;
-    double x[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) x[i] = i < nb ? X[(size_t)(k + i) * ldg + c] : 0.0;
-#pragma unroll
-    for (int i = 1; i < NB; ++i) {
-        double s = x[i];
-#pragma unroll
-        for (int t = 0; t < i; ++t) s = fma(-D[i][t], x[t], s);
-        x[i] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-        if (i < nb) X[(size_t)(k + i) * ldg + c] = x[i];
-}
-
-// block row k of the backward solve with U (upper, non-unit)
-__global__ void __launch_bounds__(128) k_lu_bwd_diag(const double* __restrict__ A0, int lda, size_t stride, double* __restrict__ X0,
-                                                     int ldg, size_t strideG, const int* __restrict__ n_arr, int extra_cols, int k) {
-    const int b = blockIdx.y;
-    const int n = n_arr[b];
-    if (k >= n) return;
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    const double* A = A0 + stride * b;
-    double* X = X0 + strideG * b;
-    __shared__ double D[NB][NB + 1];
-    for (int e = threadIdx.x; e < NB * NB; e += 128) {
-        const int i = e % NB, j = e / NB;
-        D[i][j] = (i < nb && j < nb && j >= i) ? A[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= n + extra_cols) return;
-    double x[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) x[i] = i < nb ? X[(size_t)(k + i) * ldg + c] : 0.0;
-#pragma unroll
-    for (int i = NB - 1; i >= 0; --i) {
-        double s = x[i];
-#pragma unroll
-        for (int t = i + 1; t < NB; ++t) s = fma(-D[i][t], x[t], s);
-        x[i] = s / D[i][i];
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-        if (i < nb) X[(size_t)(k + i) * ldg + c] = x[i];
-}
-
 // block row k (32 rows) of X, columns c0 .. c0+63, LEFT-looking:  X[k+i, c] -= sum_{t in [t_lo, t_hi)} M[k+i, t] * X[t, c]
 // forward solve with the unit-lower factor: t in [0, k); backward solve with U: t in [k + 32, n).  One DMMA product over the
-// whole K range: every entry of X is updated once (the right-looking rank-32 updates of round 1 re-streamed X per panel).
+// whole K range: every entry of X is updated once (the right-looking rank-32 updates of round 1 re-streamed X per panel); the
+// 32 x 32 triangle of the block row follows in the same launch.
 __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __restrict__ A0, int lda, size_t stride,
                                                               double* __restrict__ X0, int ldg, size_t strideG,
                                                               const int* __restrict__ n_arr, int extra_cols, int k, int backward) {
     using T = dmma::Tile<32, 64>;
-    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.y;
     const int n = n_arr[b];
     if (k >= n) return;
@@ -332,7 +269,6 @@ __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __r
     const int c0 = blockIdx.x * 64;
     if (c0 >= ncols) return;
     const int t_lo = backward ? k + NB : 0, t_hi = backward ? n : k;
-    if (t_hi <= t_lo) return;
     const double* A = A0 + stride * b;
     double* X = X0 + strideG * b;
     double acc[T::RM][T::RN][2];
@@ -344,6 +280,40 @@ __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __r
     T::for_each(acc, [&](int i, int j, double v) {
         if (i < NB && k + i < n && c0 + j < ncols) X[(size_t)(k + i) * ldg + c0 + j] -= v;
     });
+    // ... and the triangle of block row k for the same 64 columns (one thread per column): unit lower (forward) or upper (backward)
+    const int nb = (n - k) < NB ? (n - k) : NB;
+    double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    __syncthreads();                                   // the updated rows are visible to the CTA; the ring buffer is free
+    for (int e = threadIdx.x; e < NB * NB; e += dmma::kThreads) {
+        const int i = e % NB, j = e / NB;
+        const bool in = i < nb && j < nb && (backward ? j >= i : j < i);
+        D[i][j] = in ? A[(size_t)(k + i) + (size_t)(k + j) * lda] : ((backward && i == j) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // the 32 values of a column live in shared memory (not in registers: the tile product's occupancy decides this kernel's speed)
+    double (*xs)[65] = reinterpret_cast<double (*)[65]>(sm + NB * (NB + 1));
+    const int c = c0 + threadIdx.x;
+    if (threadIdx.x >= 64 || c >= ncols) return;
+    const int tc = threadIdx.x;
+    for (int i = 0; i < nb; ++i) xs[i][tc] = X[(size_t)(k + i) * ldg + c];
+    if (!backward) {
+        for (int i = 1; i < nb; ++i) {
+            double sacc = xs[i][tc];
+#pragma unroll 4
+            for (int tt = 0; tt < i; ++tt) sacc = fma(-D[i][tt], xs[tt][tc], sacc);
+            xs[i][tc] = sacc;
+            X[(size_t)(k + i) * ldg + c] = sacc;
+        }
+    } else {
+        for (int i = nb - 1; i >= 0; --i) {
+            double sacc = xs[i][tc];
+#pragma unroll 4
+            for (int tt = i + 1; tt < nb; ++tt) sacc = fma(-D[i][tt], xs[tt][tc], sacc);
+            sacc /= D[i][i];
+            xs[i][tc] = sacc;
+            X[(size_t)(k + i) * ldg + c] = sacc;
+        }
+    }
 }
 
 }  // namespace
@@ -351,6 +321,8 @@ __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __r
 int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const int* d_n_arr, int n_max, int batch, int* d_ipiv,
                         int ld_ipiv, int* d_info) {
     cudaStream_t s = ctx->stream;
+    static bool cfg = false;
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_lu_gemm, dmma::Tile<64, 64>::kSmemBytes)); cfg = true; }
     CU_CHECK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), s));
     for (int k0 = 0; k0 < n_max; k0 += NB) {
         // widest sub-panel whose rows fit in shared memory
@@ -382,7 +354,7 @@ int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const
         if (m <= 0) break;
         k_lu_trsm_u12<<<dim3(div_up(m, 128), batch), 128, 0, s>>>(A, lda, stride, d_n_arr, k0);
         KERNEL_POST(ctx);
-        k_lu_gemm<<<dim3(div_up(m, TS), div_up(m, TS), batch), dmma::kThreads, 0, s>>>(A, lda, stride, d_n_arr, k0);
+        k_lu_gemm<<<dim3(div_up(m, TS), div_up(m, TS), batch), dmma::kThreads, dmma::Tile<64, 64>::kSmemBytes, s>>>(A, lda, stride, d_n_arr, k0);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;
@@ -393,25 +365,21 @@ int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t s
                              const double* B, double* X, int ldg, size_t strideG, const int* d_n_arr, int n_max, int extra_cols,
                              int batch) {
     cudaStream_t s = ctx->stream;
+    static bool cfg = false;
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_lu_rows_ll, dmma::Tile<32, 64>::kSmemBytes)); cfg = true; }
     const int ncols_max = n_max + extra_cols;
     k_lu_perm<<<batch, 1, 0, s>>>(d_n_arr, d_ipiv, ld_ipiv, d_perm);
     KERNEL_POST(ctx);
     k_lu_gather_rows<<<dim3(div_up(ncols_max, 256), n_max, batch), 256, 0, s>>>(B, X, ldg, strideG, d_n_arr, extra_cols, d_perm, ld_ipiv);
     KERNEL_POST(ctx);
     for (int k = 0; k < n_max; k += NB) {
-        if (k > 0) {
-            k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 0);
-            KERNEL_POST(ctx);
-        }
-        k_lu_fwd_diag<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k);
+        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<32, 64>::kSmemBytes, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 0);
         KERNEL_POST(ctx);
     }
     const int last = (n_max - 1) / NB * NB;
     for (int k = last; k >= 0; k -= NB) {
         // (sequences shorter than n_max skip the block rows beyond their order; within a sequence the rows right of block k are final)
-        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 1);
-        KERNEL_POST(ctx);
-        k_lu_bwd_diag<<<dim3(div_up(ncols_max, 128), batch), 128, 0, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k);
+        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<32, 64>::kSmemBytes, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 1);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(dmma::kThreads) k_ekf_pp_blocks(int b0, int ma
                                                                  const double* __restrict__ X_all, int ldg, size_t strideG,
                                                                  double* __restrict__ P_all, size_t strideP, int s_tot) {
     using T = dmma::Tile<64, 64>;
-    __shared__ __align__(16) double sm[T::kSmemDoubles];
+    extern __shared__ __align__(16) double sm[];
     const int wb = blockIdx.z, b = b0 + wb;
     const int n = n_mat[b];
     const int nt = (n + 63) / 64;
@@ -470,6 +470,8 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched, const in
     cudaStream_t s = ctx->stream;
     const int n_seq = B->n_seq, max_obs = B->max_obs, s_tot = B->s_tot;
     const size_t strideP = (size_t)s_tot * s_tot;
+    static bool cfg = false;
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_ekf_pp_blocks, dmma::Tile<64, 64>::kSmemBytes)); cfg = true; }
     if (do_predict) {
         k_ekf_predict<<<div_up(n_seq, 128), 128, 0, s>>>(n_seq, B->ptz.p, B->vel.p, B->P.p, strideP, s_tot, B->prm.angle_var,
                                                         B->prm.f_var);
@@ -527,7 +529,7 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched, const in
             k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->nm_chol.p, B->X.p, B->X.p, B->ldg, strideG, B->P.p, strideP, s_tot);
             KERNEL_POST(ctx);
             const int ntc = div_up(n_max, 64);
-            k_ekf_pp_blocks<<<dim3(ntc * (ntc + 1) / 2, 2, wb), dmma::kThreads, 0, s>>>(b0, max_obs, B->nm_chol.p, B->m_ray.p, B->X.p, B->X.p, B->ldg,
+            k_ekf_pp_blocks<<<dim3(ntc * (ntc + 1) / 2, 2, wb), dmma::kThreads, dmma::Tile<64, 64>::kSmemBytes, s>>>(b0, max_obs, B->nm_chol.p, B->m_ray.p, B->X.p, B->X.p, B->ldg,
                                                                                        strideG, B->P.p, strideP, s_tot);
             KERNEL_POST(ctx);
             // the Cholesky verdicts decide whether this wave needs the LU route at all: one extra synchronisation, only while
@@ -555,7 +557,7 @@ int ekf_step(ptzba_ekf_batch* B, bool do_predict, int32_t* out_matched, const in
             k_ekf_pp_pose<<<wb, 32, 0, s>>>(b0, B->nm_lu.p, B->G.p, B->X.p, B->ldg, strideG, B->P.p, strideP, s_tot);
             KERNEL_POST(ctx);
             const int ntl = div_up(n_max_lu, 64);
-            k_ekf_pp_blocks<<<dim3(ntl * (ntl + 1) / 2, 2, wb), dmma::kThreads, 0, s>>>(b0, max_obs, B->nm_lu.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
+            k_ekf_pp_blocks<<<dim3(ntl * (ntl + 1) / 2, 2, wb), dmma::kThreads, dmma::Tile<64, 64>::kSmemBytes, s>>>(b0, max_obs, B->nm_lu.p, B->m_ray.p, B->G.p, B->X.p, B->ldg,
                                                                                        strideG, B->P.p, strideP, s_tot);
             KERNEL_POST(ctx);
             B->n_lu_total += 1;

@@ -23,21 +23,42 @@ __device__ __forceinline__ void st2(double* p, int64_t i, double a, double b) {
     reinterpret_cast<double2*>(p)[i] = make_double2(a, b);
 }
 
-// grid: (ray tiles, cameras).  out[(cam * n_ray + ray) * 2]
-__global__ void __launch_bounds__(kThreads) k_project_grid(int n_ray, const double* __restrict__ ptz, double u,
+// grid: (ray tiles, camera groups).  out[(cam * n_ray + ray) * 2]
+// A thread keeps ITS ray's direction d = (tan th, -tan ph sqrt(tan^2 th + 1), 1) in registers - the two tangents and the square
+// root are the expensive part of project_full - and walks the cameras of its group, whose trig lives in shared memory: per
+// (camera, ray) pair that leaves 13 FP64 operations, one division and one 16-byte store, i.e. the kernel is bound by the
+// pixel stream it writes.  (Round 1 evaluated tan / tan / sqrt per pair: FP64-bound at 4096 cameras x 2000 rays.)
+// The arithmetic per pair is project_full's, operation by operation, so results are bit-identical to the per-pair form.
+constexpr int kCamGroup = 32;
+__global__ void __launch_bounds__(kThreads) k_project_grid(int n_cam, int n_ray, const double* __restrict__ ptz, double u,
                                                            double v, const double* __restrict__ disp,
                                                            const double* __restrict__ rays,
                                                            double* __restrict__ out) {
-    __shared__ CamFull cam;
-    const int c = blockIdx.y;
-    if (threadIdx.x == 0) cam = make_cam(ptz[3 * c], ptz[3 * c + 1], ptz[3 * c + 2], u, v, disp);
+    __shared__ CamFull cams[kCamGroup];
+    const int c0 = blockIdx.y * kCamGroup;
+    const int nc = min(kCamGroup, n_cam - c0);
+    if (threadIdx.x < nc) {
+        const int c = c0 + threadIdx.x;
+        cams[threadIdx.x] = make_cam(ptz[3 * c], ptz[3 * c + 1], ptz[3 * c + 2], u, v, disp);
+    }
     __syncthreads();
-    const CamFull cc = cam;
     for (int r = blockIdx.x * kThreads + threadIdx.x; r < n_ray; r += gridDim.x * kThreads) {
         const double2 ray = ld2(rays, r);
-        double x, y, q2;
-        project_full(cc, ray.x, ray.y, x, y, q2);
-        st2(out, (int64_t)c * n_ray + r, x, y);
+        const double tx = tan(ray.x * PTZ_DEG2RAD);
+        const double tp = tan(ray.y * PTZ_DEG2RAD);
+        const double r0 = tx;
+        const double r1 = -tp * sqrt(tx * tx + 1.0);
+#pragma unroll 4
+        for (int k = 0; k < nc; ++k) {
+            const CamFull& c = cams[k];
+            const double a0 = c.cp * r0 - c.sp;
+            const double a2 = c.sp * r0 + c.cp;
+            const double q0 = a0 + c.d0;
+            const double q1 = c.ct * r1 + c.st * a2 + c.d1;
+            const double q2 = -c.st * r1 + c.ct * a2 + c.d2;
+            const double iz = 1.0 / q2;
+            st2(out, (int64_t)(c0 + k) * n_ray + r, c.f * q0 * iz + c.u, c.f * q1 * iz + c.v);
+        }
     }
 }
 
@@ -221,9 +242,14 @@ extern "C" int ptzba_project(ptzba_ctx* ctx, int mem, int n_cam, const double* p
     CU_CHECK(ctx, d_rays.stage(mem, rays, (size_t)n_ray * 2, s));
     CU_CHECK(ctx, d_disp.stage(PTZBA_HOST, disp, 6, s));
     CU_CHECK(ctx, d_out.stage(mem, out_xy, (size_t)n_cam * n_ray * 2));
-    dim3 grid(grid_for(ctx, n_ray), n_cam);
-    if (n_cam > 65535) return ptzba_fail(ctx, PTZBA_ERR_ARG, "n_cam > 65535: use ptzba_project_pairs");
-    k_project_grid<<<grid, kThreads, 0, s>>>(n_ray, d_ptz.d, u, v, d_disp.d, d_rays.d, d_out.d);
+    const int n_groups = div_up(n_cam, kCamGroup);
+    // enough ray tiles that the grid fills the machine a few times over even with one camera group
+    int tiles = div_up(n_ray, kThreads);
+    const int want = div_up((int64_t)ctx->sm_count * 8, n_groups);
+    if (tiles > want) tiles = want < 1 ? 1 : want;
+    dim3 grid(tiles, n_groups);
+    if (n_groups > 65535) return ptzba_fail(ctx, PTZBA_ERR_ARG, "n_cam > %d: use ptzba_project_pairs", 65535 * kCamGroup);
+    k_project_grid<<<grid, kThreads, 0, s>>>(n_cam, n_ray, d_ptz.d, u, v, d_disp.d, d_rays.d, d_out.d);
     KERNEL_POST(ctx);
     CU_CHECK(ctx, d_out.finish(s));
     if (mem == PTZBA_HOST) CU_CHECK(ctx, cudaStreamSynchronize(s));

@@ -12,9 +12,12 @@ array code:
 
 The landmark id of a keypoint is decided greedily in visiting order (pair (i,j) ascending, matches in list order): a match
 inherits the id either end already has, otherwise opens a new id; when both ends already carry different ids the match is
-kept and only reported (":624 in-consistent matching").  This is order dependent, so it is kept sequential on the host -
-it touches every match once; the flattening to the landmark-major device layout is synth.flatten_match_graph + ptzba_ba_create.
+kept and only reported (":624 in-consistent matching").  `assign_landmark_index` is that loop on the host;
+`match_graph_to_observations` is the same assignment AND the flattening into the observation list of bundle adjustment on the GPU
+(csrc/match_graph.cu: a forest of first-match pointers resolved by pointer jumping reproduces the sequential result exactly); the
+landmark-major sort then happens in ptzba_ba_create.
 """
+import ctypes
 import random
 
 import numpy as np
@@ -68,6 +71,42 @@ def assign_landmark_index(n_images, n_keypoints, pairs, verbose=False):
         dst_pt_index[i][j] = index2
         landmark_index[i][j] = lm_of[i][np.asarray(index1, dtype=np.int64)].tolist() if len(index1) else []
     return src_pt_index, dst_pt_index, landmark_index, g_index, n_inconsistent
+
+
+def match_graph_to_observations(n_keypoints, points, pairs):
+    """Device form of steps 4-5 plus the flattening of bundle_adjustment.py:67-98.
+
+    n_keypoints[i] keypoints per image, points[i] their [n_i, 2] pixels (or None: ids only), pairs = [(i, j, index1, index2), ...]
+    in the reference's visiting order.  Returns (label_per_image: list of int arrays (-1 = unmatched), landmark_num,
+    (cam_idx, lm_idx, obs_xy) or None, n_inconsistent)."""
+    from . import _lib
+    ctx = _lib.get_context()
+    n_images = len(n_keypoints)
+    off = np.concatenate([[0], np.cumsum(np.asarray(n_keypoints, dtype=np.int64))]).astype(np.int64)
+    n_node = int(off[-1])
+    ea = [off[i] + np.asarray(a, dtype=np.int64) for i, j, a, b in pairs]
+    eb = [off[j] + np.asarray(b, dtype=np.int64) for i, j, a, b in pairs]
+    edge_a = _lib.i32(np.concatenate(ea)) if ea else np.zeros(0, np.int32)
+    edge_b = _lib.i32(np.concatenate(eb)) if eb else np.zeros(0, np.int32)
+    n_edge = int(edge_a.shape[0])
+    label = np.full(max(n_node, 1), -1, np.int32)
+    n_lm = ctypes.c_int32(0)
+    flat = points is not None
+    node_img = node_xy = cam = lm = xy = None
+    if flat:
+        node_img = _lib.i32(np.repeat(np.arange(n_images), np.asarray(n_keypoints, dtype=np.int64)))
+        node_xy = _lib.f64(np.concatenate([keypoints_to_matrix(p) for p in points])) if n_node else np.zeros((0, 2))
+        cam, lm, xy = np.zeros(2 * n_edge, np.int32), np.zeros(2 * n_edge, np.int32), np.zeros((2 * n_edge, 2))
+    ctx.check(ctx.lib.ptzba_match_graph_to_observations(ctx.handle, _lib.HOST, n_node, _lib.ptr(node_img), _lib.ptr(node_xy), n_edge,
+                                                        _lib.ptr(edge_a), _lib.ptr(edge_b), _lib.ptr(label), ctypes.byref(n_lm),
+                                                        _lib.ptr(cam), _lib.ptr(lm), _lib.ptr(xy)))
+    label = label[:n_node]
+    la, lb = label[edge_a], label[edge_b]
+    # a match between two ends that were both labelled before it and carry different ids (image_process.py:624): with the final
+    # labels that is exactly the matches whose ends differ (labels never change once set)
+    n_inconsistent = int((la != lb).sum())
+    per_image = [label[off[i]:off[i + 1]].astype(np.int64) for i in range(n_images)]
+    return per_image, int(n_lm.value), ((cam, lm, xy) if flat else None), n_inconsistent
 
 
 def build_matching_graph(images, image_match_mask=[], feature_method='sift', verbose=False, detect=None, match=None,

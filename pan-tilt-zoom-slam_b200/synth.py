@@ -243,8 +243,12 @@ class FlatBA:
 
 
 def make_flat_ba(n_kf, n_landmark, n_obs, seed, pan_sweep=None, obs_noise=0.5,
-                 init_noise=(0.5, 0.5, 30.0, 0.05)):
+                 init_noise=(0.5, 0.5, 30.0, 0.05), id_order="first_keyframe"):
     """Seeded flat BA problem with exactly n_obs observations, every one inside its image.
+
+    Landmark ids follow the reference's assignment (image_process.py:612-634: the global ray index grows while the keyframes are
+    walked in order, so a landmark's id is ordered by the FIRST keyframe that observes it); id_order="random" keeps the ids in
+    the order the landmarks were drawn (no relation between id and position).
 
     Cost is O(n_obs) (candidate keyframes are drawn from the pan band that can see the landmark
     and then verified), so cfg5 (20M observations) generates in seconds, not minutes.
@@ -286,6 +290,15 @@ def make_flat_ba(n_kf, n_landmark, n_obs, seed, pan_sweep=None, obs_noise=0.5,
     if len(cam) < n_obs:
         raise RuntimeError("could not place %d observations (got %d)" % (n_obs, len(cam)))
     cam, lm, x, y = cam[:n_obs], lm[:n_obs], x[:n_obs], y[:n_obs]
+    if id_order == "first_keyframe":
+        first = np.full(n_landmark, n_kf, dtype=np.int64)
+        np.minimum.at(first, lm, cam)
+        rank = np.empty(n_landmark, dtype=np.int64)
+        rank[np.lexsort((np.arange(n_landmark), first))] = np.arange(n_landmark)     # new id of every old id
+        lm = rank[lm]
+        inv = np.empty(n_landmark, dtype=np.int64)
+        inv[rank] = np.arange(n_landmark)
+        rays_gt = rays_gt[inv]
     order = np.lexsort((cam, lm))  # landmark-major, camera ascending inside a landmark
     cam, lm, x, y = cam[order], lm[order], x[order], y[order]
     obs = np.stack([x, y], axis=1) + rng.normal(0, obs_noise, (len(x), 2))

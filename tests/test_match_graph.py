@@ -85,3 +85,49 @@ def test_assign_landmark_index_small_cases():
     assert keypoints_to_matrix([]).shape == (0, 2)
     with pytest.raises(NotImplementedError):
         build_matching_graph([0, 1], [], 'sift')
+
+
+# ---- GPU: the same assignment and the flattening on the device (csrc/match_graph.cu) ------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", range(int(G["n_cases"])))
+def test_device_match_graph_golden(c):
+    """Landmark ids, their number, the inconsistent-match count and the flat observation list of the reference golden."""
+    from ptz_slam_b200.match_graph import match_graph_to_observations
+    n = int(G["c%d_n" % c])
+    pairs = [(i, j, G["c%d_src_%d_%d" % (c, i, j)], G["c%d_dst_%d_%d" % (c, i, j)])
+             for i in range(n) for j in range(i + 1, n) if len(G["c%d_src_%d_%d" % (c, i, j)])]
+    points = [G["c%d_kp_%d" % (c, i)] for i in range(n)]
+    nk = [len(p) for p in points]
+    labels, lm_num, flat, n_bad = match_graph_to_observations(nk, points, pairs)
+    assert lm_num == int(G["c%d_landmark_num" % c]) and n_bad == int(G["c%d_n_inconsistent" % c])
+    src, dst, lmi, _, _ = assign_landmark_index(n, nk, pairs)
+    for i, j, a, b in pairs:
+        np.testing.assert_array_equal(labels[i][np.asarray(a, np.int64)], G["c%d_lm_%d_%d" % (c, i, j)])
+    cam, lm, xy = flatten_match_graph(points, src, dst, lmi)
+    np.testing.assert_array_equal(flat[0], cam)
+    np.testing.assert_array_equal(flat[1], lm)
+    np.testing.assert_array_equal(flat[2], xy)
+
+
+@pytest.mark.gpu
+def test_device_match_graph_random_graphs_equal_host_loop():
+    """Random graphs with repeated keypoints and conflicting matches: the pointer-forest assignment on the device equals the
+    sequential propagation match for match; empty and edge-free inputs are valid."""
+    from ptz_slam_b200.match_graph import match_graph_to_observations
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n_img = int(rng.integers(2, 8))
+        nk = rng.integers(3, 40, n_img)
+        pairs = []
+        for i in range(n_img):
+            for j in range(i + 1, n_img):
+                if rng.random() < 0.7:
+                    m = int(rng.integers(1, min(nk[i], nk[j]) + 1))
+                    pairs.append((i, j, rng.integers(0, nk[i], m).tolist(), rng.integers(0, nk[j], m).tolist()))
+        _, _, lmi, lm_num, n_bad = assign_landmark_index(n_img, nk, pairs)
+        labels, lm_num_d, _, n_bad_d = match_graph_to_observations(nk, None, pairs)
+        assert lm_num_d == lm_num and n_bad_d == n_bad
+        for i, j, a, b in pairs:
+            assert labels[i][np.asarray(a, np.int64)].tolist() == lmi[i][j]
+    labels, m, flat, bad = match_graph_to_observations([3, 2], [np.zeros((3, 2)), np.zeros((2, 2))], [])
+    assert m == 0 and bad == 0 and all(np.all(l == -1) for l in labels) and flat[0].shape == (0,)
