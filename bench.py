@@ -192,12 +192,17 @@ def bench_ekf(ctx, n_seq, n_rays, n_frames, seed0=2000):
     trk = BatchedEkfTracker(np.stack([q.rays0 for q in seqs]), np.stack([q.ptz_gt[0] for q in seqs]), synth.PP_U, synth.PP_V,
                             max_obs, synth.IMAGE_H, synth.IMAGE_W, jacobian_mode=_lib.JAC_CENTRAL_FD, ctx=ctx)
     packed = [trk.pack_observations([q.obs_xy[k] for q in seqs], [q.obs_idx[k] for q in seqs]) for k in range(1, n_frames + 1)]
-    matched = trk.step(*packed[0])          # warm-up frame
+    # untimed: the first half of the frames.  They take every sequence from its diagonal initial covariance (Cholesky route) to the
+    # state a tracker is in for the rest of a 100-frame run: the reference's covariance write-back has made P indefinite and the
+    # innovation covariance needs the pivoted-LU route (ptz_slam.py:281-289)
+    n_warm = max(1, n_frames // 2)
+    for k in range(n_warm):
+        trk.step(*packed[k])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     tot = 0
     flops = 0.0
-    for k in range(1, n_frames):
+    for k in range(n_warm, n_frames):
         m = trk.step(*packed[k])
         tot += int(m.sum())
         flops += float(ekf_flops(m, trk.route()).sum())
@@ -205,11 +210,11 @@ def bench_ekf(ctx, n_seq, n_rays, n_frames, seed0=2000):
     dt = time.perf_counter() - t0
     n_lu = int(trk.route().sum())
     trk.close()
-    frames = n_frames - 1
+    frames = n_frames - n_warm
     pk = fp64_peak()
     ach = flops / dt / 1e12
-    return {"workload": "%d independent sequences x %d rays, %d timed frames, host observations in / matched counts out" %
-                        (n_seq, n_rays, frames),
+    return {"workload": "%d independent sequences x %d rays, frames %d..%d of every sequence timed, host observations in / matched counts out" %
+                        (n_seq, n_rays, n_warm + 1, n_frames),
             "sequence_frames_per_s": n_seq * frames / dt, "matched_obs_per_s": tot / dt,
             "mean_matched_rays": tot / (n_seq * frames), "ms_per_frame_batch": 1e3 * dt / frames,
             "sequences_on_lu_route_at_end": n_lu,
@@ -626,7 +631,7 @@ def main():
     ap.add_argument("--no-ekf", action="store_true")
     ap.add_argument("--ekf-seqs", type=int, default=64)
     ap.add_argument("--ekf-rays", type=int, default=2000)
-    ap.add_argument("--ekf-frames", type=int, default=4)
+    ap.add_argument("--ekf-frames", type=int, default=8)
     ap.add_argument("--ramp", type=float, default=0.3, help="seconds of untimed passes before warm-up (clock ramp)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -119,12 +119,15 @@ int dense_potrf_lower_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride,
 
 namespace {
 
-// block row k (32 rows) of  L Z = G  (L column-major lower, G row-major [n x ncols], ld = ldg), columns c0 .. c0+63:
-//   G[k+i, c] -= sum_{t<k} L[k+i, t] * Z[t, c]   (left-looking, K = k; FP64 tensor cores), then the 32 x 32 triangle
+// block row k (NBS = 64 rows) of  L Z = G  (L column-major lower, G row-major [n x ncols], ld = ldg), columns c0 .. c0+63:
+//   G[k+i, c] -= sum_{t<k} L[k+i, t] * Z[t, c]   (left-looking, K = k; FP64 tensor cores), then the 64 x 64 triangle for the same
+// columns (one thread per column, the column in shared memory), so that a block row is ONE launch.  64-row blocks: a 64 x 64 tile
+// needs (64 + 64) doubles from L2 per 64 x 64 FMAs and K step - the 32-row version was L2-bandwidth bound at half the DMMA peak.
+constexpr int NBS = 64;
 __global__ void __launch_bounds__(dmma::kThreads) k_fwd_ll_update(const double* __restrict__ L0, int lda, size_t strideL,
                                                                  double* __restrict__ G0, int ldg, size_t strideG,
                                                                  const int* __restrict__ n_arr, int extra_cols, int k) {
-    using T = dmma::Tile<32, 64>;
+    using T = dmma::Tile<NBS, 64>;
     extern __shared__ __align__(16) double sm[];
     const int n = n_arr[blockIdx.y];
     if (k >= n) return;
@@ -142,28 +145,30 @@ __global__ void __launch_bounds__(dmma::kThreads) k_fwd_ll_update(const double* 
     T::for_each(acc, [&](int i, int j, double v) {
         if (k + i < n && c0 + j < ncols) G[(size_t)(k + i) * ldg + c0 + j] -= v;
     });
-    // ... and the triangle of block row k for the same 64 columns (one thread per column), so that a block row is ONE launch
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    const int nb = (n - k) < NBS ? (n - k) : NBS;
+    double (*D)[NBS + 1] = reinterpret_cast<double (*)[NBS + 1]>(sm);
+    double (*xs)[65] = reinterpret_cast<double (*)[65]>(sm + NBS * (NBS + 1));
     __syncthreads();                                   // the updated rows are visible to the CTA; the ring buffer is free
-    for (int e = threadIdx.x; e < NB * NB; e += dmma::kThreads) {
-        const int i = e % NB, j = e / NB;
+    for (int e = threadIdx.x; e < NBS * NBS; e += dmma::kThreads) {
+        const int i = e % NBS, j = e / NBS;
         D[i][j] = (i < nb && j < nb && j <= i) ? L[(size_t)(k + i) + (size_t)(k + j) * lda] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
-    // the 32 values of a column live in shared memory (not in registers: the tile product's occupancy decides this kernel's speed)
-    double (*xs)[65] = reinterpret_cast<double (*)[65]>(sm + NB * (NB + 1));
     const int c = c0 + threadIdx.x;
     if (threadIdx.x >= 64 || c >= ncols) return;
     const int tc = threadIdx.x;
     for (int i = 0; i < nb; ++i) xs[i][tc] = G[(size_t)(k + i) * ldg + c];
     for (int i = 0; i < nb; ++i) {
-        double sacc = xs[i][tc];
-#pragma unroll 4
-        for (int tt = 0; tt < i; ++tt) sacc = fma(-D[i][tt], xs[tt][tc], sacc);
-        sacc /= D[i][i];
-        xs[i][tc] = sacc;
-        G[(size_t)(k + i) * ldg + c] = sacc;
+        double s0 = xs[i][tc], s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains
+        int tt = 0;
+        for (; tt + 3 < i; tt += 4) {
+            s0 = fma(-D[i][tt], xs[tt][tc], s0); s1 = fma(-D[i][tt + 1], xs[tt + 1][tc], s1);
+            s2 = fma(-D[i][tt + 2], xs[tt + 2][tc], s2); s3 = fma(-D[i][tt + 3], xs[tt + 3][tc], s3);
+        }
+        for (; tt < i; ++tt) s0 = fma(-D[i][tt], xs[tt][tc], s0);
+        const double r = ((s0 + s1) + (s2 + s3)) / D[i][i];
+        xs[i][tc] = r;
+        G[(size_t)(k + i) * ldg + c] = r;
     }
 }
 
@@ -174,10 +179,10 @@ int dense_fwd_solve_rows_batched(ptzba_ctx* ctx, const double* L, int lda, size_
                                  const int* d_n_arr, int n_max, int extra_cols, int batch) {
     cudaStream_t s = ctx->stream;
     static bool cfg = false;
-    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_fwd_ll_update, dmma::Tile<32, 64>::kSmemBytes)); cfg = true; }
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_fwd_ll_update, dmma::Tile<NBS, 64>::kSmemBytes)); cfg = true; }
     const int ncols_max = n_max + extra_cols;
-    for (int k = 0; k < n_max; k += NB) {
-        k_fwd_ll_update<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<32, 64>::kSmemBytes, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
+    for (int k = 0; k < n_max; k += NBS) {
+        k_fwd_ll_update<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<NBS, 64>::kSmemBytes, s>>>(L, lda, strideL, G, ldg, strideG, d_n_arr, extra_cols, k);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;

@@ -253,14 +253,15 @@ __global__ void __launch_bounds__(256) k_lu_gather_rows(const double* __restrict
     X0[strideG * b + (size_t)i * ldg + c] = B0[strideG * b + (size_t)src * ldg + c];
 }
 
-// block row k (32 rows) of X, columns c0 .. c0+63, LEFT-looking:  X[k+i, c] -= sum_{t in [t_lo, t_hi)} M[k+i, t] * X[t, c]
-// forward solve with the unit-lower factor: t in [0, k); backward solve with U: t in [k + 32, n).  One DMMA product over the
+// block row k (NBS = 64 rows) of X, columns c0 .. c0+63, LEFT-looking:  X[k+i, c] -= sum_{t in [t_lo, t_hi)} M[k+i, t] * X[t, c]
+// forward solve with the unit-lower factor: t in [0, k); backward solve with U: t in [k + 64, n).  One DMMA product over the
 // whole K range: every entry of X is updated once (the right-looking rank-32 updates of round 1 re-streamed X per panel); the
-// 32 x 32 triangle of the block row follows in the same launch.
+// 64 x 64 triangle of the block row follows in the same launch (one thread per column, the column in shared memory).
+constexpr int NBS = 64;
 __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __restrict__ A0, int lda, size_t stride,
                                                               double* __restrict__ X0, int ldg, size_t strideG,
                                                               const int* __restrict__ n_arr, int extra_cols, int k, int backward) {
-    using T = dmma::Tile<32, 64>;
+    using T = dmma::Tile<NBS, 64>;
     extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.y;
     const int n = n_arr[b];
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __r
     const int ncols = n + extra_cols;
     const int c0 = blockIdx.x * 64;
     if (c0 >= ncols) return;
-    const int t_lo = backward ? k + NB : 0, t_hi = backward ? n : k;
+    const int t_lo = backward ? k + NBS : 0, t_hi = backward ? n : k;
     const double* A = A0 + stride * b;
     double* X = X0 + strideG * b;
     double acc[T::RM][T::RN][2];
@@ -278,40 +279,47 @@ __global__ void __launch_bounds__(dmma::kThreads) k_lu_rows_ll(const double* __r
         for (int c = 0; c < T::RN; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
     T::accumulate(A + k + (size_t)t_lo * lda, (size_t)lda, n - k, X + (size_t)t_lo * ldg + c0, (size_t)ldg, ncols - c0, t_hi - t_lo, acc, sm);
     T::for_each(acc, [&](int i, int j, double v) {
-        if (i < NB && k + i < n && c0 + j < ncols) X[(size_t)(k + i) * ldg + c0 + j] -= v;
+        if (k + i < n && c0 + j < ncols) X[(size_t)(k + i) * ldg + c0 + j] -= v;
     });
-    // ... and the triangle of block row k for the same 64 columns (one thread per column): unit lower (forward) or upper (backward)
-    const int nb = (n - k) < NB ? (n - k) : NB;
-    double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    const int nb = (n - k) < NBS ? (n - k) : NBS;
+    double (*D)[NBS + 1] = reinterpret_cast<double (*)[NBS + 1]>(sm);
+    double (*xs)[65] = reinterpret_cast<double (*)[65]>(sm + NBS * (NBS + 1));
     __syncthreads();                                   // the updated rows are visible to the CTA; the ring buffer is free
-    for (int e = threadIdx.x; e < NB * NB; e += dmma::kThreads) {
-        const int i = e % NB, j = e / NB;
+    for (int e = threadIdx.x; e < NBS * NBS; e += dmma::kThreads) {
+        const int i = e % NBS, j = e / NBS;
         const bool in = i < nb && j < nb && (backward ? j >= i : j < i);
         D[i][j] = in ? A[(size_t)(k + i) + (size_t)(k + j) * lda] : ((backward && i == j) ? 1.0 : 0.0);
     }
     __syncthreads();
-    // the 32 values of a column live in shared memory (not in registers: the tile product's occupancy decides this kernel's speed)
-    double (*xs)[65] = reinterpret_cast<double (*)[65]>(sm + NB * (NB + 1));
     const int c = c0 + threadIdx.x;
     if (threadIdx.x >= 64 || c >= ncols) return;
     const int tc = threadIdx.x;
     for (int i = 0; i < nb; ++i) xs[i][tc] = X[(size_t)(k + i) * ldg + c];
     if (!backward) {
         for (int i = 1; i < nb; ++i) {
-            double sacc = xs[i][tc];
-#pragma unroll 4
-            for (int tt = 0; tt < i; ++tt) sacc = fma(-D[i][tt], xs[tt][tc], sacc);
-            xs[i][tc] = sacc;
-            X[(size_t)(k + i) * ldg + c] = sacc;
+            double s0 = xs[i][tc], s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains
+            int tt = 0;
+            for (; tt + 3 < i; tt += 4) {
+                s0 = fma(-D[i][tt], xs[tt][tc], s0); s1 = fma(-D[i][tt + 1], xs[tt + 1][tc], s1);
+                s2 = fma(-D[i][tt + 2], xs[tt + 2][tc], s2); s3 = fma(-D[i][tt + 3], xs[tt + 3][tc], s3);
+            }
+            for (; tt < i; ++tt) s0 = fma(-D[i][tt], xs[tt][tc], s0);
+            const double r = (s0 + s1) + (s2 + s3);
+            xs[i][tc] = r;
+            X[(size_t)(k + i) * ldg + c] = r;
         }
     } else {
         for (int i = nb - 1; i >= 0; --i) {
-            double sacc = xs[i][tc];
-#pragma unroll 4
-            for (int tt = i + 1; tt < nb; ++tt) sacc = fma(-D[i][tt], xs[tt][tc], sacc);
-            sacc /= D[i][i];
-            xs[i][tc] = sacc;
-            X[(size_t)(k + i) * ldg + c] = sacc;
+            double s0 = xs[i][tc], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int tt = i + 1;
+            for (; tt + 3 < nb; tt += 4) {
+                s0 = fma(-D[i][tt], xs[tt][tc], s0); s1 = fma(-D[i][tt + 1], xs[tt + 1][tc], s1);
+                s2 = fma(-D[i][tt + 2], xs[tt + 2][tc], s2); s3 = fma(-D[i][tt + 3], xs[tt + 3][tc], s3);
+            }
+            for (; tt < nb; ++tt) s0 = fma(-D[i][tt], xs[tt][tc], s0);
+            const double r = ((s0 + s1) + (s2 + s3)) / D[i][i];
+            xs[i][tc] = r;
+            X[(size_t)(k + i) * ldg + c] = r;
         }
     }
 }
@@ -327,24 +335,26 @@ int dense_getrf_batched(ptzba_ctx* ctx, double* A, int lda, size_t stride, const
     for (int k0 = 0; k0 < n_max; k0 += NB) {
         // widest sub-panel whose rows fit in shared memory
         const size_t rows = (size_t)(n_max - k0);
-        const size_t lim = 200 * 1024;
+        // a single CTA's column steps are a latency chain: with more matrices than SMs two panel CTAs share an SM (narrower
+        // sub-panels), with few matrices the widest sub-panel that fits wins
+        const size_t lim = (batch > ctx->sm_count ? 100 : 200) * 1024;
         if (rows * 8 * sizeof(double) <= lim) {
             static bool cfg8 = false;
-            if (!cfg8) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg8 = true; }
+            if (!cfg8) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg8 = true; }
             k_lu_panel<8><<<batch, PT, rows * 8 * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
         } else if (rows * 4 * sizeof(double) <= lim) {
             static bool cfg4 = false;
-            if (!cfg4) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg4 = true; }
+            if (!cfg4) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg4 = true; }
             k_lu_panel<4><<<batch, PT, rows * 4 * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
         } else if (rows * 2 * sizeof(double) <= lim) {
             static bool cfg2 = false;
-            if (!cfg2) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg2 = true; }
+            if (!cfg2) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg2 = true; }
             k_lu_panel<2><<<batch, PT, rows * 2 * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
         } else {
-            if (rows * sizeof(double) > lim)
+            if (rows * sizeof(double) > 200 * 1024)
                 return ptzba_fail(ctx, PTZBA_ERR_ARG, "LU panel of %zu rows exceeds the shared-memory sub-panel", rows);
             static bool cfg1 = false;
-            if (!cfg1) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim)); cfg1 = true; }
+            if (!cfg1) { CU_CHECK(ctx, cudaFuncSetAttribute(k_lu_panel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg1 = true; }
             k_lu_panel<1><<<batch, PT, rows * sizeof(double), s>>>(A, lda, stride, d_n_arr, k0, d_ipiv, ld_ipiv, d_info);
         }
         KERNEL_POST(ctx);
@@ -366,20 +376,20 @@ int dense_getrs_rows_batched(ptzba_ctx* ctx, const double* LU, int lda, size_t s
                              int batch) {
     cudaStream_t s = ctx->stream;
     static bool cfg = false;
-    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_lu_rows_ll, dmma::Tile<32, 64>::kSmemBytes)); cfg = true; }
+    if (!cfg) { CU_CHECK(ctx, dmma::configure(k_lu_rows_ll, dmma::Tile<NBS, 64>::kSmemBytes)); cfg = true; }
     const int ncols_max = n_max + extra_cols;
     k_lu_perm<<<batch, 1, 0, s>>>(d_n_arr, d_ipiv, ld_ipiv, d_perm);
     KERNEL_POST(ctx);
     k_lu_gather_rows<<<dim3(div_up(ncols_max, 256), n_max, batch), 256, 0, s>>>(B, X, ldg, strideG, d_n_arr, extra_cols, d_perm, ld_ipiv);
     KERNEL_POST(ctx);
-    for (int k = 0; k < n_max; k += NB) {
-        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<32, 64>::kSmemBytes, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 0);
+    for (int k = 0; k < n_max; k += NBS) {
+        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<NBS, 64>::kSmemBytes, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 0);
         KERNEL_POST(ctx);
     }
-    const int last = (n_max - 1) / NB * NB;
-    for (int k = last; k >= 0; k -= NB) {
+    const int last = (n_max - 1) / NBS * NBS;
+    for (int k = last; k >= 0; k -= NBS) {
         // (sequences shorter than n_max skip the block rows beyond their order; within a sequence the rows right of block k are final)
-        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<32, 64>::kSmemBytes, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 1);
+        k_lu_rows_ll<<<dim3(div_up(ncols_max, 64), batch), dmma::kThreads, dmma::Tile<NBS, 64>::kSmemBytes, s>>>(LU, lda, stride, X, ldg, strideG, d_n_arr, extra_cols, k, 1);
         KERNEL_POST(ctx);
     }
     return PTZBA_OK;
