@@ -314,8 +314,6 @@ def run_ours(args):
         R = max(4, int(np.ceil(2.2 * 126e6 * world / algorithmic_bytes(fb_full.n_obs, fb_full.n_landmark, fb_full.n_pose))))
     probs = [BA.BAProblem(fb.n_pose, fb.n_landmark, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v, ctx=ctx) for _ in range(R)]
     for p_ in probs:      # kernel tuning knobs (include/ptzba.h PTZBA_OPT_*); the defaults are the measured best
-        if args.fused_launch is not None:
-            p_.set_option(_lib.OPT_FUSED_LAUNCH, args.fused_launch)
         if args.lm_share is not None:
             p_.set_option(_lib.OPT_FUSED_LM_SHARE, args.lm_share)
     x_dev = [torch.from_numpy(x0).cuda() for _ in range(R)]
@@ -340,13 +338,23 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # clock ramp (untimed, in addition to the W warm-up steps): ~0.3 s of passes
+    # clock ramp (untimed, in addition to the W warm-up steps): ~0.3 s of passes, in blocks of 64.  With N > 1 a step holds a
+    # collective, so every rank has to run the SAME number of steps: rank 0's clock decides after each block and the verdict
+    # is shared (ranks that each watched their own clock left the loop after different counts and dead-locked at N = 4).
     t_end = time.perf_counter() + args.ramp
     i = 0
-    while time.perf_counter() < t_end:
-        device_step(i); i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
+    go = torch.ones(1, dtype=torch.int32, device="cuda")
+    while True:
+        for _ in range(64):
+            device_step(i); i += 1
+        torch.cuda.synchronize()
+        if world > 1:
+            go.fill_(1 if time.perf_counter() < t_end else 0)
+            dist.broadcast(go, src=0)
+            if int(go.item()) == 0:
+                break
+        elif time.perf_counter() >= t_end:
+            break
     for i in range(args.warmup):
         device_step(i)
     barrier()
@@ -415,7 +423,7 @@ def run_ours(args):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                "kernel": "fused pass (k_ba_lm_pass + k_ba_cam_pass)", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
+                "kernel": "fused pass (k_ba_fused: the landmark-major and the keyframe-major CTA role in one launch)", "kernel_ms": kernel_ms, "algorithmic_bytes": abytes}
 
     # ---- e2e: HOST (pinned) buffers through the C-ABI, copies inside the timed region ------------------------------
     # The call a user of the normal equations makes: x in; the U/g_c blocks of the rank's keyframes, the V/g_l blocks of the
@@ -595,7 +603,7 @@ def run_ours(args):
                                        "%.2f MB per rank and pass); U/g_c are complete on the rank that owns the keyframe" %
                                        (n_shared, fb.n_landmark, (1 + 5 * n_shared) * 8 / 1e6)) if world > 1 else "1 GPU",
                        "n_shared": int(n_shared),
-                       "step": "one fused residual+Jacobian+normal-equation pass (k_set_params + k_ba_lm_pass + k_ba_cam_pass)%s" %
+                       "step": "one fused residual+Jacobian+normal-equation pass (k_set_params + k_ba_fused)%s" %
                                (" + exchange (k_pack_shared, ncclAllReduce, k_unpack_shared)" if world > 1 else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -624,7 +632,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--replicas", type=int, default=0, help="problem replicas the passes rotate over (0 = enough to exceed the L2)")
-    ap.add_argument("--fused-launch", type=int, default=None, help="tuning: 0 one launch with two CTA roles, 1 two launches")
     ap.add_argument("--lm-share", type=int, default=None, help="tuning: per cent of the fused pass's CTA budget for the landmark-major role")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lm", action="store_true")

@@ -223,9 +223,8 @@ int ptzba_ba_lm_iteration(ptzba_ba* ba, int mem, const double* x, const double* 
  * 2^31 observation pairs), PER_LANDMARK (one warp per landmark, one FP64 RED per block entry per observation pair; no
  * extra memory), PAIR_LIST (same as AUTO). */
 #define PTZBA_OPT_SCHUR_MODE 1
-/* PTZBA_OPT_FUSED_LAUNCH: 0 (default) the two passes of the fused pass are ONE launch with two interleaved CTA roles; 1 two launches
- * on two streams.  PTZBA_OPT_FUSED_LM_SHARE: per cent (1..99, default 57) of the CTAs' work budget given to the landmark-major role. */
-#define PTZBA_OPT_FUSED_LAUNCH 2
+/* PTZBA_OPT_FUSED_LM_SHARE: the fused pass is ONE launch with two interleaved CTA roles (landmark-major: residual, V, g_l;
+ * keyframe-major: U, g_c); this is the per cent (1..99, default 57) of the CTAs' work budget given to the landmark-major role. */
 #define PTZBA_OPT_FUSED_LM_SHARE 3
 #define PTZBA_SCHUR_AUTO 0
 #define PTZBA_SCHUR_PER_LANDMARK 1

@@ -14,7 +14,7 @@ import numpy as np
 HOST, DEVICE = 0, 1
 JAC_ANALYTIC, JAC_CENTRAL_FD = 0, 1
 OPT_SCHUR_MODE = 1
-OPT_FUSED_LAUNCH, OPT_FUSED_LM_SHARE = 2, 3
+OPT_FUSED_LM_SHARE = 3
 SCHUR_AUTO, SCHUR_PER_LANDMARK, SCHUR_PAIR_LIST = 0, 1, 2
 
 # PTZBA_LIBRARY names another build of the same library (kernel tuning experiments); it is still this library or nothing

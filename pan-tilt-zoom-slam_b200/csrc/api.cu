@@ -29,9 +29,6 @@ extern "C" int ptzba_create(int device, ptzba_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PTZBA_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
-    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return PTZBA_ERR_CUDA; }
     if (cudaMallocHost((void**)&ctx->h_scalars, 256 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_scalars, 256 * sizeof(double)) != cudaSuccess) {
         ptzba_destroy(ctx);
@@ -50,9 +47,6 @@ extern "C" void ptzba_destroy(ptzba_ctx* ctx) {
     ptzba_comm_release(ctx);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
-    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -68,7 +68,6 @@ struct ptzba_ba {
     DevBuf<int> sol_flags;                  // [0] singular V blocks, [1] potrf info
     DevBuf<double> sol_tmp_l, sol_w, sol_dinv;   // back-substitution scratch, D^2 delta, inverted diagonal blocks of chol(S)
     int grid_fused = 0;             // one wave of resident CTAs of the fused pass
-    int fused_launch = 0;           // PTZBA_OPT_FUSED_LAUNCH: 0 one launch with two CTA roles, 1 two launches on two streams
     double fused_lm_share = 57.0;   // PTZBA_OPT_FUSED_LM_SHARE: per cent of the per-observation cost that is the landmark-major role's
     // keyframe-pair-major list of observation pairs of this rank's landmark slice, built at the first solve
     int schur_mode = 0;             // PTZBA_SCHUR_* (ptzba_ba_set_option)

@@ -21,10 +21,7 @@ constexpr int kFusedThreads = 256;
 #ifndef PTZBA_LM_MINB
 #define PTZBA_LM_MINB 2
 #endif
-#ifndef PTZBA_CAM_MINB
-#define PTZBA_CAM_MINB 2
-#endif
-constexpr int kLmMinB = PTZBA_LM_MINB, kCamMinB = PTZBA_CAM_MINB;   // resident CTAs per SM the two passes are compiled for
+constexpr int kLmMinB = PTZBA_LM_MINB;   // resident CTAs per SM the fused pass is compiled for (3 = 80 registers spills: measured slower)
 
 // ---------------------------------------------------------------------------------------------------------------
 // problem set-up kernels
@@ -151,19 +148,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The fused pass = two coherent passes; every sum is formed where its operands are adjacent, nothing is scattered.
-//   k_ba_lm_pass   landmark-major: residual (written), cost, per-landmark V / g_l
-//   k_ba_cam_pass  keyframe-major: per-keyframe U / g_c live in registers across a whole run of the keyframe
-// Both kernels give every thread FOUR consecutive observations (one 128-bit index load and one 256-bit load per
-// stream), evaluate the four projections as four independent FP64 chains without a data-dependent branch between
-// them (ILP 4: the round-1 kernels were dependency-latency bound with one serial, branchy chain per thread), issue
-// the four landmark-trig gathers up front, and request the streamed operands of the NEXT iteration before the
-// arithmetic of the current one.
-// Why not one pass: FP64 has no native shared-memory atomic add and L2 REDs cost ~5 ns per entry chip-wide, so
-// whichever side is scattered costs more than re-streaming 20 B/observation and re-evaluating the geometry.  The
-// alternatives that were built, measured and removed (one pass with shared-memory CAS atomics, keyframe-major with
-// L2 REDs, CTA-wide and per-warp TMA/mbarrier rings, one launch with two CTA roles, one pass with a static per-tile
-// keyframe sort, serial 4-observation loops with look-ahead index loads) are tabulated in DESIGN.md section 5.
+// The fused pass = ONE launch (k_ba_fused) whose CTAs take one of two roles; every sum is formed where its operands are
+// adjacent, nothing is scattered.
+//   lm_role   landmark-major: residual (written), cost, per-landmark V / g_l
+//   cam_role  keyframe-major: per-keyframe U / g_c live in registers across a whole run of the keyframe
+// Both roles give every thread FOUR consecutive observations (one 128-bit index load and one 256-bit load per
+// stream), evaluate the four projections as independent FP64 chains without a data-dependent branch between them
+// (ILP 4: the round-1 kernels were dependency-latency bound with one serial, branchy chain per thread), and keep a
+// rolling half-iteration pipeline of landmark-trig gathers in registers: the rows an iteration uses first were
+// requested during the previous iteration, the rest at its top, index vectors two iterations ahead.
+// Why two roles and not one pass: FP64 has no native shared-memory atomic add and L2 REDs cost ~5 ns per entry
+// chip-wide, so whichever side is scattered costs more than re-streaming 20 B/observation and re-evaluating the
+// geometry.  The alternatives that were built, measured and removed (one pass with shared-memory CAS atomics,
+// keyframe-major with L2 REDs, CTA-wide and per-warp TMA/mbarrier rings, two launches on two streams, cp.async-staged
+// gathers, L1 prefetch, one pass with a static per-tile keyframe sort) are tabulated in DESIGN.md section 5.
 // ---------------------------------------------------------------------------------------------------------------
 struct __align__(32) D4 { double a, b, c, d; };
 
@@ -445,8 +443,7 @@ struct FusedArgs {
 // ONE launch for both passes: CTA b takes the landmark-major role iff floor((b+1) G_lm / G) > floor(b G_lm / G) (the two roles
 // are interleaved evenly in launch order, so that every SM hosts CTAs of both kinds from the first to the last cycle: the
 // landmark-major role is bound by the LSU / shared-memory pipe, the keyframe-major role by L2 gathers and the FP64 pipe).  The
-// two-launch form (two streams, fork / join events) paid ~2 x 3 us of event latency and only overlapped the tail of one kernel
-// with the head of the other.
+// two-launch form of round 1 (two streams, fork / join events) was measured against it and removed: 43.2 vs 42.1 us.
 template <int MINB, bool CAM_SMEM>
 __global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_fused(const FusedArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -459,19 +456,6 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_fused(const FusedArg
     else
         cam_role(b - before, a.it_lo, a.it_hi, a.iters_per_cta, a.iter_cam, a.c_lm, a.c_ox, a.c_oy, a.cam_trig, a.lm_trig, a.u, a.v, a.gU,
                  a.gGc);
-}
-
-// the two roles as separate launches (PTZBA_OPT_FUSED_LAUNCH = 1: two streams)
-template <int MINB, bool CAM_SMEM>
-__global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_lm_pass(const FusedArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ double sWarp[kFusedThreads / 32];
-    lm_role<CAM_SMEM>(blockIdx.x, a.lo, a.hi, a.chunk, a.s_cam, a.s_lm, a.s_ox, a.s_oy, a.orig, a.cam_trig, a.lm_trig, a.n_pose, a.u, a.v,
-                      a.resid, a.gV, a.gGl, a.gCost, smem, sWarp);
-}
-template <int MINB>
-__global__ void __launch_bounds__(kFusedThreads, MINB) k_ba_cam_pass(const FusedArgs a) {
-    cam_role(blockIdx.x, a.it_lo, a.it_hi, a.iters_per_cta, a.iter_cam, a.c_lm, a.c_ox, a.c_oy, a.cam_trig, a.lm_trig, a.u, a.v, a.gU, a.gGc);
 }
 
 // residual-only pass (trial points of the trust-region loop, and _compute_residual itself)
@@ -567,46 +551,25 @@ int ba_fused_pass(ptzba_ba* ba, double* d_resid) {
     a.cam_trig = ba->cam_trig.p; a.lm_trig = ba->lm_trig.p; a.n_pose = ba->n_pose; a.u = ba->u; a.v = ba->v;
     const int G = ba->grid_fused;                           // one wave of resident CTAs
     const double wA = nA > 0 ? (double)nA * ba->fused_lm_share : 0.0, wB = (double)nB * kCamIter * (100.0 - ba->fused_lm_share);
-    auto split_chunks = [&](int g_lm, int g_cam) {
-        a.n_lm_cta = g_lm; a.n_cam_cta = g_cam;
-        a.chunk = 1024; a.iters_per_cta = 1;
-        if (g_lm > 0) {
-            a.chunk = ((nA + g_lm - 1) / g_lm + 1023) / 1024 * 1024;
-            a.n_lm_cta = (int)((nA + a.chunk - 1) / a.chunk);
-        }
-        if (g_cam > 0) {
-            a.iters_per_cta = (nB + g_cam - 1) / g_cam;
-            a.n_cam_cta = (nB + a.iters_per_cta - 1) / a.iters_per_cta;
-        }
-    };
-    if (ba->fused_launch == 0) {
-        int g_lm = (nA > 0) ? (int)(G * wA / (wA + wB) + 0.5) : 0;
-        if (nA > 0 && g_lm < 1) g_lm = 1;
-        if (nB > 0 && g_lm > G - 1) g_lm = G - 1;
-        if (nB <= 0) g_lm = nA > 0 ? G : 0;
-        split_chunks(g_lm, nB > 0 ? G - g_lm : 0);
-        if (a.n_lm_cta + a.n_cam_cta > 0) {
-            if (ba->cam_smem) k_ba_fused<kLmMinB, true><<<a.n_lm_cta + a.n_cam_cta, kFusedThreads, smA, s>>>(a);
-            else k_ba_fused<kLmMinB, false><<<a.n_lm_cta + a.n_cam_cta, kFusedThreads, 0, s>>>(a);
-            KERNEL_POST(ctx);
-        }
-    } else {
-        // two launches; the keyframe-major one on the side stream, concurrently with the landmark-major one
-        split_chunks(nA > 0 ? G : 0, nB > 0 ? G : 0);
-        CU_CHECK(ctx, cudaEventRecord(ctx->ev_fork, s));
-        if (a.n_lm_cta > 0) {
-            if (ba->cam_smem) k_ba_lm_pass<kLmMinB, true><<<a.n_lm_cta, kFusedThreads, smA, s>>>(a);
-            else k_ba_lm_pass<kLmMinB, false><<<a.n_lm_cta, kFusedThreads, 0, s>>>(a);
-            KERNEL_POST(ctx);
-        }
-        if (a.n_cam_cta > 0) {
-            cudaStream_t sb = ctx->side_stream;
-            CU_CHECK(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
-            k_ba_cam_pass<kCamMinB><<<a.n_cam_cta, kFusedThreads, 0, sb>>>(a);
-            KERNEL_POST(ctx);
-            CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, sb));
-            CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
-        }
+    int g_lm = (nA > 0) ? (int)(G * wA / (wA + wB) + 0.5) : 0;
+    if (nA > 0 && g_lm < 1) g_lm = 1;
+    if (nB > 0 && g_lm > G - 1) g_lm = G - 1;
+    if (nB <= 0) g_lm = nA > 0 ? G : 0;
+    const int g_cam = nB > 0 ? G - g_lm : 0;
+    a.n_lm_cta = g_lm; a.n_cam_cta = g_cam;
+    a.chunk = 1024; a.iters_per_cta = 1;
+    if (g_lm > 0) {
+        a.chunk = ((nA + g_lm - 1) / g_lm + 1023) / 1024 * 1024;
+        a.n_lm_cta = (int)((nA + a.chunk - 1) / a.chunk);
+    }
+    if (g_cam > 0) {
+        a.iters_per_cta = (nB + g_cam - 1) / g_cam;
+        a.n_cam_cta = (nB + a.iters_per_cta - 1) / a.iters_per_cta;
+    }
+    if (a.n_lm_cta + a.n_cam_cta > 0) {
+        if (ba->cam_smem) k_ba_fused<kLmMinB, true><<<a.n_lm_cta + a.n_cam_cta, kFusedThreads, smA, s>>>(a);
+        else k_ba_fused<kLmMinB, false><<<a.n_lm_cta + a.n_cam_cta, kFusedThreads, 0, s>>>(a);
+        KERNEL_POST(ctx);
     }
     if (ev1) CU_CHECK(ctx, cudaEventRecord(ev1, s));
     if (ba->part_world > 1) PROPAGATE(ptzba_comm_allreduce_f64(ctx, ba->acc.base, (int64_t)ba->acc.count));
@@ -781,7 +744,6 @@ extern "C" int ptzba_ba_create(ptzba_ctx* ctx, int mem, int n_pose, int n_landma
         int pa = 1;
         if (ba->cam_smem) {
             CU_TRY(cudaFuncSetAttribute(k_ba_fused<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-            CU_TRY(cudaFuncSetAttribute(k_ba_lm_pass<kLmMinB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_fused<kLmMinB, true>, kFusedThreads, smA));
         } else {
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pa, k_ba_fused<kLmMinB, false>, kFusedThreads, 0));
@@ -826,10 +788,6 @@ extern "C" int ptzba_ba_set_option(ptzba_ba* ba, int option, int value) {
         case PTZBA_OPT_SCHUR_MODE:
             ARG_CHECK(ctx, value == PTZBA_SCHUR_AUTO || value == PTZBA_SCHUR_PER_LANDMARK || value == PTZBA_SCHUR_PAIR_LIST);
             ba->schur_mode = value;
-            return PTZBA_OK;
-        case PTZBA_OPT_FUSED_LAUNCH:
-            ARG_CHECK(ctx, value == 0 || value == 1);
-            ba->fused_launch = value;
             return PTZBA_OK;
         case PTZBA_OPT_FUSED_LM_SHARE:
             ARG_CHECK(ctx, value >= 1 && value <= 99);

@@ -13,8 +13,6 @@ struct ptzba_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;     // the stream all kernels are enqueued on
-    cudaStream_t side_stream = nullptr; // fork/join partner of `stream` (the two independent kernels of the fused BA pass)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 148;
     int64_t launches = 0;
     std::string err;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage (on the GPU box, one GPU, through gpurun):  scripts/gpu_ncu_capture.sh <tag> <kernel regex> [ENV=VALUE ...]
-# e.g.  scripts/gpu_ncu_capture.sh ring 'k_ba_(lm|cam)_pass' PTZBA_FUSED_RING=1
-#       scripts/gpu_ncu_capture.sh pairlist 'k_schur_pair' PTZBA_SCHUR_PAIRLIST=1
+# e.g.  scripts/gpu_ncu_capture.sh fused 'k_ba_fused'
+#       scripts/gpu_ncu_capture.sh pairs 'k_schur_pair'
 # 1. runs the short bench WITHOUT ncu first (a number printed under a profiler is never a bench value), 2. takes the launch list
 # of the same command, 3. takes one `--set full` capture of the kernels matching the regex (after 40 matching launches of warm-up).
 # Outputs: gpurun_out/bench_<tag>.json, launches_<tag>.csv, prof_<tag>.ncu-rep  (read here with `ncu -i ... --page raw --csv`).
