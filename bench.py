@@ -265,6 +265,41 @@ def bench_cfg2(ctx, n_rays=3000, n_frames=20):
     return out
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa_node(local):
+    """Multi-rank runs: bind this process (and the pinned host buffers it first-touches afterwards) to the CPUs of the NUMA
+    node its GPU hangs off, so that the host<->device copies of the e2e leg do not cross the socket interconnect.  Best
+    effort: returns a one-line description of what was done (or why nothing was) for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dom, bus, dev = (getattr(pr, k, None) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id"))
+        if bus is None:
+            return "not pinned: torch does not report the PCI address"
+        node_path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom or 0, bus, dev or 0)
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return "not pinned: the platform reports no NUMA node for the GPU"
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if len(use) < 2:
+            return "not pinned: %d of this process's %d CPUs are on NUMA node %d" % (len(use), len(allowed), node)
+        os.sched_setaffinity(0, use)
+        return "pinned to %d CPUs of NUMA node %d" % (len(use), node)
+    except Exception as e:       # no sysfs, no permission, ...: the run goes on unpinned
+        return "not pinned: %s" % (str(e).splitlines()[0] if str(e) else type(e).__name__)
+
+
 # -------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------------
@@ -285,6 +320,7 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _lib.get_context(local)
@@ -433,6 +469,12 @@ def run_ours(args):
     import ctypes as _ct2
     N, M = fb.n_pose, fb.n_landmark
     lm_lo, lm_hi = (int(fb.lm_idx.min()), int(fb.lm_idx.max()) + 1) if fb.n_obs else (0, 0)
+    lm_rule = "the span of the landmark ids the rank observes"
+    if world > 1:      # every landmark is downloaded by ONE rank: the one that owns its first keyframe (a contiguous id range)
+        own_r = pdist.owned_landmark_range(fb_full.cam_idx, fb_full.lm_idx, fb_full.n_landmark, kf_range)
+        if own_r is not None:
+            lm_lo, lm_hi = own_r
+            lm_rule = "the landmarks the rank owns (first observed by one of its keyframes: ids %d..%d)" % (lm_lo, lm_hi)
     nk, nl = kf_range[1] - kf_range[0], lm_hi - lm_lo
     pin = lambda n: torch.empty(max(n, 1), dtype=torch.float64).pin_memory().numpy()
     hx = [pin(len(x0)) for _ in range(R)]
@@ -472,7 +514,7 @@ def run_ours(args):
            "d2h_bytes_per_step": int(8 * (nk * 9 + nl * 5 + 1)), "steps": e2e_steps,
            "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "call": "ptzba_ba_normal_equations_begin / ptzba_ba_wait (pinned host buffers, copies of one replica overlap the kernels of the "
-                   "next): x in; U, g_c of the rank's keyframes, V, g_l of its landmarks, cost out"}
+                   "next): x in; U, g_c of the rank's keyframes, V, g_l of " + lm_rule + ", cost out; bytes are per rank"}
     # the same pass with the residual vector requested as well (synchronous call, 16 B per observation more to download)
     hr = pin(2 * fb.n_obs)
     fU, fgc, fV, fgl = pin(N * 6), pin(N * 3), pin(M * 3), pin(M * 2)
@@ -509,7 +551,29 @@ def run_ours(args):
         solve_s = time.perf_counter() - t0
         lm = {"lm_iters_per_s": 1.0 / lm_s, "ms_per_lm_iter": 1e3 * lm_s,
               "solve": {"ftol": 1e-4, "ms": 1e3 * solve_s, "nfev": rep["nfev"], "njev": rep["njev"], "status": rep["status"],
-                        "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"]}}
+                        "n_factor": rep["n_factor"], "cost0": rep["cost0"], "cost": rep["cost"],
+                        "call": "BAProblem.solve -> ptzba_ba_solve(mem=HOST), the reference's entry point (bundle_adjustment.py:200-208): "
+                                "x in and x out through host buffers inside the timed region, wall clock",
+                        "h2d_bytes": int(8 * len(x0)), "d2h_bytes": int(8 * len(x0))}}
+
+    if lm is not None and not args.no_cpu_baseline:
+        # the same iteration on the host cores: C port for the passes, scipy.sparse / LAPACK for Schur + Cholesky (one iteration,
+        # ~5-10 s); its predicted reduction and trial cost are printed beside the GPU's (informational: the asserted parity of the
+        # solver is in tests/test_gpu_ba.py and tests/test_gpu_configs.py)
+        try:
+            from oracle import ptz_oracle as O, c_port
+            t0 = time.perf_counter()
+            _, pred_c, trial_c = O.ba_lm_iteration_sparse(x0, fb.n_pose, ref_pose, fb.cam_idx, fb.lm_idx, fb.obs_xy, u, v, 1e-3,
+                                                         fused=c_port.ba_fused, residual=c_port.ba_residual)
+            c_s = time.perf_counter() - t0
+            pred_g, trial_g = probs[0].lm_iteration(x0, ref_pose, alpha=1e-3)
+            lm["lm_cpu_baseline"] = {"value": 1.0 / c_s, "unit": "LM iterations/s", "cores": c_port.max_threads(), "kind": "port",
+                                     "sample": "1 iteration of the same problem at the same damping: oracle.ba_lm_iteration_sparse (passes: "
+                                               "oracle/ptz_oracle_c.c on all threads; Schur complement: scipy.sparse, one thread; Cholesky: LAPACK)",
+                                     "gpu_vs_cpu_rel_diff": {"predicted_reduction": abs(pred_g - pred_c) / abs(pred_c),
+                                                             "trial_cost": abs(trial_g - trial_c) / abs(trial_c)}}
+        except Exception as e:
+            lm["lm_cpu_baseline"] = {"error": (str(e).splitlines() or [type(e).__name__])[0]}
 
     if world > 1 and not args.no_lm:
         # distributed solve, STRONG scaling of one problem of the named workload: every rank holds the whole observation
@@ -602,7 +666,7 @@ def run_ours(args):
                                        "of the cost and of the V/g_l blocks of the landmarks observed by more than one rank (n_shared = %d of %d landmarks, "
                                        "%.2f MB per rank and pass); U/g_c are complete on the rank that owns the keyframe" %
                                        (n_shared, fb.n_landmark, (1 + 5 * n_shared) * 8 / 1e6)) if world > 1 else "1 GPU",
-                       "n_shared": int(n_shared),
+                       "n_shared": int(n_shared), "numa": numa,
                        "step": "one fused residual+Jacobian+normal-equation pass (k_set_params + k_ba_fused)%s" %
                                (" + exchange (k_pack_shared, ncclAllReduce, k_unpack_shared)" if world > 1 else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -387,6 +387,71 @@ def ba_jacobian_sparse(poses, rays, cam_idx, lm_idx):
                          shape=(2 * n_obs, 3 * (N - 1) + 2 * M))
 
 
+def ba_lm_iteration_sparse(x, n_pose, reference_pose, cam_idx, lm_idx, obs_xy, u, v, alpha, fused=None, residual=None):
+    """One Levenberg-Marquardt iteration at fixed damping alpha on the CPU - what ptzba_ba_lm_iteration does on the GPU, with
+    the tools a CPU user of the reference has (numpy / scipy.sparse / LAPACK): blocks of J^T J and J^T r (bundle_adjustment.py
+    :25-106 differentiated analytically), x_scale='jac' column norms D (least_squares call at bundle_adjustment.py:200-202),
+    the step (J^T J + alpha D^2) d = -J^T r through the Schur complement over the landmarks (sparse products, dense Cholesky of
+    the reduced camera system), the predicted reduction and the cost at the trial point.
+    `fused` / `residual`: optional faster evaluators with the signatures of oracle.c_port.ba_fused / ba_residual (bench.py passes
+    the multi-threaded C port); default: the numpy restatement.
+    Returns (step[3(N-1)+2M], predicted_reduction, cost_trial)."""
+    import scipy.sparse as sp
+    import scipy.linalg as sla
+    cam_idx = np.asarray(cam_idx); lm_idx = np.asarray(lm_idx)
+    poses, rays = ba_unpack(np.asarray(x, dtype=np.float64), n_pose, reference_pose)
+    N, M = len(poses), len(rays)
+    nc = 3 * (N - 1)
+    if fused is None:
+        r, U, gc, V, gl, cost = ba_normal_equations(poses, rays, cam_idx, lm_idx, obs_xy, u, v)
+        V3 = np.stack([V[:, 0, 0], V[:, 0, 1], V[:, 1, 1]], axis=1)
+        Ufull = U
+    else:
+        r, U6, gc, V3, gl, cost = fused(poses, rays, cam_idx, lm_idx, obs_xy, u, v, want_residual=False)
+        Ufull = np.empty((N, 3, 3))
+        iu = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+        for k, (a, b) in enumerate(iu):
+            Ufull[:, a, b] = U6[:, k]; Ufull[:, b, a] = U6[:, k]
+    c = poses[cam_idx]; l = rays[lm_idx]
+    Jc, Jr = jacobian_blocks_analytic(c[:, 0], c[:, 1], c[:, 2], l[:, 0], l[:, 1])
+    free = cam_idx > 0
+    Wb = np.einsum('nki,nkj->nij', Jc[free], Jr[free])                      # per observation: J_c^T J_l (3 x 2)
+    cf = cam_idx[free].astype(np.int64) - 1; lf = lm_idx[free].astype(np.int64)
+    rows = (3 * cf[:, None, None] + np.arange(3)[None, :, None] + np.zeros((1, 1, 2), np.int64)).ravel()
+    cols = (2 * lf[:, None, None] + np.zeros((1, 3, 1), np.int64) + np.arange(2)[None, None, :]).ravel()
+    W = sp.csr_matrix((Wb.ravel(), (rows, cols)), shape=(nc, 2 * M))
+    # x_scale='jac': D = column norms of J (zero columns -> 1, _lsq/common.py:compute_jac_scale)
+    Dc2 = np.stack([Ufull[1:, 0, 0], Ufull[1:, 1, 1], Ufull[1:, 2, 2]], axis=1).ravel()
+    Dl2 = np.stack([V3[:, 0], V3[:, 2]], axis=1).ravel()
+    Dc2 = np.where(Dc2 > 0, Dc2, 1.0); Dl2 = np.where(Dl2 > 0, Dl2, 1.0)
+    a = V3[:, 0] + alpha * Dl2[0::2]; b = V3[:, 1]; d = V3[:, 2] + alpha * Dl2[1::2]
+    det = a * d - b * b
+    i00, i01, i11 = d / det, -b / det, a / det                               # (V + alpha D^2)^-1, 2 x 2 blocks
+    k = np.arange(M)
+    Vinv = sp.csr_matrix((np.concatenate([i00, i01, i01, i11]),
+                          (np.concatenate([2 * k, 2 * k, 2 * k + 1, 2 * k + 1]), np.concatenate([2 * k, 2 * k + 1, 2 * k, 2 * k + 1]))),
+                         shape=(2 * M, 2 * M))
+    X = W @ Vinv
+    S = -(X @ W.T).toarray()
+    for i in range(N - 1):
+        S[3 * i:3 * i + 3, 3 * i:3 * i + 3] += Ufull[i + 1]
+    S[np.arange(nc), np.arange(nc)] += alpha * Dc2
+    g_c = gc[1:].ravel(); g_l = gl.ravel()
+    rhs = -(g_c - X @ g_l)
+    cf_ = sla.cho_factor(S, lower=True, check_finite=False)
+    dc = sla.cho_solve(cf_, rhs, check_finite=False)
+    dl = Vinv @ (-g_l - W.T @ dc)
+    step = np.concatenate([dc, dl])
+    # ||J d||^2 from the per-observation blocks
+    dcf = np.concatenate([np.zeros(3), dc]).reshape(N, 3)[cam_idx]
+    dlf = dl.reshape(M, 2)[lm_idx]
+    Jd = np.einsum('nki,ni->nk', Jc, dcf) + np.einsum('nki,ni->nk', Jr, dlf)
+    pred = -(float(np.dot(np.concatenate([g_c, g_l]), step)) + 0.5 * float(np.sum(Jd * Jd)))
+    pt, rt = ba_unpack(np.asarray(x, dtype=np.float64) + step, n_pose, reference_pose)
+    rr = ba_residual_flat(pt, rt, cam_idx, lm_idx, obs_xy, u, v) if residual is None else residual(pt, rt, cam_idx, lm_idx, obs_xy, u, v)
+    return step, pred, 0.5 * float(np.sum(rr * rr))
+
+
 # ---------------------------------------------------------------------------------------------
 # trust-region least squares driver
 # Third-party algorithm: scipy.optimize.least_squares(method='trf', x_scale='jac', tr_solver='exact'),

@@ -67,6 +67,28 @@ def shard_by_keyframe(cam_idx, lm_idx, obs_xy, n_pose, rank, world_size):
     return cam_idx[sel], np.asarray(lm_idx)[sel], np.asarray(obs_xy)[sel], (lo, hi)
 
 
+def owned_landmark_range(cam_idx, lm_idx, n_landmark, kf_range):
+    """Landmarks OWNED by the rank of keyframe range `kf_range` when the observations are sharded by keyframe: a landmark
+    belongs to the rank of the lowest-numbered keyframe that observes it, so every observed landmark has exactly one owner
+    and that owner observes it (after the shared-landmark exchange its V / g_l blocks are complete there).  The reference
+    numbers landmarks in the order they are first seen (image_process.py:609-667), which makes the owned ids one contiguous
+    range: returns (lo, hi) then, None when the ids of this problem are not ordered that way (a caller then falls back to
+    the span of the ids the rank observes).  `cam_idx` / `lm_idx` are the WHOLE problem's lists."""
+    cam_idx, lm_idx = np.asarray(cam_idx), np.asarray(lm_idx)
+    big = np.iinfo(np.int64).max
+    first = np.full(int(n_landmark), big, dtype=np.int64)
+    np.minimum.at(first, lm_idx, cam_idx.astype(np.int64))
+    ids = np.nonzero((first >= kf_range[0]) & (first < kf_range[1]))[0]
+    if ids.size == 0:
+        return (0, 0)
+    lo, hi = int(ids[0]), int(ids[-1]) + 1
+    inside = first[lo:hi]
+    # unobserved ids inside the range are harmless (their blocks are zero); ids owned by another rank are not
+    if np.any((inside != big) & ((inside < kf_range[0]) | (inside >= kf_range[1]))):
+        return None
+    return (lo, hi)
+
+
 def solve_partition(lm_idx, n_landmark, world_size):
     """Work slices of the distributed solve (ptzba_ba_set_partition), one per rank: contiguous landmark ranges balanced by
     observation count, and equal contiguous slices of the keyframe-major observation list.

@@ -271,7 +271,7 @@ class PtzSlam:
                 masked_index = keypoints_masking(kp, bounding_box)
                 kp, des = np.asarray(kp)[masked_index], np.asarray(des)[masked_index]
             frame.feature_pts, frame.feature_des = kp, des
-            camera.set_ptz(self.rf_map.relocalize(frame))
+            camera.set_ptz(self.rf_map.relocalize(frame, [pan, tilt, focal_length]))      # ptz_slam.py:491
         elif len(self.keyframe_map.keyframe_list) > 1:
             lost_pose = camera.pan, camera.tilt, camera.focal_length
             camera.set_ptz(relocalization_camera(self.keyframe_map, img, lost_pose, detect=self._front("detect"),

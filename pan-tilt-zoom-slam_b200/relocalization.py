@@ -232,8 +232,10 @@ class NNBasedMap(Map):
 
     compute_residual = staticmethod(_compute_residual)          # :65-85
 
-    def relocalize(self, keyframe, verbose=0):
-        """:88-99: refine (pan, tilt, f) of `keyframe` on its descriptor matches into the map; returns the pose [3]."""
+    def relocalize(self, keyframe, init_ptz=None, verbose=0):
+        """:88-99: refine (pan, tilt, f) of `keyframe` on its descriptor matches into the map; returns the pose [3].
+        `init_ptz` is accepted for PtzSlam.relocalize, which hands every rf_map the start pose (ptz_slam.py:491); the start
+        pose used is the keyframe's own, as in the reference."""
         keypoint_index, ray_index = self.find_nearest(keyframe.feature_des)
         pose = np.array([keyframe.pan, keyframe.tilt, keyframe.f], dtype=np.float64)
         if len(ray_index) == 0:

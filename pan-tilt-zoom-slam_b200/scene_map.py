@@ -96,12 +96,16 @@ class RandomForestMap:
     MAX_BA_FRAME = 10           # scene_map.py:210
 
     def __init__(self, keyframe_location="./keyframes/", mat_path_file="./train_feature_file.txt", create_map=None,
-                 build_matching_graph=None, bundle_adjustment_fn=None):
+                 build_matching_graph=None, bundle_adjustment_fn=None, relocalizer=None, relocalize_file="./relocalize.mat"):
         """scene_map.py:170-180 with the hard-coded Windows paths turned into arguments.  `create_map(mat_path_file)` stands
-        for RFMap.createMap (:197-198); `bundle_adjustment_fn` defaults to the GPU bundle adjustment of this package."""
+        for RFMap.createMap (:197-198) and `relocalizer(relocalize_file, init_ptz)` for RFMap.relocalization (:259-268): the
+        random-forest C++ library is not part of this package.  `bundle_adjustment_fn` defaults to the GPU bundle adjustment
+        of this package."""
         self.keyframe_location = keyframe_location
         self.mat_path_file = mat_path_file
         self.create_map = create_map
+        self.relocalizer = relocalizer
+        self.relocalize_file = relocalize_file
         self.build_matching_graph = build_matching_graph
         self.bundle_adjustment_fn = bundle_adjustment_fn
         self.keyframe_list = []
@@ -146,3 +150,34 @@ class RandomForestMap:
             else:
                 print('warning: key frame, %d, image index %d is not included in the map' % (i, image_indices[i]))
         return landmarks
+
+    def add_keyframes(self, keyframe_list):
+        """scene_map.py:246-257: a no-op in the reference (its body is commented out)."""
+        pass
+
+    def relocalize(self, relocalize_frame, init_ptz):
+        """scene_map.py:259-268: the lost frame's features are written to `relocalize_file` and the forest's pose estimate
+        (started from init_ptz) comes back as a flat [pan, tilt, f]."""
+        if self.relocalizer is None:
+            raise RuntimeError("RandomForestMap.relocalize needs the relocalizer callable (the random-forest library is external)")
+        relocalize_frame.save_to_mat(self.relocalize_file)
+        return np.asarray(self.relocalizer(self.relocalize_file, init_ptz), dtype=np.float64).ravel()
+
+    def good_keyframe(self, ptz, threshold1=5, threshold2=20, im_width=1280, verbose=False):
+        """scene_map.py:270-298: the overlap rule of Map.good_new_keyframe against the poses stored in the exported keyframe
+        files (the list add_keyframe wrote to mat_path_file)."""
+        import scipy.io as sio
+        ptz = np.asarray(ptz)
+        assert ptz.shape[0] == 3
+        with open(self.mat_path_file, 'r') as f:
+            files = f.read().splitlines()
+        if len(files) == 0:
+            print("Warning: Not existing keyframes")
+        overlaps = []
+        for path in files:
+            map_ptz = np.asarray(sio.loadmat(path)['ptz'], dtype=np.float64).ravel()
+            overlaps.append(overlap_pan_angle(ptz[2], ptz[0], map_ptz[2], map_ptz[0], im_width))
+        if verbose:
+            print('candidate key frame overlap: ', overlaps)
+        max_overlap = max(overlaps)
+        return max_overlap > threshold1 and max_overlap < threshold2

@@ -114,3 +114,31 @@ def test_world2_sharded_blocks_sum_to_full(tmp_path):
     full = np.concatenate([[cost], U.ravel(), V.ravel(), gc.ravel(), gl.ravel()])
     np.testing.assert_allclose(packed, full, rtol=1e-11, atol=1e-9 * np.abs(full).max())
     np.testing.assert_array_equal(np.load(tmp_path / "seqs.npy"), np.arange(11))
+
+
+def test_owned_landmark_ranges_tile_the_landmarks():
+    """Keyframe-sharded mode: every observed landmark has exactly one owner (the rank of its first keyframe), the owner observes
+    it, and with landmark ids numbered in first-seen order (image_process.py:609-667) the owned ids are contiguous ranges that
+    tile [0, n_landmark) in rank order.  Random ids: no contiguous ownership, the function says so."""
+    fb = synth.make_flat_ba(24, 3000, 30000, seed=5)
+    for world in (2, 3, 8):
+        prev = 0
+        for rank in range(world):
+            cam, lm, xy, kr = pdist.shard_by_keyframe(fb.cam_idx, fb.lm_idx, fb.obs_xy, fb.n_pose, rank, world)
+            own = pdist.owned_landmark_range(fb.cam_idx, fb.lm_idx, fb.n_landmark, kr)
+            assert own is not None
+            if own == (0, 0):                                               # a rank whose keyframes see nothing new
+                continue
+            assert own[0] == prev
+            prev = own[1]
+            ids = np.arange(*own)
+            assert np.isin(ids, np.unique(lm)).all()                        # the owner observes every landmark it owns
+            first = np.array([fb.cam_idx[fb.lm_idx == i].min() for i in ids[:: max(1, len(ids) // 50)]])
+            assert ((first >= kr[0]) & (first < kr[1])).all()
+        assert prev == int(fb.lm_idx.max()) + 1                              # (ids nobody observes come last)
+    perm = np.random.default_rng(0).permutation(fb.n_landmark)
+    kr = pdist.keyframe_ranges(fb.cam_idx, fb.n_pose, 2)[0]                 # owns some but not all landmarks (checked above)
+    lo, hi = pdist.owned_landmark_range(fb.cam_idx, fb.lm_idx, fb.n_landmark, kr)
+    assert 0 < hi - lo < int(fb.lm_idx.max()) + 1
+    assert pdist.owned_landmark_range(fb.cam_idx, perm[fb.lm_idx], fb.n_landmark, kr) is None
+    assert pdist.owned_landmark_range(fb.cam_idx, fb.lm_idx, fb.n_landmark, (fb.n_pose, fb.n_pose)) == (0, 0)

@@ -178,6 +178,56 @@ def test_random_forest_map_add_keyframe_exports(tmp_path):
     assert d["keypoint"].shape == (6, 2) and d["ptz"].ravel()[0] == pytest.approx(55.02)
 
 
+def test_random_forest_map_relocalize_and_good_keyframe(tmp_path):
+    """scene_map.py:246-298: relocalize(frame, init_ptz) exports the frame and returns the forest's flat pose (the forest is an
+    injected callable), good_keyframe applies the overlap rule to the poses stored in the exported keyframe files, add_keyframes
+    is the reference's no-op; PtzSlam.relocalize(enable_rf=True) hands the start pose as the second argument (ptz_slam.py:491)."""
+    import scipy.io as sio
+    from ptz_slam_b200.scene_map import RandomForestMap, Map
+    from ptz_slam_b200.bundle_adjustment import overlap_pan_angle
+    run, _ = _recording_ba(7)
+    seen = []
+
+    def forest(path, init_ptz):
+        seen.append((path, list(init_ptz), sio.loadmat(path)["keypoint"].shape))
+        return np.array([[51.0], [-7.5], [3100.0]])
+
+    m = RandomForestMap(keyframe_location=str(tmp_path), mat_path_file=str(tmp_path / "list.txt"), bundle_adjustment_fn=run,
+                        relocalizer=forest, relocalize_file=str(tmp_path / "lost.mat"))
+    cc, rot = np.zeros(3), np.eye(3)
+    for idx, pan in ((3, 50.0), (9, 58.0)):
+        kf = KeyFrame(None, idx, cc, rot, 640.0, 360.0, pan, -8.0, 3000.0)
+        kf.feature_pts, kf.feature_des = np.zeros((4, 2)), np.ones((4, 8))
+        m.add_keyframe(kf)
+    assert m.add_keyframes([1, 2]) is None and len(m.keyframe_list) == 2
+    lost = KeyFrame(None, -1, cc, rot, 640.0, 360.0, 49.0, -8.0, 3000.0)
+    lost.feature_pts, lost.feature_des = np.zeros((5, 2)), np.ones((5, 8))
+    ptz = m.relocalize(lost, [49.0, -8.0, 3000.0])
+    assert ptz.shape == (3,) and list(ptz) == [51.0, -7.5, 3100.0]
+    assert seen == [(str(tmp_path / "lost.mat"), [49.0, -8.0, 3000.0], (5, 2))]
+    stored = [sio.loadmat(p)["ptz"].ravel() for p in open(str(tmp_path / "list.txt")).read().split()]
+    for cand in ([52.0, -8.0, 3000.0], [70.0, -8.0, 3000.0], [58.0, -8.0, 3000.0]):
+        mx = max(overlap_pan_angle(cand[2], cand[0], q[2], q[0], 1280) for q in stored)
+        assert m.good_keyframe(np.array(cand), 5, 20) == (5 < mx < 20)
+    with pytest.raises(RuntimeError):
+        RandomForestMap(mat_path_file=str(tmp_path / "list.txt")).relocalize(lost, [0, 0, 1])
+    # the tracker passes the start pose on
+    from ptz_slam_b200.ptz_slam import PtzSlam
+    from ptz_slam_b200.ptz_camera import PTZCamera
+
+    class FE:
+        @staticmethod
+        def detect_keypoints(img, n):
+            return np.zeros((6, 2)), np.ones((6, 8))
+
+    slam = PtzSlam.__new__(PtzSlam)
+    slam.front_end, slam.rf_map, slam.keyframe_map, slam.tracking_lost = FE, m, Map('sift'), True
+    cam = PTZCamera((640.0, 360.0), cc, rot)
+    cam.set_ptz([49.0, -8.0, 3000.0])
+    out = slam.relocalize(None, cam, enable_rf=True)
+    assert list(out.get_ptz()) == [51.0, -7.5, 3100.0] and seen[-1][1] == [49.0, -8.0, 3000.0] and not slam.tracking_lost
+
+
 def test_map_save_keyframes_to_mat(tmp_path):
     import scipy.io as sio
     m = _map()

@@ -163,3 +163,28 @@ def test_trf_restatement_converges_to_reference_solution():
     assert e2[:3 * (N - 1)].reshape(-1, 3)[:, :2].max() < tol_deg and e2[3 * (N - 1):].max() < tol_deg
     assert e2[:3 * (N - 1)].reshape(-1, 3)[:, 2].max() < 1e-3
     assert res2["nfev"] == int(d["nfev_asis"])
+
+
+def test_sparse_lm_iteration_equals_dense_damped_normal_equations():
+    """oracle.ba_lm_iteration_sparse (bench.py's CPU baseline of one LM iteration: Schur complement over the landmarks) against the
+    dense solve of (J^T J + alpha D^2) d = -J^T r with D = column norms of J, on a problem small enough to form J densely; the
+    C-port evaluators give the same step."""
+    from oracle import c_port
+    fb = synth.make_flat_ba(10, 300, 1800, seed=4)
+    x0, ref, alpha = fb.x0(), fb.ptz_init[0], 1e-3
+    args = (x0, fb.n_pose, ref, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V, alpha)
+    step, pred, trial = O.ba_lm_iteration_sparse(*args)
+    poses, rays = O.ba_unpack(x0, fb.n_pose, ref)
+    J = O.ba_jacobian_sparse(poses, rays, fb.cam_idx, fb.lm_idx).toarray()
+    r = O.ba_residual_flat(poses, rays, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V).ravel()
+    D2 = (J * J).sum(0)
+    D2[D2 == 0] = 1.0
+    d = np.linalg.solve(J.T @ J + alpha * np.diag(D2), -J.T @ r)
+    assert np.abs(step - d).max() < 1e-10 * np.abs(d).max()
+    Jd = J @ d
+    assert abs(pred + (r @ Jd + 0.5 * Jd @ Jd)) < 1e-10 * abs(pred)
+    pt, rt = O.ba_unpack(x0 + d, fb.n_pose, ref)
+    rr = O.ba_residual_flat(pt, rt, fb.cam_idx, fb.lm_idx, fb.obs_xy, synth.PP_U, synth.PP_V)
+    assert abs(trial - 0.5 * np.sum(rr * rr)) < 1e-9 * trial and trial < 0.5 * r @ r
+    s2, p2, t2 = O.ba_lm_iteration_sparse(*args, fused=c_port.ba_fused, residual=c_port.ba_residual)
+    assert np.abs(s2 - step).max() < 1e-10 * np.abs(step).max() and abs(p2 - pred) < 1e-10 * abs(pred) and abs(t2 - trial) < 1e-9 * trial
