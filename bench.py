@@ -300,6 +300,29 @@ def pin_to_gpu_numa_node(local):
         return "not pinned: %s" % (str(e).splitlines()[0] if str(e) else type(e).__name__)
 
 
+def clock_ramp(step, seconds, world, sync, device, block=64):
+    """Runs step(0), step(1), ... for about `seconds` in blocks of `block`; returns how many ran.  With world > 1 a step
+    holds a collective, so every rank has to run the SAME number of steps: rank 0's clock decides after each block and the
+    verdict is broadcast (ranks that each watched their own clock left the loop after different counts and dead-locked
+    the 4-GPU run of round 2).  `sync` waits for the enqueued steps (torch.cuda.synchronize on the GPU)."""
+    import torch
+    t_end = time.perf_counter() + seconds
+    i = 0
+    go = torch.ones(1, dtype=torch.int32, device=device)
+    while True:
+        for _ in range(block):
+            step(i); i += 1
+        sync()
+        if world > 1:
+            import torch.distributed as dist
+            go.fill_(1 if time.perf_counter() < t_end else 0)
+            dist.broadcast(go, src=0)
+            if int(go.item()) == 0:
+                return i
+        elif time.perf_counter() >= t_end:
+            return i
+
+
 # -------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------------
@@ -374,23 +397,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # clock ramp (untimed, in addition to the W warm-up steps): ~0.3 s of passes, in blocks of 64.  With N > 1 a step holds a
-    # collective, so every rank has to run the SAME number of steps: rank 0's clock decides after each block and the verdict
-    # is shared (ranks that each watched their own clock left the loop after different counts and dead-locked at N = 4).
-    t_end = time.perf_counter() + args.ramp
-    i = 0
-    go = torch.ones(1, dtype=torch.int32, device="cuda")
-    while True:
-        for _ in range(64):
-            device_step(i); i += 1
-        torch.cuda.synchronize()
-        if world > 1:
-            go.fill_(1 if time.perf_counter() < t_end else 0)
-            dist.broadcast(go, src=0)
-            if int(go.item()) == 0:
-                break
-        elif time.perf_counter() >= t_end:
-            break
+    # clock ramp (untimed, in addition to the W warm-up steps): ~0.3 s of passes; every rank runs the same number of them
+    clock_ramp(device_step, args.ramp, world, torch.cuda.synchronize, "cuda")
     for i in range(args.warmup):
         device_step(i)
     barrier()
@@ -688,6 +696,25 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def start_watchdog(seconds):
+    """A run that has not finished after `seconds` is a hang (a collective some rank never entered, a wedged device): say so on
+    stderr and end THIS process with exit code 124, so that torchrun tears the other ranks down and the box is handed back
+    instead of sitting in a collective until somebody else's time limit expires.  0 disables it."""
+    if seconds <= 0:
+        return None
+
+    def bark():
+        sys.stderr.write("bench.py: watchdog: rank %s still running after %d s - aborting the process (exit code 124)\n" %
+                         (os.environ.get("RANK", "0"), seconds))
+        sys.stderr.flush()
+        os._exit(124)
+
+    t = threading.Timer(seconds, bark)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -704,7 +731,9 @@ def main():
     ap.add_argument("--ekf-rays", type=int, default=2000)
     ap.add_argument("--ekf-frames", type=int, default=8)
     ap.add_argument("--ramp", type=float, default=0.3, help="seconds of untimed passes before warm-up (clock ramp)")
+    ap.add_argument("--watchdog", type=float, default=1500.0, help="abort the process after this many seconds (0 = never); a hang must not hold the box")
     args = ap.parse_args()
+    start_watchdog(args.watchdog)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

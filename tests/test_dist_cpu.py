@@ -142,3 +142,33 @@ def test_owned_landmark_ranges_tile_the_landmarks():
     assert 0 < hi - lo < int(fb.lm_idx.max()) + 1
     assert pdist.owned_landmark_range(fb.cam_idx, perm[fb.lm_idx], fb.n_landmark, kr) is None
     assert pdist.owned_landmark_range(fb.cam_idx, fb.lm_idx, fb.n_landmark, (fb.n_pose, fb.n_pose)) == (0, 0)
+
+
+def _worker_ramp(rank, world, port, out_dir):
+    """bench.clock_ramp with a collective inside every step and ranks of very different speed."""
+    import time
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    acc = torch.zeros(1, dtype=torch.float64)
+
+    def step(i):
+        if rank == 1 and i % 8 == 0:
+            time.sleep(0.004)            # a slow rank: its own clock would end the ramp after far fewer steps
+        t = torch.ones(1, dtype=torch.float64)
+        dist.all_reduce(t)               # the collective a sharded pass ends with
+        acc.add_(t)
+
+    n = bench.clock_ramp(step, 0.15, world, lambda: None, "cpu", block=16)
+    np.save(os.path.join(out_dir, "ramp_%d.npy" % rank), np.array([n, acc.item()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_clock_ramp_runs_the_same_number_of_steps_on_every_rank(tmp_path):
+    world = 2
+    mp.spawn(_worker_ramp, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "ramp_0.npy"), np.load(tmp_path / "ramp_1.npy")
+    assert r0[0] == r1[0] and r0[0] >= 16 and r0[0] % 16 == 0
+    assert r0[1] == r1[1] == world * r0[0]
