@@ -172,6 +172,27 @@ def fp64_peak():
         return {"dfma_tflops": 34.0, "dmma_tflops": 37.0, "source": "fallback (round-2 measurement)"}
 
 
+def verbatim_reference_record():
+    """The UNMODIFIED reference timed on host cores (scripts/time_verbatim_reference.py -> profiles/r2_verbatim_reference_cpu.json).
+    /root/reference does not travel to the GPU box, so these figures come from the authoring container and are quoted, not
+    re-measured: a reported baseline beside `cpu_baseline` (which IS measured on this box), never an input of any ratio."""
+    p = os.path.join(ROOT, "profiles", "r2_verbatim_reference_cpu.json")
+    try:
+        j = json.load(open(p))
+        res = max(j["compute_residual"], key=lambda r: r["observations"])
+        ls = max(j["least_squares"], key=lambda r: r["observations"])
+        ekf = {str(r["rays"]): r["verbatim_reference"]["frames_per_s"] for r in j["ekf_update"]}
+        return {"where": "authoring container, %d host CPUs, NOT this box (%s)" % (j["host"]["cpus"], "profiles/r2_verbatim_reference_cpu.json"),
+                "compute_residual_obs_per_s": res["verbatim_reference"]["obs_per_s"],
+                "compute_residual_sample": "%d keyframes x %d landmarks x %d observations, one core (pure-Python loops)" % (res["keyframes"], res["landmarks"], res["observations"]),
+                "least_squares_s_per_lm_iteration": ls["verbatim_reference"]["s_per_lm_iteration"],
+                "least_squares_sample": "%d keyframes x %d landmarks x %d observations, %d parameters: %.1f s, nfev %d" %
+                                        (ls["keyframes"], ls["landmarks"], ls["observations"], ls["parameters"], ls["verbatim_reference"]["s"], ls["verbatim_reference"]["nfev"]),
+                "ekf_update_frames_per_s_by_rays": ekf}
+    except Exception:
+        return None
+
+
 def ekf_flops(n_matched, lu_route):
     """Algorithmic FP64 flops of one EKF update with n matched rays (m = 2n rows, s = 3 + 2n state columns), BASELINE.md section 4:
     Cholesky route m^3/3 + m^2 (s+1) + 2 n^2 m (+ 2 m s); pivoted-LU route 2 m^3/3 + 2 m^2 (s+1) + 2 n^2 m (+ 2 m s)."""
@@ -679,6 +700,9 @@ def run_ours(args):
                                (" + exchange (k_pack_shared, ncclAllReduce, k_unpack_shared)" if world > 1 else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        vr = verbatim_reference_record()
+        if vr:
+            line["verbatim_reference_cpu"] = vr
         if parity:
             line["parity"] = parity
         if lm:
