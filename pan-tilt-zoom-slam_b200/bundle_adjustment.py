@@ -256,10 +256,15 @@ def bundle_adjustment(images, image_indices, feature_method, initial_ptzs, cente
     from .key_frame import KeyFrame
     keyframes = []
     for i in range(N):
-        pairs = set()
+        # (local, global) pairs with image i as source, then as destination, de-duplicated through ONE set built from the
+        # whole list: the iteration order of a set depends on how it was filled, and it is the order of landmark_index /
+        # feature_pts in the keyframe (bundle_adjustment.py:222-241)
+        pairs = []
         for j in range(N):
-            pairs.update(zip(src_pt_index[i][j], landmark_index[i][j]))
-            pairs.update(zip(dst_pt_index[j][i], landmark_index[j][i]))
+            pairs.extend(zip(src_pt_index[i][j], landmark_index[i][j]))
+        for j in range(N):
+            pairs.extend(zip(dst_pt_index[j][i], landmark_index[j][i]))
+        pairs = set((int(a), int(b)) for a, b in pairs)
         local_index = [p[0] for p in pairs]
         global_index = [p[1] for p in pairs]
         key_frame = KeyFrame(images[i], image_indices[i], center, rotation, u, v, all_poses[i, 0], all_poses[i, 1], all_poses[i, 2])

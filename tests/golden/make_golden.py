@@ -18,6 +18,8 @@ Goldens (reference function -> file):
   RandomForestMap.bundle_adjustment_processing (BA call replaced by a recorder)   -> sliding_window.npz
   relocalization._compute_residual + its least_squares call (as-is and tight)     -> relocalization.npz
   PtzSlam.init_system + tracking over a sequence (OpenCV calls replaced)          -> tracking.npz
+  config 1 end to end: 150-frame court sequence, tracking + add_keyframe ->
+  Map.add_keyframe_with_ba -> bundle_adjustment -> least_squares (OpenCV replaced) -> cfg1_court.npz
   util.add_gauss / add_outliers / uniform_point_sample_on_field / compute_error_data  -> util_noise.npz
   PTZCamera matrices, project_3d_point(s), back_project_to_3d_point(s)            -> camera_3d.npz
 """
@@ -670,6 +672,114 @@ def gen_util_noise():
     print("util_noise: clamped %d, outliers moved %d" % (((g == 0) | (g[:, :1] == W - 1)).sum(), (np.abs(o - pts) > 20).any(1).sum()))
 
 
+def court_rays_from_reference(n_points):
+    """The reference's court landmarks: DataSynthesize.generate_points (synthesized_court_sequence/synthesize_basketball.py:34-59,
+    random.seed(1) inside) executed UNMODIFIED - only the class definition is compiled from the file, because the module body
+    loads .mat files that are not shipped - and TransFunction.from_3dpoint_to_ray (transformation.py) for the rays."""
+    import ast
+    import random
+    import cv2 as cv
+    path = os.path.join(ref_import.REFERENCE_DIR, "synthesized_court_sequence", "synthesize_basketball.py")
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DataSynthesize"][0]
+    ns = {"np": np, "random": random}
+    exec(compile(ast.Module([cls], []), path, "exec"), ns)
+    pts = ns["DataSynthesize"].generate_points(n_points).astype(np.float64)
+    R = np.zeros((3, 3))
+    cv.Rodrigues(BASE_ROT, R)
+    rays = np.array([ref.TransFunction.from_3dpoint_to_ray(CC, p, R) for p in pts])
+    return pts, rays
+
+
+def gen_cfg1():
+    """Config 1 end to end with the UNMODIFIED reference classes: the loop of experiment.py:22-46 (init_system, add_keyframe,
+    per frame tracking and - when the new-keyframe rule fires - add_keyframe -> Map.add_keyframe_with_ba -> bundle_adjustment
+    -> build_matching_graph -> least_squares) over a 150-frame synthesized basketball-court sequence.  Only the OpenCV calls
+    are replaced (tests/court_sequence.py), plus the debug image dump of bundle_adjustment.py:153-162."""
+    import random
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from court_sequence import CourtSequence
+    import ptz_slam as ref_ptz_slam
+    import image_process as ref_ip
+    import bundle_adjustment as ref_ba
+    n_points, n_frames, seed = 1000, 150, 1001
+    pts3d, court_rays = court_rays_from_reference(n_points)
+    fe = CourtSequence(court_rays, n_frames, seed)
+    out = {"court_points": pts3d, "court_rays": court_rays, "n_frames": np.array(n_frames), "seed": np.array(seed)}
+    saved = (ref_ptz_slam.detect_compute_sift_array, ref_ptz_slam.matching_and_ransac, ref_ptz_slam.np,
+             ref_ip.detect_compute_sift, ref_ip.match_sift_features, ref_ba.draw_matches, ref_ba.cv)
+    ref_ptz_slam.detect_compute_sift_array = lambda img, n, norm=True: fe.detect_keypoints(img, n)
+    ref_ptz_slam.matching_and_ransac = fe.matching_and_ransac
+    ref_ptz_slam.np = _IntIndexNp()
+    ref_ip.detect_compute_sift = lambda im, nf, verbose=False: fe.detect_sift(im)
+    ref_ip.match_sift_features = lambda kp1, des1, kp2, des2, verbose=False: fe.match_sift(kp1, des1, kp2, des2)
+    ref_ba.draw_matches = lambda *a, **k: None
+    ref_ba.cv = types.SimpleNamespace(imwrite=lambda *a, **k: True)
+    random.seed(seed)
+    ba_events = []
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            slam = ref.PtzSlam()
+            cam0_ptz = fe.gt[0] + np.array([0.02, -0.01, 3.0])
+            cam0 = make_camera(cam0_ptz)
+            slam.init_system(fe.image(0), cam0, fe.bounding_box)
+            slam.add_keyframe(fe.image(0), cam0, 0, enable_rf=False)
+            out["cam0"] = cam0_ptz
+            out["rays_0"] = slam.rays.copy()
+            for k in range(1, n_frames):
+                img = fe.image(k)
+                slam.tracking(img, 80, fe.bounding_box)
+                flags = [slam.new_keyframe, slam.tracking_lost, slam.bad_tracking_cnt, len(slam.cameras)]
+                assert not slam.tracking_lost, "the cfg1 sequence is meant to track throughout (frame %d)" % k
+                if slam.new_keyframe:
+                    slam.add_keyframe(img, slam.current_camera, k, enable_rf=False)
+                    e = len(ba_events)
+                    ba_events.append(k)
+                    kfs = slam.keyframe_map.keyframe_list
+                    out["ba%d_kf_ptz" % e] = np.array([[kf.pan, kf.tilt, kf.f] for kf in kfs])
+                    out["ba%d_kf_index" % e] = np.array([kf.img_index for kf in kfs], np.int64)
+                    out["ba%d_global_ray" % e] = np.asarray(slam.keyframe_map.global_ray, np.float64)
+                    for i, kf in enumerate(kfs):
+                        out["ba%d_lm_%d" % (e, i)] = np.asarray(kf.landmark_index, np.int64)
+                        out["ba%d_pts_%d" % (e, i)] = np.array([p.pt for p in kf.feature_pts], np.float64).reshape(-1, 2)
+                out["ptz_%d" % k] = slam.current_camera.get_ptz()
+                out["vel_%d" % k] = np.array(slam.velocity)
+                out["flags_%d" % k] = np.array(flags, np.int64)
+                out["prev_idx_%d" % k] = np.asarray(slam.previous_keypoints_index, np.float64)
+                out["n_rays_%d" % k] = np.array(len(slam.rays))
+                if k in (50, 100):
+                    # full state of the reference: the test re-starts from it, because the EKF recursion amplifies rounding
+                    # differences by ~10x every 10 frames (DESIGN.md section 2 finding 4) - free-running segments stay short
+                    out["ck%d_rays" % k], out["ck%d_cov" % k] = slam.rays.copy(), slam.state_cov.copy()
+                    out["ck%d_des" % k] = np.asarray(slam.des)
+                    out["ck%d_prev_kp" % k] = np.asarray(slam.previous_keypoints, np.float64)
+                    out["ck%d_prev_idx" % k] = np.asarray(slam.previous_keypoints_index, np.float64)
+                    out["ck%d_vel" % k], out["ck%d_ptz" % k] = np.array(slam.velocity), slam.cameras[-1].get_ptz()
+                    out["ck%d_counts" % k] = np.array([slam.bad_tracking_cnt, len(slam.cameras)], np.int64)
+                    kfs = slam.keyframe_map.keyframe_list
+                    out["ck%d_kf_ptz" % k] = np.array([[kf.pan, kf.tilt, kf.f] for kf in kfs])
+                    out["ck%d_kf_index" % k] = np.array([kf.img_index for kf in kfs], np.int64)
+                if k % 25 == 0 or k == n_frames - 1:
+                    out["rays_%d" % k] = slam.rays.copy()
+                    out["prev_kp_%d" % k] = np.asarray(slam.previous_keypoints, np.float64)
+                    out["cov_diag_%d" % k] = np.diag(slam.state_cov).copy()
+                    out["cov_probe_%d" % k] = slam.state_cov @ cov_probe_vector(slam.state_cov.shape[0])
+    finally:
+        (ref_ptz_slam.detect_compute_sift_array, ref_ptz_slam.matching_and_ransac, ref_ptz_slam.np,
+         ref_ip.detect_compute_sift, ref_ip.match_sift_features, ref_ba.draw_matches, ref_ba.cv) = saved
+    out["ba_frames"] = np.array(ba_events, np.int64)
+    out["checkpoints"] = np.array([50, 100], np.int64)
+    err = np.array([out["ptz_%d" % k] - fe.gt[k] for k in range(1, n_frames)])
+    print("cfg1: %d frames, rays %d -> %d, keyframe BA at frames %s (keyframes after the last: %d, landmarks %d)" %
+          (n_frames, len(out["rays_0"]), int(out["n_rays_%d" % (n_frames - 1)]), ba_events,
+           len(out["ba%d_kf_ptz" % (len(ba_events) - 1)]) if ba_events else 1,
+           len(out["ba%d_global_ray" % (len(ba_events) - 1)]) if ba_events else 0))
+    print("   pose error vs ground truth: mean |d| %s, max |d| %s" % (np.abs(err).mean(0), np.abs(err).max(0)))
+    np.savez_compressed(os.path.join(OUT, "cfg1_court.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                           # regenerate only the named goldens: make_golden.py ray_bookkeeping ...
         for name in sys.argv[1:]:
@@ -681,6 +791,7 @@ if __name__ == "__main__":
     gen_sliding_window()
     gen_relocalization()
     gen_tracking()
+    gen_cfg1()
     gen_util_noise()
     gen_camera_3d()
     gen_keyframe_map()
