@@ -1,8 +1,8 @@
-"""CPU check of the ALGORITHM behind the opt-in keyframe-pair-major Schur formation (csrc/ba_solver.cu: k_pl_emit, k_schur_pairlist):
+"""CPU check of the ALGORITHM behind the keyframe-pair-major Schur formation, the default route (csrc/ba_solver.cu: k_pl_emit, k_schur_pairlist):
 listing every (observation, observation) pair of every landmark by keyframe pair - weight 2 for distinct positions of the same
 keyframe, lower triangle only on diagonal blocks - and summing Y_max W_min^T per key reproduces the dense Schur complement
 S = U - W (V + alpha I)^-1 W^T computed from the oracle's analytic Jacobian blocks, duplicates included.  The CUDA kernel itself
-is exercised by the GPU parity tests when PTZBA_SCHUR_PAIRLIST=1."""
+is exercised by every GPU solver test (and against the per-landmark route in tests/test_gpu_ba.py::test_schur_per_landmark_route_equals_pair_list)."""
 import numpy as np
 
 from oracle import ptz_oracle as O
