@@ -38,10 +38,20 @@ def court_trajectory(n_frames, seed):
     return gt
 
 
+def relocalization_box():
+    """The fixed mask relocalization.py:103-104 / :50-51 applies to detected keypoints (the broadcast's score banner)."""
+    box = np.ones([H, W])
+    box[13:51, 303:976] = 0
+    return box
+
+
 class CourtSequence:
-    def __init__(self, court_rays, n_frames, seed, obs_noise=0.5):
+    def __init__(self, court_rays, n_frames, seed, obs_noise=0.5, blackout=None):
+        """`blackout = (a, b)`: the optical flow loses 70 % of its matches on frames a <= k < b, which walks bad_tracking_cnt to
+        tracking_lost (ptz_slam.py:404-411) and sends the caller through relocalize + init_system."""
         self.court_rays = np.asarray(court_rays, dtype=np.float64)
         self.n_frames, self.seed, self.obs_noise = int(n_frames), int(seed), float(obs_noise)
+        self.blackout = (self.n_frames, self.n_frames) if blackout is None else (int(blackout[0]), int(blackout[1]))
         self.gt = court_trajectory(self.n_frames, self.seed)
         self.bounding_box = np.ones((H, W), np.uint8)
         self.bounding_box[300:520, 500:640] = 0                         # a "player"
@@ -87,7 +97,7 @@ class CourtSequence:
         x, y, _ = O.project_rays_vec(g2[0], g2[1], g2[2], U, V, rays)
         cur = np.stack([x, y], 1) + rng.normal(0, 0.3, (len(kp1), 2))
         inside = (cur[:, 0] > 1) & (cur[:, 0] < W - 1) & (cur[:, 1] > 1) & (cur[:, 1] < H - 1)
-        flow_ok = inside & (rng.uniform(size=len(kp1)) > 0.03)
+        flow_ok = inside & (rng.uniform(size=len(kp1)) > (0.7 if self.blackout[0] <= k2 < self.blackout[1] else 0.03))
         local = np.nonzero(flow_ok)[0]
         ransac_in = rng.uniform(size=len(local)) > 0.04
         return cur[local][ransac_in], kp1_index[local][ransac_in], kp1_index[local][~ransac_in]
@@ -107,6 +117,29 @@ class CourtSequence:
         id1, id2 = np.asarray(des1)[:, 0].astype(np.int64), np.asarray(des2)[:, 0].astype(np.int64)
         common, i1, i2 = np.intersect1d(id1, id2, return_indices=True)
         return None, i1.tolist(), None, i2.tolist()
+
+    # -- the two OpenCV calls of relocalization.relocalization_camera -------------------------------------------------------
+    def detect_array(self, img, n, *_, **__):
+        """detect_compute_sift_array(img, n, norm=False) (relocalization.py:101, :126, :54-55): keypoints [m,2] and descriptors."""
+        ids, pts = self._detect(self.frame_of(img))
+        ids, pts = ids[:n], pts[:n]
+        return pts, ids.astype(np.float32).reshape(-1, 1)
+
+    def detect(self, img, n):
+        """The product's hook: detection + the relocaliser's fixed banner mask (relocalization.py:103-108)."""
+        from ptz_slam_b200.ptz_slam import keypoints_masking
+        pts, des = self.detect_array(img, n)
+        keep = keypoints_masking(pts, relocalization_box())
+        return pts[keep], des[keep]
+
+    @staticmethod
+    def match(kp1, des1, kp2, des2, *_, **__):
+        """match_sift_features(..., pts_array=True): (pt1, index1, pt2, index2) with matched pixel arrays."""
+        id1, id2 = np.asarray(des1)[:, 0].astype(np.int64), np.asarray(des2)[:, 0].astype(np.int64)
+        common, i1, i2 = np.intersect1d(id1, id2, return_indices=True)
+        if len(common) == 0:
+            return None, None, None, None
+        return np.asarray(kp1)[i1], i1.tolist(), np.asarray(kp2)[i2], i2.tolist()
 
     def build_matching_graph(self, images, image_match_mask, feature_method, verbose):
         """The product's front-end hook (scene_map.Map / bundle_adjustment): the reference's build_matching_graph with the

@@ -20,6 +20,8 @@ Goldens (reference function -> file):
   PtzSlam.init_system + tracking over a sequence (OpenCV calls replaced)          -> tracking.npz
   config 1 end to end: 150-frame court sequence, tracking + add_keyframe ->
   Map.add_keyframe_with_ba -> bundle_adjustment -> least_squares (OpenCV replaced) -> cfg1_court.npz
+  the same loop with a flow blackout: tracking_lost -> relocalize -> relocalization_camera
+  -> init_system                                                                  -> cfg1_relocalize.npz
   util.add_gauss / add_outliers / uniform_point_sample_on_field / compute_error_data  -> util_noise.npz
   PTZCamera matrices, project_3d_point(s), back_project_to_3d_point(s)            -> camera_3d.npz
 """
@@ -691,11 +693,12 @@ def court_rays_from_reference(n_points):
     return pts, rays
 
 
-def gen_cfg1():
-    """Config 1 end to end with the UNMODIFIED reference classes: the loop of experiment.py:22-46 (init_system, add_keyframe,
-    per frame tracking and - when the new-keyframe rule fires - add_keyframe -> Map.add_keyframe_with_ba -> bundle_adjustment
-    -> build_matching_graph -> least_squares) over a 150-frame synthesized basketball-court sequence.  Only the OpenCV calls
-    are replaced (tests/court_sequence.py), plus the debug image dump of bundle_adjustment.py:153-162."""
+def _reference_court_run(out_name, n_frames, blackout, checkpoints):
+    """The loop of experiment.py:22-46 with the UNMODIFIED reference classes over the synthesized court sequence: init_system,
+    add_keyframe, per frame `tracking`, then - as the reference's driver does - relocalize + init_system when tracking is lost,
+    add_keyframe -> Map.add_keyframe_with_ba -> bundle_adjustment -> build_matching_graph -> least_squares when the new-keyframe
+    rule fires.  Only the OpenCV calls are replaced (tests/court_sequence.py), plus the debug image dumps of
+    bundle_adjustment.py:153-162 and relocalization.py:177-178."""
     import random
     import types
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -703,21 +706,27 @@ def gen_cfg1():
     import ptz_slam as ref_ptz_slam
     import image_process as ref_ip
     import bundle_adjustment as ref_ba
-    n_points, n_frames, seed = 1000, 150, 1001
+    import relocalization as ref_reloc
+    n_points, seed = 1000, 1001
     pts3d, court_rays = court_rays_from_reference(n_points)
-    fe = CourtSequence(court_rays, n_frames, seed)
-    out = {"court_points": pts3d, "court_rays": court_rays, "n_frames": np.array(n_frames), "seed": np.array(seed)}
-    saved = (ref_ptz_slam.detect_compute_sift_array, ref_ptz_slam.matching_and_ransac, ref_ptz_slam.np,
-             ref_ip.detect_compute_sift, ref_ip.match_sift_features, ref_ba.draw_matches, ref_ba.cv)
-    ref_ptz_slam.detect_compute_sift_array = lambda img, n, norm=True: fe.detect_keypoints(img, n)
-    ref_ptz_slam.matching_and_ransac = fe.matching_and_ransac
-    ref_ptz_slam.np = _IntIndexNp()
-    ref_ip.detect_compute_sift = lambda im, nf, verbose=False: fe.detect_sift(im)
-    ref_ip.match_sift_features = lambda kp1, des1, kp2, des2, verbose=False: fe.match_sift(kp1, des1, kp2, des2)
-    ref_ba.draw_matches = lambda *a, **k: None
-    ref_ba.cv = types.SimpleNamespace(imwrite=lambda *a, **k: True)
+    fe = CourtSequence(court_rays, n_frames, seed, blackout=blackout)
+    out = {"court_points": pts3d, "court_rays": court_rays, "n_frames": np.array(n_frames), "seed": np.array(seed),
+           "blackout": np.array(fe.blackout, np.int64)}
+    patched = [(ref_ptz_slam, "detect_compute_sift_array", lambda img, n, norm=True: fe.detect_keypoints(img, n)),
+               (ref_ptz_slam, "matching_and_ransac", fe.matching_and_ransac),
+               (ref_ptz_slam, "np", _IntIndexNp()),
+               (ref_ip, "detect_compute_sift", lambda im, nf, verbose=False: fe.detect_sift(im)),
+               (ref_ip, "match_sift_features", lambda kp1, des1, kp2, des2, verbose=False: fe.match_sift(kp1, des1, kp2, des2)),
+               (ref_ba, "draw_matches", lambda *a, **k: None),
+               (ref_ba, "cv", types.SimpleNamespace(imwrite=lambda *a, **k: True)),
+               (ref_reloc, "detect_compute_sift_array", lambda img, n, norm=False: fe.detect_array(img, n)),
+               (ref_reloc, "match_sift_features", lambda kp1, des1, kp2, des2, pts_array=True: fe.match(kp1, des1, kp2, des2)),
+               (ref_reloc, "cv", types.SimpleNamespace(imwrite=lambda *a, **k: True))]
+    saved = [(m, name, getattr(m, name)) for m, name, _ in patched]
+    for m, name, fn in patched:
+        setattr(m, name, fn)
     random.seed(seed)
-    ba_events = []
+    ba_events, reloc_events = [], []
     try:
         with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -732,8 +741,13 @@ def gen_cfg1():
                 img = fe.image(k)
                 slam.tracking(img, 80, fe.bounding_box)
                 flags = [slam.new_keyframe, slam.tracking_lost, slam.bad_tracking_cnt, len(slam.cameras)]
-                assert not slam.tracking_lost, "the cfg1 sequence is meant to track throughout (frame %d)" % k
-                if slam.new_keyframe:
+                if slam.tracking_lost:                                                  # experiment.py:39-43
+                    out["lost_ptz_%d" % k] = slam.current_camera.get_ptz()
+                    relocalized_camera = slam.relocalize(img, slam.current_camera, enable_rf=False)
+                    out["reloc_ptz_%d" % k] = relocalized_camera.get_ptz()
+                    slam.init_system(img, relocalized_camera, fe.bounding_box)
+                    reloc_events.append(k)
+                elif slam.new_keyframe:                                                 # :45-46
                     slam.add_keyframe(img, slam.current_camera, k, enable_rf=False)
                     e = len(ba_events)
                     ba_events.append(k)
@@ -749,7 +763,7 @@ def gen_cfg1():
                 out["flags_%d" % k] = np.array(flags, np.int64)
                 out["prev_idx_%d" % k] = np.asarray(slam.previous_keypoints_index, np.float64)
                 out["n_rays_%d" % k] = np.array(len(slam.rays))
-                if k in (50, 100):
+                if k in checkpoints:
                     # full state of the reference: the test re-starts from it, because the EKF recursion amplifies rounding
                     # differences by ~10x every 10 frames (DESIGN.md section 2 finding 4) - free-running segments stay short
                     out["ck%d_rays" % k], out["ck%d_cov" % k] = slam.rays.copy(), slam.state_cov.copy()
@@ -767,17 +781,31 @@ def gen_cfg1():
                     out["cov_diag_%d" % k] = np.diag(slam.state_cov).copy()
                     out["cov_probe_%d" % k] = slam.state_cov @ cov_probe_vector(slam.state_cov.shape[0])
     finally:
-        (ref_ptz_slam.detect_compute_sift_array, ref_ptz_slam.matching_and_ransac, ref_ptz_slam.np,
-         ref_ip.detect_compute_sift, ref_ip.match_sift_features, ref_ba.draw_matches, ref_ba.cv) = saved
+        for m, name, fn in saved:
+            setattr(m, name, fn)
     out["ba_frames"] = np.array(ba_events, np.int64)
-    out["checkpoints"] = np.array([50, 100], np.int64)
+    out["reloc_frames"] = np.array(reloc_events, np.int64)
+    out["checkpoints"] = np.array(sorted(checkpoints), np.int64)
     err = np.array([out["ptz_%d" % k] - fe.gt[k] for k in range(1, n_frames)])
-    print("cfg1: %d frames, rays %d -> %d, keyframe BA at frames %s (keyframes after the last: %d, landmarks %d)" %
-          (n_frames, len(out["rays_0"]), int(out["n_rays_%d" % (n_frames - 1)]), ba_events,
+    print("%s: %d frames, rays %d -> %d, keyframe BA at frames %s (keyframes after the last: %d, landmarks %d), relocalised at %s" %
+          (out_name, n_frames, len(out["rays_0"]), int(out["n_rays_%d" % (n_frames - 1)]), ba_events,
            len(out["ba%d_kf_ptz" % (len(ba_events) - 1)]) if ba_events else 1,
-           len(out["ba%d_global_ray" % (len(ba_events) - 1)]) if ba_events else 0))
+           len(out["ba%d_global_ray" % (len(ba_events) - 1)]) if ba_events else 0, reloc_events))
+    for k in reloc_events:
+        print("   frame %d: lost pose error %s -> relocalised pose error %s" % (k, out["lost_ptz_%d" % k] - fe.gt[k], out["reloc_ptz_%d" % k] - fe.gt[k]))
     print("   pose error vs ground truth: mean |d| %s, max |d| %s" % (np.abs(err).mean(0), np.abs(err).max(0)))
-    np.savez_compressed(os.path.join(OUT, "cfg1_court.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, out_name), **out)
+
+
+def gen_cfg1():
+    """Config 1 end to end: 150 frames, the tracker never loses the sequence; keyframe bundle adjustments of 2, 3, 4 and 5 keyframes."""
+    _reference_court_run("cfg1_court.npz", 150, None, (50, 100))
+
+
+def gen_cfg1_relocalize():
+    """The same sequence with an optical-flow blackout on frames 55-58: tracking_lost at frame 58 -> PtzSlam.relocalize ->
+    relocalization_camera (nearest keyframe by match count, its pixels -> rays, 3-parameter least_squares) -> init_system."""
+    _reference_court_run("cfg1_relocalize.npz", 90, (55, 59), ())
 
 
 if __name__ == "__main__":
@@ -792,6 +820,7 @@ if __name__ == "__main__":
     gen_relocalization()
     gen_tracking()
     gen_cfg1()
+    gen_cfg1_relocalize()
     gen_util_noise()
     gen_camera_3d()
     gen_keyframe_map()

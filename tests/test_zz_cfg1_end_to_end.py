@@ -27,12 +27,14 @@ import pytest
 from oracle import ptz_oracle as O
 import ptz_slam_b200  # noqa: F401
 from ptz_slam_b200 import bundle_adjustment as BA
+from ptz_slam_b200 import relocalization as R
 from ptz_slam_b200 import synth
 from ptz_slam_b200.ptz_slam import PtzSlam
 from court_sequence import CourtSequence, CC, BASE_ROT, U, V
 from test_tracking_loop import OracleCamera, oracle_ekf_update, cov_probe_vector
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_court.npz"))
+G_LOST = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_relocalize.npz"))
 TOL_RAD_DEG = np.degrees(1e-6)          # BASELINE.json: converged camera / ray parameters within 1e-6 rad, 1e-3 px focal
 
 
@@ -80,7 +82,7 @@ def _rotation():
     return Rotation.from_rotvec(BASE_ROT).as_matrix()
 
 
-def _restore(slam, fe, k, make_camera):
+def _restore(G, slam, fe, k, make_camera):
     """Put `slam` into the reference's state after frame k (golden checkpoint)."""
     from ptz_slam_b200.key_frame import KeyFrame
     c = "ck%d_" % k
@@ -99,7 +101,7 @@ def _restore(slam, fe, k, make_camera):
                                        for i, p in zip(G[c + "kf_index"], G[c + "kf_ptz"])]
 
 
-def _check_ba(slam, e, tol):
+def _check_ba(G, slam, e, tol):
     kfs = slam.keyframe_map.keyframe_list
     np.testing.assert_array_equal([kf.img_index for kf in kfs], G["ba%d_kf_index" % e])
     d = np.abs(np.array([[kf.pan, kf.tilt, kf.f] for kf in kfs]) - G["ba%d_kf_ptz" % e]).max(0)
@@ -111,7 +113,7 @@ def _check_ba(slam, e, tol):
         np.testing.assert_array_equal(pts, G["ba%d_pts_%d" % (e, i)])
 
 
-def _check_frame(slam, k, tol, worst):
+def _check_frame(G, slam, k, tol, worst):
     np.testing.assert_array_equal(np.asarray(slam.previous_keypoints_index, np.float64), G["prev_idx_%d" % k], err_msg="frame %d" % k)
     d = np.abs(slam.current_camera.get_ptz() - G["ptz_%d" % k])
     np.maximum(worst, d, out=worst)
@@ -127,43 +129,54 @@ def _check_frame(slam, k, tol, worst):
                                    atol=tol["cov"] * np.abs(probe).max())
 
 
-def _run_against_golden(make_camera, tol, slam_cls=PtzSlam, last_frame=None):
+def _run_against_golden(G, make_camera, tol, slam_cls=PtzSlam, last_frame=None):
     """The loop of experiment.py:22-46 against the reference run, re-started from the reference's state at the checkpoints."""
     n_frames, seed = int(G["n_frames"]), int(G["seed"])
     last_frame = n_frames - 1 if last_frame is None else last_frame
-    fe = CourtSequence(G["court_rays"], n_frames, seed)
+    fe = CourtSequence(G["court_rays"], n_frames, seed, blackout=G["blackout"])
     random.seed(seed)                                   # build_matching_graph thins pairs of > 200 matches with random.shuffle
     slam = slam_cls(front_end=fe)
     cam0 = make_camera(G["cam0"])
     slam.init_system(fe.image(0), cam0, fe.bounding_box)
     slam.add_keyframe(fe.image(0), cam0, 0, enable_rf=False)
     np.testing.assert_allclose(slam.rays, G["rays_0"], rtol=0, atol=tol["ray"])
-    ba_frames, checkpoints = G["ba_frames"].tolist(), G["checkpoints"].tolist()
-    events = 0
+    ba_frames, checkpoints, reloc_frames = G["ba_frames"].tolist(), G["checkpoints"].tolist(), G["reloc_frames"].tolist()
+    events = relocs = 0
     worst = np.zeros(3)
     for k in range(1, last_frame + 1):
         img = fe.image(k)
         slam.tracking(img, 80, fe.bounding_box)
         flags = [slam.new_keyframe, slam.tracking_lost, slam.bad_tracking_cnt, len(slam.cameras)]
         np.testing.assert_array_equal(np.array(flags, np.int64), G["flags_%d" % k], err_msg="frame %d" % k)
-        if slam.new_keyframe:
+        if slam.tracking_lost:                                          # experiment.py:39-43
+            assert k in reloc_frames
+            d = np.abs(slam.current_camera.get_ptz() - G["lost_ptz_%d" % k])
+            assert d[0] < tol["angle"] and d[1] < tol["angle"] and d[2] < tol["f"], ("lost pose", k, d)
+            cam = slam.relocalize(img, slam.current_camera, enable_rf=False)
+            d = np.abs(cam.get_ptz() - G["reloc_ptz_%d" % k])
+            assert d[0] < tol["angle"] and d[1] < tol["angle"] and d[2] < tol["f"], ("relocalised pose", k, d)
+            assert not slam.tracking_lost
+            slam.init_system(img, cam, fe.bounding_box)
+            relocs += 1
+        elif slam.new_keyframe:                                         # :45-46
             assert events < len(ba_frames) and ba_frames[events] == k
             slam.add_keyframe(img, slam.current_camera, k, enable_rf=False)
-            _check_ba(slam, events, tol)
+            _check_ba(G, slam, events, tol)
             events += 1
-        _check_frame(slam, k, tol, worst)
+        _check_frame(G, slam, k, tol, worst)
         if k in checkpoints:
             np.testing.assert_allclose(slam.rays, G["ck%d_rays" % k], rtol=0, atol=tol["ray"])
             scale = np.abs(G["ck%d_cov" % k]).max()
             assert np.abs(slam.state_cov - G["ck%d_cov" % k]).max() <= tol["cov"] * scale, ("covariance at checkpoint", k)
-            _restore(slam, fe, k, make_camera)
+            _restore(G, slam, fe, k, make_camera)
     if last_frame == n_frames - 1:
-        assert events == len(ba_frames) == 4
-        assert len(slam.keyframe_map.keyframe_list) == len(G["ba3_kf_ptz"]) == 5
+        assert events == len(ba_frames) and relocs == len(reloc_frames)
+        assert len(slam.keyframe_map.keyframe_list) == len(G["ba%d_kf_ptz" % (events - 1)])
         err = np.abs(slam.current_camera.get_ptz() - fe.gt[n_frames - 1])
         assert err[0] < 0.05 and err[1] < 0.05 and err[2] < 30.0        # the filter is on the ground-truth trajectory
-    print("cfg1 vs the reference run, frames 1..%d, %d keyframe BAs: worst |d pan|, |d tilt| (deg), |d f| (px)" % (last_frame, events), worst)
-    return slam
+    print("court sequence vs the reference run, frames 1..%d, %d keyframe BAs, %d relocalisations: worst |d pan|, |d tilt| (deg), |d f| (px)" %
+          (last_frame, events, relocs), worst)
+    return slam, events, relocs
 
 
 class TwinSlam(PtzSlam):
@@ -179,6 +192,18 @@ class TwinSlam(PtzSlam):
             BA.bundle_adjustment_core = saved
 
 
+    def relocalize(self, img, camera, enable_rf=False, bounding_box=None):
+        saved = (R.refine_pose, R.TransFunction.from_image_to_rays_batch)
+        R.refine_pose = lambda pose, rays, points, u, v, ftol=1e-4, verbose=0: O.reloc_refine(pose, rays, points, u, v, ftol=ftol)
+        R.TransFunction.from_image_to_rays_batch = staticmethod(
+            lambda u, v, ptz, points, cam_idx=None: O.back_project_to_rays_vec(ptz[0], ptz[1], ptz[2], u, v, points))
+        try:
+            return PtzSlam.relocalize(self, img, camera, enable_rf, bounding_box)
+        finally:
+            R.refine_pose = saved[0]
+            R.TransFunction.from_image_to_rays_batch = staticmethod(saved[1])
+
+
 HOST_TOL = {"angle": TOL_RAD_DEG, "f": 1e-3, "vel": 1e-3, "ray": TOL_RAD_DEG, "px": 1e-3, "cov": 1e-3,
             "ba_angle": TOL_RAD_DEG, "ba_f": 1e-3}
 
@@ -186,7 +211,16 @@ HOST_TOL = {"angle": TOL_RAD_DEG, "f": 1e-3, "vel": 1e-3, "ray": TOL_RAD_DEG, "p
 def test_cfg1_host_logic_golden():
     """BASELINE.json's tolerance (1e-6 rad, 1e-3 px) on every frame of every segment; flags, index arrays, keyframe events and the
     landmark bookkeeping of the four bundle adjustments exact."""
-    _run_against_golden(CourtOracleCamera, HOST_TOL, slam_cls=TwinSlam)
+    _, events, relocs = _run_against_golden(G, CourtOracleCamera, HOST_TOL, slam_cls=TwinSlam)
+    assert events == 4 and relocs == 0
+
+
+def test_cfg1_relocalization_host_logic_golden():
+    """The same loop through a lost frame: an optical-flow blackout walks bad_tracking_cnt to tracking_lost at frame 58, the caller
+    relocalises on the keyframe map (relocalization.py:96-189: nearest keyframe by match count, its pixels -> rays, 3-parameter
+    least_squares), re-initialises the filter (ptz_slam.py:140-208) and tracks on; bundle adjustments at frames 42 and 74."""
+    _, events, relocs = _run_against_golden(G_LOST, CourtOracleCamera, HOST_TOL, slam_cls=TwinSlam)
+    assert events == 2 and relocs == 1
 
 
 def _device_camera(ptz):
@@ -199,12 +233,12 @@ def _device_camera(ptz):
 @pytest.mark.gpu
 def test_cfg1_device_first_frames_golden():
     """Free running from the initial frame, 25 frames, against the reference run: BASELINE.json's tolerance."""
-    _run_against_golden(_device_camera, HOST_TOL, last_frame=25)
+    _run_against_golden(G, _device_camera, HOST_TOL, last_frame=25)
 
 
-def _lockstep(dev_cls, dev_camera):
+def _lockstep(G, dev_cls, dev_camera):
     n_frames, seed = int(G["n_frames"]), int(G["seed"])
-    fe = CourtSequence(G["court_rays"], n_frames, seed)
+    fe = CourtSequence(G["court_rays"], n_frames, seed, blackout=G["blackout"])
     random.seed(seed)
     twin, dev = TwinSlam(front_end=fe), dev_cls(front_end=fe)
     for slam, mk in ((twin, CourtOracleCamera), (dev, dev_camera)):
@@ -212,7 +246,7 @@ def _lockstep(dev_cls, dev_camera):
         slam.init_system(fe.image(0), cam0, fe.bounding_box)
         slam.add_keyframe(fe.image(0), cam0, 0, enable_rf=False)
     np.testing.assert_allclose(dev.rays, twin.rays, rtol=0, atol=TOL_RAD_DEG)
-    events, worst, worst_ba = 0, np.zeros(3), np.zeros(3)
+    events, relocs, worst, worst_ba = 0, 0, np.zeros(3), np.zeros(3)
     for k in range(1, n_frames):
         # the device instance takes over the twin's continuous state (the discrete state is asserted equal below)
         dev.rays, dev.state_cov = np.array(twin.rays), np.array(twin.state_cov)
@@ -227,7 +261,6 @@ def _lockstep(dev_cls, dev_camera):
         dev.tracking(img, 80, fe.bounding_box)
         assert [dev.new_keyframe, dev.tracking_lost, dev.bad_tracking_cnt, len(dev.cameras)] == \
                [twin.new_keyframe, twin.tracking_lost, twin.bad_tracking_cnt, len(twin.cameras)], k
-        assert not twin.tracking_lost
         np.testing.assert_array_equal(np.asarray(dev.previous_keypoints_index), np.asarray(twin.previous_keypoints_index), err_msg="frame %d" % k)
         d = np.abs(dev.current_camera.get_ptz() - twin.current_camera.get_ptz())
         worst = np.maximum(worst, d)
@@ -238,7 +271,17 @@ def _lockstep(dev_cls, dev_camera):
         if k % 10 == 0:
             scale = np.abs(twin.state_cov).max()
             assert np.abs(dev.state_cov - twin.state_cov).max() <= 1e-6 * scale, ("covariance", k)
-        if twin.new_keyframe:
+        if twin.tracking_lost:                          # experiment.py:39-43: relocalise on the keyframe map, start the filter again
+            cam_t = twin.relocalize(img, twin.current_camera, enable_rf=False)
+            cam_d = dev.relocalize(img, dev.current_camera, enable_rf=False)
+            d = np.abs(cam_d.get_ptz() - cam_t.get_ptz())
+            assert d[0] < TOL_RAD_DEG and d[1] < TOL_RAD_DEG and d[2] < 1e-3, ("relocalised pose", k, d)
+            twin.init_system(img, cam_t, fe.bounding_box)
+            dev.init_system(img, cam_d, fe.bounding_box)
+            assert np.abs(dev.rays - twin.rays).max() < TOL_RAD_DEG and not dev.tracking_lost and len(dev.cameras) == len(twin.cameras)
+            np.testing.assert_array_equal(np.asarray(dev.previous_keypoints_index), np.asarray(twin.previous_keypoints_index))
+            relocs += 1
+        elif twin.new_keyframe:
             state = random.getstate()                   # both bundle adjustments thin their match lists with the same shuffle
             twin.add_keyframe(img, twin.current_camera, k, enable_rf=False)
             random.setstate(state)
@@ -252,22 +295,32 @@ def _lockstep(dev_cls, dev_camera):
             for a, b in zip(ka, kb):
                 np.testing.assert_array_equal(a.landmark_index, b.landmark_index)
             events += 1
-    assert events >= 3 and len(dev.keyframe_map.keyframe_list) == events + 1
+    assert len(dev.keyframe_map.keyframe_list) == events + 1
     err = np.abs(dev.current_camera.get_ptz() - fe.gt[n_frames - 1])
     assert err[0] < 0.05 and err[1] < 0.05 and err[2] < 30.0
-    print("cfg1, 149 frames one step from the CPU twin, %d keyframe BAs: worst |d pan|, |d tilt| (deg), |d f| (px) per frame" % events,
-          worst, "; after a bundle adjustment", worst_ba)
-    return events
+    print("court sequence, %d frames one step from the CPU twin, %d keyframe BAs, %d relocalisations: worst |d pan|, |d tilt| (deg), |d f| (px) "
+          "per frame" % (n_frames - 1, events, relocs), worst, "; after a bundle adjustment", worst_ba)
+    return events, relocs
 
 
 def test_cfg1_lockstep_harness_on_cpu():
     """The lock-step driver of the GPU test below, with a second CPU twin in the device's place: the state hand-over, the shared
     shuffle state and the keyframe-map synchronisation reproduce the twin exactly, and the twin raises the reference's four
     keyframe events on this machine."""
-    assert _lockstep(TwinSlam, CourtOracleCamera) == 4
+    assert _lockstep(G, TwinSlam, CourtOracleCamera) == (4, 0)
+    assert _lockstep(G_LOST, TwinSlam, CourtOracleCamera) == (2, 1)
 
 
 @pytest.mark.gpu
 def test_cfg1_device_lockstep_with_cpu_twin():
     """All 150 frames and the keyframe bundle adjustments on the GPU, every frame one step away from the CPU twin's state."""
-    _lockstep(PtzSlam, _device_camera)
+    events, relocs = _lockstep(G, PtzSlam, _device_camera)
+    assert events >= 3 and relocs == 0
+
+
+@pytest.mark.gpu
+def test_cfg1_relocalization_device_lockstep_with_cpu_twin():
+    """The sequence with the flow blackout on the GPU: tracking_lost -> relocalize (residual + analytic Jacobian of the 3-parameter
+    refinement on the device) -> init_system -> tracking, and the bundle adjustments either side of it."""
+    events, relocs = _lockstep(G_LOST, PtzSlam, _device_camera)
+    assert events >= 1 and relocs == 1
