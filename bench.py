@@ -194,6 +194,32 @@ def verbatim_reference_record():
         return None
 
 
+def solver_phase_times(prob, x0, ref_pose, n_iter=3):
+    """CUDA-event time of every phase of an LM iteration: the library prints them to stderr when PTZBA_TRACE is set (read at
+    every solver call), so a few extra iterations run with fd 2 pointed at a temporary file.  Returns {phase: median us}."""
+    import re
+    import tempfile
+    sys.stderr.flush()
+    saved = os.dup(2)
+    tmp = tempfile.TemporaryFile(mode="w+b")
+    os.environ["PTZBA_TRACE"] = "1"
+    try:
+        os.dup2(tmp.fileno(), 2)
+        for _ in range(n_iter):
+            prob.lm_iteration(x0, ref_pose, alpha=1e-3)
+    finally:
+        os.dup2(saved, 2)
+        os.close(saved)
+        os.environ.pop("PTZBA_TRACE", None)
+    tmp.seek(0)
+    text = tmp.read().decode(errors="replace")
+    tmp.close()
+    phases = {}
+    for name, us in re.findall(r"([A-Za-z_+|0-9]+)=([0-9.]+)us", text):
+        phases.setdefault(name, []).append(float(us))
+    return {k: statistics.median(v) for k, v in phases.items()}
+
+
 def ekf_flops(n_matched, lu_route):
     """Algorithmic FP64 flops of one EKF update with n matched rays (m = 2n rows, s = 3 + 2n state columns), BASELINE.md section 4:
     Cholesky route m^3/3 + m^2 (s+1) + 2 n^2 m (+ 2 m s); pivoted-LU route 2 m^3/3 + 2 m^2 (s+1) + 2 n^2 m (+ 2 m s)."""
@@ -243,6 +269,39 @@ def bench_ekf(ctx, n_seq, n_rays, n_frames, seed0=2000):
             "roofline": {"bound": "fp64", "achieved": ach, "peak": pk["dfma_tflops"], "unit": "TFLOP/s", "frac": ach / pk["dfma_tflops"],
                          "peak_kind": pk["source"], "peak_dmma": pk["dmma_tflops"],
                          "flops": "algorithmic: factorisation of S + triangular solves of [G | y] + covariance down-date, per route (bench.py:ekf_flops)"}}
+
+
+def bench_projection(ctx, stream, n_cam=4096, n_ray=2000, reps=50):
+    """North-star subsystem 1 at the BASELINE config 4 shape (one pose per sequence x all rays): k_project_grid on device-resident
+    buffers, CUDA events on the library's stream, rotating over output buffers larger than the L2 in total.  Algorithmic bytes:
+    16 B per ray read + 16 B per (camera, ray) pixel written.  Same measurement as scripts/proj_bench.py."""
+    import torch
+    from ptz_slam_b200 import _lib, synth
+    rng = np.random.default_rng(1)
+    ptz = torch.from_numpy(np.stack([rng.uniform(50, 70, n_cam), rng.uniform(-10, -6, n_cam), rng.uniform(2000, 4000, n_cam)], 1)).cuda()
+    rays = torch.from_numpy(synth.make_ray_cloud(n_ray, 3)).cuda()
+    n_buf = max(1, int(np.ceil(300e6 / (n_cam * n_ray * 16))))
+    outs = [torch.empty(n_cam * n_ray * 2, dtype=torch.float64, device="cuda") for _ in range(n_buf)]
+    P = lambda t: _lib.ptr(int(t.data_ptr()))
+
+    def proj(i):
+        ctx.check(ctx.lib.ptzba_project(ctx.handle, _lib.DEVICE, n_cam, P(ptz), synth.PP_U, synth.PP_V, None, n_ray, P(rays), P(outs[i % n_buf])))
+    for i in range(5):
+        proj(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(reps):
+        proj(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = n_ray * 16 + n_cam * n_ray * 16
+    peaks, peak_kind = measured_peaks()
+    gbs = nbytes / ms / 1e6
+    return {"workload": "%d poses x %d rays (BASELINE config 4 shape), device-resident, %d output buffers in rotation" % (n_cam, n_ray, n_buf),
+            "pairs_per_s": n_cam * n_ray / (ms * 1e-3), "us_per_launch": ms * 1e3,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "peak_kind": peak_kind, "kernel": "k_project_grid", "algorithmic_bytes": nbytes}}
 
 
 def bench_cfg2(ctx, n_rays=3000, n_frames=20):
@@ -605,6 +664,23 @@ def run_ours(args):
         except Exception as e:
             lm["lm_cpu_baseline"] = {"error": (str(e).splitlines() or [type(e).__name__])[0]}
 
+    if lm is not None:
+        # FP64-pipe roofline of the dense step of the solve: the Cholesky of the reduced camera system
+        try:
+            ph = solver_phase_times(probs[0], x0, ref_pose)
+            n_red = 3 * (fb.n_pose - 1)
+            t_potrf = ph["potrf+block_inverses"] * 1e-6
+            pk = fp64_peak()
+            ach = n_red ** 3 / 3.0 / t_potrf / 1e12
+            lm["roofline_dense"] = {"bound": "fp64", "achieved": ach, "peak": pk["dfma_tflops"], "unit": "TFLOP/s", "frac": ach / pk["dfma_tflops"],
+                                    "peak_kind": pk["source"], "kernel_us": ph["potrf+block_inverses"],
+                                    "kernel": "k_potrf_coop: Cholesky of the reduced camera system, order %d (n^3/3 flops), + the 128x128 block "
+                                              "inverses, one persistent cooperative launch" % n_red,
+                                    "note": "latency-bound at this order (panels x device-wide barriers), not FP64-bound: DESIGN.md section 6"}
+            lm["lm_phases_us"] = ph
+        except Exception as e:
+            lm["roofline_dense"] = {"error": (str(e).splitlines() or [type(e).__name__])[0]}
+
     if world > 1 and not args.no_lm:
         # distributed solve, STRONG scaling of one problem of the named workload: every rank holds the whole observation
         # list (replicated data) and visits its landmark / keyframe-major slices (partitioned work); partial blocks, the
@@ -673,6 +749,13 @@ def run_ours(args):
     if rank == 0 and not args.no_ekf:
         cfg2 = bench_cfg2(ctx)
 
+    projection = None
+    if rank == 0 and world == 1:
+        try:
+            projection = bench_projection(ctx, stream)
+        except Exception as e:
+            projection = {"error": (str(e).splitlines() or [type(e).__name__])[0]}
+
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -712,6 +795,8 @@ def run_ours(args):
             line["ekf"] = ekf
         if cfg2:
             line["ekf_cfg2"] = cfg2
+        if projection:
+            line["projection"] = projection
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
