@@ -5,7 +5,7 @@ The court landmarks are the reference's own point mixture (synthesized_court_seq
 turned into rays by the reference's TransFunction.from_3dpoint_to_ray; tests/golden/make_golden.py:gen_cfg1 generates them WITH THE
 REFERENCE and stores them in tests/golden/cfg1_court.npz, so nothing here restates that code.  This module is the seeded stand-in
 for the OpenCV calls of the loop (feature detection, optical-flow matching + RANSAC, SIFT detection / matching between keyframes),
-shared by the golden generator (which plugs it into the UNMODIFIED reference classes) and by tests/test_zz_cfg1_end_to_end.py
+shared by the golden generator (which plugs it into the UNMODIFIED reference classes) and by tests/test_zx_cfg1_end_to_end.py
 (which plugs it into the product).  Ground truth geometry comes from the oracle's projection functions.  Test infrastructure only."""
 import numpy as np
 
