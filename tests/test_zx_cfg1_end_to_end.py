@@ -17,7 +17,7 @@ GPU: the product end to end - projection, back-projection, the EKF on the reside
 through the C-ABI - (a) free running over the first 25 frames against the golden and (b) all 150 frames in lock-step with the
 CPU twin above: before every frame the device instance takes over the twin's state, so each comparison is one predict + update +
 ray bookkeeping (and, at the four keyframe events, one bundle adjustment) away from a state the CPU test has pinned to the
-reference.  (The file sorts last on purpose: it is the longest GPU test.)"""
+reference.  (The file sorts late on purpose: these are the longest GPU tests and they were written after the last GPU run of the round.)"""
 import os
 import random
 
