@@ -8,6 +8,7 @@ Goldens (reference function -> file):
   PTZCamera.back_project_to_ray(s), TransFunction.from_image_to_ray               -> backprojection.npz
   PtzSlam.compute_h_jacobian                                                      -> h_jacobian.npz
   PtzSlam.ekf_update + predict lines ptz_slam.py:418-426 (6 frames)               -> ekf.npz
+  the same at the config 2 size (3 000 rays, 10 frames)                           -> cfg2_reference.npz
   bundle_adjustment._compute_residual                                             -> ba_residual.npz
   scipy least_squares call of bundle_adjustment.py:200-202 (as-is and tight)      -> ba_solve.npz
   util.overlap_pan_angle, scene_map.Map.good_new_keyframe                         -> keyframe_map.npz
@@ -144,6 +145,34 @@ def gen_ekf():
         out["ptz_%d" % k] = slam.current_camera.get_ptz()
         out["vel_%d" % k] = np.array(slam.velocity)
     np.savez_compressed(os.path.join(OUT, "ekf.npz"), **out)
+
+
+def gen_cfg2_reference():
+    """Config 2 shape (3 000 rays, every visible ray observed): 10 consecutive frames of PtzSlam.ekf_update + the predict lines
+    ptz_slam.py:418-426 by the UNMODIFIED reference (2.8 s per frame here) on the sequence tests/test_gpu_ekf.py uses for its
+    50-frame comparison against the oracle - the direct pin of that oracle (and of the device) at this size."""
+    n_rays, n_frames = 3000, 10
+    seq = synth.make_ekf_sequence(n_rays, n_frames + 1, seed=1002, keep_prob=1.0)
+    slam = ref.PtzSlam()
+    slam.cameras = [make_camera(seq.ptz_gt[0])]
+    slam.rays = seq.rays0.copy()
+    slam.state_cov = slam.angle_var * np.eye(3 + 2 * len(slam.rays))   # ptz_slam.py:199-200
+    slam.state_cov[2][2] = slam.f_var
+    out = {"n_rays": np.array(n_rays), "n_frames": np.array(n_frames), "seed": np.array(1002)}
+    for k in range(1, n_frames + 1):
+        slam.current_camera = copy.deepcopy(slam.cameras[-1])          # predict, ptz_slam.py:418-426
+        slam.current_camera.set_ptz(slam.current_camera.get_ptz() + slam.velocity)
+        slam.cameras.append(slam.current_camera)
+        slam.state_cov[0:3, 0:3] = slam.state_cov[0:3, 0:3] + 5 * np.diag([slam.angle_var, slam.angle_var, slam.f_var])
+        slam.ekf_update(seq.obs_xy[k], seq.obs_idx[k], H, W)
+        out["ptz_%d" % k] = slam.current_camera.get_ptz()
+        out["vel_%d" % k] = np.array(slam.velocity)
+        if k in (5, n_frames):
+            out["rays_%d" % k] = slam.rays.copy()
+            out["cov_diag_%d" % k] = np.diag(slam.state_cov).copy()
+            out["cov_probe_%d" % k] = slam.state_cov @ cov_probe_vector(slam.state_cov.shape[0])
+        print("cfg2 reference frame %d: ptz error vs ground truth %s" % (k, out["ptz_%d" % k] - seq.ptz_gt[k]), flush=True)
+    np.savez_compressed(os.path.join(OUT, "cfg2_reference.npz"), **out)
 
 
 def _graph_to_npz(g, out):
@@ -821,6 +850,7 @@ if __name__ == "__main__":
     gen_tracking()
     gen_cfg1()
     gen_cfg1_relocalize()
+    gen_cfg2_reference()
     gen_util_noise()
     gen_camera_3d()
     gen_keyframe_map()

@@ -97,6 +97,29 @@ def test_ekf_six_frames():
     assert np.any(s.state_cov[3::2, 3::2][~np.eye((len(s.rays)), dtype=bool)] != 0)
 
 
+def test_ekf_cfg2_size_ten_frames():
+    """The oracle against the UNMODIFIED reference at the config 2 size: 3 000 rays, every visible ray observed (~1 000 matched per
+    frame), 10 consecutive predict + update steps (golden cfg2_reference.npz: the reference takes 2.8 s per frame).  BASELINE.json's
+    parameter tolerance, 1e-6 rad / 1e-3 px; measured 2e-11 degrees / 1e-9 px."""
+    d = load_golden("cfg2_reference.npz")
+    n_frames = int(d["n_frames"])
+    seq = synth.make_ekf_sequence(int(d["n_rays"]), n_frames + 1, seed=int(d["seed"]), keep_prob=1.0)
+    s = O.EkfState(seq.rays0, seq.ptz_gt[0], synth.PP_U, synth.PP_V)
+    tol = np.degrees(1e-6)
+    for k in range(1, n_frames + 1):
+        O.ekf_predict(s)
+        O.ekf_update(s, seq.obs_xy[k], seq.obs_idx[k], synth.IMAGE_H, synth.IMAGE_W)
+        e = np.abs(s.ptz - d["ptz_%d" % k])
+        assert e[0] < tol and e[1] < tol and e[2] < 1e-3, (k, e)
+        assert np.abs(s.velocity - d["vel_%d" % k]).max() < 1e-3
+        if "rays_%d" % k in d.files:
+            assert np.abs(s.rays - d["rays_%d" % k]).max() < tol
+            np.testing.assert_allclose(np.diag(s.state_cov), d["cov_diag_%d" % k], rtol=1e-6, atol=1e-12)
+            probe = d["cov_probe_%d" % k]
+            v = np.random.default_rng(s.state_cov.shape[0]).uniform(0.5, 1.5, s.state_cov.shape[0])
+            np.testing.assert_allclose(s.state_cov @ v, probe, rtol=1e-6, atol=1e-9 * np.abs(probe).max())
+
+
 def test_ba_residual_lists_and_flat():
     d = load_golden("ba_residual.npz")
     u, v = d["uv"]

@@ -231,6 +231,28 @@ def _device_camera(ptz):
 
 
 @pytest.mark.gpu
+def test_cfg2_size_device_vs_reference_golden():
+    """Config 2 size (3 000 rays, ~1 000 matched per frame) on the resident filter state, free running for 8 frames against the run of
+    the UNMODIFIED reference (golden cfg2_reference.npz); BASELINE.json's tolerance.  (tests/test_gpu_ekf.py compares 50 frames with
+    the oracle; tests/test_oracle.py pins that oracle to this golden.)"""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg2_reference.npz"))
+    seq = synth.make_ekf_sequence(int(d["n_rays"]), int(d["n_frames"]) + 1, seed=int(d["seed"]), keep_prob=1.0)
+    slam = PtzSlam()
+    slam.init_rays(seq.rays0, _device_camera(seq.ptz_gt[0]))
+    worst = np.zeros(3)
+    for k in range(1, 9):
+        slam.predict()
+        slam.ekf_update(seq.obs_xy[k], seq.obs_idx[k], synth.IMAGE_H, synth.IMAGE_W)
+        e = np.abs(slam.current_camera.get_ptz() - d["ptz_%d" % k])
+        worst = np.maximum(worst, e)
+        assert e[0] < TOL_RAD_DEG and e[1] < TOL_RAD_DEG and e[2] < 1e-3, (k, e)
+        if "rays_%d" % k in d.files:
+            assert np.abs(slam.rays - d["rays_%d" % k]).max() < TOL_RAD_DEG
+            np.testing.assert_allclose(np.diag(slam.state_cov), d["cov_diag_%d" % k], rtol=1e-4, atol=1e-10)
+    print("cfg2 size on the device, 8 frames against the reference run: worst |d pan|, |d tilt| (deg), |d f| (px)", worst)
+
+
+@pytest.mark.gpu
 def test_cfg1_device_first_frames_golden():
     """Free running from the initial frame, 25 frames, against the reference run: BASELINE.json's tolerance."""
     _run_against_golden(G, _device_camera, HOST_TOL, last_frame=25)
