@@ -230,11 +230,7 @@ def _device_camera(ptz):
     return cam
 
 
-@pytest.mark.gpu
-def test_cfg2_size_device_vs_reference_golden():
-    """Config 2 size (3 000 rays, ~1 000 matched per frame) on the resident filter state, free running for 8 frames against the run of
-    the UNMODIFIED reference (golden cfg2_reference.npz); BASELINE.json's tolerance.  (tests/test_gpu_ekf.py compares 50 frames with
-    the oracle; tests/test_oracle.py pins that oracle to this golden.)"""
+def _cfg2_size_vs_reference_golden():
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg2_reference.npz"))
     seq = synth.make_ekf_sequence(int(d["n_rays"]), int(d["n_frames"]) + 1, seed=int(d["seed"]), keep_prob=1.0)
     slam = PtzSlam()
@@ -249,7 +245,33 @@ def test_cfg2_size_device_vs_reference_golden():
         if "rays_%d" % k in d.files:
             assert np.abs(slam.rays - d["rays_%d" % k]).max() < TOL_RAD_DEG
             np.testing.assert_allclose(np.diag(slam.state_cov), d["cov_diag_%d" % k], rtol=1e-4, atol=1e-10)
-    print("cfg2 size on the device, 8 frames against the reference run: worst |d pan|, |d tilt| (deg), |d f| (px)", worst)
+    print("cfg2 size through PtzSlam's resident-state path, 8 frames against the reference run: worst |d pan|, |d tilt| (deg), |d f| (px)", worst)
+
+
+def test_device_path_host_logic_on_fake_device(monkeypatch):
+    """The four GPU tests below, on a machine without a GPU: `_lib.get_context` is routed to tests/fake_device.py (the slice of the
+    C-ABI that PtzSlam / PTZCamera / the relocaliser call, answered by the oracle) and the bundle-adjustment solve to the oracle, so
+    what runs is the product's HOST side of the device path - which copy of rays / state_cov is current, when the resident batch is
+    uploaded, re-created, compacted and grown, how observation buffers are padded - under exactly the call pattern of those tests
+    (state handed over before every frame, ray count changing every frame, init_system in mid-sequence after a relocalisation)."""
+    import fake_device
+    ctx = fake_device.install(monkeypatch)
+    monkeypatch.setattr(BA, "bundle_adjustment_core", oracle_ba_core)
+    _cfg2_size_vs_reference_golden()
+    _run_against_golden(G, _device_camera, HOST_TOL, last_frame=25)
+    assert _lockstep(G, PtzSlam, _device_camera) == (4, 0)
+    assert _lockstep(G_LOST, PtzSlam, _device_camera) == (2, 1)
+    calls = ctx.lib.calls
+    assert calls["update_only"] >= 8 + 25 + 149 + 89 and calls["remove_rays"] > 100 and calls["add_rays"] > 50
+    assert calls["create"] == calls["destroy"] or calls["create"] == calls["destroy"] + 1      # nothing leaks but the live batch
+
+
+@pytest.mark.gpu
+def test_cfg2_size_device_vs_reference_golden():
+    """Config 2 size (3 000 rays, ~1 000 matched per frame) on the resident filter state, free running for 8 frames against the run of
+    the UNMODIFIED reference (golden cfg2_reference.npz); BASELINE.json's tolerance.  (tests/test_gpu_ekf.py compares 50 frames with
+    the oracle; tests/test_oracle.py pins that oracle to this golden.)"""
+    _cfg2_size_vs_reference_golden()
 
 
 @pytest.mark.gpu
