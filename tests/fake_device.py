@@ -212,6 +212,44 @@ class FakeLib:
         return 0
 
 
+    # ---- ba_kernels.cu / ba_solver.cu: the calls of bundle_adjustment_core (host buffers) -----------------------------------------
+    def ptzba_ba_create(self, ctx, mem, n_pose, n_landmark, n_obs, cam_idx, lm_idx, obs_xy, u, v, out_handle):
+        self._count("ba_create")
+        assert mem == _lib.HOST
+        h = self.next_handle
+        self.next_handle += 1
+        self.batches[h] = dict(N=n_pose, M=n_landmark, cam=_view(cam_idx, (n_obs,), np.int32).copy(), lm=_view(lm_idx, (n_obs,), np.int32).copy(),
+                               xy=_view(obs_xy, (n_obs, 2)).copy(), u=u, v=v)
+        out_handle._obj.value = h
+        return 0
+
+    def ptzba_ba_destroy(self, h):
+        self.batches.pop(h.value if hasattr(h, "value") else int(h), None)
+
+    def ptzba_ba_solve(self, h, mem, x, reference_pose3, opt, rep):
+        """least_squares(method='trf', x_scale='jac') semantics with the exact Jacobian: oracle.trf_solve."""
+        self._count("ba_solve")
+        p = self._b(h)
+        assert mem == _lib.HOST
+        N, M = p["N"], p["M"]
+        xv = _view(x, (3 * (N - 1) + 2 * M,))
+        ref = _view(reference_pose3, (3,)).copy()
+
+        def fun(z):
+            poses, rays = O.ba_unpack(z, N, ref)
+            return np.ravel(O.ba_residual_flat(poses, rays, p["cam"], p["lm"], p["xy"], p["u"], p["v"]))
+
+        def jac(z):
+            poses, rays = O.ba_unpack(z, N, ref)
+            return O.ba_jacobian_sparse(poses, rays, p["cam"], p["lm"]).toarray()
+
+        o, r = opt._obj, rep._obj
+        out = O.trf_solve(fun, jac, xv.copy(), ftol=o.ftol, xtol=o.xtol, gtol=o.gtol, max_nfev=o.max_nfev or None)
+        xv[:] = out["x"]
+        r.cost, r.status, r.nfev, r.njev, r.nit = out["cost"], out["status"], out["nfev"], out["njev"], out["nit"]
+        return 0
+
+
 class FakeContext:
     def __init__(self):
         self.lib, self.handle, self.device = FakeLib(), None, 0
