@@ -26,3 +26,32 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small", "--gpus", "2"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_helpers():
+    """Host-side helpers of bench.py that only run on the GPU box otherwise."""
+    sys.path.insert(0, ROOT)
+    import bench
+    # algorithmic bytes of the fused pass: BASELINE.md section 4 (cfg3 = 85 624 576 B, the judge's own recomputation in VERDICT.md)
+    assert bench.algorithmic_bytes(2000000, 100000, 256) == 85624576
+    # EKF flop model: the LU route costs twice the factorisation + solve terms of the Cholesky route
+    import numpy as np
+    n = np.array([100.0, 575.0])
+    chol, lu = bench.ekf_flops(n, [0, 0]), bench.ekf_flops(n, [1, 1])
+    m, s_ = 2 * n, 3 + 2 * n
+    np.testing.assert_allclose(lu - chol, m ** 3 / 3 + m * m * (s_ + 1))
+    assert bench._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    # best effort by contract: without a GPU (or sysfs) it says why and never raises
+    import torch
+    if not torch.cuda.is_available():
+        assert bench.pin_to_gpu_numa_node(0).startswith("not pinned")
+    vr = bench.verbatim_reference_record()
+    assert vr and vr["compute_residual_obs_per_s"] > 1e4 and set(vr["ekf_update_frames_per_s_by_rays"]) >= {"128", "3000"}
+    pk = bench.fp64_peak()
+    assert 20 < pk["dfma_tflops"] < 60 and 20 < pk["dmma_tflops"] < 60
+
+
+def test_watchdog_ends_a_stuck_run():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg3", "--watchdog", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 124 and "watchdog" in out.stderr and out.stdout.strip() == ""
